@@ -1,0 +1,248 @@
+/*
+ * pnc_b200.h -- C ABI of the batched whole-body-control engine (B200, sm_100a).
+ *
+ * The reference (junhyeokahn/PyPnC) has no FFI on this path: the boundary is two
+ * Python classes.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   pnc_model_create         PinocchioRobotSystem._config_robot
+ *                            pnc/robot_system/pinocchio_robot_system.py:33-93
+ *   pnc_update_system        PinocchioRobotSystem.update_system        :128-179
+ *                            + every getter the controller calls per tick:
+ *                            get_mass_matrix :202, get_gravity :205, get_coriolis :209,
+ *                            get_com_pos/lin_vel :214-220, get_com_lin_jacobian :222,
+ *                            get_com_lin_jacobian_dot :226, get_link_iso :231,
+ *                            get_link_vel :239, get_link_jacobian :252,
+ *                            get_link_jacobian_dot_times_qdot :265
+ *   pnc_ws_*                 the getters above, as device pointers into the workspace
+ *   pnc_problem_create       <Robot>TCIContainer.__init__ + <Robot>Controller.__init__
+ *                            pnc/atlas_pnc/atlas_tci_container.py:10-99,
+ *                            pnc/atlas_pnc/atlas_controller.py:10-49
+ *   pnc_ihwbc_solve          BasicTask.update_jacobian/update_cmd  pnc/wbc/basic_task.py:25-137
+ *                            Contact.update_contact                pnc/wbc/basic_contact.py:24-173
+ *                            IHWBC.update_setting + IHWBC.solve    pnc/wbc/ihwbc/ihwbc.py:84-379
+ *                            (QP: qpsolvers->quadprog at ihwbc.py:330; algorithm of
+ *                             external_source/Goldfarb/QuadProg++.cc:115-502)
+ *   pnc_task_eval            Task.jacobian / jacobian_dot_q_dot / op_cmd (debug + parity)
+ *   pnc_joint_integrate      JointIntegrator.integrate  pnc/wbc/ihwbc/joint_integrator.py:73-82
+ *   pnc_wbc_tick_host        <Robot>Controller.get_command body  atlas_controller.py:51-86,
+ *                            host buffers in, host buffers out (the e2e call)
+ *
+ * Conventions: fp64 everywhere; quaternions scalar-last (x,y,z,w);
+ * spatial quantities at the API are [angular; linear]; generalized velocity =
+ * [base lin (base frame); base ang (base frame); joints]; reaction force of a surface
+ * contact = [torque(3); force(3)] in world axes; all batched arrays are row-major with
+ * the batch index first.  Pointers named d_* are DEVICE pointers, h_* HOST pointers.
+ * Every call is asynchronous on `stream` (a cudaStream_t passed as void*) unless it
+ * says otherwise; calls on one handle are stream-ordered, not re-entrant.
+ *
+ * Return value: 0 on success, a negative PNC_E_* code on API misuse / CUDA failure.
+ * Per-state solver outcomes are reported in `status[B]` (PNC_QP_*), never by abort.
+ */
+#ifndef PNC_B200_H
+#define PNC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNC_OK 0
+#define PNC_E_ARG (-1)
+#define PNC_E_CUDA (-2)
+#define PNC_E_SIZE (-3)    /* model/problem exceeds a compiled-in limit */
+#define PNC_E_NOGPU (-4)
+
+/* joint types (model tables) */
+#define PNC_JOINT_FREEFLYER 0
+#define PNC_JOINT_REVOLUTE 1
+
+/* task types: pnc/wbc/basic_task.py:26-105 */
+#define PNC_TASK_JOINT 0
+#define PNC_TASK_SELECTED_JOINT 1
+#define PNC_TASK_LINK_XYZ 2
+#define PNC_TASK_LINK_ORI 3
+#define PNC_TASK_COM 4
+
+/* contact types: pnc/wbc/basic_contact.py:13,54 */
+#define PNC_CONTACT_POINT 0   /* dim 3, 6 cone rows  */
+#define PNC_CONTACT_SURFACE 1 /* dim 6, 18 cone rows */
+
+/* per-state QP status */
+#define PNC_QP_OK 0
+#define PNC_QP_INFEASIBLE 1     /* QuadProg++.cc:402-407 returns inf            */
+#define PNC_QP_NOT_PD 2         /* Cholesky pivot <= 0, QuadProg++.cc:715-722   */
+#define PNC_QP_EQ_DEPENDENT 3   /* "Constraints are linearly dependent" :268-271 */
+#define PNC_QP_MAX_ITER 4
+
+/* limits compiled into the kernels */
+#define PNC_MAX_BODIES 32   /* one warp lane per movable body */
+#define PNC_MAX_NV 40
+#define PNC_MAX_FRAMES 12   /* distinct task/contact frames of one problem */
+#define PNC_MAX_TASKS 16
+#define PNC_MAX_CONTACTS 4
+#define PNC_MAX_IC 4        /* internal-constraint rows */
+
+/* ---- model ------------------------------------------------------------- */
+typedef struct {
+  int32_t nb;         /* movable bodies; body 0 is the free-flyer on a floating base */
+  int32_t nq, nv, na; /* as RobotSystem.n_q / n_q_dot / n_a */
+  int32_t n_floating; /* 0 or 6 */
+  int32_t nf;         /* frames */
+  double total_mass;  /* sum of all link masses (wrapper's total_mass, :73-74) */
+  double mass_dyn;    /* mass seen by the centre-of-mass algorithms (moving bodies) */
+  const int32_t* parent;   /* [nb] -1 = universe; parent[i] < i, DFS numbering */
+  const int32_t* jtype;    /* [nb] */
+  const int32_t* idx_v;    /* [nb] */
+  const int32_t* subtree;  /* [nb] bodies i..i+subtree[i]-1 form the subtree of i */
+  const double* place_R;   /* [nb*9] joint placement in parent joint frame, row-major */
+  const double* place_p;   /* [nb*3] */
+  const double* axis;      /* [nb*3] unit axis (revolute) */
+  const double* mass;      /* [nb] */
+  const double* com;       /* [nb*3] joint frame */
+  const double* inertia;   /* [nb*9] about com, joint-frame axes */
+  const int32_t* frame_parent; /* [nf] body index, -1 = universe */
+  const double* frame_R;   /* [nf*9] placement in the parent joint frame */
+  const double* frame_p;   /* [nf*3] */
+} pnc_model_desc;
+
+typedef struct pnc_model pnc_model;
+
+int pnc_model_create(const pnc_model_desc* desc, int device, pnc_model** out);
+void pnc_model_destroy(pnc_model* m);
+
+/* ---- WBC problem (tasks, contacts, internal constraints, selection) ---- */
+typedef struct {
+  int32_t type;      /* PNC_TASK_* */
+  int32_t dim;
+  int32_t frame;     /* model frame index (LINK_*), else -1 */
+  int32_t joint_off; /* SELECTED_JOINT: offset into joint_sel[] (v indices) */
+  int32_t des_off;   /* offset of this task in the per-state `des` row:
+                        pos_des (dim; 4 = quat xyzw for LINK_ORI), vel_des (dim), acc_des (dim) */
+  int32_t gain_off;  /* offset into kp[] / kd[] */
+} pnc_task_desc;
+
+typedef struct {
+  int32_t type;  /* PNC_CONTACT_* */
+  int32_t frame; /* model frame index */
+  double mu, x, y; /* friction, half sizes (surface only) */
+} pnc_contact_desc;
+
+typedef struct {
+  int32_t ntask;
+  const pnc_task_desc* tasks;
+  int32_t ncontact;
+  const pnc_contact_desc* contacts;
+  int32_t n_joint_sel;
+  const int32_t* joint_sel; /* v indices referenced by SELECTED_JOINT tasks */
+  int32_t n_gain;
+  const double* kp;
+  const double* kd;
+  int32_t n_ic;            /* rows of the internal-constraint Jacobian (0 = none) */
+  const double* ic_jac;    /* [n_ic*nv] constant rows (draco3_rolling_joint_constraint.py:9-16) */
+  int32_t nact;            /* rows of Sa */
+  const int32_t* act_idx;  /* [nact] v index of each actuated joint (Sa one-hot columns) */
+  int32_t b_trq_limit;     /* WBCConfig.B_TRQ_LIMIT */
+  const double* trq_limit; /* [nact*2] lower, upper (ihwbc.trq_limit) */
+  double lambda_q_ddot;
+  double lambda_rf;
+  int32_t ndes;            /* length of one per-state `des` row */
+} pnc_problem_desc;
+
+typedef struct pnc_problem pnc_problem;
+
+int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* desc, pnc_problem** out);
+void pnc_problem_destroy(pnc_problem* p);
+/* sizes derived from the descriptor: QP n = nv + nc, p = 6 + n_ic, m = ncone + 2*nact */
+int pnc_problem_dims(const pnc_problem* p, int32_t* nc, int32_t* ncone, int32_t* n, int32_t* p_eq,
+                     int32_t* m_ineq);
+
+/* ---- workspace: per-state rigid-body quantities kept in HBM ------------- */
+typedef struct pnc_workspace pnc_workspace;
+
+/* frames[nframes]: the model frames whose iso/vel/J/Jdot*qdot are materialised */
+int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* frames, int32_t nframes,
+                         pnc_workspace** out);
+void pnc_workspace_destroy(pnc_workspace* ws);
+int64_t pnc_workspace_bytes(const pnc_workspace* ws);
+
+/* robot_system.update_system for B states (fixed base: pass NULL base pointers).
+ * base_lin_vel / base_ang_vel are WORLD-frame (base_joint_*), rotated into the base
+ * frame inside, as pinocchio_robot_system.py:149-162 does. */
+int pnc_update_system(pnc_workspace* ws, int32_t B, const double* d_base_pos, const double* d_base_quat,
+                      const double* d_base_lin_vel, const double* d_base_ang_vel,
+                      const double* d_joint_pos, const double* d_joint_vel, void* stream);
+
+/* device pointers into the workspace, valid until the workspace is destroyed.
+ * Shapes (row-major, batch first): q [B,nq], qdot [B,nv], M [B,nv,nv], grav [B,nv],
+ * cori [B,nv], com [B,3], vcom [B,3], jcom [B,3,nv], jcomdot [B,3,nv], jcomdot_qdot [B,3],
+ * frame_iso [B,nfr,12] (R row-major 9, p 3), frame_vel [B,nfr,6] ([ang;lin]),
+ * frame_jac [B,nfr,6,nv] ([ang;lin] rows), frame_jdqd [B,nfr,6] ([ang;lin]). */
+double* pnc_ws_q(pnc_workspace* ws);
+double* pnc_ws_qdot(pnc_workspace* ws);
+double* pnc_ws_mass_matrix(pnc_workspace* ws);
+double* pnc_ws_gravity(pnc_workspace* ws);
+double* pnc_ws_coriolis(pnc_workspace* ws);
+double* pnc_ws_com_pos(pnc_workspace* ws);
+double* pnc_ws_com_vel(pnc_workspace* ws);
+double* pnc_ws_com_jac(pnc_workspace* ws);
+double* pnc_ws_com_jacdot(pnc_workspace* ws);
+double* pnc_ws_com_jdqd(pnc_workspace* ws);
+double* pnc_ws_frame_iso(pnc_workspace* ws);
+double* pnc_ws_frame_vel(pnc_workspace* ws);
+double* pnc_ws_frame_jac(pnc_workspace* ws);
+double* pnc_ws_frame_jdqd(pnc_workspace* ws);
+
+/* ---- IHWBC ---------------------------------------------------------------- */
+/* One launch: task Jacobians/commands, contact cones, cost + constraint assembly,
+ * batched Goldfarb-Idnani solve, torque recovery.  Requires pnc_update_system on `ws`.
+ *   d_des        [B,ndes]     task desireds (layout: pnc_task_desc.des_off)
+ *   d_w          [B,ntask]    w_hierarchy per task
+ *   d_rf_z_max   [B,ncontact] (values <= 0 are replaced by 1e-3, contact.py:37-41)
+ * outputs
+ *   d_trq [B,nact]  d_acc [B,nact]  d_rf [B,nc]  d_qddot [B,nv] (may be NULL)
+ *   d_status [B] int32 PNC_QP_*   d_iters [B] int32 (active-set iterations)
+ *   d_active [B, ceil(m/64)] uint64 bit i set <=> inequality i active at the solution
+ *            (inequality order = rows of ineq_mat, ihwbc.py:255-317: cones, -trq, +trq) */
+int pnc_ihwbc_solve(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* d_des,
+                    const double* d_w, const double* d_rf_z_max, double* d_trq, double* d_acc,
+                    double* d_rf, double* d_qddot, int32_t* d_status, int32_t* d_iters,
+                    uint64_t* d_active, void* stream);
+
+/* Task.jacobian [B,dim,nv], jacobian_dot_q_dot [B,dim], op_cmd [B,dim], pos_err [B,dim]
+ * of task `itask` (any output may be NULL). */
+int pnc_task_eval(const pnc_problem* p, pnc_workspace* ws, int32_t B, int32_t itask, const double* d_des,
+                  double* d_jac, double* d_jdqd, double* d_op_cmd, double* d_pos_err, void* stream);
+
+/* Contact.jacobian [B,dim,nv], cone_constraint_mat [B,rows,dim], cone_constraint_vec [B,rows] */
+int pnc_contact_eval(const pnc_problem* p, pnc_workspace* ws, int32_t B, int32_t icontact,
+                     const double* d_rf_z_max, double* d_jac, double* d_cone_mat, double* d_cone_vec,
+                     void* stream);
+
+/* JointIntegrator.integrate: state vel/pos [B,na] updated in place, returned as the
+ * commands.  limits are [na*2]. */
+int pnc_joint_integrate(int32_t B, int32_t na, const double* d_acc, const double* d_joint_pos,
+                        double* d_vel_state, double* d_pos_state, const double* d_pos_limit,
+                        const double* d_vel_limit, double alpha_vel, double alpha_pos, double dt,
+                        void* stream);
+
+/* Whole controller tick with HOST buffers: H2D of the inputs, update_system, solve,
+ * D2H of the outputs; synchronous.  Any output may be NULL. */
+int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,
+                      const double* h_base_quat, const double* h_base_lin_vel,
+                      const double* h_base_ang_vel, const double* h_joint_pos, const double* h_joint_vel,
+                      const double* h_des, const double* h_w, const double* h_rf_z_max, double* h_trq,
+                      double* h_acc, double* h_rf, int32_t* h_status, int32_t* h_iters,
+                      uint64_t* h_active);
+
+/* number of kernels this library has launched since load (bench `gpu_launches`) */
+int64_t pnc_launch_count(void);
+/* DFMA-chain microbenchmark: measured fp64 FMA peak of the device in TFLOP/s */
+int pnc_measure_fp64_peak(int device, double* tflops);
+const char* pnc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNC_B200_H */

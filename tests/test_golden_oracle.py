@@ -1,0 +1,82 @@
+"""The C oracle reproduces the golden vectors made by the reference's own Python classes
+(tests/golden/make_golden.py: IHWBC / BasicTask / contacts / containers from /root/reference)."""
+import os
+
+import numpy as np
+import pytest
+
+from pypnc_b200 import robots
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+ROBOTS = ['atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie']
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    states = {k[3:]: z[k] for k in z.files if k.startswith('in_') and k not in ('in_des', 'in_w', 'in_rf_z_max')}
+    return z, states
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+
+
+@pytest.mark.parametrize("name", ROBOTS)
+def test_oracle_tick_matches_reference_python(oracle_mod, name):
+    spec = robots.PROBLEMS[name]()
+    op = oracle_mod.OracleProblem(spec)
+    z, states = load_golden(name)
+    out = op.tick_batch(states, z['in_des'], z['in_w'], z['in_rf_z_max'])
+    assert np.all(out['status'] == 0)
+    # tolerance: 1e-9 relative (north_star), numpy/BLAS vs plain-C summation order in the assembly
+    assert rel_err(out['trq'], z['out_trq']) < 1e-9
+    assert rel_err(out['acc'], z['out_acc']) < 1e-9
+    assert rel_err(out['rf'], z['out_rf']) < 1e-9
+
+
+@pytest.mark.parametrize("name", ROBOTS)
+def test_oracle_task_and_contact_eval_match_reference(oracle_mod, name):
+    spec = robots.PROBLEMS[name]()
+    op = oracle_mod.OracleProblem(spec)
+    z, states = load_golden(name)
+    B = z['in_des'].shape[0]
+    for b in range(B):
+        q, v = op.om.pack_state(*[states[k][b] for k in ('base_pos', 'base_quat', 'base_lin_vel', 'base_ang_vel',
+                                                         'joint_pos', 'joint_vel')])
+        r0 = 0
+        for i, t in enumerate(spec.tasks):
+            e = op.task_eval(q, v, z['in_des'][b], i)
+            d = t['dim']
+            np.testing.assert_allclose(e['jacobian'], z['out_task_jac'][b, r0:r0 + d], atol=1e-13)
+            np.testing.assert_allclose(e['jacobian_dot_q_dot'], z['out_task_jdqd'][b, r0:r0 + d], atol=1e-11)
+            np.testing.assert_allclose(e['op_cmd'], z['out_task_op'][b, r0:r0 + d], rtol=1e-11, atol=1e-10)
+            r0 += d
+        o = 0
+        ov = 0
+        for i, c in enumerate(spec.contacts):
+            e = op.contact_eval(q, v, z['in_rf_z_max'][b, i], i)
+            k = e['cone_constraint_mat'].size
+            np.testing.assert_allclose(e['cone_constraint_mat'].ravel(), z['out_cone_mat'][b, o:o + k], atol=1e-14)
+            kv = e['cone_constraint_vec'].size
+            np.testing.assert_allclose(e['cone_constraint_vec'], z['out_cone_vec'][b, ov:ov + kv], atol=0)
+            o += k
+            ov += kv
+
+
+def test_atlas_static_weight_balance(oracle_mod):
+    """upright Atlas at rest, zero desired accelerations -> sum fz = m g."""
+    spec = robots.atlas_problem()
+    op = oracle_mod.OracleProblem(spec)
+    jp0, z0, q0 = robots.nominal_pose('atlas', spec.model)
+    st = dict(base_pos=np.array([[0, 0, z0]]), base_quat=q0[None], base_lin_vel=np.zeros((1, 3)),
+              base_ang_vel=np.zeros((1, 3)), joint_pos=jp0[None], joint_vel=np.zeros((1, 30)))
+    act = op.task_actuals(st)
+    des = np.zeros((1, spec.ndes))
+    for i, t in enumerate(spec.tasks):
+        npos = 4 if t['type'] == 3 else t['dim']
+        des[0, t['des_off']:t['des_off'] + npos] = act['task_pos'][i][0]
+    out = op.tick_batch(st, des, np.array([spec.w_default]), np.array([[2000., 2000.]]))
+    assert out['status'][0] == 0
+    fz = out['rf'][0, 5] + out['rf'][0, 11]
+    assert abs(fz - spec.model.total_mass * 9.81) < 1e-3 * spec.model.total_mass * 9.81
+    assert np.abs(out['qddot'][0]).max() < 1e-2

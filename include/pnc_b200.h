@@ -241,6 +241,10 @@ int64_t pnc_launch_count(void);
 /* DFMA-chain microbenchmark: measured fp64 FMA peak of the device in TFLOP/s */
 int pnc_measure_fp64_peak(int device, double* tflops);
 const char* pnc_version(void);
+/* debug: while d_buf != NULL the solve kernel writes, for state `state`, the assembled QP pieces
+ * (Hessian lower triangle n*n, g0 n, constraint rows nrow*n, their offsets nrow, cone matrix nu*6,
+ * cone vector nu, unconstrained minimiser n) into d_buf.  Pass NULL to switch it off. */
+int pnc_debug_set_dump(double* d_buf, int state);
 
 #ifdef __cplusplus
 }

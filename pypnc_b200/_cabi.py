@@ -137,6 +137,7 @@ def load_library():
     lib.pnc_launch_count.argtypes = []
     lib.pnc_launch_count.restype = i64
     lib.pnc_measure_fp64_peak.argtypes = [C.c_int, c_double_p]
+    lib.pnc_debug_set_dump.argtypes = [vp, C.c_int]
     lib.pnc_version.argtypes = []
     lib.pnc_version.restype = C.c_char_p
     _lib = lib
@@ -150,5 +151,5 @@ EXPORTED_SYMBOLS = [
     'pnc_ws_coriolis', 'pnc_ws_com_pos', 'pnc_ws_com_vel', 'pnc_ws_com_jac', 'pnc_ws_com_jacdot',
     'pnc_ws_com_jdqd', 'pnc_ws_frame_iso', 'pnc_ws_frame_vel', 'pnc_ws_frame_jac', 'pnc_ws_frame_jdqd',
     'pnc_ihwbc_solve', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_wbc_tick_host',
-    'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version',
+    'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version', 'pnc_debug_set_dump',
 ]

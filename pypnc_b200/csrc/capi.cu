@@ -1,0 +1,535 @@
+// capi.cu -- the C ABI of include/pnc_b200.h: handles, HBM workspace, kernel launches.
+//
+// Host-side only plumbing; the arithmetic lives in dynamics.cu / ihwbc.cu / icprep.cu.
+// There is no CPU fallback: every compute entry point launches a CUDA kernel or fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pnc_dev.cuh"
+#include "pnc_launch.h"
+
+namespace pnc {
+unsigned long long g_launch_count = 0;
+}
+using namespace pnc;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      fprintf(stderr, "pnc_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return PNC_E_CUDA;                                                                          \
+    }                                                                                             \
+  } while (0)
+
+struct pnc_model {
+  int device, num_sms;
+  DevModel h;
+  DevModel* d;
+  int nf;
+  std::vector<int> frame_parent;
+  std::vector<double> frame_R, frame_p;
+};
+
+struct pnc_problem {
+  const pnc_model* m;
+  DevProblem h;
+  DevProblem* d;
+  int task_model_frame[PNC_MAX_TASKS];
+  int contact_model_frame[PNC_MAX_CONTACTS];
+  IhwbcLayout lay;
+};
+
+struct pnc_workspace {
+  const pnc_model* m;
+  int cap, nfr;
+  DevFrames hfr;
+  DevFrames* dfr;
+  WsPtrs p;
+  char* slab;
+  size_t bytes;
+  int* counter;  // work-distribution counter of the solve kernel
+  // internal-constraint scratch (allocated lazily for problems with n_ic > 0)
+  char* ic_slab;
+  size_t ic_bytes;
+  int ic_nc, ic_nact;
+  // staging buffers of pnc_wbc_tick_host
+  char* stage;
+  size_t stage_bytes;
+  cudaStream_t tick_stream[2];
+  cudaEvent_t tick_ev[2];
+  bool tick_init;
+};
+
+extern "C" {
+
+const char* pnc_version(void) { return "pypnc_b200 0.1 (sm_100a)"; }
+int64_t pnc_launch_count(void) { return (int64_t)g_launch_count; }
+
+int pnc_model_create(const pnc_model_desc* dsc, int device, pnc_model** out) {
+  if (!dsc || !out) return PNC_E_ARG;
+  if (dsc->nb < 1 || dsc->nb > PNC_MAX_BODIES || dsc->nv > PNC_MAX_NV) return PNC_E_SIZE;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PNC_E_NOGPU;
+  if (device < 0 || device >= ndev) return PNC_E_ARG;
+  CK(cudaSetDevice(device));
+  pnc_model* m = new pnc_model();
+  m->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  m->num_sms = prop.multiProcessorCount;
+  DevModel& h = m->h;
+  memset(&h, 0, sizeof(h));
+  h.nb = dsc->nb; h.nq = dsc->nq; h.nv = dsc->nv; h.na = dsc->na; h.nfl = dsc->n_floating; h.nf = dsc->nf;
+  h.total_mass = dsc->total_mass; h.mass_dyn = dsc->mass_dyn;
+  int maxdepth = 0;
+  for (int i = 0; i < h.nb; i++) {
+    h.parent[i] = dsc->parent[i];
+    if (h.parent[i] >= i) { delete m; return PNC_E_ARG; }
+    h.jtype[i] = dsc->jtype[i];
+    h.idx_v[i] = dsc->idx_v[i];
+    h.subtree[i] = dsc->subtree[i];
+    h.depth[i] = h.parent[i] < 0 ? 0 : h.depth[h.parent[i]] + 1;
+    if (h.depth[i] > maxdepth) maxdepth = h.depth[i];
+    for (int k = 0; k < 9; k++) h.place_R[i][k] = dsc->place_R[9 * i + k];
+    for (int k = 0; k < 3; k++) {
+      h.place_p[i][k] = dsc->place_p[3 * i + k];
+      h.axis[i][k] = dsc->axis[3 * i + k];
+      h.com[i][k] = dsc->com[3 * i + k];
+    }
+    h.mass[i] = dsc->mass[i];
+    const double* I = dsc->inertia + 9 * i;
+    h.inertia[i][0] = I[0]; h.inertia[i][1] = I[1]; h.inertia[i][2] = I[2];
+    h.inertia[i][3] = I[4]; h.inertia[i][4] = I[5]; h.inertia[i][5] = I[8];
+  }
+  h.maxdepth = maxdepth;
+  m->nf = dsc->nf;
+  m->frame_parent.assign(dsc->frame_parent, dsc->frame_parent + dsc->nf);
+  m->frame_R.assign(dsc->frame_R, dsc->frame_R + 9 * (size_t)dsc->nf);
+  m->frame_p.assign(dsc->frame_p, dsc->frame_p + 3 * (size_t)dsc->nf);
+  CK(cudaMalloc(&m->d, sizeof(DevModel)));
+  CK(cudaMemcpy(m->d, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
+  *out = m;
+  return PNC_OK;
+}
+
+void pnc_model_destroy(pnc_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaFree(m->d);
+  delete m;
+}
+
+// ---------------------------------------------------------------------------------------
+int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* dsc, pnc_problem** out) {
+  if (!m || !dsc || !out) return PNC_E_ARG;
+  if (dsc->ntask > PNC_MAX_TASKS || dsc->ncontact > PNC_MAX_CONTACTS || dsc->n_ic > PNC_MAX_IC ||
+      dsc->nact > PNC_MAX_NV || dsc->n_gain > 64 || dsc->n_joint_sel > 2 * PNC_MAX_NV)
+    return PNC_E_SIZE;
+  if (m->h.nfl != 6) return PNC_E_ARG;  // IHWBC needs the floating base rows (Sf), ihwbc.py:225
+  CK(cudaSetDevice(m->device));
+  pnc_problem* p = new pnc_problem();
+  p->m = m;
+  DevProblem& h = p->h;
+  memset(&h, 0, sizeof(h));
+  h.ntask = dsc->ntask; h.ncontact = dsc->ncontact; h.n_ic = dsc->n_ic; h.nact = dsc->nact;
+  h.b_trq_limit = dsc->b_trq_limit ? 1 : 0; h.ndes = dsc->ndes;
+  h.nv = m->h.nv;
+  h.lambda_q_ddot = dsc->lambda_q_ddot; h.lambda_rf = dsc->lambda_rf;
+  int row = 0, dense = 0;
+  for (int i = 0; i < dsc->ntask; i++) {
+    const pnc_task_desc& t = dsc->tasks[i];
+    DevTask& o = h.tasks[i];
+    o.type = t.type; o.dim = t.dim; o.ws_frame = -1; o.joint_off = t.joint_off; o.des_off = t.des_off;
+    o.gain_off = t.gain_off; o.row_off = row; o.dense_off = -1;
+    p->task_model_frame[i] = t.frame;
+    bool is_dense = t.type == PNC_TASK_LINK_XYZ || t.type == PNC_TASK_LINK_ORI || t.type == PNC_TASK_COM;
+    if (is_dense) {
+      if (t.dim != 3) { delete p; return PNC_E_ARG; }
+      if (t.type != PNC_TASK_COM && (t.frame < 0 || t.frame >= m->nf)) { delete p; return PNC_E_ARG; }
+      o.dense_off = dense;
+      dense += 3;
+    } else if (t.type == PNC_TASK_JOINT) {
+      if (t.dim != m->h.na) { delete p; return PNC_E_ARG; }
+    } else if (t.type == PNC_TASK_SELECTED_JOINT) {
+      if (t.joint_off < 0 || t.joint_off + t.dim > dsc->n_joint_sel) { delete p; return PNC_E_ARG; }
+    } else {
+      delete p;
+      return PNC_E_ARG;  // basic_task.py:105 raises ValueError on an unknown task type
+    }
+    row += t.dim;
+  }
+  if (row > PNC_MAX_TASK_ROWS) { delete p; return PNC_E_SIZE; }
+  h.ntaskrows = row;
+  h.ndense = dense;
+  int nc = 0, nu = 0;
+  for (int i = 0; i < dsc->ncontact; i++) {
+    const pnc_contact_desc& c = dsc->contacts[i];
+    DevContact& o = h.contacts[i];
+    if (c.frame < 0 || c.frame >= m->nf) { delete p; return PNC_E_ARG; }
+    o.type = c.type; o.ws_frame = -1;
+    o.dim = c.type == PNC_CONTACT_SURFACE ? 6 : 3;
+    o.rows = c.type == PNC_CONTACT_SURFACE ? 18 : 6;
+    o.rf_off = nc; o.cone_off = nu;
+    o.mu = c.mu; o.x = c.x; o.y = c.y;
+    p->contact_model_frame[i] = c.frame;
+    for (int r = 0; r < o.rows; r++) h.cone_contact[nu + r] = i;
+    nc += o.dim; nu += o.rows;
+  }
+  h.nc = nc; h.nu = nu;
+  h.n = h.nv + nc;
+  h.p = 6 + h.n_ic;
+  h.m = nu + (h.b_trq_limit ? 2 * h.nact : 0);
+  if (h.n > PNC_MAX_N || h.m > PNC_MAX_M) { delete p; return PNC_E_SIZE; }
+  for (int i = 0; i < dsc->n_joint_sel; i++) h.joint_sel[i] = dsc->joint_sel[i];
+  for (int i = 0; i < dsc->n_gain; i++) { h.kp[i] = dsc->kp[i]; h.kd[i] = dsc->kd[i]; }
+  for (int i = 0; i < dsc->nact; i++) {
+    h.act_idx[i] = dsc->act_idx[i];
+    if (h.act_idx[i] < 6 || h.act_idx[i] >= h.nv) { delete p; return PNC_E_ARG; }
+    if (dsc->b_trq_limit) { h.trq_lo[i] = dsc->trq_limit[2 * i]; h.trq_hi[i] = dsc->trq_limit[2 * i + 1]; }
+  }
+  for (int i = 0; i < dsc->n_ic; i++)
+    for (int j = 0; j < h.nv; j++) h.ic_jac[i][j] = dsc->ic_jac[i * h.nv + j];
+  p->lay = ihwbc_layout(h);
+  CK(cudaMalloc(&p->d, sizeof(DevProblem)));
+  CK(cudaMemcpy(p->d, &h, sizeof(DevProblem), cudaMemcpyHostToDevice));
+  *out = p;
+  return PNC_OK;
+}
+
+void pnc_problem_destroy(pnc_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->m->device);
+  cudaFree(p->d);
+  delete p;
+}
+
+int pnc_problem_dims(const pnc_problem* p, int32_t* nc, int32_t* ncone, int32_t* n, int32_t* p_eq, int32_t* m_ineq) {
+  if (!p) return PNC_E_ARG;
+  if (nc) *nc = p->h.nc;
+  if (ncone) *ncone = p->h.nu;
+  if (n) *n = p->h.n;
+  if (p_eq) *p_eq = p->h.p;
+  if (m_ineq) *m_ineq = p->h.m;
+  return PNC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* frames, int32_t nframes,
+                         pnc_workspace** out) {
+  if (!m || !out || capacity < 1 || nframes < 0 || (nframes > 0 && !frames)) return PNC_E_ARG;
+  if (nframes > PNC_MAX_FRAMES) return PNC_E_SIZE;
+  CK(cudaSetDevice(m->device));
+  pnc_workspace* ws = new pnc_workspace();
+  memset(&ws->p, 0, sizeof(ws->p));
+  ws->m = m; ws->cap = capacity; ws->nfr = nframes;
+  ws->ic_slab = nullptr; ws->ic_bytes = 0; ws->ic_nc = ws->ic_nact = 0;
+  ws->stage = nullptr; ws->stage_bytes = 0; ws->tick_init = false;
+  memset(&ws->hfr, 0, sizeof(ws->hfr));
+  ws->hfr.nfr = nframes;
+  for (int f = 0; f < nframes; f++) {
+    int mf = frames[f];
+    if (mf < 0 || mf >= m->nf) { delete ws; return PNC_E_ARG; }
+    ws->hfr.model_frame[f] = mf;
+    ws->hfr.body[f] = m->frame_parent[mf];
+    for (int k = 0; k < 9; k++) ws->hfr.R[f][k] = m->frame_R[9 * (size_t)mf + k];
+    for (int k = 0; k < 3; k++) ws->hfr.p[f][k] = m->frame_p[3 * (size_t)mf + k];
+  }
+  const size_t B = capacity, nv = m->h.nv, nq = m->h.nq, nfr = nframes;
+  size_t sizes[14] = {B * nq, B * nv, B * nv * nv, B * nv, B * nv, B * 3, B * 3, B * 3 * nv, B * 3 * nv, B * 3,
+                      B * nfr * 12, B * nfr * 6, B * nfr * 6 * nv, B * nfr * 6};
+  size_t total = 0, off[14];
+  for (int i = 0; i < 14; i++) { off[i] = total; total += align_up(sizes[i] * sizeof(double)); }
+  total += 256;  // counter
+  CK(cudaMalloc(&ws->slab, total));
+  CK(cudaMemset(ws->slab, 0, total));
+  ws->bytes = total;
+  double** dst[14] = {&ws->p.q, &ws->p.qdot, &ws->p.M, &ws->p.grav, &ws->p.cori, &ws->p.com, &ws->p.vcom,
+                      &ws->p.jcom, &ws->p.jcomdot, &ws->p.jcomdot_qdot, &ws->p.fr_iso, &ws->p.fr_vel,
+                      &ws->p.fr_jac, &ws->p.fr_jdqd};
+  for (int i = 0; i < 14; i++) *dst[i] = reinterpret_cast<double*>(ws->slab + off[i]);
+  ws->counter = reinterpret_cast<int*>(ws->slab + total - 256);
+  CK(cudaMalloc(&ws->dfr, sizeof(DevFrames)));
+  CK(cudaMemcpy(ws->dfr, &ws->hfr, sizeof(DevFrames), cudaMemcpyHostToDevice));
+  *out = ws;
+  return PNC_OK;
+}
+
+void pnc_workspace_destroy(pnc_workspace* ws) {
+  if (!ws) return;
+  cudaSetDevice(ws->m->device);
+  cudaFree(ws->slab);
+  cudaFree(ws->dfr);
+  if (ws->ic_slab) cudaFree(ws->ic_slab);
+  if (ws->stage) cudaFree(ws->stage);
+  if (ws->tick_init) {
+    for (int i = 0; i < 2; i++) { cudaStreamDestroy(ws->tick_stream[i]); cudaEventDestroy(ws->tick_ev[i]); }
+  }
+  delete ws;
+}
+
+int64_t pnc_workspace_bytes(const pnc_workspace* ws) {
+  return ws ? (int64_t)(ws->bytes + ws->ic_bytes + ws->stage_bytes) : 0;
+}
+
+static int update_system_at(pnc_workspace* ws, int off, int32_t B, const double* bp, const double* bq,
+                            const double* blv, const double* bav, const double* jp, const double* jv,
+                            cudaStream_t st) {
+  const pnc_model* m = ws->m;
+  if (m->h.nfl && (!bp || !bq || !blv || !bav)) return PNC_E_ARG;
+  WsPtrs w = ws_offset(ws->p, off, m->h.nq, m->h.nv, ws->nfr, 0, 0, 0);
+  launch_update_system(m->d, ws->dfr, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_update_system(pnc_workspace* ws, int32_t B, const double* d_base_pos, const double* d_base_quat,
+                      const double* d_base_lin_vel, const double* d_base_ang_vel, const double* d_joint_pos,
+                      const double* d_joint_vel, void* stream) {
+  if (!ws || B < 0 || B > ws->cap || !d_joint_pos || !d_joint_vel) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  return update_system_at(ws, 0, B, d_base_pos, d_base_quat, d_base_lin_vel, d_base_ang_vel, d_joint_pos,
+                          d_joint_vel, (cudaStream_t)stream);
+}
+
+double* pnc_ws_q(pnc_workspace* ws) { return ws->p.q; }
+double* pnc_ws_qdot(pnc_workspace* ws) { return ws->p.qdot; }
+double* pnc_ws_mass_matrix(pnc_workspace* ws) { return ws->p.M; }
+double* pnc_ws_gravity(pnc_workspace* ws) { return ws->p.grav; }
+double* pnc_ws_coriolis(pnc_workspace* ws) { return ws->p.cori; }
+double* pnc_ws_com_pos(pnc_workspace* ws) { return ws->p.com; }
+double* pnc_ws_com_vel(pnc_workspace* ws) { return ws->p.vcom; }
+double* pnc_ws_com_jac(pnc_workspace* ws) { return ws->p.jcom; }
+double* pnc_ws_com_jacdot(pnc_workspace* ws) { return ws->p.jcomdot; }
+double* pnc_ws_com_jdqd(pnc_workspace* ws) { return ws->p.jcomdot_qdot; }
+double* pnc_ws_frame_iso(pnc_workspace* ws) { return ws->p.fr_iso; }
+double* pnc_ws_frame_vel(pnc_workspace* ws) { return ws->p.fr_vel; }
+double* pnc_ws_frame_jac(pnc_workspace* ws) { return ws->p.fr_jac; }
+double* pnc_ws_frame_jdqd(pnc_workspace* ws) { return ws->p.fr_jdqd; }
+
+// ---------------------------------------------------------------------------------------
+static int resolve_frames(const pnc_problem* p, const pnc_workspace* ws, FrameMap* fm) {
+  for (int i = 0; i < p->h.ntask; i++) {
+    fm->task_f[i] = -1;
+    int mf = p->task_model_frame[i];
+    if (p->h.tasks[i].type == PNC_TASK_LINK_XYZ || p->h.tasks[i].type == PNC_TASK_LINK_ORI) {
+      for (int f = 0; f < ws->nfr; f++)
+        if (ws->hfr.model_frame[f] == mf) fm->task_f[i] = f;
+      if (fm->task_f[i] < 0) return PNC_E_ARG;
+    }
+  }
+  for (int i = 0; i < p->h.ncontact; i++) {
+    fm->contact_f[i] = -1;
+    for (int f = 0; f < ws->nfr; f++)
+      if (ws->hfr.model_frame[f] == p->contact_model_frame[i]) fm->contact_f[i] = f;
+    if (fm->contact_f[i] < 0) return PNC_E_ARG;
+  }
+  return PNC_OK;
+}
+
+static int ensure_ic(pnc_workspace* ws, const pnc_problem* p) {
+  if (p->h.n_ic == 0) return PNC_OK;
+  if (ws->ic_slab && ws->ic_nc == p->h.nc && ws->ic_nact == p->h.nact) return PNC_OK;
+  if (ws->ic_slab) { cudaFree(ws->ic_slab); ws->ic_slab = nullptr; }
+  const size_t B = ws->cap, nv = p->h.nv, nc = p->h.nc, nact = p->h.nact, n = p->h.n;
+  size_t sizes[4] = {B * nv, B * nc * nv, B * nact * n, B * nact};
+  size_t total = 0, off[5];
+  for (int i = 0; i < 4; i++) { off[i] = total; total += align_up(sizes[i] * sizeof(double)); }
+  off[4] = total;
+  total += align_up(B * sizeof(int));
+  CK(cudaMalloc(&ws->ic_slab, total));
+  CK(cudaMemset(ws->ic_slab, 0, total));
+  ws->ic_bytes = total;
+  ws->p.ic_cg = reinterpret_cast<double*>(ws->ic_slab + off[0]);
+  ws->p.ic_jcni = reinterpret_cast<double*>(ws->ic_slab + off[1]);
+  ws->p.ic_tq = reinterpret_cast<double*>(ws->ic_slab + off[2]);
+  ws->p.ic_tq0 = reinterpret_cast<double*>(ws->ic_slab + off[3]);
+  ws->p.ic_status = reinterpret_cast<int*>(ws->ic_slab + off[4]);
+  ws->ic_nc = p->h.nc; ws->ic_nact = p->h.nact;
+  return PNC_OK;
+}
+
+static int solve_at(const pnc_problem* p, pnc_workspace* ws, int off, int32_t B, const double* des,
+                    const double* w, const double* rfz, double* trq, double* acc, double* rf, double* qddot,
+                    int32_t* status, int32_t* iters, uint64_t* active, cudaStream_t st, int* counter) {
+  FrameMap fm;
+  int rc = resolve_frames(p, ws, &fm);
+  if (rc) return rc;
+  rc = ensure_ic(ws, p);
+  if (rc) return rc;
+  WsPtrs wsp = ws_offset(ws->p, off, ws->m->h.nq, p->h.nv, ws->nfr, p->h.nc, p->h.nact, p->h.n);
+  if (p->h.n_ic > 0) {
+    launch_ic_prepare(p->d, p->h, wsp, fm, ws->nfr, B, ws->m->num_sms, st);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+  SolveIO io;
+  io.des = des; io.w = w; io.rfz = rfz; io.trq = trq; io.acc = acc; io.rf = rf; io.qddot = qddot;
+  io.status = status; io.iters = iters; io.active = reinterpret_cast<unsigned long long*>(active); io.counter = counter;
+  launch_ihwbc_solve(p->d, p->h, p->lay, wsp, fm, ws->nfr, B, io, ws->m->num_sms, st);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_ihwbc_solve(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* d_des, const double* d_w,
+                    const double* d_rf_z_max, double* d_trq, double* d_acc, double* d_rf, double* d_qddot,
+                    int32_t* d_status, int32_t* d_iters, uint64_t* d_active, void* stream) {
+  if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m) return PNC_E_ARG;
+  if (!d_des || !d_w || (p->h.ncontact && !d_rf_z_max) || !d_status) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  return solve_at(p, ws, 0, B, d_des, d_w, d_rf_z_max, d_trq, d_acc, d_rf, d_qddot, d_status, d_iters, d_active,
+                  (cudaStream_t)stream, ws->counter);
+}
+
+int pnc_task_eval(const pnc_problem* p, pnc_workspace* ws, int32_t B, int32_t itask, const double* d_des,
+                  double* d_jac, double* d_jdqd, double* d_op_cmd, double* d_pos_err, void* stream) {
+  if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m || itask < 0 || itask >= p->h.ntask || !d_des)
+    return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  FrameMap fm;
+  int rc = resolve_frames(p, ws, &fm);
+  if (rc) return rc;
+  launch_task_eval(p->d, ws->p, fm, ws->nfr, B, itask, p->h.tasks[itask].dim, p->h.nv, d_des, d_jac, d_jdqd,
+                   d_op_cmd, d_pos_err, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_contact_eval(const pnc_problem* p, pnc_workspace* ws, int32_t B, int32_t icontact,
+                     const double* d_rf_z_max, double* d_jac, double* d_cone_mat, double* d_cone_vec,
+                     void* stream) {
+  if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m || icontact < 0 || icontact >= p->h.ncontact ||
+      !d_rf_z_max)
+    return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  FrameMap fm;
+  int rc = resolve_frames(p, ws, &fm);
+  if (rc) return rc;
+  launch_contact_eval(p->d, ws->p, fm, ws->nfr, B, icontact, p->h.nv, d_rf_z_max, d_jac, d_cone_mat, d_cone_vec,
+                      (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_joint_integrate(int32_t B, int32_t na, const double* d_acc, const double* d_joint_pos, double* d_vel_state,
+                        double* d_pos_state, const double* d_pos_limit, const double* d_vel_limit,
+                        double alpha_vel, double alpha_pos, double dt, void* stream) {
+  if (B < 0 || na < 1 || !d_acc || !d_joint_pos || !d_vel_state || !d_pos_state || !d_pos_limit || !d_vel_limit)
+    return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  launch_joint_integrate(B, na, d_acc, d_joint_pos, d_vel_state, d_pos_state, d_pos_limit, d_vel_limit, alpha_vel,
+                         alpha_pos, dt, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Whole tick with host buffers.  The batch is cut into chunks that ping-pong over two
+// streams so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels
+// of chunk k.  Chunks own disjoint slices of the workspace, so they never alias.
+int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,
+                      const double* h_base_quat, const double* h_base_lin_vel, const double* h_base_ang_vel,
+                      const double* h_joint_pos, const double* h_joint_vel, const double* h_des, const double* h_w,
+                      const double* h_rf_z_max, double* h_trq, double* h_acc, double* h_rf, int32_t* h_status,
+                      int32_t* h_iters, uint64_t* h_active) {
+  if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m) return PNC_E_ARG;
+  if (!h_base_pos || !h_base_quat || !h_base_lin_vel || !h_base_ang_vel || !h_joint_pos || !h_joint_vel ||
+      !h_des || !h_w || (p->h.ncontact && !h_rf_z_max))
+    return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  const DevProblem& P = p->h;
+  const size_t na = ws->m->h.na, nv = P.nv;
+  const int mw = (P.m + 63) / 64 > 0 ? (P.m + 63) / 64 : 1;
+  // per-state doubles in / out
+  const size_t in_d = 3 + 4 + 3 + 3 + 2 * na + P.ndes + P.ntask + P.ncontact;
+  const size_t out_d = 2 * (size_t)P.nact + P.nc + nv;
+  const size_t per_state = (in_d + out_d) * 8 + 8 /*status, iters*/ + 8 * (size_t)mw;
+  const size_t need = per_state * (size_t)ws->cap + 64 * 256;
+  if (ws->stage_bytes < need) {
+    if (ws->stage) cudaFree(ws->stage);
+    CK(cudaMalloc(&ws->stage, need));
+    ws->stage_bytes = need;
+  }
+  if (!ws->tick_init) {
+    for (int i = 0; i < 2; i++) {
+      CK(cudaStreamCreateWithFlags(&ws->tick_stream[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ws->tick_ev[i], cudaEventDisableTiming));
+    }
+    ws->tick_init = true;
+  }
+  // carve the staging slab (capacity-sized arrays)
+  char* cur = ws->stage;
+  auto take = [&](size_t bytes) { char* r = cur; cur += align_up(bytes); return r; };
+  const size_t C = ws->cap;
+  double* d_bp = (double*)take(C * 3 * 8);
+  double* d_bq = (double*)take(C * 4 * 8);
+  double* d_blv = (double*)take(C * 3 * 8);
+  double* d_bav = (double*)take(C * 3 * 8);
+  double* d_jp = (double*)take(C * na * 8);
+  double* d_jv = (double*)take(C * na * 8);
+  double* d_des = (double*)take(C * P.ndes * 8);
+  double* d_w = (double*)take(C * P.ntask * 8);
+  double* d_rfz = (double*)take(C * (P.ncontact ? P.ncontact : 1) * 8);
+  double* d_trq = (double*)take(C * P.nact * 8);
+  double* d_acc = (double*)take(C * P.nact * 8);
+  double* d_rf = (double*)take(C * (P.nc ? P.nc : 1) * 8);
+  int32_t* d_status = (int32_t*)take(C * 4);
+  int32_t* d_iters = (int32_t*)take(C * 4);
+  uint64_t* d_active = (uint64_t*)take(C * mw * 8);
+  int* counters = (int*)take(256);
+
+  int nchunk = B >= 8192 ? 4 : 1;
+  int chunk = (B + nchunk - 1) / nchunk;
+  for (int c = 0; c < nchunk; c++) {
+    int o = c * chunk, nb = B - o < chunk ? B - o : chunk;
+    if (nb <= 0) break;
+    cudaStream_t st = ws->tick_stream[c & 1];
+#define H2D(dst, src, per) CK(cudaMemcpyAsync((dst) + (size_t)o * (per), (src) + (size_t)o * (per), (size_t)nb * (per) * 8, cudaMemcpyHostToDevice, st))
+    H2D(d_bp, h_base_pos, 3); H2D(d_bq, h_base_quat, 4); H2D(d_blv, h_base_lin_vel, 3); H2D(d_bav, h_base_ang_vel, 3);
+    H2D(d_jp, h_joint_pos, na); H2D(d_jv, h_joint_vel, na); H2D(d_des, h_des, P.ndes); H2D(d_w, h_w, P.ntask);
+    if (P.ncontact) H2D(d_rfz, h_rf_z_max, P.ncontact);
+#undef H2D
+    int rc = update_system_at(ws, o, nb, d_bp + (size_t)o * 3, d_bq + (size_t)o * 4, d_blv + (size_t)o * 3,
+                              d_bav + (size_t)o * 3, d_jp + (size_t)o * na, d_jv + (size_t)o * na, st);
+    if (rc) return rc;
+    rc = solve_at(p, ws, o, nb, d_des + (size_t)o * P.ndes, d_w + (size_t)o * P.ntask,
+                  d_rfz + (size_t)o * P.ncontact, d_trq + (size_t)o * P.nact, d_acc + (size_t)o * P.nact,
+                  d_rf + (size_t)o * P.nc, nullptr, d_status + o, d_iters + o, d_active + (size_t)o * mw, st,
+                  counters + 8 * c);
+    if (rc) return rc;
+#define D2H(dst, src, per, esz) if (dst) CK(cudaMemcpyAsync((char*)(dst) + (size_t)o * (per) * (esz), (const char*)(src) + (size_t)o * (per) * (esz), (size_t)nb * (per) * (esz), cudaMemcpyDeviceToHost, st))
+    D2H(h_trq, d_trq, P.nact, 8); D2H(h_acc, d_acc, P.nact, 8); D2H(h_rf, d_rf, P.nc, 8);
+    D2H(h_status, d_status, 1, 4); D2H(h_iters, d_iters, 1, 4); D2H(h_active, d_active, mw, 8);
+#undef D2H
+  }
+  CK(cudaStreamSynchronize(ws->tick_stream[0]));
+  CK(cudaStreamSynchronize(ws->tick_stream[1]));
+  return PNC_OK;
+}
+
+int pnc_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return PNC_E_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PNC_E_NOGPU;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double best = 0;
+  int rc = measure_fp64_peak(prop.multiProcessorCount, &best);
+  if (rc) return PNC_E_CUDA;
+  *tflops = best;
+  return PNC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,395 @@
+// dynamics.cu -- batched robot_system update: one robot state per warp, one lane per body.
+//
+// Replaces, for B states at once, PinocchioRobotSystem.update_system and every getter the
+// controller calls per tick (reference pnc/robot_system/pinocchio_robot_system.py:128-278):
+// forward kinematics, frame placements / velocities / Jacobians / Jdot*qdot, centre of mass
+// and its Jacobian (+ time derivative), CRBA mass matrix, gravity and Coriolis vectors.
+//
+// Formulation (B200-first, not pinocchio's body-frame recursions): every spatial quantity is
+// expressed in WORLD axes about one reference point (the floating-base origin), so that
+//   * a body's velocity / bias acceleration is a sum over its ANCESTORS of joint terms, and
+//   * joint torques / composite inertias are sums over its SUBTREE of body terms.
+// Bodies are numbered depth-first, so subtree(i) = lanes [i, i+subtree[i]) and both kinds of
+// sum become masked loops over lanes through shared memory -- no per-level transforms on the
+// way back up the tree.  Joint tables are staged once per CTA in shared memory.
+#include "pnc_dev.cuh"
+
+namespace pnc {
+
+constexpr int DYN_WARPS = 4;
+constexpr int XF_LD = 25;   // R(9) p(3) v(6) a(6) + pad (odd stride: conflict-free rows)
+constexpr int SUB_LD = 19;  // m, h(3), Io(6), fc(6), P(3)
+constexpr int SF_LD = 7;    // 6 + pad
+
+struct DynSmemLayout {
+  int per_warp_doubles;
+  int off_xf, off_sub, off_S, off_F, off_S0, off_F0, off_fr, off_M;
+};
+
+__host__ __device__ inline DynSmemLayout dyn_layout(int nv) {
+  DynSmemLayout L;
+  int o = 0;
+  L.off_sub = o; o += 32 * SUB_LD;
+  L.off_S = o; o += 32 * SF_LD;
+  L.off_F = o; o += 32 * SF_LD;
+  L.off_S0 = o; o += 36;
+  L.off_F0 = o; o += 36;
+  L.off_fr = o; o += PNC_MAX_FRAMES * 4;  // frame world point (3) + pad
+  // xf (phase 2..6) and the M staging tile (phase 7) share storage
+  L.off_xf = o; L.off_M = o;
+  int a = 32 * XF_LD, b = nv * nv;
+  o += (a > b ? a : b);
+  L.per_warp_doubles = (o + 1) & ~1;
+  return L;
+}
+
+size_t dyn_smem_bytes(int nv) {
+  return sizeof(DevModel) + sizeof(DevFrames) + (size_t)DYN_WARPS * dyn_layout(nv).per_warp_doubles * sizeof(double);
+}
+
+__device__ __forceinline__ V3 ld3(const double* p) { return V3{p[0], p[1], p[2]}; }
+__device__ __forceinline__ void st3(double* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+
+__global__ void __launch_bounds__(DYN_WARPS * 32)
+k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ gfr, WsPtrs ws, int B,
+                const double* __restrict__ base_pos, const double* __restrict__ base_quat,
+                const double* __restrict__ base_lin_vel, const double* __restrict__ base_ang_vel,
+                const double* __restrict__ joint_pos, const double* __restrict__ joint_vel) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevModel* sm = reinterpret_cast<DevModel*>(smem_raw);
+  DevFrames* sfr = reinterpret_cast<DevFrames*>(smem_raw + sizeof(DevModel));
+  double* wbase = reinterpret_cast<double*>(smem_raw + sizeof(DevModel) + sizeof(DevFrames));
+
+  // stage the joint tables once per CTA
+  {
+    const int* src = reinterpret_cast<const int*>(gm);
+    int* dst = reinterpret_cast<int*>(sm);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += blockDim.x) dst[i] = src[i];
+    const int* src2 = reinterpret_cast<const int*>(gfr);
+    int* dst2 = reinterpret_cast<int*>(sfr);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevFrames) / 4); i += blockDim.x) dst2[i] = src2[i];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = sm->nb, nv = sm->nv, na = sm->na, nfl = sm->nfl, nq = sm->nq, nfr = sfr->nfr;
+  const DynSmemLayout L = dyn_layout(nv);
+  double* W = wbase + (size_t)warp * L.per_warp_doubles;
+  double* xf = W + L.off_xf;
+  double* sub = W + L.off_sub;
+  double* Ss = W + L.off_S;
+  double* Fs = W + L.off_F;
+  double* S0 = W + L.off_S0;
+  double* F0 = W + L.off_F0;
+  double* frp = W + L.off_fr;
+  double* Mst = W + L.off_M;
+
+  const bool active = lane < nb;
+  const int i = active ? lane : 0;
+  // per-lane constants
+  const int parent = sm->parent[i], jtype = sm->jtype[i], iv = sm->idx_v[i], nsub = sm->subtree[i],
+            depth = sm->depth[i];
+  const bool isff = active && jtype == PNC_JOINT_FREEFLYER;
+  const double mass_i = sm->mass[i];
+  const double inv_mdyn = 1.0 / sm->mass_dyn, inv_mtot = 1.0 / sm->total_mass;
+  const double GZ = 9.81;
+
+  const int total_warps = gridDim.x * DYN_WARPS;
+  for (int s = blockIdx.x * DYN_WARPS + warp; s < B; s += total_warps) {
+    // ---------------- phase 0/1: joint state and local transform -----------------------
+    double Rl[9];  // joint frame in parent joint frame
+    V3 pl;
+    double qd = 0.0;
+    V3 vloc_lin = mk(0, 0, 0), vloc_ang = mk(0, 0, 0);  // free-flyer twist in the base frame
+    V3 bpos = mk(0, 0, 0);
+    if (isff) {
+      double qq[4] = {base_quat[4 * (size_t)s], base_quat[4 * (size_t)s + 1], base_quat[4 * (size_t)s + 2],
+                      base_quat[4 * (size_t)s + 3]};
+      double Rj[9];
+      quat_to_rot(qq, Rj);
+      mul33(sm->place_R[i], Rj, Rl);
+      bpos = ld3(base_pos + 3 * (size_t)s);
+      pl = mk(0, 0, 0);  // reference point = base origin; bpos is added back on output
+      // pinocchio_robot_system.py:149-162: world twist -> base frame
+      vloc_lin = mulRt(Rj, ld3(base_lin_vel + 3 * (size_t)s));
+      vloc_ang = mulRt(Rj, ld3(base_ang_vel + 3 * (size_t)s));
+      double* qo = ws.q + (size_t)s * nq;
+      qo[0] = bpos.x; qo[1] = bpos.y; qo[2] = bpos.z;
+      qo[3] = qq[0]; qo[4] = qq[1]; qo[5] = qq[2]; qo[6] = qq[3];
+      double* vo = ws.qdot + (size_t)s * nv;
+      vo[0] = vloc_lin.x; vo[1] = vloc_lin.y; vo[2] = vloc_lin.z;
+      vo[3] = vloc_ang.x; vo[4] = vloc_ang.y; vo[5] = vloc_ang.z;
+    } else if (active) {
+      double qj = joint_pos[(size_t)s * na + iv - nfl];
+      qd = joint_vel[(size_t)s * na + iv - nfl];
+      ws.q[(size_t)s * nq + (nfl ? iv + 1 : iv)] = qj;
+      ws.qdot[(size_t)s * nv + iv] = qd;
+      double sn, c;
+      sincos(qj, &sn, &c);
+      const double* ax = sm->axis[i];
+      double t = 1.0 - c, Rj[9];
+      Rj[0] = c + t * ax[0] * ax[0];          Rj[1] = t * ax[0] * ax[1] - sn * ax[2]; Rj[2] = t * ax[0] * ax[2] + sn * ax[1];
+      Rj[3] = t * ax[1] * ax[0] + sn * ax[2]; Rj[4] = c + t * ax[1] * ax[1];          Rj[5] = t * ax[1] * ax[2] - sn * ax[0];
+      Rj[6] = t * ax[2] * ax[0] - sn * ax[1]; Rj[7] = t * ax[2] * ax[1] + sn * ax[0]; Rj[8] = c + t * ax[2] * ax[2];
+      mul33(sm->place_R[i], Rj, Rl);
+      pl = ld3(sm->place_p[i]);
+    }
+    // the base position of this state, for every lane (lane 0 is the free-flyer when floating)
+    if (nfl) {
+      bpos.x = __shfl_sync(0xffffffffu, bpos.x, 0);
+      bpos.y = __shfl_sync(0xffffffffu, bpos.y, 0);
+      bpos.z = __shfl_sync(0xffffffffu, bpos.z, 0);
+    }
+
+    // ---------------- phase 2: propagate (R, p, v, a) down the tree, level by level ----
+    double R[9];
+    V3 p = mk(0, 0, 0), vl = mk(0, 0, 0), w = mk(0, 0, 0), al = mk(0, 0, 0), aw = mk(0, 0, 0);
+    V3 Sl = mk(0, 0, 0), Sa = mk(0, 0, 0);  // own joint screw (revolute): motion [lin; ang] about the ref point
+    for (int k = 0; k < 9; k++) R[k] = 0;
+    const int maxdepth = sm->maxdepth;
+    for (int d = 0; d <= maxdepth; d++) {
+      if (active && depth == d) {
+        V3 pp = mk(0, 0, 0), pvl = mk(0, 0, 0), pw = mk(0, 0, 0), pal = mk(0, 0, 0), paw = mk(0, 0, 0);
+        if (parent >= 0) {
+          const double* pr = xf + parent * XF_LD;
+          mul33(pr, Rl, R);
+          pp = ld3(pr + 9);
+          p = pp + mulR(pr, pl);
+          pvl = ld3(pr + 12); pw = ld3(pr + 15); pal = ld3(pr + 18); paw = ld3(pr + 21);
+        } else {
+          for (int k = 0; k < 9; k++) R[k] = Rl[k];
+          p = pl;
+        }
+        V3 vJl, vJa;
+        if (isff) {
+          vJl = mulR(R, vloc_lin);
+          vJa = mulR(R, vloc_ang);  // reference point == base origin -> no p x w term
+        } else {
+          Sa = mulR(R, ld3(sm->axis[i]));
+          Sl = cross(p, Sa);
+          vJl = qd * Sl;
+          vJa = qd * Sa;
+        }
+        vl = pvl + vJl;
+        w = pw + vJa;
+        // a_i = a_parent + v_i x vJ_i   (spatial motion cross product; qddot = 0, no gravity)
+        al = pal + cross(w, vJl) + cross(vl, vJa);
+        aw = paw + cross(w, vJa);
+        double* me = xf + i * XF_LD;
+        for (int k = 0; k < 9; k++) me[k] = R[k];
+        st3(me + 9, p); st3(me + 12, vl); st3(me + 15, w); st3(me + 18, al); st3(me + 21, aw);
+      }
+      __syncwarp();
+    }
+
+    // ---------------- phase 3: world-frame body inertia, momentum, bias force ----------
+    V3 cw = mk(0, 0, 0), h = mk(0, 0, 0), P = mk(0, 0, 0), fcl = mk(0, 0, 0), fca = mk(0, 0, 0);
+    double Io[6] = {0, 0, 0, 0, 0, 0};
+    if (active) {
+      cw = p + mulR(R, ld3(sm->com[i]));
+      h = mass_i * cw;
+      // Iw = R Ic R^T
+      const double* Ic = sm->inertia[i];
+      double T[9];
+      // T = R * Ic (Ic symmetric)
+      for (int r = 0; r < 3; r++) {
+        T[3 * r + 0] = R[3 * r] * Ic[0] + R[3 * r + 1] * Ic[1] + R[3 * r + 2] * Ic[2];
+        T[3 * r + 1] = R[3 * r] * Ic[1] + R[3 * r + 1] * Ic[3] + R[3 * r + 2] * Ic[4];
+        T[3 * r + 2] = R[3 * r] * Ic[2] + R[3 * r + 1] * Ic[4] + R[3 * r + 2] * Ic[5];
+      }
+      double cc = dot(cw, cw);
+      Io[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + mass_i * (cc - cw.x * cw.x);
+      Io[1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - mass_i * cw.x * cw.y;
+      Io[2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - mass_i * cw.x * cw.z;
+      Io[3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + mass_i * (cc - cw.y * cw.y);
+      Io[4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - mass_i * cw.y * cw.z;
+      Io[5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + mass_i * (cc - cw.z * cw.z);
+      // momentum  (P, Lm) = I v ;  I a ;  bias force fc = I a + v x* (I v)
+      P = mass_i * vl - cross(h, w);
+      V3 Lm = cross(h, vl) + mulS(Io, w);
+      V3 Ial = mass_i * al - cross(h, aw);
+      V3 Iaa = cross(h, al) + mulS(Io, aw);
+      fcl = Ial + cross(w, P);
+      fca = Iaa + cross(w, Lm) + cross(vl, P);
+      double* row = sub + i * SUB_LD;
+      row[0] = mass_i; st3(row + 1, h);
+      for (int k = 0; k < 6; k++) row[4 + k] = Io[k];
+      st3(row + 10, fcl); st3(row + 13, fca); st3(row + 16, P);
+    }
+    __syncwarp();
+
+    // ---------------- phase 4: subtree sums (composite inertia, bias force, momentum) ---
+    double acc[SUB_LD];
+    for (int k = 0; k < SUB_LD; k++) acc[k] = 0.0;
+    if (active) {
+      for (int c = 0; c < nsub; c++) {
+        const double* row = sub + (i + c) * SUB_LD;
+#pragma unroll
+        for (int k = 0; k < SUB_LD; k++) acc[k] += row[k];
+      }
+    }
+    const double mS = acc[0];
+    const V3 hS = mk(acc[1], acc[2], acc[3]);
+    const double* IS = acc + 4;
+    const V3 fSl = mk(acc[10], acc[11], acc[12]), fSa = mk(acc[13], acc[14], acc[15]);
+    const V3 PS = mk(acc[16], acc[17], acc[18]);
+    // whole-robot totals (lane 0's subtree is the whole robot on a single-rooted tree)
+    double tot[7] = {0, 0, 0, 0, 0, 0, 0};  // h(3) P(3)... assembled below
+    double tfcl[3] = {0, 0, 0};
+    if (lane == 0) {
+      tot[0] = acc[1]; tot[1] = acc[2]; tot[2] = acc[3]; tot[3] = acc[16]; tot[4] = acc[17]; tot[5] = acc[18];
+      tfcl[0] = acc[10]; tfcl[1] = acc[11]; tfcl[2] = acc[12];
+      for (int c = nsub; c < nb; c++) {  // forest (several bodies hang off the universe)
+        const double* row = sub + c * SUB_LD;
+        tot[0] += row[1]; tot[1] += row[2]; tot[2] += row[3]; tot[3] += row[16]; tot[4] += row[17]; tot[5] += row[18];
+        tfcl[0] += row[10]; tfcl[1] += row[11]; tfcl[2] += row[12];
+      }
+      double* o = ws.com + 3 * (size_t)s;
+      o[0] = bpos.x + tot[0] * inv_mdyn; o[1] = bpos.y + tot[1] * inv_mdyn; o[2] = bpos.z + tot[2] * inv_mdyn;
+      o = ws.vcom + 3 * (size_t)s;
+      o[0] = tot[3] * inv_mdyn; o[1] = tot[4] * inv_mdyn; o[2] = tot[5] * inv_mdyn;
+      o = ws.jcomdot_qdot + 3 * (size_t)s;  // (dAg_lin . qdot) / total_mass, basic_task.py:133-135
+      o[0] = tfcl[0] * inv_mtot; o[1] = tfcl[1] * inv_mtot; o[2] = tfcl[2] * inv_mtot;
+    }
+
+    // ---------------- phase 5: per-dof outputs: gravity, Coriolis, CoM Jacobians, F = Ic S
+    if (active) {
+      const int ndof = isff ? 6 : 1;
+      double* grav = ws.grav + (size_t)s * nv;
+      double* cori = ws.cori + (size_t)s * nv;
+      double* jc = ws.jcom + (size_t)s * 3 * nv;
+      double* jcd = ws.jcomdot + (size_t)s * 3 * nv;
+      const V3 gvec = mk(0, 0, GZ);
+      const V3 fgl = mS * gvec, fga = cross(hS, gvec);
+      for (int d = 0; d < ndof; d++) {
+        V3 sl, sa;
+        if (isff) {
+          V3 col = mk(R[d % 3], R[3 + d % 3], R[6 + d % 3]);
+          if (d < 3) { sl = col; sa = mk(0, 0, 0); }
+          else { sa = col; sl = cross(p, col); }
+          double* s0 = S0 + d * 6;
+          st3(s0, sl); st3(s0 + 3, sa);
+        } else {
+          sl = Sl; sa = Sa;
+          double* sr = Ss + i * SF_LD;
+          st3(sr, sl); st3(sr + 3, sa);
+        }
+        grav[iv + d] = dot(sl, fgl) + dot(sa, fga);
+        cori[iv + d] = dot(sl, fSl) + dot(sa, fSa);
+        V3 jcol = inv_mdyn * (mS * sl + cross(sa, hS));
+        jc[iv + d] = jcol.x; jc[nv + iv + d] = jcol.y; jc[2 * nv + iv + d] = jcol.z;
+        // dS = v_i x S ;  dAg_lin col = -Pdot_sub x S_ang + m dS_lin - h x dS_ang
+        V3 dsl = cross(w, sl) + cross(vl, sa), dsa = cross(w, sa);
+        V3 dcol = inv_mtot * (mS * dsl - cross(PS, sa) - cross(hS, dsa));
+        jcd[iv + d] = dcol.x; jcd[nv + iv + d] = dcol.y; jcd[2 * nv + iv + d] = dcol.z;
+        // F = Ic_sub S : lin = m S_lin - h x S_ang ; ang = h x S_lin + Io S_ang
+        V3 Fl = mS * sl - cross(hS, sa);
+        V3 Fa = cross(hS, sl) + mulS(IS, sa);
+        double* fr = isff ? (F0 + d * 6) : (Fs + i * SF_LD);
+        st3(fr, Fl); st3(fr + 3, Fa);
+      }
+    }
+    __syncwarp();
+
+    // ---------------- phase 6: frames (placement, velocity, Jdot*qdot, Jacobian columns) --
+    if (lane < nfr) {
+      const int f = lane, b = sfr->body[f];
+      double Rw[9];
+      V3 pf, fvl = mk(0, 0, 0), fw = mk(0, 0, 0), fal = mk(0, 0, 0), faw = mk(0, 0, 0);
+      if (b >= 0) {
+        const double* br = xf + b * XF_LD;
+        mul33(br, sfr->R[f], Rw);
+        pf = ld3(br + 9) + mulR(br, ld3(sfr->p[f]));
+        V3 bvl = ld3(br + 12), bw = ld3(br + 15), bal = ld3(br + 18), baw = ld3(br + 21);
+        fw = bw;
+        fvl = bvl + cross(bw, pf);
+        faw = baw;
+        fal = bal + cross(baw, pf) + cross(bw, fvl);  // classical acceleration: + w x v
+      } else {
+        for (int k = 0; k < 9; k++) Rw[k] = sfr->R[f][k];
+        pf = ld3(sfr->p[f]) - bpos;
+      }
+      st3(frp + 4 * f, pf);
+      double* iso = ws.fr_iso + ((size_t)s * nfr + f) * 12;
+      for (int k = 0; k < 9; k++) iso[k] = Rw[k];
+      iso[9] = pf.x + bpos.x; iso[10] = pf.y + bpos.y; iso[11] = pf.z + bpos.z;
+      double* fv = ws.fr_vel + ((size_t)s * nfr + f) * 6;
+      st3(fv, fw); st3(fv + 3, fvl);
+      double* fa = ws.fr_jdqd + ((size_t)s * nfr + f) * 6;
+      st3(fa, faw); st3(fa + 3, fal);
+    }
+    __syncwarp();
+    if (active) {
+      const int ndof = isff ? 6 : 1;
+      for (int f = 0; f < nfr; f++) {
+        const int b = sfr->body[f];
+        const bool on_path = (b >= 0) && (i <= b) && (b < i + nsub);
+        const V3 pf = ld3(frp + 4 * f);
+        double* J = ws.fr_jac + ((size_t)s * nfr + f) * 6 * nv;
+        for (int d = 0; d < ndof; d++) {
+          V3 sl, sa;
+          if (isff) { sl = ld3(S0 + d * 6); sa = ld3(S0 + d * 6 + 3); }
+          else { sl = Sl; sa = Sa; }
+          V3 lin = mk(0, 0, 0), ang = mk(0, 0, 0);
+          if (on_path) { ang = sa; lin = sl + cross(sa, pf); }
+          // rows [ang; lin], pinocchio_robot_system.py:259-261
+          J[iv + d] = ang.x; J[nv + iv + d] = ang.y; J[2 * nv + iv + d] = ang.z;
+          J[3 * nv + iv + d] = lin.x; J[4 * nv + iv + d] = lin.y; J[5 * nv + iv + d] = lin.z;
+        }
+      }
+    }
+    __syncwarp();  // everyone is done with xf before the M tile overwrites it
+
+    // ---------------- phase 7: CRBA rows into a shared tile, then coalesced store -------
+    for (int k = lane; k < nv * nv; k += 32) Mst[k] = 0.0;
+    __syncwarp();
+    if (active) {
+      // entries between body i and each ancestor-or-self j:  M[vi, vj] = F_i . S_j
+      for (int j = 0; j <= i; j++) {
+        const int sj = sm->subtree[j];
+        if (!(i < j + sj)) continue;
+        const bool jff = sm->jtype[j] == PNC_JOINT_FREEFLYER;
+        const int jv = sm->idx_v[j], ndj = jff ? 6 : 1, ndi = isff ? 6 : 1;
+        for (int di = 0; di < ndi; di++) {
+          const double* Fi = isff ? (F0 + di * 6) : (Fs + i * SF_LD);
+          for (int dj = 0; dj < ndj; dj++) {
+            const double* Sj = jff ? (S0 + dj * 6) : (Ss + j * SF_LD);
+            double val = Fi[0] * Sj[0] + Fi[1] * Sj[1] + Fi[2] * Sj[2] + Fi[3] * Sj[3] + Fi[4] * Sj[4] + Fi[5] * Sj[5];
+            Mst[(iv + di) * nv + jv + dj] = val;
+            Mst[(jv + dj) * nv + iv + di] = val;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    {
+      double* Mo = ws.M + (size_t)s * nv * nv;
+      for (int k = lane; k < nv * nv; k += 32) Mo[k] = Mst[k];
+    }
+    __syncwarp();
+  }
+}
+
+void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs& ws, int B, int nv,
+                          const double* base_pos, const double* base_quat, const double* base_lin_vel,
+                          const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
+                          int num_sms, cudaStream_t stream) {
+  size_t smem = dyn_smem_bytes(nv);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(k_update_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  int grid = num_sms * ctas_per_sm;
+  int need = (B + DYN_WARPS - 1) / DYN_WARPS;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  k_update_system<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, ws, B, base_pos, base_quat, base_lin_vel,
+                                                          base_ang_vel, joint_pos, joint_vel);
+  g_launch_count++;
+}
+
+}  // namespace pnc

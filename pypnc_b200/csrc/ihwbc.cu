@@ -1,0 +1,1083 @@
+// ihwbc.cu -- batched IHWBC: task/contact evaluation, QP assembly and a dual active-set
+// (Goldfarb-Idnani) solve, one robot state per warp, everything resident in shared memory.
+//
+// Replaces, for B states at once (reference paths relative to the PyPnC checkout):
+//   BasicTask.update_jacobian / update_cmd            pnc/wbc/basic_task.py:25-137
+//   PointContact / SurfaceContact._update_*           pnc/wbc/basic_contact.py:24-173
+//   IHWBC.update_setting + IHWBC.solve                pnc/wbc/ihwbc/ihwbc.py:84-379
+//   qpsolvers.solve_qp(..., solver="quadprog")        ihwbc.py:330  (algorithm restated from
+//                                                     external_source/Goldfarb/QuadProg++.cc:115-502)
+//
+// B200-first formulation, not a translation of either solver:
+//   * The QP is never materialised densely.  Its Hessian is block diagonal
+//     (task block nv x nv, reaction-force block lambda_rf I), so only the task block is
+//     factorised; every constraint normal is a row of one small matrix
+//     Arows = [M | -Jc^T] (equalities = floating-base rows, torque limits = +/- actuated rows)
+//     or a 3/6-entry wrench-cone row.
+//   * J = L^-T is built in place of the Hessian; R is kept packed by columns.
+//   * Adding a constraint uses ONE Householder reflection of the null-space block
+//     (J2 <- J2 - beta (J2 v) v^T, with J2 v = z - alpha J[:,iq] already known) instead of the
+//     n-iq sequential Givens rotations of QuadProg++.cc:544-608: same iterates x, u and
+//     active set in exact arithmetic, half the flops and no dependent chain.
+//   * Constraint selection, step lengths, drop rule and termination test follow
+//     QuadProg++.cc:282-500 so the active set is the one the reference solver reaches.
+#include <math.h>
+
+#include "pnc_launch.h"
+
+namespace pnc {
+
+#define FULL 0xffffffffu
+#define QP_EPS 2.220446049250313e-16
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+// lexicographic (value, index) minimum over the warp; every lane gets the result
+__device__ __forceinline__ void wargmin(double& v, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(FULL, v, o);
+    int oi = __shfl_xor_sync(FULL, idx, o);
+    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+__device__ __forceinline__ double qp_distance(double a, double b) {  // QuadProg++.cc:681-692
+  double a1 = fabs(a), b1 = fabs(b);
+  if (a1 > b1) { double t = b1 / a1; return a1 * sqrt(1.0 + t * t); }
+  if (b1 > a1) { double t = a1 / b1; return b1 * sqrt(1.0 + t * t); }
+  return a1 * sqrt(2.0);
+}
+
+// util/util.py:61-72
+__device__ __forceinline__ void quat_to_exp(const double* q, double* e) {
+  double theta = 2.0 * asin(sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]));
+  if (fabs(theta) < 1e-4) { e[0] = e[1] = e[2] = 0.0; return; }
+  double sn = sin(theta / 2.0);
+  e[0] = q[0] / sn * theta; e[1] = q[1] / sn * theta; e[2] = q[2] / sn * theta;
+}
+
+// ---------------------------------------------------------------------------------------
+// BasicTask.update_cmd for the 3-row tasks (COM, LINK_XYZ, LINK_ORI), basic_task.py:25-109
+struct TaskVals {
+  double perr[3], op[3], jd[3];
+};
+
+__device__ void eval_dense_task(const DevProblem& P, const DevTask& T, int wsf, const WsPtrs& ws, size_t s, int nfr,
+                                const double* __restrict__ des, TaskVals& o) {
+  const double* pos_des = des + T.des_off;
+  const int npos = T.type == PNC_TASK_LINK_ORI ? 4 : 3;
+  const double* vel_des = pos_des + npos;
+  const double* acc_des = vel_des + 3;
+  double vact[3];
+  if (T.type == PNC_TASK_COM) {
+    for (int i = 0; i < 3; i++) {
+      o.perr[i] = pos_des[i] - ws.com[3 * s + i];
+      vact[i] = ws.vcom[3 * s + i];
+      o.jd[i] = ws.jcomdot_qdot[3 * s + i];
+    }
+  } else {
+    const double* iso = ws.fr_iso + (s * nfr + wsf) * 12;
+    const double* fv = ws.fr_vel + (s * nfr + wsf) * 6;
+    const double* fa = ws.fr_jdqd + (s * nfr + wsf) * 6;
+    if (T.type == PNC_TASK_LINK_XYZ) {
+      for (int i = 0; i < 3; i++) { o.perr[i] = pos_des[i] - iso[9 + i]; vact[i] = fv[3 + i]; o.jd[i] = fa[3 + i]; }
+    } else {  // LINK_ORI, basic_task.py:62-78
+      double Rdes[9], Ract[9], Rerr[9], qa[4], qe[4];
+      quat_to_rot(pos_des, Rdes);
+      double Rl[9];
+      for (int k = 0; k < 9; k++) Rl[k] = iso[k];
+      rot_to_quat(Rl, qa);  // R.from_matrix(rot) -> quaternion -> back to a rotation
+      quat_to_rot(qa, Ract);
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+          Rerr[3 * i + j] = Rdes[3 * i] * Ract[3 * j] + Rdes[3 * i + 1] * Ract[3 * j + 1] + Rdes[3 * i + 2] * Ract[3 * j + 2];
+      rot_to_quat(Rerr, qe);
+      quat_to_exp(qe, o.perr);
+      for (int i = 0; i < 3; i++) { vact[i] = fv[i]; o.jd[i] = fa[i]; }
+    }
+  }
+  for (int i = 0; i < 3; i++)
+    o.op[i] = acc_des[i] + P.kp[T.gain_off + i] * o.perr[i] + P.kd[T.gain_off + i] * (vel_des[i] - vact[i]);
+}
+
+// JOINT / SELECTED_JOINT row i, basic_task.py:27-47
+__device__ __forceinline__ void eval_joint_row(const DevProblem& P, const DevTask& T, int i, const WsPtrs& ws, size_t s,
+                                               int nq, const double* __restrict__ des, int& vi, double& perr,
+                                               double& op) {
+  const double* pos_des = des + T.des_off;
+  const double* vel_des = pos_des + T.dim;
+  const double* acc_des = vel_des + T.dim;
+  vi = T.type == PNC_TASK_JOINT ? 6 + i : P.joint_sel[T.joint_off + i];
+  double qj = ws.q[s * nq + vi + 1];
+  double qd = ws.qdot[s * P.nv + vi];
+  perr = pos_des[i] - qj;
+  op = acc_des[i] + P.kp[T.gain_off + i] * perr + P.kd[T.gain_off + i] * (vel_des[i] - qd);
+}
+
+__device__ __forceinline__ const double* dense_row_ptr(const DevTask& T, int wsf, const WsPtrs& ws, size_t s, int nfr,
+                                                       int nv, int i) {
+  if (T.type == PNC_TASK_COM) return ws.jcom + (s * 3 + i) * nv;
+  const double* J = ws.fr_jac + (s * nfr + wsf) * 6 * nv;
+  return J + (T.type == PNC_TASK_LINK_XYZ ? 3 + i : i) * nv;
+}
+
+// wrench-cone row `lr` of a contact in its own frame, basic_contact.py:24-51 / 89-173
+__device__ __forceinline__ void cone_row_local(const DevContact& C, int lr, double* u6) {
+  for (int k = 0; k < 6; k++) u6[k] = 0.0;
+  const double mu = C.mu;
+  if (C.type == PNC_CONTACT_POINT) {
+    switch (lr) {
+      case 0: u6[2] = 1.0; break;
+      case 1: u6[0] = 1.0; u6[2] = mu; break;
+      case 2: u6[0] = -1.0; u6[2] = mu; break;
+      case 3: u6[1] = 1.0; u6[2] = mu; break;
+      case 4: u6[1] = -1.0; u6[2] = mu; break;
+      default: u6[2] = -1.0; break;
+    }
+    return;
+  }
+  const double x = C.x, y = C.y;
+  if (lr == 0) u6[5] = 1.0;
+  else if (lr == 1) { u6[3] = 1.0; u6[5] = mu; }
+  else if (lr == 2) { u6[3] = -1.0; u6[5] = mu; }
+  else if (lr == 3) { u6[4] = 1.0; u6[5] = mu; }
+  else if (lr == 4) { u6[4] = -1.0; u6[5] = mu; }
+  else if (lr == 5) { u6[0] = 1.0; u6[5] = y; }
+  else if (lr == 6) { u6[0] = -1.0; u6[5] = y; }
+  else if (lr == 7) { u6[1] = 1.0; u6[5] = x; }
+  else if (lr == 8) { u6[1] = -1.0; u6[5] = x; }
+  else if (lr == 17) u6[5] = -1.0;
+  else {
+    // rows 9..16: signs of the (mu, mu, 1, y, x) columns, basic_contact.py:121-169
+    const int r = lr - 9;
+    const double s0 = (r & 2) ? 1.0 : -1.0;            // -,-,+,+,-,-,+,+
+    const double s1 = (r & 1) ? 1.0 : -1.0;            // -,+,-,+,-,+,-,+
+    const double s2 = (r & 4) ? -1.0 : 1.0;            // +,+,+,+,-,-,-,-
+    const double s3 = ((r & 2) ? -1.0 : 1.0) * s2;     // +,+,-,-,-,-,+,+
+    const double s4 = ((r & 1) ? -1.0 : 1.0) * s2;     // +,-,+,-,-,+,-,+
+    u6[0] = s0 * mu; u6[1] = s1 * mu; u6[2] = s2; u6[3] = s3 * y; u6[4] = s4 * x; u6[5] = (x + y) * mu;
+  }
+}
+
+// cone row in world axes: Uf = U blockdiag(R^T, R^T)  (surface, :72-87); point cones are not rotated (:31 unused)
+__device__ __forceinline__ void cone_row_world(const DevContact& C, int lr, const double* __restrict__ iso, double* u6) {
+  double l[6];
+  cone_row_local(C, lr, l);
+  if (C.type == PNC_CONTACT_POINT) {
+    for (int k = 0; k < 6; k++) u6[k] = l[k];
+    return;
+  }
+  for (int j = 0; j < 3; j++) {
+    u6[j] = l[0] * iso[3 * j] + l[1] * iso[3 * j + 1] + l[2] * iso[3 * j + 2];
+    u6[3 + j] = l[3] * iso[3 * j] + l[4] * iso[3 * j + 1] + l[5] * iso[3 * j + 2];
+  }
+}
+
+__device__ __forceinline__ const double* contact_jac_row(const DevContact& C, int wsf, const WsPtrs& ws, size_t s, int nfr,
+                                                         int nv, int k) {
+  const double* J = ws.fr_jac + (s * nfr + wsf) * 6 * nv;
+  return J + (C.type == PNC_CONTACT_POINT ? 3 + k : k) * nv;
+}
+
+// ---------------------------------------------------------------------------------------
+// one state's QP, resident in shared memory; all members are warp-uniform
+struct QP {
+  int lane, n, ld, p, m, iq;
+  double *J, *R, *x, *z, *d, *np, *hw, *r, *u;
+  double R_norm;
+  __device__ __forceinline__ double* Rcol(int c) const { return R + (c * (c + 3)) / 2; }
+};
+
+// d = J^T np restricted to rows k0..k1-1 of np (np is zero elsewhere), QuadProg++.cc:504-516
+__device__ void qp_compute_d(const QP& q, int k0, int k1) {
+  const int n = q.n, ld = q.ld, lane = q.lane;
+  if (k1 - k0 <= 8) {
+    for (int j = lane; j < n; j += 32) {
+      double sum = 0.0;
+      for (int k = k0; k < k1; k++) sum += q.J[k * ld + j] * q.np[k];
+      q.d[j] = sum;
+    }
+  } else {
+    // two lanes per column, each over half of the k range
+    const int kr = k1 - k0, kh = (kr + 1) >> 1;
+    const int h = lane & 1;
+    const int ka = k0 + h * kh, kb = min(k1, ka + kh);
+    for (int base = 0; base < 2 * n; base += 32) {
+      const int j = (base + lane) >> 1;
+      double s0 = 0.0, s1 = 0.0;
+      if (j < n) {
+        int k = ka;
+        for (; k + 1 < kb; k += 2) {
+          s0 += q.J[k * ld + j] * q.np[k];
+          s1 += q.J[(k + 1) * ld + j] * q.np[k + 1];
+        }
+        if (k < kb) s0 += q.J[k * ld + j] * q.np[k];
+      }
+      double sum = s0 + s1;
+      sum += __shfl_xor_sync(FULL, sum, 1);
+      if (j < n && h == 0) q.d[j] = sum;
+    }
+  }
+  __syncwarp();
+}
+
+// z = J[:, iq:] d[iq:]  (QuadProg++.cc:518-528); returns z.z and z.np
+__device__ void qp_compute_z(const QP& q, double& zz, double& znp) {
+  const int n = q.n, ld = q.ld, lane = q.lane, iq = q.iq;
+  const int jr = n - iq, jh = (jr + 1) >> 1;
+  const int h = lane & 1;
+  const int ja = iq + h * jh, jb = min(n, ja + jh);
+  double pzz = 0.0, pzn = 0.0;
+  for (int base = 0; base < 2 * n; base += 32) {
+    const int k = (base + lane) >> 1;
+    double s0 = 0.0, s1 = 0.0;
+    if (k < n) {
+      const double* row = q.J + k * ld;
+      int j = ja;
+      for (; j + 1 < jb; j += 2) {
+        s0 += row[j] * q.d[j];
+        s1 += row[j + 1] * q.d[j + 1];
+      }
+      if (j < jb) s0 += row[j] * q.d[j];
+    }
+    double sum = s0 + s1;
+    sum += __shfl_xor_sync(FULL, sum, 1);
+    if (k < n && h == 0) {
+      q.z[k] = sum;
+      pzz += sum * sum;
+      pzn += sum * q.np[k];
+    }
+  }
+  zz = wsum(pzz);
+  znp = wsum(pzn);
+  __syncwarp();
+}
+
+// r = R^-1 d[0:iq]  (QuadProg++.cc:530-542), column-oriented back substitution
+__device__ void qp_compute_r(const QP& q) {
+  const int iq = q.iq, lane = q.lane;
+  double acc0 = 0.0, acc1 = 0.0;  // rows lane, lane + 32
+  for (int i = iq - 1; i >= 0; i--) {
+    const double* col = q.Rcol(i);
+    double mine = (i & 32) ? acc1 : acc0;
+    double ri = (q.d[i] - mine) / col[i];
+    ri = __shfl_sync(FULL, ri, i & 31);
+    if (lane == (i & 31)) q.r[i] = ri;
+    if (lane < i) acc0 += col[lane] * ri;
+    if (lane + 32 < i) acc1 += col[lane + 32] * ri;
+  }
+  __syncwarp();
+}
+
+// QuadProg++.cc:544-608 with the Givens sweep replaced by one Householder reflection.
+// Needs q.z = J2 d2 of the current (J, d).  Returns false when the new constraint is
+// linearly dependent on the active set (nothing is modified in that case).
+__device__ bool qp_add_constraint(QP& q) {
+  const int n = q.n, ld = q.ld, lane = q.lane, iq = q.iq;
+  double part = 0.0;
+  for (int j = iq + lane; j < n; j += 32) part += q.d[j] * q.d[j];
+  const double sigma = sqrt(wsum(part));
+  if (sigma <= QP_EPS * q.R_norm) return false;
+  const double d0 = q.d[iq];
+  const double alpha = d0 > 0.0 ? -sigma : sigma;
+  const double v0 = d0 - alpha;
+  const double beta = 1.0 / (sigma * (sigma + fabs(d0)));
+  // R gains the column [d1; alpha]
+  double* col = q.Rcol(iq);
+  for (int i = lane; i < iq; i += 32) col[i] = q.d[i];
+  if (lane == 0) { col[iq] = alpha; q.d[iq] = v0; }
+  __syncwarp();
+  // J2 <- J2 - beta (z - alpha J[:,iq]) v^T,  v = [v0, d[iq+1:]]
+  for (int k = lane; k < n; k += 32) q.hw[k] = beta * (q.z[k] - alpha * q.J[k * ld + iq]);
+  __syncwarp();
+  const int jr = n - iq, jh = (jr + 1) >> 1;
+  const int h = lane & 1;
+  const int ja = iq + h * jh, jb = min(n, ja + jh);
+  for (int base = 0; base < 2 * n; base += 32) {
+    const int k = (base + lane) >> 1;
+    if (k < n) {
+      double* row = q.J + k * ld;
+      const double hwk = q.hw[k];
+      for (int j = ja; j < jb; j++) row[j] -= hwk * q.d[j];
+    }
+  }
+  q.iq = iq + 1;
+  q.R_norm = fmax(q.R_norm, sigma);
+  __syncwarp();
+  return true;
+}
+
+// QuadProg++.cc:610-679: drop the active constraint stored at position qq (>= p)
+__device__ void qp_delete_constraint(QP& q, int* A, int qq) {
+  const int n = q.n, ld = q.ld, lane = q.lane;
+  int iq = q.iq;
+  // shift A, u and the columns of R (column c keeps rows 0..c, i.e. one sub-diagonal entry)
+  for (int i = qq; i < iq - 1; i++) {
+    const double* src = q.Rcol(i + 1);
+    double* dst = q.Rcol(i);
+    double v0 = 0.0, v1 = 0.0;
+    if (lane <= i + 1) v0 = src[lane];
+    if (lane + 32 <= i + 1) v1 = src[lane + 32];
+    int ai = A[i + 1];
+    double ui = q.u[i + 1];
+    __syncwarp();
+    if (lane <= i + 1) dst[lane] = v0;
+    if (lane + 32 <= i + 1) dst[lane + 32] = v1;
+    if (lane == 0) { A[i] = ai; q.u[i] = ui; }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    A[iq - 1] = A[iq];
+    q.u[iq - 1] = q.u[iq];
+    A[iq] = 0;
+    q.u[iq] = 0.0;
+  }
+  iq--;
+  q.iq = iq;
+  __syncwarp();
+  if (iq == 0) return;
+  for (int j = qq; j < iq; j++) {
+    double* cj = q.Rcol(j);
+    double cc = cj[j], ss = cj[j + 1];
+    const double hh = qp_distance(cc, ss);
+    if (fabs(hh) < QP_EPS) continue;
+    cc = cc / hh;
+    ss = ss / hh;
+    __syncwarp();
+    double diag = hh;
+    if (cc < 0.0) { diag = -hh; cc = -cc; ss = -ss; }
+    if (lane == 0) { cj[j] = diag; cj[j + 1] = 0.0; }
+    const double xny = ss / (1.0 + cc);
+    for (int k = j + 1 + lane; k < iq; k += 32) {
+      double* ck = q.Rcol(k);
+      const double t1 = ck[j], t2 = ck[j + 1];
+      const double nj = t1 * cc + t2 * ss;
+      ck[j] = nj;
+      ck[j + 1] = xny * (t1 + nj) - t2;
+    }
+    for (int k = lane; k < n; k += 32) {
+      double* row = q.J + k * ld;
+      const double t1 = row[j], t2 = row[j + 1];
+      const double nj = t1 * cc + t2 * ss;
+      row[j] = nj;
+      row[j + 1] = xny * (nj + t1) - t2;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+struct DebugDump {
+  double* buf;
+  int state;
+};
+__device__ DebugDump g_dump = {nullptr, -1};
+
+__global__ void __launch_bounds__(32)
+k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, FrameMap fm, int nfr, int nq, int B, SolveIO io) {
+  extern __shared__ __align__(16) double smem[];
+  const DevProblem& P = *gp;
+  const int lane = threadIdx.x;
+  const int nv = P.nv, nc = P.nc, nu = P.nu, n = P.n, p = P.p, m = P.m, nact = P.nact, ld = L.ld, ldv = L.ldv;
+  const bool trq = P.b_trq_limit != 0;
+  const bool has_ic = P.n_ic > 0;
+  double* W = smem;
+  double* Jm = W + L.oJ;
+  double* Rp = W + L.oR;
+  double* Jd = Rp;  // dense task Jacobian staging (dead before R is first written)
+  double* Ar = W + L.oA;
+  double* a0 = W + L.oa0;
+  double* Uf = W + L.oUf;
+  double* uf = W + L.ouf;
+  double* x = W + L.ox;
+  double* g0 = W + L.og0;
+  double* xold = W + L.oxold;
+  double* uold = W + L.ouold;
+  double* sl = W + L.os;
+  double* ev = W + L.oe;
+  double* wt = W + L.owt;
+  int* Aact = reinterpret_cast<int*>(W + L.oint);
+  int* Aold = Aact + (n + 1);
+  int* iai = Aold + (n + 1);
+  int* iaexcl = iai + (m > 0 ? m : 1);
+  QP q;
+  q.lane = lane; q.n = n; q.ld = ld; q.p = p; q.m = m;
+  q.J = Jm; q.R = Rp; q.x = x; q.z = W + L.oz; q.d = W + L.od; q.np = W + L.onp; q.hw = W + L.ohw;
+  q.r = W + L.orr; q.u = W + L.ou;
+
+  for (;;) {
+    int si = 0;
+    if (lane == 0) si = atomicAdd(io.counter, 1);
+    si = __shfl_sync(FULL, si, 0);
+    if (si >= B) break;
+    const size_t s = (size_t)si;
+    const double* des = io.des + s * P.ndes;
+    int status = PNC_QP_OK, iter = 0;
+    q.iq = 0;
+    q.R_norm = 1.0;
+
+    // ---- tasks: error terms e = Jdot qdot - xddot_cmd and weights (ihwbc.py:159-172) ----
+    for (int t = 0; t < P.ntask; t++) {
+      const DevTask& T = P.tasks[t];
+      const double wt_t = io.w[s * P.ntask + t];
+      if (T.dense_off >= 0) {
+        if (lane == 0) {
+          TaskVals tv;
+          eval_dense_task(P, T, fm.task_f[t], ws, s, nfr, des, tv);
+          for (int i = 0; i < 3; i++) { ev[T.row_off + i] = tv.jd[i] - tv.op[i]; wt[T.row_off + i] = wt_t; }
+        }
+      } else {
+        for (int i = lane; i < T.dim; i += 32) {
+          int vi;
+          double perr, op;
+          eval_joint_row(P, T, i, ws, s, nq, des, vi, perr, op);
+          ev[T.row_off + i] = -op;
+          wt[T.row_off + i] = wt_t;
+        }
+      }
+    }
+    // stage the dense task Jacobian rows, zero the J / Hessian area
+    for (int t = 0; t < P.ntask; t++) {
+      const DevTask& T = P.tasks[t];
+      if (T.dense_off < 0) continue;
+      for (int i = 0; i < 3; i++) {
+        const double* src = dense_row_ptr(T, fm.task_f[t], ws, s, nfr, nv, i);
+        double* dst = Jd + (T.dense_off + i) * ldv;
+        for (int c = lane; c < nv; c += 32) dst[c] = src[c];
+      }
+    }
+    for (int k = lane; k < n * ld; k += 32) Jm[k] = 0.0;
+    for (int k = lane; k < n; k += 32) g0[k] = 0.0;
+    __syncwarp();
+
+    // ---- Hessian task block (lower triangle) = sum_t w_t J_t^T J_t + lambda_q_ddot M ----
+    {
+      const double* Mg = ws.M + s * nv * nv;
+      const int nt = (nv + 1) >> 1, ntile = nt * (nt + 1) / 2;
+      for (int idx = lane; idx < ntile; idx += 32) {
+        int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
+        while (ti * (ti + 1) / 2 > idx) ti--;
+        const int tj = idx - ti * (ti + 1) / 2;
+        const int r0 = 2 * ti, c0 = 2 * tj;
+        const bool r1ok = r0 + 1 < nv, c1ok = c0 + 1 < nv;
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+        for (int t = 0; t < P.ntask; t++) {
+          const DevTask& T = P.tasks[t];
+          if (T.dense_off < 0) continue;
+          const double wk = wt[T.row_off];
+          if (wk == 0.0) continue;
+          double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
+          for (int i = 0; i < 3; i++) {
+            const double* row = Jd + (T.dense_off + i) * ldv;
+            const double ra = row[r0], rb = r1ok ? row[r0 + 1] : 0.0;
+            const double ca = row[c0], cb = c1ok ? row[c0 + 1] : 0.0;
+            t00 += ra * ca; t01 += ra * cb; t10 += rb * ca; t11 += rb * cb;
+          }
+          a00 += wk * t00; a01 += wk * t01; a10 += wk * t10; a11 += wk * t11;
+        }
+        const double lam = P.lambda_q_ddot;
+        Jm[r0 * ld + c0] = a00 + lam * Mg[r0 * nv + c0];
+        if (c1ok && c0 + 1 <= r0) Jm[r0 * ld + c0 + 1] = a01 + lam * Mg[r0 * nv + c0 + 1];
+        if (r1ok) {
+          Jm[(r0 + 1) * ld + c0] = a10 + lam * Mg[(r0 + 1) * nv + c0];
+          if (c1ok) Jm[(r0 + 1) * ld + c0 + 1] = a11 + lam * Mg[(r0 + 1) * nv + c0 + 1];
+        }
+      }
+      // linear term of the dense tasks
+      for (int c = lane; c < nv; c += 32) {
+        double acc = 0.0;
+        for (int t = 0; t < P.ntask; t++) {
+          const DevTask& T = P.tasks[t];
+          if (T.dense_off < 0) continue;
+          const double wk = wt[T.row_off];
+          if (wk == 0.0) continue;
+          double tt = 0.0;
+          for (int i = 0; i < 3; i++) tt += ev[T.row_off + i] * Jd[(T.dense_off + i) * ldv + c];
+          acc += wk * tt;
+        }
+        g0[c] = acc;
+      }
+      __syncwarp();
+      // one-hot rows of the joint tasks
+      for (int t = 0; t < P.ntask; t++) {
+        const DevTask& T = P.tasks[t];
+        if (T.dense_off >= 0) continue;
+        for (int i = lane; i < T.dim; i += 32) {
+          const int vi = T.type == PNC_TASK_JOINT ? 6 + i : P.joint_sel[T.joint_off + i];
+          const double wk = wt[T.row_off + i];
+          Jm[vi * ld + vi] += wk;
+          g0[vi] += wk * ev[T.row_off + i];
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- constraint rows: Arows = [M | -(Jc Ni)^T] on the floating-base / actuated rows ----
+    {
+      const double* Mg = ws.M + s * nv * nv;
+      const int nrow = L.nrow;
+      for (int rI = 0; rI < nrow; rI++) {
+        double* row = Ar + rI * ld;
+        if (rI >= 6 && rI < p) {  // internal-constraint rows [Ji | 0]
+          for (int c = lane; c < n; c += 32) row[c] = c < nv ? P.ic_jac[rI - 6][c] : 0.0;
+          if (lane == 0) a0[rI] = 0.0;
+          continue;
+        }
+        if (has_ic && rI >= p) {  // S [M | -(Jc Ni)^T] from the projection kernel
+          const double* src = ws.ic_tq + (s * nact + (rI - p)) * n;
+          for (int c = lane; c < n; c += 32) row[c] = src[c];
+          if (lane == 0) a0[rI] = ws.ic_tq0[s * nact + (rI - p)];
+          continue;
+        }
+        const int v = rI < 6 ? rI : P.act_idx[rI - p];
+        for (int c = lane; c < nv; c += 32) row[c] = Mg[v * nv + c];
+        for (int c = lane; c < nc; c += 32) {
+          double val;
+          if (has_ic) {
+            val = ws.ic_jcni[(s * nc + c) * nv + v];
+          } else {
+            int ci = 0;
+            while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
+            val = contact_jac_row(P.contacts[ci], fm.contact_f[ci], ws, s, nfr, nv, c - P.contacts[ci].rf_off)[v];
+          }
+          row[nv + c] = -val;
+        }
+        if (lane == 0) a0[rI] = has_ic ? ws.ic_cg[s * nv + v] : ws.cori[s * nv + v] + ws.grav[s * nv + v];
+      }
+      // wrench cones
+      for (int r = lane; r < nu; r += 32) {
+        const int ci = P.cone_contact[r];
+        const DevContact& C = P.contacts[ci];
+        const int lr = r - C.cone_off;
+        double u6[6];
+        cone_row_world(C, lr, ws.fr_iso + (s * nfr + fm.contact_f[ci]) * 12, u6);
+        for (int k = 0; k < 6; k++) Uf[r * 6 + k] = u6[k];
+        double rz = io.rfz[s * P.ncontact + ci];
+        if (rz <= 0.0) rz = 1e-3;  // contact.py:37-41
+        uf[r] = lr == C.rows - 1 ? -rz : 0.0;
+      }
+      __syncwarp();
+    }
+
+    if (g_dump.buf && g_dump.state == si) {
+      double* o = g_dump.buf;
+      for (int k = lane; k < n * n; k += 32) o[k] = Jm[(k / n) * ld + (k % n)];
+      o += n * n;
+      for (int k = lane; k < n; k += 32) o[k] = g0[k];
+      o += n;
+      for (int k = lane; k < L.nrow * n; k += 32) o[k] = Ar[(k / n) * ld + (k % n)];
+      o += L.nrow * n;
+      for (int k = lane; k < L.nrow; k += 32) o[k] = a0[k];
+      o += L.nrow;
+      for (int k = lane; k < nu * 6; k += 32) o[k] = Uf[k];
+      o += nu * 6;
+      for (int k = lane; k < nu; k += 32) o[k] = uf[k];
+    }
+
+    // ---- Cholesky of the task block (QuadProg++.cc:705-730), left-looking, lanes = rows ----
+    double c1 = 0.0, c2 = 0.0;
+    {
+      double tr = 0.0;
+      for (int i = lane; i < nv; i += 32) tr += Jm[i * ld + i];
+      c1 = wsum(tr) + nc * P.lambda_rf;
+    }
+    double* dl = q.hw;  // diagonal of L
+    bool pd = true;
+    for (int j = 0; j < nv; j++) {
+      double t0 = 0.0, t1 = 0.0;
+      const double* rj = Jm + j * ld;
+      {
+        const int i = lane;
+        if (i >= j && i < nv) {
+          const double* ri = Jm + i * ld;
+          double sum = ri[j], sum2 = 0.0;
+          int k = 0;
+          for (; k + 1 < j; k += 2) { sum -= ri[k] * rj[k]; sum2 -= ri[k + 1] * rj[k + 1]; }
+          if (k < j) sum -= ri[k] * rj[k];
+          t0 = sum + sum2;
+        }
+      }
+      {
+        const int i = lane + 32;
+        if (i >= j && i < nv) {
+          const double* ri = Jm + i * ld;
+          double sum = ri[j], sum2 = 0.0;
+          int k = 0;
+          for (; k + 1 < j; k += 2) { sum -= ri[k] * rj[k]; sum2 -= ri[k + 1] * rj[k + 1]; }
+          if (k < j) sum -= ri[k] * rj[k];
+          t1 = sum + sum2;
+        }
+      }
+      const double piv = __shfl_sync(FULL, (j & 32) ? t1 : t0, j & 31);
+      if (!(piv > 0.0)) { pd = false; break; }
+      const double dj = sqrt(piv);
+      __syncwarp();
+      if (lane == (j & 31)) { Jm[j * ld + j] = dj; dl[j] = dj; }
+      if (lane > j && lane < nv) Jm[lane * ld + j] = t0 / dj;
+      if (lane + 32 > j && lane + 32 < nv) Jm[(lane + 32) * ld + j] = t1 / dj;
+      __syncwarp();
+    }
+    if (!pd || !(P.lambda_rf > 0.0 || nc == 0)) {
+      status = PNC_QP_NOT_PD;
+    } else {
+      // ---- J = L^-T in place (QuadProg++.cc:203-210): lane i forward-solves L z = e_i ----
+      for (int j = 0; j < nv; j++) {
+        const double* Lj = Jm + j * ld;
+        const double djj = dl[j];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+          const int i = lane + 32 * rr;
+          if (i <= j && i < nv) {
+            double* zi = Jm + i * ld;
+            double sum = i == j ? 1.0 : 0.0, sum2 = 0.0;
+            int k = i;
+            for (; k + 1 < j; k += 2) { sum -= Lj[k] * zi[k]; sum2 -= Lj[k + 1] * zi[k + 1]; }
+            if (k < j) sum -= Lj[k] * zi[k];
+            zi[j] = (sum + sum2) / djj;
+          }
+        }
+        // rows only write their own upper part and read the strict lower part of row j,
+        // except the diagonal z_i[i] which overwrites L[i][i]: dl[] keeps the pivots
+        __syncwarp();
+      }
+      // clear the strict lower triangle (the factor), set the reaction-force block
+      for (int i = 1; i < nv; i++)
+        for (int k = lane; k < i; k += 32) Jm[i * ld + k] = 0.0;
+      const double jrf = 1.0 / sqrt(P.lambda_rf > 0.0 ? P.lambda_rf : 1.0);
+      for (int c = lane; c < nc; c += 32) Jm[(nv + c) * ld + nv + c] = jrf;
+      __syncwarp();
+      {
+        double tr = 0.0;
+        for (int i = lane; i < n; i += 32) tr += Jm[i * ld + i];
+        c2 = wsum(tr);
+      }
+      // ---- unconstrained minimiser x = -G^-1 g0 = -J (J^T g0)  (:222-224) ----
+      for (int k = lane; k < n; k += 32) q.np[k] = g0[k];
+      __syncwarp();
+      q.iq = 0;
+      qp_compute_d(q, 0, nv);
+      double zz, znp;
+      qp_compute_z(q, zz, znp);
+      for (int k = lane; k < n; k += 32) x[k] = -q.z[k];
+      for (int k = lane; k <= n; k += 32) { q.u[k] = 0.0; Aact[k] = 0; }
+      __syncwarp();
+      if (g_dump.buf && g_dump.state == si) {
+        double* o = g_dump.buf + n * n + n + L.nrow * n + L.nrow + nu * 6 + nu;
+        for (int k = lane; k < n; k += 32) o[k] = x[k];
+      }
+
+      // ---- equality constraints (:232-272) ----
+      for (int i = 0; i < p && status == PNC_QP_OK; i++) {
+        const double* row = Ar + i * ld;
+        double pnx = 0.0;
+        for (int k = lane; k < n; k += 32) { const double v = row[k]; q.np[k] = v; pnx += v * x[k]; }
+        pnx = wsum(pnx);
+        __syncwarp();
+        qp_compute_d(q, 0, n);
+        qp_compute_z(q, zz, znp);
+        qp_compute_r(q);
+        double t2 = 0.0;
+        if (fabs(zz) > QP_EPS) t2 = (-pnx - a0[i]) / znp;
+        for (int k = lane; k < n; k += 32) x[k] += t2 * q.z[k];
+        for (int k = lane; k < q.iq; k += 32) q.u[k] -= t2 * q.r[k];
+        if (lane == 0) { q.u[q.iq] = t2; Aact[i] = -i - 1; }
+        __syncwarp();
+        if (!qp_add_constraint(q)) status = PNC_QP_EQ_DEPENDENT;
+      }
+
+      // ---- active-set loop (:274-500) ----
+      if (status == PNC_QP_OK && m > 0) {
+        for (int i = lane; i < m; i += 32) iai[i] = i;
+        __syncwarp();
+        const double psi_tol = (double)m * QP_EPS * c1 * c2 * 100.0;
+        bool done = false;
+        while (!done) {
+          // l1: a full step was taken (or first pass)
+          iter++;
+          for (int i = p + lane; i < q.iq; i += 32) iai[Aact[i]] = -1;
+          // slacks s = CI^T x + ci0 (:293-301)
+          double psi = 0.0;
+          if (trq) {
+            for (int a = lane; a < nact; a += 32) {
+              const double* row = Ar + (p + a) * ld;
+              double t0 = 0.0, t1 = 0.0;
+              int k = 0;
+              for (; k + 1 < n; k += 2) { t0 += row[k] * x[k]; t1 += row[k + 1] * x[k + 1]; }
+              if (k < n) t0 += row[k] * x[k];
+              const double tau = t0 + t1 + a0[p + a];
+              const double slo = tau - P.trq_lo[a], shi = P.trq_hi[a] - tau;
+              sl[nu + a] = slo;
+              sl[nu + nact + a] = shi;
+              psi += fmin(0.0, slo) + fmin(0.0, shi);
+            }
+          }
+          for (int r = lane; r < nu; r += 32) {
+            const DevContact& C = P.contacts[P.cone_contact[r]];
+            const double* xr = x + nv + C.rf_off;
+            double acc = 0.0;
+            for (int k = 0; k < C.dim; k++) acc += Uf[r * 6 + k] * xr[k];
+            acc -= uf[r];
+            sl[r] = acc;
+            psi += fmin(0.0, acc);
+          }
+          for (int i = lane; i < m; i += 32) iaexcl[i] = 1;
+          psi = wsum(psi);
+          __syncwarp();
+          if (fabs(psi) <= psi_tol) break;  // numerically feasible: optimum reached
+          if (iter > 40 * (n + m)) { status = PNC_QP_MAX_ITER; break; }
+          for (int i = lane; i < q.iq; i += 32) { uold[i] = q.u[i]; Aold[i] = Aact[i]; }
+          for (int i = lane; i < n; i += 32) xold[i] = x[i];
+          __syncwarp();
+
+          bool next_l1 = false;
+          while (!next_l1 && !done) {
+            // l2: choose the most violated constraint (:323-334)
+            double ss = 0.0;
+            int ip = 0x7fffffff;
+            for (int i = lane; i < m; i += 32) {
+              const double v = sl[i];
+              if (v < ss && iai[i] != -1 && iaexcl[i]) { ss = v; ip = i; }
+            }
+            wargmin(ss, ip);
+            if (ss >= 0.0) { done = true; break; }
+            // constraint normal np = CI[:, ip]
+            int k0, k1;
+            for (int k = lane; k < n; k += 32) q.np[k] = 0.0;
+            __syncwarp();
+            if (ip < nu) {
+              const DevContact& C = P.contacts[P.cone_contact[ip]];
+              k0 = nv + C.rf_off; k1 = k0 + C.dim;
+              if (lane < C.dim) q.np[k0 + lane] = Uf[ip * 6 + lane];
+            } else {
+              const int a = (ip - nu) % nact;
+              const double sg = (ip - nu) >= nact ? -1.0 : 1.0;
+              const double* row = Ar + (p + a) * ld;
+              for (int k = lane; k < n; k += 32) q.np[k] = sg * row[k];
+              k0 = 0; k1 = n;
+            }
+            if (lane == 0) { q.u[q.iq] = 0.0; Aact[q.iq] = ip; }
+            __syncwarp();
+
+            // l2a: step direction in primal (z) and dual (r) space
+            for (;;) {
+              qp_compute_d(q, k0, k1);
+              qp_compute_z(q, zz, znp);
+              qp_compute_r(q);
+              // partial step length t1 (:366-378)
+              double t1 = INFINITY;
+              int kk = 0x7fffffff;
+              for (int k = p + lane; k < q.iq; k += 32) {
+                const double rk = q.r[k];
+                if (rk > 0.0) {
+                  const double v = q.u[k] / rk;
+                  if (v < t1) { t1 = v; kk = k; }
+                }
+              }
+              wargmin(t1, kk);
+              const int l = kk != 0x7fffffff ? Aact[kk] : 0;
+              // full step length t2 (:380-388)
+              double t2 = INFINITY;
+              if (fabs(zz) > QP_EPS) {
+                t2 = -sl[ip] / znp;
+                if (t2 < 0.0) t2 = INFINITY;
+              }
+              const double t = fmin(t1, t2);
+              if (t >= INFINITY) {  // :402-407: QP infeasible
+                status = PNC_QP_INFEASIBLE;
+                done = true;
+                break;
+              }
+              if (t2 >= INFINITY) {
+                // step in dual space only, drop constraint l (:409-423)
+                for (int k = lane; k < q.iq; k += 32) q.u[k] -= t * q.r[k];
+                if (lane == 0) { q.u[q.iq] += t; iai[l] = l; }
+                __syncwarp();
+                qp_delete_constraint(q, Aact, kk);
+                continue;
+              }
+              // step in primal and dual space (:425-434)
+              for (int k = lane; k < n; k += 32) x[k] += t * q.z[k];
+              for (int k = lane; k < q.iq; k += 32) q.u[k] -= t * q.r[k];
+              if (lane == 0) q.u[q.iq] += t;
+              __syncwarp();
+              if (fabs(t - t2) < QP_EPS) {
+                // full step: add constraint ip to the active set (:441-474)
+                if (!qp_add_constraint(q)) {
+                  // linearly dependent: exclude ip, restore the iterate
+                  if (lane == 0) iaexcl[ip] = 0;
+                  for (int i = lane; i < m; i += 32) iai[i] = i;
+                  __syncwarp();
+                  for (int i = p + lane; i < q.iq; i += 32) {
+                    Aact[i] = Aold[i];
+                    q.u[i] = uold[i];
+                    iai[Aold[i]] = -1;
+                  }
+                  for (int i = lane; i < n; i += 32) x[i] = xold[i];
+                  __syncwarp();
+                  break;  // back to l2
+                }
+                if (lane == 0) iai[ip] = -1;
+                __syncwarp();
+                next_l1 = true;
+                break;
+              }
+              // partial step: drop constraint l, update s[ip], try again (:476-499)
+              if (lane == 0) iai[l] = l;
+              __syncwarp();
+              qp_delete_constraint(q, Aact, kk);
+              double acc = 0.0;
+              for (int k = k0 + lane; k < k1; k += 32) acc += q.np[k] * x[k];
+              acc = wsum(acc);
+              double ci0;
+              if (ip < nu) ci0 = -uf[ip];
+              else {
+                const int a = (ip - nu) % nact;
+                ci0 = (ip - nu) >= nact ? P.trq_hi[a] - a0[p + a] : a0[p + a] - P.trq_lo[a];
+              }
+              if (lane == 0) sl[ip] = acc + ci0;
+              __syncwarp();
+            }
+          }
+        }
+      }
+    }
+
+    // ---- outputs: x = [qddot; rf], torque recovery (ihwbc.py:339-356) ----
+    const bool bad = status == PNC_QP_NOT_PD || status == PNC_QP_EQ_DEPENDENT || status == PNC_QP_INFEASIBLE;
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    if (io.qddot)
+      for (int k = lane; k < nv; k += 32) io.qddot[s * nv + k] = bad ? nanv : x[k];
+    if (io.rf)
+      for (int k = lane; k < nc; k += 32) io.rf[s * nc + k] = bad ? nanv : x[nv + k];
+    if (io.acc)
+      for (int a = lane; a < nact; a += 32) io.acc[s * nact + a] = bad ? nanv : x[P.act_idx[a]];
+    if (io.trq) {
+      for (int a = lane; a < nact; a += 32) {
+        double tau;
+        if (trq) {
+          const double* row = Ar + (p + a) * ld;
+          double t0 = 0.0;
+          for (int k = 0; k < n; k++) t0 += row[k] * x[k];
+          tau = t0 + a0[p + a];
+        } else if (has_ic) {
+          const double* row = ws.ic_tq + (s * nact + a) * n;
+          double t0 = 0.0;
+          for (int k = 0; k < n; k++) t0 += row[k] * x[k];
+          tau = t0 + ws.ic_tq0[s * nact + a];
+        } else {
+          const int v = P.act_idx[a];
+          const double* Mr = ws.M + (s * nv + v) * nv;
+          double t0 = 0.0;
+          for (int k = 0; k < nv; k++) t0 += Mr[k] * x[k];
+          for (int ci = 0; ci < P.ncontact; ci++) {
+            const DevContact& C = P.contacts[ci];
+            for (int k = 0; k < C.dim; k++)
+              t0 -= contact_jac_row(C, fm.contact_f[ci], ws, s, nfr, nv, k)[v] * x[nv + C.rf_off + k];
+          }
+          tau = t0 + ws.cori[s * nv + v] + ws.grav[s * nv + v];
+        }
+        io.trq[s * nact + a] = bad ? nanv : tau;
+      }
+    }
+    if (io.active) {
+      const int mw = (m + 63) / 64 > 0 ? (m + 63) / 64 : 1;
+      for (int wd = lane; wd < mw; wd += 32) {
+        unsigned long long bits = 0ull;
+        for (int i = p; i < q.iq; i++) {
+          const int c = Aact[i];
+          if (c >= 0 && (c >> 6) == wd) bits |= 1ull << (c & 63);
+        }
+        io.active[s * mw + wd] = bits;
+      }
+    }
+    if (lane == 0) {
+      io.status[s] = status;
+      if (io.iters) io.iters[s] = iter;
+    }
+    __syncwarp();
+  }
+}
+
+void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcLayout& L, const WsPtrs& ws,
+                        const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream) {
+  const size_t smem = (size_t)L.per_state * sizeof(double);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(k_ihwbc_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 16) per_sm = 16;
+  int grid = num_sms * per_sm;
+  if (grid > B) grid = B;
+  const int nq = hp.nv + 1;
+  k_ihwbc_solve<<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, nq, B, io);
+  g_launch_count++;
+}
+
+// ---------------------------------------------------------------------------------------
+// Task / contact accessors (parity with Task.jacobian, .jacobian_dot_q_dot, .op_cmd,
+// Contact.jacobian, .cone_constraint_mat/vec): one thread per state.
+__global__ void k_task_eval(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int nq, int B, int it,
+                            const double* __restrict__ des_all, double* jac, double* jdqd, double* op_cmd,
+                            double* pos_err) {
+  const DevProblem& P = *gp;
+  const DevTask& T = P.tasks[it];
+  const int nv = P.nv, dim = T.dim;
+  for (size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x; s < (size_t)B; s += (size_t)gridDim.x * blockDim.x) {
+    const double* des = des_all + s * P.ndes;
+    if (T.dense_off >= 0) {
+      TaskVals tv;
+      eval_dense_task(P, T, fm.task_f[it], ws, s, nfr, des, tv);
+      for (int i = 0; i < 3; i++) {
+        if (jdqd) jdqd[s * 3 + i] = tv.jd[i];
+        if (op_cmd) op_cmd[s * 3 + i] = tv.op[i];
+        if (pos_err) pos_err[s * 3 + i] = tv.perr[i];
+        if (jac) {
+          const double* src = dense_row_ptr(T, fm.task_f[it], ws, s, nfr, nv, i);
+          for (int c = 0; c < nv; c++) jac[(s * 3 + i) * nv + c] = src[c];
+        }
+      }
+    } else {
+      for (int i = 0; i < dim; i++) {
+        int vi;
+        double perr, op;
+        eval_joint_row(P, T, i, ws, s, nq, des, vi, perr, op);
+        if (jdqd) jdqd[s * dim + i] = 0.0;
+        if (op_cmd) op_cmd[s * dim + i] = op;
+        if (pos_err) pos_err[s * dim + i] = perr;
+        if (jac)
+          for (int c = 0; c < nv; c++) jac[(s * dim + i) * nv + c] = c == vi ? 1.0 : 0.0;
+      }
+    }
+  }
+}
+
+void launch_task_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int itask, int dim,
+                      int nv, const double* des, double* jac, double* jdqd, double* op_cmd, double* pos_err,
+                      cudaStream_t stream) {
+  (void)dim;
+  int grid = (B + 127) / 128;
+  k_task_eval<<<grid, 128, 0, stream>>>(dp, ws, fm, nfr, nv + 1, B, itask, des, jac, jdqd, op_cmd, pos_err);
+  g_launch_count++;
+}
+
+__global__ void k_contact_eval(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B, int ic,
+                               const double* __restrict__ rfz, double* jac, double* cone_mat, double* cone_vec) {
+  const DevProblem& P = *gp;
+  const DevContact& C = P.contacts[ic];
+  const int nv = P.nv;
+  for (size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x; s < (size_t)B; s += (size_t)gridDim.x * blockDim.x) {
+    if (jac)
+      for (int k = 0; k < C.dim; k++) {
+        const double* src = contact_jac_row(C, fm.contact_f[ic], ws, s, nfr, nv, k);
+        for (int c = 0; c < nv; c++) jac[(s * C.dim + k) * nv + c] = src[c];
+      }
+    double rz = rfz[s * P.ncontact + ic];
+    if (rz <= 0.0) rz = 1e-3;
+    for (int r = 0; r < C.rows; r++) {
+      double u6[6];
+      cone_row_world(C, r, ws.fr_iso + (s * nfr + fm.contact_f[ic]) * 12, u6);
+      if (cone_mat)
+        for (int k = 0; k < C.dim; k++) cone_mat[(s * C.rows + r) * C.dim + k] = u6[k];
+      if (cone_vec) cone_vec[s * C.rows + r] = r == C.rows - 1 ? -rz : 0.0;
+    }
+  }
+}
+
+void launch_contact_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int icontact,
+                         int nv, const double* rfz, double* jac, double* cone_mat, double* cone_vec,
+                         cudaStream_t stream) {
+  (void)nv;
+  int grid = (B + 127) / 128;
+  k_contact_eval<<<grid, 128, 0, stream>>>(dp, ws, fm, nfr, B, icontact, rfz, jac, cone_mat, cone_vec);
+  g_launch_count++;
+}
+
+// JointIntegrator.integrate, pnc/wbc/ihwbc/joint_integrator.py:73-82
+__global__ void k_joint_integrate(int B, int na, const double* __restrict__ acc, const double* __restrict__ joint_pos,
+                                  double* vel_state, double* pos_state, const double* __restrict__ pos_limit,
+                                  const double* __restrict__ vel_limit, double alpha_vel, double alpha_pos, double dt) {
+  const size_t total = (size_t)B * na;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % na);
+    double v = (1.0 - alpha_vel) * vel_state[i] + acc[i] * dt;
+    v = fmin(fmax(v, vel_limit[2 * j]), vel_limit[2 * j + 1]);
+    double ps = (1.0 - alpha_pos) * pos_state[i] + alpha_pos * joint_pos[i] + v * dt;
+    ps = fmin(fmax(ps, pos_limit[2 * j]), pos_limit[2 * j + 1]);
+    vel_state[i] = v;
+    pos_state[i] = ps;
+  }
+}
+
+void launch_joint_integrate(int B, int na, const double* acc, const double* joint_pos, double* vel_state,
+                            double* pos_state, const double* pos_limit, const double* vel_limit, double alpha_vel,
+                            double alpha_pos, double dt, cudaStream_t stream) {
+  size_t total = (size_t)B * na;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_joint_integrate<<<grid, 256, 0, stream>>>(B, na, acc, joint_pos, vel_state, pos_state, pos_limit, vel_limit,
+                                              alpha_vel, alpha_pos, dt);
+  g_launch_count++;
+}
+
+// ---------------------------------------------------------------------------------------
+// DFMA-chain microbenchmark: the fp64 roofline denominator (MEASURED_PEAKS.json has none)
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int measure_fp64_peak(int num_sms, double* tflops) {
+  const int grid = num_sms * 8, block = 256, iters = 4096;
+  double* out = nullptr;
+  if (cudaMalloc(&out, (size_t)grid * block * sizeof(double)) != cudaSuccess) return -1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<grid, block>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return -1; }
+    g_launch_count++;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * iters * (double)grid * block;
+    const double tf = flops / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return 0;
+}
+
+extern "C" int pnc_debug_set_dump(double* d_buf, int state) {
+  DebugDump h;
+  h.buf = d_buf;
+  h.state = state;
+  return cudaMemcpyToSymbol(g_dump, &h, sizeof(h)) == cudaSuccess ? 0 : PNC_E_CUDA;
+}
+
+}  // namespace pnc

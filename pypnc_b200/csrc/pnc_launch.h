@@ -1,0 +1,87 @@
+// pnc_launch.h -- host-side launch interface between capi.cu and the kernel files.
+#pragma once
+#include "pnc_dev.cuh"
+
+namespace pnc {
+
+// shared-memory layout of ONE state's QP in the solve kernel (offsets in doubles)
+struct IhwbcLayout {
+  int n, ld, ldv, nrow;
+  int oJ, oR, oA, oa0, oUf, ouf, ox, oz, od, onp, ohw, oxold, og0, orr, ou, ouold, os, oe, owt, oint;
+  int per_state;  // doubles, even
+};
+
+__host__ __device__ inline IhwbcLayout ihwbc_layout(const DevProblem& P) {
+  IhwbcLayout L;
+  const int n = P.n, m = P.m > 0 ? P.m : 1;
+  L.n = n;
+  L.ld = n | 1;
+  L.ldv = P.nv | 1;
+  L.nrow = P.p + (P.b_trq_limit ? P.nact : 0);
+  int o = 0;
+  L.oJ = o; o += n * L.ld;
+  int rsz = n * (n + 3) / 2, stg = P.ndense * L.ldv;
+  L.oR = o; o += (rsz > stg ? rsz : stg);
+  L.oA = o; o += L.nrow * L.ld;
+  L.oa0 = o; o += L.nrow;
+  L.oUf = o; o += (P.nu > 0 ? P.nu : 1) * 6;
+  L.ouf = o; o += (P.nu > 0 ? P.nu : 1);
+  L.ox = o; o += n;
+  L.oz = o; o += n;
+  L.od = o; o += n;
+  L.onp = o; o += n;
+  L.ohw = o; o += n;
+  L.oxold = o; o += n;
+  L.og0 = o; o += n;
+  L.orr = o; o += n + 1;
+  L.ou = o; o += n + 1;
+  L.ouold = o; o += n + 1;
+  L.os = o; o += m;
+  L.oe = o; o += P.ntaskrows > 0 ? P.ntaskrows : 1;
+  L.owt = o; o += P.ntaskrows > 0 ? P.ntaskrows : 1;
+  L.oint = o; o += (2 * (n + 1) + 2 * m + 1) / 2 + 1;
+  L.per_state = (o + 1) & ~1;
+  return L;
+}
+
+struct SolveIO {
+  const double *des, *w, *rfz;
+  double *trq, *acc, *rf, *qddot;
+  int *status, *iters;
+  unsigned long long* active;
+  int* counter;
+};
+
+// workspace pointers advanced by `off` states
+inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, int nc, int nact, int n) {
+  WsPtrs w = a;
+  w.q += off * nq; w.qdot += off * nv; w.M += off * nv * nv; w.grav += off * nv; w.cori += off * nv;
+  w.com += off * 3; w.vcom += off * 3; w.jcom += off * 3 * nv; w.jcomdot += off * 3 * nv; w.jcomdot_qdot += off * 3;
+  w.fr_iso += off * nfr * 12; w.fr_vel += off * nfr * 6; w.fr_jac += off * nfr * 6 * nv; w.fr_jdqd += off * nfr * 6;
+  if (w.ic_cg) {
+    w.ic_cg += off * nv; w.ic_jcni += off * nc * nv; w.ic_tq += off * nact * n; w.ic_tq0 += off * nact;
+    w.ic_status += off;
+  }
+  return w;
+}
+
+void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs& ws, int B, int nv,
+                          const double* base_pos, const double* base_quat, const double* base_lin_vel,
+                          const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
+                          int num_sms, cudaStream_t stream);
+void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcLayout& L, const WsPtrs& ws,
+                        const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream);
+void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
+                       int B, int num_sms, cudaStream_t stream);
+void launch_task_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int itask, int dim,
+                      int nv, const double* des, double* jac, double* jdqd, double* op_cmd, double* pos_err,
+                      cudaStream_t stream);
+void launch_contact_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int icontact,
+                         int nv, const double* rfz, double* jac, double* cone_mat, double* cone_vec,
+                         cudaStream_t stream);
+void launch_joint_integrate(int B, int na, const double* acc, const double* joint_pos, double* vel_state,
+                            double* pos_state, const double* pos_limit, const double* vel_limit, double alpha_vel,
+                            double alpha_pos, double dt, cudaStream_t stream);
+int measure_fp64_peak(int num_sms, double* tflops);
+
+}  // namespace pnc

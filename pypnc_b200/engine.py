@@ -1,0 +1,164 @@
+"""Thin Python handles over the C ABI (include/pnc_b200.h).
+
+torch is used for device memory and streams only; every computation is a kernel of
+``pypnc_b200/csrc/libpnc_b200.so``.  Nothing here has a CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+vp = C.c_void_p
+
+
+def _check(rc, what):
+    if rc != 0:
+        names = {-1: 'PNC_E_ARG', -2: 'PNC_E_CUDA', -3: 'PNC_E_SIZE', -4: 'PNC_E_NOGPU'}
+        raise RuntimeError("%s failed: %s" % (what, names.get(rc, rc)))
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-resident contiguous tensor required"
+    return vp(t.data_ptr())
+
+
+def _stream():
+    return vp(torch.cuda.current_stream().cuda_stream)
+
+
+class Model:
+    """Device copy of the compiled joint tables (PinocchioRobotSystem._config_robot)."""
+
+    def __init__(self, model, device=0):
+        self.lib = _cabi.load_library()
+        self.model = model
+        self.device = int(device)
+        self._desc, self._keep = _cabi.make_model_desc(model)
+        h = vp()
+        _check(self.lib.pnc_model_create(C.byref(self._desc), self.device, C.byref(h)), 'pnc_model_create')
+        self.h = h
+
+    def __del__(self):
+        try:
+            self.lib.pnc_model_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Problem:
+    """Tasks / contacts / internal constraints / actuation of one controller."""
+
+    def __init__(self, dev_model, spec):
+        self.lib = dev_model.lib
+        self.dev_model = dev_model
+        self.spec = spec
+        self._desc, self._keep = _cabi.make_problem_desc(spec)
+        h = vp()
+        _check(self.lib.pnc_problem_create(dev_model.h, C.byref(self._desc), C.byref(h)), 'pnc_problem_create')
+        self.h = h
+        d = [C.c_int32() for _ in range(5)]
+        _check(self.lib.pnc_problem_dims(h, *[C.byref(x) for x in d]), 'pnc_problem_dims')
+        self.nc, self.ncone, self.n, self.p, self.m = [x.value for x in d]
+        self.mw = max(1, (self.m + 63) // 64)
+
+    def __del__(self):
+        try:
+            self.lib.pnc_problem_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Workspace:
+    """Per-state rigid-body quantities in HBM for up to `capacity` states."""
+
+    _FIELDS = dict(q='q', qdot='qdot', M='mass_matrix', grav='gravity', cori='coriolis', com='com_pos',
+                   vcom='com_vel', jcom='com_jac', jcomdot='com_jacdot', jcom_jdqd='com_jdqd',
+                   frame_iso='frame_iso', frame_vel='frame_vel', frame_jac='frame_jac', frame_jdqd='frame_jdqd')
+
+    def __init__(self, dev_model, capacity, frames):
+        self.lib = dev_model.lib
+        self.dev_model = dev_model
+        self.capacity = int(capacity)
+        self.frames = [int(f) for f in frames]
+        arr = np.ascontiguousarray(self.frames, dtype=np.int32)
+        h = vp()
+        _check(self.lib.pnc_workspace_create(dev_model.h, self.capacity, arr.ctypes.data_as(_cabi.c_int32_p),
+                                             len(self.frames), C.byref(h)), 'pnc_workspace_create')
+        self.h = h
+        self.B = 0
+
+    def __del__(self):
+        try:
+            self.lib.pnc_workspace_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def nbytes(self):
+        return int(self.lib.pnc_workspace_bytes(self.h))
+
+    def update_system(self, base_pos, base_quat, base_lin_vel, base_ang_vel, joint_pos, joint_vel):
+        B = joint_pos.shape[0]
+        _check(self.lib.pnc_update_system(self.h, B, _ptr(base_pos), _ptr(base_quat), _ptr(base_lin_vel),
+                                          _ptr(base_ang_vel), _ptr(joint_pos), _ptr(joint_vel), _stream()),
+               'pnc_update_system')
+        self.B = B
+
+    def view(self, name, B=None):
+        """A torch view (no copy) of one workspace array for the first B states."""
+        m = self.dev_model.model
+        B = self.B if B is None else B
+        nfr, nv, nq = len(self.frames), m.nv, m.nq
+        shapes = dict(q=(B, nq), qdot=(B, nv), M=(B, nv, nv), grav=(B, nv), cori=(B, nv), com=(B, 3), vcom=(B, 3),
+                      jcom=(B, 3, nv), jcomdot=(B, 3, nv), jcom_jdqd=(B, 3), frame_iso=(B, nfr, 12),
+                      frame_vel=(B, nfr, 6), frame_jac=(B, nfr, 6, nv), frame_jdqd=(B, nfr, 6))
+        ptr = getattr(self.lib, 'pnc_ws_' + self._FIELDS[name])(self.h)
+        return _from_ptr(ptr, shapes[name], self.dev_model.device)
+
+
+def _from_ptr(ptr, shape, device):
+    n = int(np.prod(shape))
+    if n == 0:
+        return torch.empty(shape, dtype=torch.float64, device='cuda:%d' % device)
+    iface = {'shape': (n,), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+
+    class _H:
+        __cuda_array_interface__ = iface
+
+    with torch.cuda.device(device):
+        t = torch.as_tensor(_H(), device='cuda:%d' % device)
+    return t.view(*shape)
+
+
+def ihwbc_solve(problem, ws, des, w, rf_z_max, want_qddot=True):
+    """pnc_ihwbc_solve on device tensors.  Returns a dict of device tensors."""
+    spec = problem.spec
+    B = des.shape[0]
+    dev = des.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    out = dict(trq=torch.empty((B, spec.nact), **f64), acc=torch.empty((B, spec.nact), **f64),
+               rf=torch.empty((B, problem.nc), **f64),
+               qddot=torch.empty((B, spec.model.nv), **f64) if want_qddot else None,
+               status=torch.empty(B, dtype=torch.int32, device=dev),
+               iters=torch.empty(B, dtype=torch.int32, device=dev),
+               active=torch.empty((B, problem.mw), dtype=torch.int64, device=dev))
+    _check(problem.lib.pnc_ihwbc_solve(problem.h, ws.h, B, _ptr(des), _ptr(w), _ptr(rf_z_max), _ptr(out['trq']),
+                                       _ptr(out['acc']), _ptr(out['rf']), _ptr(out['qddot']), _ptr(out['status']),
+                                       _ptr(out['iters']), _ptr(out['active']), _stream()), 'pnc_ihwbc_solve')
+    return out
+
+
+def unpack_active(active_words, m):
+    """[B, mw] int64 bit masks -> [B, m] uint8 numpy."""
+    a = active_words.detach().cpu().numpy().astype(np.uint64)
+    B = a.shape[0]
+    out = np.zeros((B, max(m, 1)), dtype=np.uint8)
+    for i in range(m):
+        out[:, i] = (a[:, i >> 6] >> np.uint64(i & 63)) & np.uint64(1)
+    return out[:, :m]

@@ -366,7 +366,7 @@ static int solve_at(const pnc_problem* p, pnc_workspace* ws, int off, int32_t B,
   if (rc) return rc;
   WsPtrs wsp = ws_offset(ws->p, off, ws->m->h.nq, p->h.nv, ws->nfr, p->h.nc, p->h.nact, p->h.n);
   if (p->h.n_ic > 0) {
-    launch_ic_prepare(p->d, p->h, wsp, fm, ws->nfr, B, ws->m->num_sms, st);
+    launch_ic_prepare(p->d, p->h, wsp, fm, ws->nfr, B, ws->m->num_sms, st, counter + 1);
     CK(cudaGetLastError());
   }
   CK(cudaMemsetAsync(counter, 0, sizeof(int), st));

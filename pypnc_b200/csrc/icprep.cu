@@ -1,5 +1,319 @@
-// icprep.cu -- internal-constraint projection products (ihwbc.py:124-146) -- placeholder
+// icprep.cu -- internal-constraint projection products, one robot state per warp.
+//
+// Replaces the numpy block at the top of IHWBC.solve (reference pnc/wbc/ihwbc/ihwbc.py:124-146
+// with util/util.py:91-95 weighted_pinv) for problems with internal constraints
+// (Draco3 rolling knee joints, pnc/draco3_pnc/draco3_rolling_joint_constraint.py):
+//   Lambda = pinv(Ji M^-1 Ji^T)            Jibar = M^-1 Ji^T Lambda       Ni = I - Jibar Ji
+//   A = (Sa Ni)[:, 6:]   W = M^-1[6:, 6:]  B = (W A^T pinv(A W A^T))^T    S = [0 | B]
+// and writes what the QP kernel consumes: Ni^T (c+g), Jc Ni, S [M | -(Jc Ni)^T], S Ni^T (c+g).
+//
+// No explicit inverse is formed.  With M = L L^T:  Ji M^-1 Ji^T = Y^T Y (Y = L^-1 Ji^T),
+// A W A^T = Z^T Z with Z = L^-1 [0 | A]^T, and W A^T = rows 6.. of L^-T Z.  Both pseudo-inverses
+// are applied as Cholesky solves: for the shipped robots the two Gram matrices are full rank
+// (singular-value ratio > 1e-4, far above the reference's rcond = 1e-15), where pinv == inverse.
+// A rank-deficient Gram matrix is reported through ic_status (the QP then returns
+// PNC_QP_EQ_DEPENDENT for that state) instead of being silently truncated.
+#include <math.h>
+
 #include "pnc_launch.h"
+
 namespace pnc {
-void launch_ic_prepare(const DevProblem*, const DevProblem&, const WsPtrs&, const FrameMap&, int, int, int, cudaStream_t) {}
+
+#define FULL 0xffffffffu
+
+struct IcLayout {
+  int ld, ldz, ldb;
+  int oL, oZ, oV, oG, oBt, oY, oJb, oLam, odiag, ocg, oncg, oJcJb;
+  int total;
+};
+
+__host__ __device__ inline IcLayout ic_layout(int nv, int nact, int nc, int k) {
+  IcLayout L;
+  L.ld = nv | 1; L.ldz = nact | 1; L.ldb = nact | 1;
+  int o = 0;
+  L.oL = o; o += nv * L.ld;
+  L.oZ = o; o += nv * L.ldz;       // Z = L^-1 Atilde^T, later V = L^-T Z
+  L.oG = o; o += nact * L.ldz;     // Z^T Z and its Cholesky factor
+  L.oBt = o; o += (nv - 6) * L.ldb;  // B^T  [(nv-6) x nact]
+  L.oY = o; o += nv * k;
+  L.oJb = o; o += nv * k;
+  L.oLam = o; o += k * k + 2 * k;
+  L.odiag = o; o += nv;
+  L.ocg = o; o += nv;
+  L.oncg = o; o += nv;
+  L.oJcJb = o; o += (nc > 0 ? nc : 1) * k;
+  L.oV = L.oZ;
+  L.total = (o + 1) & ~1;
+  return L;
 }
+
+__global__ void __launch_bounds__(32)
+k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap fm, int nfr, int B, int* counter) {
+  extern __shared__ __align__(16) double sm[];
+  const DevProblem& P = *gp;
+  const int lane = threadIdx.x;
+  const int nv = P.nv, k = P.n_ic, nact = P.nact, nc = P.nc, n = P.n, ld = L.ld, ldz = L.ldz, ldb = L.ldb;
+  const int nj = nv - 6;
+  double* Lm = sm + L.oL;
+  double* Z = sm + L.oZ;
+  double* G = sm + L.oG;
+  double* Bt = sm + L.oBt;
+  double* Y = sm + L.oY;
+  double* Jb = sm + L.oJb;
+  double* Lam = sm + L.oLam;
+  double* Mdiag = sm + L.odiag;
+  double* cg = sm + L.ocg;
+  double* ncg = sm + L.oncg;
+  double* JcJb = sm + L.oJcJb;
+
+  for (;;) {
+    int si = 0;
+    if (lane == 0) si = atomicAdd(counter, 1);
+    si = __shfl_sync(FULL, si, 0);
+    if (si >= B) break;
+    const size_t s = (size_t)si;
+    int bad = 0;
+    const double* Mg = ws.M + s * nv * nv;
+    for (int i = 0; i < nv; i++)
+      for (int c = lane; c < nv; c += 32) Lm[i * ld + c] = Mg[i * nv + c];
+    for (int c = lane; c < nv; c += 32) { Mdiag[c] = Mg[c * nv + c]; cg[c] = ws.cori[s * nv + c] + ws.grav[s * nv + c]; }
+    __syncwarp();
+    // ---- M = L L^T (lower triangle of Lm; the strict upper triangle keeps M) ----
+    for (int j = 0; j < nv; j++) {
+      double t[2] = {0.0, 0.0};
+      const double* rj = Lm + j * ld;
+      for (int rr = 0; rr < 2; rr++) {
+        const int i = lane + 32 * rr;
+        if (i >= j && i < nv) {
+          const double* ri = Lm + i * ld;
+          double sum = ri[j];
+          for (int c = 0; c < j; c++) sum -= ri[c] * rj[c];
+          t[rr] = sum;
+        }
+      }
+      const double piv = __shfl_sync(FULL, (j & 32) ? t[1] : t[0], j & 31);
+      if (!(piv > 0.0)) { bad = 1; break; }
+      const double dj = sqrt(piv);
+      __syncwarp();
+      for (int rr = 0; rr < 2; rr++) {
+        const int i = lane + 32 * rr;
+        if (i == j) Lm[j * ld + j] = dj;
+        else if (i > j && i < nv) Lm[i * ld + j] = t[rr] / dj;
+      }
+      __syncwarp();
+    }
+    if (!bad) {
+      // ---- Y = L^-1 Ji^T (lane c < k solves column c), Lambda = (Y^T Y)^-1 ----
+      if (lane < k) {
+        for (int i = 0; i < nv; i++) {
+          double sum = P.ic_jac[lane][i];
+          for (int c = 0; c < i; c++) sum -= Lm[i * ld + c] * Y[c * k + lane];
+          Y[i * k + lane] = sum / Lm[i * ld + i];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        double a[PNC_MAX_IC][2 * PNC_MAX_IC];
+        for (int r = 0; r < k; r++)
+          for (int c = 0; c < k; c++) {
+            double sum = 0.0;
+            for (int i = 0; i < nv; i++) sum += Y[i * k + r] * Y[i * k + c];
+            a[r][c] = sum;
+            a[r][k + c] = r == c ? 1.0 : 0.0;
+          }
+        double amax = 0.0;
+        for (int r = 0; r < k; r++) amax = fmax(amax, fabs(a[r][r]));
+        for (int c = 0; c < k; c++) {  // Gauss-Jordan with partial pivoting
+          int pr = c;
+          for (int r = c + 1; r < k; r++)
+            if (fabs(a[r][c]) > fabs(a[pr][c])) pr = r;
+          if (!(fabs(a[pr][c]) > 1e-13 * amax)) { bad = 1; break; }
+          for (int cc = 0; cc < 2 * k; cc++) { double tmp = a[c][cc]; a[c][cc] = a[pr][cc]; a[pr][cc] = tmp; }
+          const double d = a[c][c];
+          for (int cc = 0; cc < 2 * k; cc++) a[c][cc] /= d;
+          for (int r = 0; r < k; r++) {
+            if (r == c) continue;
+            const double f = a[r][c];
+            for (int cc = 0; cc < 2 * k; cc++) a[r][cc] -= f * a[c][cc];
+          }
+        }
+        for (int r = 0; r < k; r++)
+          for (int c = 0; c < k; c++) Lam[r * k + c] = a[r][k + c];
+      }
+      bad = __shfl_sync(FULL, bad, 0);
+      __syncwarp();
+    }
+    if (!bad) {
+      // ---- Jibar = L^-T (Y Lambda): lane c < k back-substitutes column c ----
+      if (lane < k) {
+        for (int i = nv - 1; i >= 0; i--) {
+          double sum = 0.0;
+          for (int t = 0; t < k; t++) sum += Y[i * k + t] * Lam[t * k + lane];
+          for (int c = i + 1; c < nv; c++) sum -= Lm[c * ld + i] * Jb[c * k + lane];
+          Jb[i * k + lane] = sum / Lm[i * ld + i];
+        }
+      }
+      __syncwarp();
+      // ---- Ni^T (c+g) = cg - Ji^T (Jibar^T cg) ----
+      {
+        double jt[PNC_MAX_IC];
+        for (int t = 0; t < k; t++) {
+          double part = 0.0;
+          for (int i = lane; i < nv; i += 32) part += Jb[i * k + t] * cg[i];
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+          jt[t] = part;
+        }
+        for (int i = lane; i < nv; i += 32) {
+          double v = cg[i];
+          for (int t = 0; t < k; t++) v -= P.ic_jac[t][i] * jt[t];
+          ncg[i] = v;
+          ws.ic_cg[s * nv + i] = v;
+        }
+      }
+      // ---- Jc Ni = Jc - (Jc Jibar) Ji ----
+      for (int c = lane; c < nc; c += 32) {
+        int ci = 0;
+        while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
+        const DevContact& C = P.contacts[ci];
+        const double* Jrow = ws.fr_jac + (s * nfr + fm.contact_f[ci]) * 6 * nv +
+                             (C.type == PNC_CONTACT_POINT ? 3 + (c - C.rf_off) : (c - C.rf_off)) * nv;
+        double acc[PNC_MAX_IC];
+        for (int t = 0; t < k; t++) acc[t] = 0.0;
+        for (int i = 0; i < nv; i++) {
+          const double v = Jrow[i];
+          for (int t = 0; t < k; t++) acc[t] += v * Jb[i * k + t];
+        }
+        for (int t = 0; t < k; t++) JcJb[c * k + t] = acc[t];
+        for (int i = 0; i < nv; i++) {
+          double v = Jrow[i];
+          for (int t = 0; t < k; t++) v -= acc[t] * P.ic_jac[t][i];
+          ws.ic_jcni[(s * nc + c) * nv + i] = v;
+        }
+      }
+      __syncwarp();
+      // ---- Z = L^-1 Atilde^T, Atilde[a][j] = Ni[act_idx[a]][j] for j >= 6 (lane a solves column a) ----
+      for (int a = lane; a < nact; a += 32) {
+        const int va = P.act_idx[a];
+        for (int i = 0; i < nv; i++) {
+          double sum = 0.0;
+          if (i >= 6) {
+            sum = i == va ? 1.0 : 0.0;
+            for (int t = 0; t < k; t++) sum -= Jb[va * k + t] * P.ic_jac[t][i];
+          }
+          for (int c = 0; c < i; c++) sum -= Lm[i * ld + c] * Z[c * ldz + a];
+          Z[i * ldz + a] = sum / Lm[i * ld + i];
+        }
+      }
+      __syncwarp();
+      // ---- G = Z^T Z (lower triangle), then its Cholesky factor ----
+      for (int idx = lane; idx < nact * (nact + 1) / 2; idx += 32) {
+        int r = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+        while ((r + 1) * (r + 2) / 2 <= idx) r++;
+        while (r * (r + 1) / 2 > idx) r--;
+        const int c = idx - r * (r + 1) / 2;
+        double sum = 0.0;
+        for (int i = 0; i < nv; i++) sum += Z[i * ldz + r] * Z[i * ldz + c];
+        G[r * ldz + c] = sum;
+      }
+      __syncwarp();
+      double gmax = 0.0;
+      for (int a = lane; a < nact; a += 32) gmax = fmax(gmax, G[a * ldz + a]);
+      for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(FULL, gmax, o));
+      for (int j = 0; j < nact; j++) {
+        double t[2] = {0.0, 0.0};
+        const double* rj = G + j * ldz;
+        for (int rr = 0; rr < 2; rr++) {
+          const int i = lane + 32 * rr;
+          if (i >= j && i < nact) {
+            const double* ri = G + i * ldz;
+            double sum = ri[j];
+            for (int c = 0; c < j; c++) sum -= ri[c] * rj[c];
+            t[rr] = sum;
+          }
+        }
+        const double piv = __shfl_sync(FULL, (j & 32) ? t[1] : t[0], j & 31);
+        if (!(piv > 1e-13 * gmax)) { bad = 1; break; }
+        const double dj = sqrt(piv);
+        __syncwarp();
+        for (int rr = 0; rr < 2; rr++) {
+          const int i = lane + 32 * rr;
+          if (i == j) G[j * ldz + j] = dj;
+          else if (i > j && i < nact) G[i * ldz + j] = t[rr] / dj;
+        }
+        __syncwarp();
+      }
+    }
+    if (!bad) {
+      // ---- V = L^-T Z in place (lane a back-substitutes column a); W A^T = rows 6.. of V ----
+      for (int a = lane; a < nact; a += 32) {
+        for (int i = nv - 1; i >= 0; i--) {
+          double sum = Z[i * ldz + a];
+          for (int c = i + 1; c < nv; c++) sum -= Lm[c * ld + i] * Z[c * ldz + a];
+          Z[i * ldz + a] = sum / Lm[i * ld + i];
+        }
+      }
+      __syncwarp();
+      // ---- B^T[j][:] = (A W A^T)^-1 (W A^T)[j][:]^T : lane j solves with the factor of G ----
+      for (int j = lane; j < nj; j += 32) {
+        double* b = Bt + j * ldb;
+        const double* rhs = Z + (6 + j) * ldz;
+        for (int i = 0; i < nact; i++) {  // forward
+          double sum = rhs[i];
+          for (int c = 0; c < i; c++) sum -= G[i * ldz + c] * b[c];
+          b[i] = sum / G[i * ldz + i];
+        }
+        for (int i = nact - 1; i >= 0; i--) {  // backward
+          double sum = b[i];
+          for (int c = i + 1; c < nact; c++) sum -= G[c * ldz + i] * b[c];
+          b[i] = sum / G[i * ldz + i];
+        }
+      }
+      __syncwarp();
+      // ---- S [M | -(Jc Ni)^T] and S Ni^T (c+g), S = [0 | B] ----
+      for (int a = 0; a < nact; a++) {
+        double* out = ws.ic_tq + (s * nact + a) * n;
+        for (int c = lane; c < n; c += 32) {
+          double sum = 0.0;
+          if (c < nv) {
+            for (int j = 0; j < nj; j++) {
+              const int r = 6 + j;
+              const double mv = r == c ? Mdiag[c] : (r < c ? Lm[r * ld + c] : Lm[c * ld + r]);
+              sum += Bt[j * ldb + a] * mv;
+            }
+          } else {
+            const double* jr = ws.ic_jcni + (s * nc + (c - nv)) * nv;
+            for (int j = 0; j < nj; j++) sum -= Bt[j * ldb + a] * jr[6 + j];
+          }
+          out[c] = sum;
+        }
+        double part = 0.0;
+        for (int j = lane; j < nj; j += 32) part += Bt[j * ldb + a] * ncg[6 + j];
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+        if (lane == 0) ws.ic_tq0[s * nact + a] = part;
+      }
+    }
+    if (lane == 0) ws.ic_status[s] = bad;
+    __syncwarp();
+  }
+}
+
+void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
+                       int B, int num_sms, cudaStream_t stream, int* counter) {
+  IcLayout L = ic_layout(hp.nv, hp.nact, hp.nc, hp.n_ic);
+  const size_t smem = (size_t)L.total * sizeof(double);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(k_ic_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 16) per_sm = 16;
+  int grid = num_sms * per_sm;
+  if (grid > B) grid = B;
+  cudaMemsetAsync(counter, 0, sizeof(int), stream);
+  k_ic_prepare<<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, B, counter);
+  g_launch_count++;
+}
+
+}  // namespace pnc

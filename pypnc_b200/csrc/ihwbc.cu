@@ -409,6 +409,8 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
   int* Aold = Aact + (n + 1);
   int* iai = Aold + (n + 1);
   int* iaexcl = iai + (m > 0 ? m : 1);
+  int* Aacc = iaexcl + (m > 0 ? m : 1);
+  double* xacc = W + L.oxacc;
   QP q;
   q.lane = lane; q.n = n; q.ld = ld; q.p = p; q.m = m;
   q.J = Jm; q.R = Rp; q.x = x; q.z = W + L.oz; q.d = W + L.od; q.np = W + L.onp; q.hw = W + L.ohw;
@@ -422,6 +424,7 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
     const size_t s = (size_t)si;
     const double* des = io.des + s * P.ndes;
     int status = PNC_QP_OK, iter = 0;
+    if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;  // rank-deficient projection (icprep.cu)
     q.iq = 0;
     q.R_norm = 1.0;
 
@@ -629,7 +632,7 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
     }
     if (!pd || !(P.lambda_rf > 0.0 || nc == 0)) {
       status = PNC_QP_NOT_PD;
-    } else {
+    } else if (status == PNC_QP_OK) {
       // ---- J = L^-T in place (QuadProg++.cc:203-210): lane i forward-solves L z = e_i ----
       for (int j = 0; j < nv; j++) {
         const double* Lj = Jm + j * ld;
@@ -699,8 +702,15 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
       if (status == PNC_QP_OK && m > 0) {
         for (int i = lane; i < m; i += 32) iai[i] = i;
         __syncwarp();
+        // QuadProg++.cc:306-312 stops when |psi| <= m eps c1 c2 100 -- a loose bound (1e-4 .. 1e-3 here)
+        // under which a slightly infeasible iterate can be returned, depending on how exact ties
+        // between redundant cone rows were broken.  We remember the first iterate that meets the
+        // reference bound and keep iterating to psi_refine; if the refinement cannot complete
+        // (numerical infeasibility / iteration cap) the remembered iterate is returned.
         const double psi_tol = (double)m * QP_EPS * c1 * c2 * 100.0;
-        bool done = false;
+        const double psi_refine = psi_tol * 1e-6;
+        bool done = false, accepted = false;
+        int iq_acc = 0;
         while (!done) {
           // l1: a full step was taken (or first pass)
           iter++;
@@ -733,7 +743,16 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
           for (int i = lane; i < m; i += 32) iaexcl[i] = 1;
           psi = wsum(psi);
           __syncwarp();
-          if (fabs(psi) <= psi_tol) break;  // numerically feasible: optimum reached
+          if (fabs(psi) <= psi_tol) {  // numerically feasible by the reference's test
+            if (fabs(psi) <= psi_refine) break;
+            if (!accepted) {
+              accepted = true;
+              iq_acc = q.iq;
+              for (int i = lane; i < n; i += 32) xacc[i] = x[i];
+              for (int i = lane; i < q.iq; i += 32) Aacc[i] = Aact[i];
+              __syncwarp();
+            }
+          }
           if (iter > 40 * (n + m)) { status = PNC_QP_MAX_ITER; break; }
           for (int i = lane; i < q.iq; i += 32) { uold[i] = q.u[i]; Aold[i] = Aact[i]; }
           for (int i = lane; i < n; i += 32) xold[i] = x[i];
@@ -848,6 +867,13 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
               __syncwarp();
             }
           }
+        }
+        if (accepted && status != PNC_QP_OK) {  // refinement failed: fall back to the accepted iterate
+          status = PNC_QP_OK;
+          q.iq = iq_acc;
+          for (int i = lane; i < n; i += 32) x[i] = xacc[i];
+          for (int i = lane; i < iq_acc; i += 32) Aact[i] = Aacc[i];
+          __syncwarp();
         }
       }
     }

@@ -7,7 +7,7 @@ namespace pnc {
 // shared-memory layout of ONE state's QP in the solve kernel (offsets in doubles)
 struct IhwbcLayout {
   int n, ld, ldv, nrow;
-  int oJ, oR, oA, oa0, oUf, ouf, ox, oz, od, onp, ohw, oxold, og0, orr, ou, ouold, os, oe, owt, oint;
+  int oJ, oR, oA, oa0, oUf, ouf, ox, oz, od, onp, ohw, oxold, oxacc, og0, orr, ou, ouold, os, oe, owt, oint;
   int per_state;  // doubles, even
 };
 
@@ -32,6 +32,7 @@ __host__ __device__ inline IhwbcLayout ihwbc_layout(const DevProblem& P) {
   L.onp = o; o += n;
   L.ohw = o; o += n;
   L.oxold = o; o += n;
+  L.oxacc = o; o += n;
   L.og0 = o; o += n;
   L.orr = o; o += n + 1;
   L.ou = o; o += n + 1;
@@ -39,7 +40,7 @@ __host__ __device__ inline IhwbcLayout ihwbc_layout(const DevProblem& P) {
   L.os = o; o += m;
   L.oe = o; o += P.ntaskrows > 0 ? P.ntaskrows : 1;
   L.owt = o; o += P.ntaskrows > 0 ? P.ntaskrows : 1;
-  L.oint = o; o += (2 * (n + 1) + 2 * m + 1) / 2 + 1;
+  L.oint = o; o += (3 * (n + 1) + 2 * m + 1) / 2 + 1;
   L.per_state = (o + 1) & ~1;
   return L;
 }
@@ -72,7 +73,7 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs
 void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcLayout& L, const WsPtrs& ws,
                         const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream);
 void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
-                       int B, int num_sms, cudaStream_t stream);
+                       int B, int num_sms, cudaStream_t stream, int* counter);
 void launch_task_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int itask, int dim,
                       int nv, const double* des, double* jac, double* jdqd, double* op_cmd, double* pos_err,
                       cudaStream_t stream);

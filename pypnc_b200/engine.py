@@ -162,3 +162,31 @@ def unpack_active(active_words, m):
     for i in range(m):
         out[:, i] = (a[:, i >> 6] >> np.uint64(i & 63)) & np.uint64(1)
     return out[:, :m]
+
+
+def task_actuals_from_workspace(spec, ws):
+    """Per-task actual position / velocity ([B,dim], quaternion [B,4] for LINK_ORI) read back from
+    the workspace after update_system -- the inputs robots.synth_desireds needs."""
+    from scipy.spatial.transform import Rotation
+    m = spec.model
+    iso = ws.view('frame_iso').cpu().numpy()
+    vel = ws.view('frame_vel').cpu().numpy()
+    com, vcom = ws.view('com').cpu().numpy(), ws.view('vcom').cpu().numpy()
+    q, v = ws.view('q').cpu().numpy(), ws.view('qdot').cpu().numpy()
+    B = q.shape[0]
+    pos, vl = [], []
+    for t in spec.tasks:
+        if t['type'] in (2, 3):
+            f = ws.frames.index(t['frame'])
+            if t['type'] == 2:
+                pos.append(iso[:, f, 9:12].copy()); vl.append(vel[:, f, 3:6].copy())
+            else:
+                pos.append(Rotation.from_matrix(iso[:, f, :9].reshape(B, 3, 3)).as_quat())
+                vl.append(vel[:, f, 0:3].copy())
+        elif t['type'] == 4:
+            pos.append(com.copy()); vl.append(vcom.copy())
+        else:
+            idx = spec.joint_sel[t['joint_off']:t['joint_off'] + t['dim']] if t['type'] == 1 else \
+                list(range(6, 6 + t['dim']))
+            pos.append(q[:, [i + 1 for i in idx]].copy()); vl.append(v[:, idx].copy())
+    return dict(task_pos=pos, task_vel=vl)

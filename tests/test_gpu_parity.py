@@ -1,0 +1,411 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+vectors made by the reference's own Python classes.  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from pypnc_b200 import robots
+
+pytestmark = pytest.mark.gpu
+
+ROBOTS = ['atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie']
+KEYS = ('base_pos', 'base_quat', 'base_lin_vel', 'base_ang_vel', 'joint_pos', 'joint_vel')
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+# tolerance of BASELINE.json north_star: 1e-9 relative in fp64
+RTOL = 1e-9
+
+
+def per_state_rel(a, b):
+    return np.abs(a - b).max(axis=tuple(range(1, a.ndim))) / np.maximum(1e-300, np.abs(b).max(axis=tuple(range(1, b.ndim))))
+
+
+class Ctx:
+    """model + problem + workspace + one solved synthetic batch of a robot (GPU and oracle)."""
+
+    def __init__(self, name, oracle_mod, B=96, seed=0):
+        import torch
+        from pypnc_b200 import engine
+        self.torch, self.engine = torch, engine
+        self.name, self.B = name, B
+        self.spec = robots.PROBLEMS[name]()
+        self.op = oracle_mod.OracleProblem(self.spec)
+        self.st = robots.synth_states(name, self.spec, B, seed=seed)
+        self.des, self.w, self.rfz = robots.synth_desireds(name, self.spec, self.st, self.op.task_actuals(self.st), seed=seed)
+        self.ref = self.op.tick_batch(self.st, self.des, self.w, self.rfz)
+        self.dm = engine.Model(self.spec.model, 0)
+        self.pb = engine.Problem(self.dm, self.spec)
+        self.ws = engine.Workspace(self.dm, B, self.spec.frames)
+        self.d_st = [torch.from_numpy(np.ascontiguousarray(self.st[k])).cuda() for k in KEYS]
+        self.ws.update_system(*self.d_st)
+        self.d_in = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (self.des, self.w, self.rfz)]
+        self.out = engine.ihwbc_solve(self.pb, self.ws, *self.d_in)
+        torch.cuda.synchronize()
+
+    def qv(self, b):
+        return self.op.om.pack_state(*[self.st[k][b] for k in KEYS])
+
+
+_CTX = {}
+
+
+@pytest.fixture
+def ctx(request, oracle_mod):
+    name = request.param
+    if name not in _CTX:
+        _CTX[name] = Ctx(name, oracle_mod)
+    return _CTX[name]
+
+
+@pytest.mark.parametrize("ctx", ROBOTS, indirect=True)
+def test_update_system_matches_oracle(ctx):
+    """FK, frame placements/velocities/Jacobians/Jdot*qdot, CoM + Jacobians, CRBA, RNEA terms."""
+    ws, om, spec = ctx.ws, ctx.op.om, ctx.spec
+    g = {k: ws.view(k).cpu().numpy() for k in ('q', 'qdot', 'M', 'grav', 'cori', 'com', 'vcom', 'jcom', 'jcomdot',
+                                                'jcom_jdqd', 'frame_iso', 'frame_vel', 'frame_jac', 'frame_jdqd')}
+    rel = lambda a, b: np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+    for b in range(0, ctx.B, 4):
+        q, v = ctx.qv(b)
+        assert rel(g['q'][b], q) == 0.0
+        assert rel(g['qdot'][b], v) < 1e-14
+        M = om.mass_matrix(q)
+        assert rel(g['M'][b], M) < 1e-13
+        assert np.array_equal(g['M'][b], g['M'][b].T)
+        assert rel(g['grav'][b], om.gravity(q)) < 1e-13
+        # coriolis = nle - g: cancellation, compare against the size of nle
+        nle_scale = max(np.abs(om.coriolis(q, v)).max(), np.abs(om.gravity(q)).max() * 1e-3)
+        assert np.abs(g['cori'][b] - om.coriolis(q, v)).max() < 1e-12 * max(1.0, nle_scale) * 10
+        com, vcom = om.com(q, v)
+        assert rel(g['com'][b], com) < 1e-13 and rel(g['vcom'][b], vcom) < 1e-13
+        assert rel(g['jcom'][b], om.com_jacobian(q)) < 1e-13
+        dJ = om.com_jacobian_dot(q, v)
+        assert rel(g['jcomdot'][b], dJ) < 1e-12
+        assert rel(g['jcom_jdqd'][b], dJ @ v) < 1e-11
+        for fi, f in enumerate(spec.frames):
+            T = om.link_iso(q, f)
+            assert rel(g['frame_iso'][b, fi], np.concatenate([T[:3, :3].ravel(), T[:3, 3]])) < 1e-13
+            assert rel(g['frame_vel'][b, fi], om.link_vel(q, v, f)) < 1e-12
+            assert rel(g['frame_jac'][b, fi], om.link_jacobian(q, f)) < 1e-13
+            assert rel(g['frame_jdqd'][b, fi], om.link_jdqd(q, v, f)) < 1e-12
+
+
+def _active_sets_equivalent(ctx, b, act_gpu, act_ref):
+    """Degenerate vertices (e.g. the redundant rows of the 18-row surface wrench cone) admit
+    several active sets for the same solution; quadprog picks among exactly tied constraints by
+    rounding noise.  Sets are accepted when they differ only in constraints that are tight at the
+    oracle's solution."""
+    if np.array_equal(act_gpu, act_ref):
+        return True
+    q, v = ctx.qv(b)
+    qp = ctx.op.assemble(q, v, ctx.des[b], ctx.w[b], ctx.rfz[b])
+    x = np.concatenate([ctx.ref['qddot'][b], ctx.ref['rf'][b]])
+    slack = qp['h'] - qp['G'] @ x
+    scale = np.maximum(1.0, np.abs(qp['G']) @ np.abs(x))
+    tight = np.abs(slack) <= 1e-9 * scale
+    diff = act_gpu != act_ref
+    return bool(tight[diff].all())
+
+
+@pytest.mark.parametrize("ctx", ROBOTS, indirect=True)
+def test_tick_matches_oracle(ctx):
+    """joint torques, accelerations, reaction forces within 1e-9 relative; same QP active set."""
+    out, ref = ctx.out, ctx.ref
+    status = out['status'].cpu().numpy()
+    assert np.array_equal(status, ref['status'])
+    ok = status == 0
+    assert ok.sum() >= 0.9 * ctx.B
+    for k in ('trq', 'acc', 'rf', 'qddot'):
+        err = per_state_rel(out[k].cpu().numpy()[ok], ref[k][ok])
+        assert err.max() < RTOL, (k, err.max())
+    act = ctx.engine.unpack_active(out['active'], ctx.pb.m)
+    identical = 0
+    for b in np.where(ok)[0]:
+        same = np.array_equal(act[b], ref['active'][b])
+        identical += same
+        assert same or _active_sets_equivalent(ctx, b, act[b], ref['active'][b]), \
+            (b, np.where(act[b])[0], np.where(ref['active'][b])[0])
+    # point-contact cones have no redundant rows: the active set must be bit-identical there
+    if ctx.name == 'laikago':
+        assert identical == ok.sum()
+    assert identical >= 0.4 * ok.sum()
+
+
+@pytest.mark.parametrize("ctx", ROBOTS, indirect=True)
+def test_task_and_contact_eval_match_oracle(ctx):
+    torch, lib = ctx.torch, ctx.dm.lib
+    B, spec, nv = ctx.B, ctx.spec, ctx.spec.model.nv
+    vp = C.c_void_p
+    P = lambda t: vp(t.data_ptr())
+    for it, t in enumerate(spec.tasks):
+        d = t['dim']
+        jac = torch.zeros((B, d, nv), dtype=torch.float64, device='cuda')
+        jd, op, pe = [torch.zeros((B, d), dtype=torch.float64, device='cuda') for _ in range(3)]
+        assert lib.pnc_task_eval(ctx.pb.h, ctx.ws.h, B, it, P(ctx.d_in[0]), P(jac), P(jd), P(op), P(pe), None) == 0
+        torch.cuda.synchronize()
+        for b in range(0, B, 8):
+            q, v = ctx.qv(b)
+            e = ctx.op.task_eval(q, v, ctx.des[b], it)
+            np.testing.assert_allclose(jac[b].cpu().numpy(), e['jacobian'], atol=1e-13)
+            np.testing.assert_allclose(jd[b].cpu().numpy(), e['jacobian_dot_q_dot'], rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(pe[b].cpu().numpy(), e['pos_err'], rtol=1e-10, atol=1e-13)
+            np.testing.assert_allclose(op[b].cpu().numpy(), e['op_cmd'], rtol=1e-10, atol=1e-10)
+    for ic, c in enumerate(spec.contacts):
+        d, rows = (6, 18) if c['type'] == 1 else (3, 6)
+        jac = torch.zeros((B, d, nv), dtype=torch.float64, device='cuda')
+        cm = torch.zeros((B, rows, d), dtype=torch.float64, device='cuda')
+        cv = torch.zeros((B, rows), dtype=torch.float64, device='cuda')
+        assert lib.pnc_contact_eval(ctx.pb.h, ctx.ws.h, B, ic, P(ctx.d_in[2]), P(jac), P(cm), P(cv), None) == 0
+        torch.cuda.synchronize()
+        for b in range(0, B, 8):
+            q, v = ctx.qv(b)
+            e = ctx.op.contact_eval(q, v, ctx.rfz[b, ic], ic)
+            np.testing.assert_allclose(jac[b].cpu().numpy(), e['jacobian'], atol=1e-13)
+            np.testing.assert_allclose(cm[b].cpu().numpy(), e['cone_constraint_mat'], atol=1e-14)
+            np.testing.assert_array_equal(cv[b].cpu().numpy(), e['cone_constraint_vec'])
+
+
+@pytest.mark.parametrize("name", ROBOTS)
+def test_golden_vectors_from_reference_python(name):
+    """tests/golden/<robot>.npz: outputs of the reference's own IHWBC / BasicTask / contact
+    classes (tests/golden/make_golden.py) on committed inputs."""
+    import torch
+    from pypnc_b200 import engine
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    spec = robots.PROBLEMS[name]()
+    B = z['in_des'].shape[0]
+    dm = engine.Model(spec.model, 0)
+    pb = engine.Problem(dm, spec)
+    ws = engine.Workspace(dm, B, spec.frames)
+    ws.update_system(*[torch.from_numpy(np.ascontiguousarray(z['in_' + k])).cuda() for k in KEYS])
+    out = engine.ihwbc_solve(pb, ws, *[torch.from_numpy(np.ascontiguousarray(z[k])).cuda()
+                                       for k in ('in_des', 'in_w', 'in_rf_z_max')])
+    torch.cuda.synchronize()
+    assert (out['status'].cpu().numpy() == 0).all()
+    for k in ('trq', 'acc', 'rf'):
+        err = per_state_rel(out[k].cpu().numpy(), z['out_' + k])
+        assert err.max() < RTOL, (k, err.max())
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    assert rel(ws.view('M').cpu().numpy(), z['out_M']) < 1e-13
+    assert rel(ws.view('grav').cpu().numpy(), z['out_grav']) < 1e-13
+
+
+def test_tick_host_equals_device_path(oracle_mod):
+    """pnc_wbc_tick_host (host buffers, chunked over two streams) == the device-resident calls."""
+    import torch
+    ctx = _CTX.get('atlas') or Ctx('atlas', oracle_mod)
+    B, spec, pb = ctx.B, ctx.spec, ctx.pb
+    h_in = [np.ascontiguousarray(ctx.st[k]) for k in KEYS] + [np.ascontiguousarray(a) for a in (ctx.des, ctx.w, ctx.rfz)]
+    trq, acc = np.zeros((B, spec.nact)), np.zeros((B, spec.nact))
+    rf = np.zeros((B, pb.nc))
+    status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    active = np.zeros((B, pb.mw), dtype=np.uint64)
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = ctx.dm.lib.pnc_wbc_tick_host(pb.h, ctx.ws.h, B, *[hp(a) for a in h_in], hp(trq), hp(acc), hp(rf), hp(status),
+                                      hp(iters), hp(active))
+    assert rc == 0
+    assert np.array_equal(status, ctx.out['status'].cpu().numpy())
+    assert np.array_equal(iters, ctx.out['iters'].cpu().numpy())
+    assert np.array_equal(trq, ctx.out['trq'].cpu().numpy())
+    assert np.array_equal(rf, ctx.out['rf'].cpu().numpy())
+    assert np.array_equal(active.view(np.int64), ctx.out['active'].cpu().numpy())
+
+
+def test_full_batch_properties_atlas_64k():
+    """BASELINE size (Atlas, 64K states): size-independent properties of the solution --
+    feasibility of every constraint, floating-base dynamics residual, determinism, and
+    permutation equivariance (states are independent)."""
+    import torch
+    from pypnc_b200 import engine
+    name, B = 'atlas', 65536
+    spec = robots.PROBLEMS[name]()
+    dm = engine.Model(spec.model, 0)
+    pb = engine.Problem(dm, spec)
+    ws = engine.Workspace(dm, B, spec.frames)
+    st = robots.synth_states(name, spec, B, seed=1)
+    d_st = [torch.from_numpy(np.ascontiguousarray(st[k])).cuda() for k in KEYS]
+    ws.update_system(*d_st)
+    des, w, rfz = robots.synth_desireds(name, spec, st, engine.task_actuals_from_workspace(spec, ws), seed=1)
+    d_in = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (des, w, rfz)]
+    out = engine.ihwbc_solve(pb, ws, *d_in)
+    out2 = engine.ihwbc_solve(pb, ws, *d_in)
+    torch.cuda.synchronize()
+    status = out['status'].cpu().numpy()
+    assert (status == 0).mean() > 0.999
+    ok = torch.from_numpy(status == 0).cuda()
+    for k in ('trq', 'acc', 'rf', 'qddot', 'active', 'iters'):
+        assert torch.equal(out[k], out2[k]), k  # deterministic
+    M, nv = ws.view('M'), spec.model.nv
+    cg = ws.view('cori') + ws.view('grav')
+    qdd, rf, trq = out['qddot'], out['rf'], out['trq']
+    fj = ws.view('frame_jac')
+    Jc = torch.cat([fj[:, ws.frames.index(c['frame'])] for c in spec.contacts], dim=1)  # [B, 12, nv]
+    tau_full = torch.einsum('bij,bj->bi', M, qdd) + cg - torch.einsum('bci,bc->bi', Jc, rf)
+    scale = tau_full.abs().amax(dim=1).clamp_min(1.0)
+    # floating-base rows are equality constraints (ihwbc.py:225-232)
+    assert ((tau_full[:, :6].abs().amax(dim=1) / scale)[ok] < 1e-9).all()
+    # actuated rows are the returned torques (:344-354) and respect the limits (:266-296)
+    assert ((tau_full[:, 6:] - trq).abs().amax(dim=1)[ok] / scale[ok] < 1e-9).all()
+    lim = torch.from_numpy(spec.trq_limit).cuda()
+    assert (trq[ok] >= lim[:, 0] - 1e-6 * lim[:, 0].abs()).all() and (trq[ok] <= lim[:, 1] + 1e-6 * lim[:, 1].abs()).all()
+    # wrench cones: unilateral force, bounded by rf_z_max
+    iso = ws.view('frame_iso')
+    for ci, c in enumerate(spec.contacts):
+        R = iso[:, ws.frames.index(c['frame']), :9].reshape(B, 3, 3)
+        fz = torch.einsum('bij,bi->bj', R, rf[:, 6 * ci + 3:6 * ci + 6])[:, 2]  # normal force in the foot frame
+        assert (fz[ok] >= -1e-6).all()
+        assert (fz[ok] <= d_in[2][:, ci][ok] * (1 + 1e-9) + 1e-6).all()
+    # permutation equivariance on a slice
+    perm = torch.randperm(4096, device='cuda')
+    ws2 = engine.Workspace(dm, 4096, spec.frames)
+    ws2.update_system(*[t[:4096][perm].contiguous() for t in d_st])
+    o3 = engine.ihwbc_solve(pb, ws2, *[t[:4096][perm].contiguous() for t in d_in])
+    torch.cuda.synchronize()
+    assert torch.equal(o3['trq'], out['trq'][:4096][perm])
+    assert torch.equal(o3['active'], out['active'][:4096][perm])
+
+
+def test_joint_integrate_matches_reference_formula():
+    """JointIntegrator.integrate, pnc/wbc/ihwbc/joint_integrator.py:73-82."""
+    import torch
+    from pypnc_b200 import _cabi
+    lib = _cabi.load_library()
+    rng = np.random.default_rng(3)
+    B, na, dt, av, ap = 257, 30, 0.01, 0.1, 0.2
+    acc, jp = rng.normal(0, 5, (B, na)), rng.normal(0, 1, (B, na))
+    vel, pos = rng.normal(0, 1, (B, na)), rng.normal(0, 1, (B, na))
+    pl = np.stack([-np.abs(rng.normal(1, .3, na)), np.abs(rng.normal(1, .3, na))], 1)
+    vl = np.stack([-np.abs(rng.normal(1, .3, na)), np.abs(rng.normal(1, .3, na))], 1)
+    ev = np.clip((1.0 - av) * vel + acc * dt, vl[:, 0], vl[:, 1])
+    ep = np.clip((1.0 - ap) * pos + ap * jp + ev * dt, pl[:, 0], pl[:, 1])
+    d = [torch.from_numpy(a.copy()).cuda() for a in (acc, jp, vel, pos, pl, vl)]
+    P = lambda t: C.c_void_p(t.data_ptr())
+    assert lib.pnc_joint_integrate(B, na, P(d[0]), P(d[1]), P(d[2]), P(d[3]), P(d[4]), P(d[5]), av, ap, dt, None) == 0
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(d[2].cpu().numpy(), ev, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(d[3].cpu().numpy(), ep, rtol=0, atol=1e-15)
+
+
+def test_edge_cases_and_error_codes(oracle_mod):
+    import torch
+    from pypnc_b200 import engine, _cabi
+    ctx = _CTX.get('atlas') or Ctx('atlas', oracle_mod)
+    lib, spec, pb, ws = ctx.dm.lib, ctx.spec, ctx.pb, ctx.ws
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st_ptrs = [P(t) for t in ctx.d_st]
+    # empty batch is a no-op, over-capacity and missing buffers are argument errors
+    assert lib.pnc_update_system(ws.h, 0, *st_ptrs, None) == 0
+    assert lib.pnc_update_system(ws.h, ctx.B + 1, *st_ptrs, None) == -1
+    assert lib.pnc_update_system(ws.h, ctx.B, None, *st_ptrs[1:], None) == -1
+    assert lib.pnc_ihwbc_solve(pb.h, ws.h, ctx.B, None, None, None, None, None, None, None, None, None, None, None) == -1
+    # unknown task type (basic_task.py:105 raises ValueError)
+    bad = robots.atlas_problem()
+    bad.tasks[0]['type'] = 9
+    with pytest.raises(RuntimeError):
+        engine.Problem(ctx.dm, bad)
+    # rf_z_max <= 0 is replaced by 1e-3 (contact.py:37-41); w = 0 on every foot task; single state
+    B = 8
+    rfz = ctx.rfz[:B].copy()
+    rfz[:, 0] = 0.0
+    rfz[1, 1] = -5.0
+    w = ctx.w[:B].copy()
+    w[2, 3:7] = 0.0
+    sub = {k: ctx.st[k][:B] for k in KEYS}
+    ref = ctx.op.tick_batch(sub, ctx.des[:B], w, rfz)
+    ws2 = engine.Workspace(ctx.dm, B, spec.frames)
+    ws2.update_system(*[t[:B].contiguous() for t in ctx.d_st])
+    out = engine.ihwbc_solve(pb, ws2, ctx.d_in[0][:B].contiguous(), torch.from_numpy(w).cuda(), torch.from_numpy(rfz).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(out['status'].cpu().numpy(), ref['status'])
+    ok = ref['status'] == 0
+    for k in ('trq', 'rf'):
+        assert per_state_rel(out[k].cpu().numpy()[ok], ref[k][ok]).max() < 1e-8, k
+    # infeasible QP: torque limits nobody can meet -> same status as QuadProg++ (inf, :402-407)
+    tiny = robots.atlas_problem()
+    tiny.trq_limit = np.stack([np.full(tiny.nact, 10.0), np.full(tiny.nact, -10.0)], 1)  # lo > hi
+    pb2 = engine.Problem(ctx.dm, tiny)
+    op2 = oracle_mod.OracleProblem(tiny)
+    ref2 = op2.tick_batch(sub, ctx.des[:B], ctx.w[:B], ctx.rfz[:B])
+    out2 = engine.ihwbc_solve(pb2, ws2, ctx.d_in[0][:B].contiguous(), ctx.d_in[1][:B].contiguous(),
+                              ctx.d_in[2][:B].contiguous())
+    torch.cuda.synchronize()
+    assert np.array_equal(out2['status'].cpu().numpy(), ref2['status'])
+    assert (ref2['status'] != 0).all()
+    # Hessian not positive definite: all task weights and both regularisers zero
+    npd = robots.atlas_problem()
+    npd.lambda_q_ddot = 0.0
+    pb3 = engine.Problem(ctx.dm, npd)
+    out3 = engine.ihwbc_solve(pb3, ws2, ctx.d_in[0][:B].contiguous(), torch.zeros((B, len(spec.tasks)), dtype=torch.float64, device='cuda'),
+                              ctx.d_in[2][:B].contiguous())
+    torch.cuda.synchronize()
+    assert (out3['status'].cpu().numpy() == 2).all()
+
+
+def test_fp64_peak_microbenchmark_runs():
+    from pypnc_b200 import _cabi
+    lib = _cabi.load_library()
+    v = C.c_double(0)
+    assert lib.pnc_measure_fp64_peak(0, C.byref(v)) == 0
+    assert 5.0 < v.value < 100.0
+
+
+def test_reference_style_api_atlas(oracle_mod):
+    """The RobotSystem / BasicTask / SurfaceContact / IHWBC mirror, driven the way
+    AtlasController.get_command drives the reference (atlas_controller.py:10-86,
+    atlas_tci_container.py:17-99), reproduces the engine-level result."""
+    import torch
+    from pypnc_b200.robot_system import BatchedRobotSystem
+    from pypnc_b200.wbc import BasicTask, SurfaceContact, IHWBC
+    ctx = _CTX.get('atlas') or Ctx('atlas', oracle_mod)
+    spec, B = ctx.spec, ctx.B
+    robot = BatchedRobotSystem(spec.model, None, False, False, capacity=B)
+    d = dict(zip(KEYS, ctx.d_st))
+    robot.update_system(None, None, None, None, d['base_pos'], d['base_quat'], d['base_lin_vel'], d['base_ang_vel'],
+                        d['joint_pos'], d['joint_vel'])
+    assert robot.n_q == 37 and robot.n_q_dot == 36 and robot.n_a == 30
+    assert abs(robot.total_mass - spec.model.total_mass) == 0
+    tasks = []
+    des = ctx.d_in[0]
+    for i, t in enumerate(spec.tasks):
+        ttype = [k for k, v in robots.TASK_TYPE_NAMES.items() if v == t['type']][0]
+        task = BasicTask(robot, ttype, t['dim'], t['target'] if ttype != 'COM' else None)
+        task.kp = np.array(spec.kp[t['gain_off']:t['gain_off'] + t['dim']])
+        task.kd = np.array(spec.kd[t['gain_off']:t['gain_off'] + t['dim']])
+        task.w_hierarchy = ctx.d_in[1][:, i]
+        npos = 4 if t['type'] == 3 else t['dim']
+        o = t['des_off']
+        task.update_desired(des[:, o:o + npos], des[:, o + npos:o + npos + t['dim']],
+                            des[:, o + npos + t['dim']:o + npos + 2 * t['dim']])
+        tasks.append(task)
+    contacts = []
+    for i, c in enumerate(spec.contacts):
+        sc = SurfaceContact(robot, c['link'], c['x'], c['y'], c['mu'])
+        sc.rf_z_max = ctx.d_in[2][:, i]
+        contacts.append(sc)
+    nv, na = robot.n_q_dot, robot.n_a
+    sa = np.zeros((na, nv)); sa[:, 6:] = np.eye(na)
+    sf = np.zeros((6, nv)); sf[:, :6] = np.eye(6)
+    ihwbc = IHWBC(sf, sa, np.zeros((0, nv)))
+    ihwbc.trq_limit = robot.joint_trq_limit
+    ihwbc.lambda_q_ddot, ihwbc.lambda_rf = 1e-8, 1e-7
+    M = robot.get_mass_matrix()
+    ihwbc.update_setting(M, None, robot.get_coriolis(), robot.get_gravity())
+    trq, acc, rf = ihwbc.solve(tasks, contacts, [], verbose=False)
+    torch.cuda.synchronize()
+    assert torch.equal(trq, ctx.out['trq']) and torch.equal(acc, ctx.out['acc']) and torch.equal(rf, ctx.out['rf'])
+    # task / contact properties, getters
+    q, v = ctx.qv(0)
+    e = ctx.op.task_eval(q, v, ctx.des[0], 1)
+    np.testing.assert_allclose(tasks[1].op_cmd[0].cpu().numpy(), e['op_cmd'], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(tasks[1].jacobian[0].cpu().numpy(), e['jacobian'], atol=1e-13)
+    ce = ctx.op.contact_eval(q, v, ctx.rfz[0, 0], 0)
+    np.testing.assert_allclose(contacts[0].cone_constraint_mat[0].cpu().numpy(), ce['cone_constraint_mat'], atol=1e-14)
+    T = robot.get_link_iso('l_hand')
+    np.testing.assert_allclose(T[0].cpu().numpy(), ctx.op.om.link_iso(q, spec.model.frame_id('l_hand')), atol=1e-13)
+    J = robot.get_link_jacobian('head') if 'head' in robot.link_id else robot.get_link_jacobian('pelvis')
+    assert J.shape == (B, 6, nv)
+    cmd = robot.create_cmd_ordered_dict(acc, acc, trq)
+    assert list(cmd['joint_trq'].keys()) == list(robot.joint_id.keys())
+    with pytest.raises(ValueError):
+        BasicTask(robot, "NOT_A_TASK", 3)

@@ -1,0 +1,941 @@
+// ihwbc_reg.cu -- the IHWBC solve with the active-set operator J = L^-T Q held in REGISTERS.
+//
+// Same algorithm and reference mapping as ihwbc.cu (IHWBC.solve pnc/wbc/ihwbc/ihwbc.py:90-379,
+// Goldfarb-Idnani as in external_source/Goldfarb/QuadProg++.cc:115-502, Householder instead of
+// the Givens sweep when a constraint is added); what changes is where the data lives and how
+// much code the loop is:
+//
+//   * one robot state per warp; lane l owns row l of the n x n matrix J (n = nv + nc <= 48) in
+//     registers, rows 32.. are split over lane pairs (half a row each) -- 72 doubles per lane
+//     for Atlas.  z = J2 d2 and the rank-1 Householder update are pure register FMAs against
+//     vectors broadcast from shared memory (LDS.128, one wavefront per two FMAs);
+//   * d = J^T n+ goes through a 6-row scratch tile in shared memory: one pass for a wrench-cone
+//     normal (3 or 6 non-zeros), n/6 passes for a dense normal (equalities, torque limits);
+//   * the Hessian, its Cholesky factor and L^-T are built once per state in shared memory with
+//     compact loops, then the rows move into registers;
+//   * the kernel is instruction-fetch sensitive (few warps per SM, each walking its own path),
+//     so every routine of the active-set loop exists at exactly one call site -- equalities run
+//     through the same step code as inequalities -- and the only unrolled code is what register
+//     indexing forces.  Dynamic column indices (iq, the Givens pairs of a dropped constraint) are
+//     warp-uniform and go through switch statements (jump tables), never local memory.
+#include "ihwbc_common.cuh"
+
+namespace pnc {
+
+template <int NV_, int NC_>
+struct RCfg {
+  static constexpr int NV = NV_, NC = NC_, N = NV_ + NC_;
+  static constexpr bool EXT = N > 32;                         // rows 32.. live in lane pairs
+  static constexpr int E = EXT ? N - 32 : 0;
+  static constexpr int HW = EXT ? ((N + 3) / 4) * 2 : 0;      // half-row width (even)
+  static constexpr int NP = EXT ? 2 * HW : ((N + 1) & ~1);    // padded vector length (even)
+  static constexpr int NB = HW > 0 ? HW : 2;
+  static constexpr int LDV = NV | 1;                          // pitch of the nv x nv factor block
+  static constexpr int LDT = NP + 2;                          // pitch of the d scratch tile
+  static_assert(E <= 16, "rows beyond 32 must fit one lane pair each");
+  static_assert(N <= 64, "n too large for the register kernel");
+};
+
+struct RegLayout {
+  int lda, nrow;
+  int oA, oa0, oRT, oT, orinv, oUf, ouf, ox, oz, odv, odm, ovm, onp, orr, ou, oxold, ouold, oxacc, osl, oev, owt, oint;
+  int per_state;
+};
+
+template <class C>
+__host__ __device__ inline RegLayout reg_layout(const DevProblem& P) {
+  RegLayout L;
+  const int n = C::N, m = P.m > 0 ? P.m : 1;
+  int lda = C::NP;  // conflict-free LDS.128 by row needs lda = 2 (mod 16)
+  while ((lda & 15) != 2) lda++;
+  L.lda = lda;
+  L.nrow = P.p + (P.b_trq_limit ? P.nact : 0);
+  int o = 0;
+  int asz = L.nrow * lda, jds = P.ndense * C::LDV;  // the staged task Jacobians borrow the Arows region
+  if (jds > asz) asz = jds;
+  L.oA = o; o += (asz + 1) & ~1;
+  L.oa0 = o; o += (L.nrow + 1) & ~1;
+  const int rsz = (n * (n + 3) / 2 + 1) & ~1, tsz = 6 * C::LDT, gsz = C::NV * C::LDV;
+  int reg = rsz + tsz;
+  if (gsz > reg) reg = gsz;
+  L.oRT = o; L.oT = o + rsz; o += (reg + 1) & ~1;
+  L.orinv = o; o += C::NP;
+  L.oUf = o; o += (P.nu > 0 ? P.nu : 1) * 6;
+  L.ouf = o; o += ((P.nu > 0 ? P.nu : 1) + 1) & ~1;
+  L.ox = o; o += C::NP;
+  L.oz = o; o += C::NP;
+  L.odv = o; o += C::NP;
+  L.odm = o; o += C::NP;
+  L.ovm = o; o += C::NP;
+  L.onp = o; o += C::NP;
+  L.orr = o; o += C::NP + 2;
+  L.ou = o; o += C::NP + 2;
+  L.oxold = o; o += C::NP;
+  L.ouold = o; o += C::NP + 2;
+  L.oxacc = o; o += C::NP;
+  L.osl = o; o += (m + 1) & ~1;
+  const int tr = ((P.ntaskrows > 0 ? P.ntaskrows : 1) + 1) & ~1;
+  L.oev = o; o += tr;
+  L.owt = o; o += tr;
+  L.oint = o; o += (3 * (n + 2) + 1) / 2 + 1;
+  L.per_state = (o + 1) & ~1;
+  return L;
+}
+
+// ---- register-array access by a warp-uniform dynamic index (jump table, no local memory) ----
+#define PNC_R8(M, B) M(B + 0) M(B + 1) M(B + 2) M(B + 3) M(B + 4) M(B + 5) M(B + 6) M(B + 7)
+#define PNC_R64(M) PNC_R8(M, 0) PNC_R8(M, 8) PNC_R8(M, 16) PNC_R8(M, 24) PNC_R8(M, 32) PNC_R8(M, 40) PNC_R8(M, 48) PNC_R8(M, 56)
+
+template <int LEN>
+__device__ __forceinline__ double reg_pick(const double (&A)[LEN], int idx) {
+  double v = 0.0;
+#define PNC_CASE(K) case (K): if constexpr ((K) < LEN) v = A[(K) < LEN ? (K) : 0]; break;
+  switch (idx) { PNC_R64(PNC_CASE) default: break; }
+#undef PNC_CASE
+  return v;
+}
+
+// Givens rotations of the column pairs (j, j+1), j = j0 .. j1-1, of one register row, with the
+// coefficients (cc, ss, xny) of pair j at rot[3 j ..] (QuadProg++.cc:660-676).  Enters the
+// unrolled chain at j0 (jump table) and leaves at j1.
+template <int LEN>
+__device__ __forceinline__ void reg_rot_range(double (&A)[LEN], int j0, int j1, const double* rot) {
+#define PNC_CASE(K)                                                                         \
+  case (K):                                                                                 \
+    if constexpr ((K) + 1 < LEN) {                                                          \
+      if ((K) >= j1) break;                                                                 \
+      const double cc = rot[3 * (K)], ss = rot[3 * (K) + 1], xny = rot[3 * (K) + 2];        \
+      if (cc <= 1.5) { /* cc = 2 marks a pair QuadProg++ leaves untouched (|h| < eps) */    \
+        const double t1 = A[(K) + 1 < LEN ? (K) : 0], t2 = A[(K) + 1 < LEN ? (K) + 1 : 0];  \
+        const double nj = t1 * cc + t2 * ss;                                                \
+        A[(K) + 1 < LEN ? (K) : 0] = nj;                                                    \
+        A[(K) + 1 < LEN ? (K) + 1 : 0] = xny * (nj + t1) - t2;                              \
+      }                                                                                     \
+    }
+  switch (j0) { PNC_R64(PNC_CASE) default: break; }
+#undef PNC_CASE
+}
+
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// =======================================================================================
+template <int NV, int NC>
+__global__ void __launch_bounds__(32)
+k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap fm, int nfr, int B, SolveIO io) {
+  using C = RCfg<NV, NC>;
+  constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV;
+  constexpr bool EXT = C::EXT;
+  extern __shared__ __align__(16) double smem[];
+  const DevProblem& P = *gp;
+  const int lane = threadIdx.x;
+  const int p = P.p, m = P.m, nu = P.nu, nact = P.nact, lda = L.lda, nq = NV + 1;
+  const bool trq = P.b_trq_limit != 0, has_ic = P.n_ic > 0;
+  double* W = smem;
+  double* Ar = W + L.oA;
+  double* Jd = Ar;   // staged dense task Jacobian rows (dead before Arows is filled)
+  double* a0 = W + L.oa0;
+  double* Rp = W + L.oRT;
+  double* Gm = Rp;   // nv x nv Hessian / factor / L^-T block (dead before R is written)
+  double* Ts = W + L.oT;
+  double* rinv = W + L.orinv;
+  double* Uf = W + L.oUf;
+  double* uf = W + L.ouf;
+  double* x = W + L.ox;
+  double* zv = W + L.oz;
+  double* dv = W + L.odv;
+  double* dm = W + L.odm;
+  double* vm = W + L.ovm;
+  double* np = W + L.onp;
+  double* rv = W + L.orr;
+  double* uv = W + L.ou;
+  double* xold = W + L.oxold;
+  double* uold = W + L.ouold;
+  double* xacc = W + L.oxacc;
+  double* sl = W + L.osl;
+  double* ev = W + L.oev;
+  double* wt = W + L.owt;
+  int* Aact = reinterpret_cast<int*>(W + L.oint);
+  int* Aold = Aact + (N + 2);
+  int* Aacc = Aold + (N + 2);
+  auto Rcol = [&](int c) { return Rp + (c * (c + 3)) / 2; };
+  double* rot = Ts;  // the d scratch tile doubles as the Givens coefficient table of a drop
+  static_assert(6 * LDT >= 3 * NP, "rotation table must fit the scratch tile");
+
+  // rows beyond 32: lane pair (2e, 2e+1) owns row 32+e, half eh of the columns
+  const int eh = lane & 1, epair = lane >> 1;
+  const int erow = 32 + epair;
+  const bool evalid = EXT && epair < E;
+
+  double Ja[NP];
+  double Jb[NB];
+
+#pragma unroll 1
+  for (;;) {
+    int si = 0;
+    if (lane == 0) si = atomicAdd(io.counter, 1);
+    si = __shfl_sync(FULL, si, 0);
+    if (si >= B) break;
+    const size_t s = (size_t)si;
+    const double* des = io.des + s * P.ndes;
+    int status = PNC_QP_OK, iter = 0, iq = 0;
+    double R_norm = 1.0;
+    if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
+
+    // ---- tasks: e = Jdot qdot - xddot_cmd, weights (ihwbc.py:159-172) ----
+#pragma unroll 1
+    for (int k = lane; k < NP; k += 32) { x[k] = 0.0; zv[k] = 0.0; dv[k] = 0.0; dm[k] = 0.0; vm[k] = 0.0; np[k] = 0.0; }
+#pragma unroll 1
+    for (int t = 0; t < P.ntask; t++) {
+      const DevTask& T = P.tasks[t];
+      const double wt_t = io.w[s * P.ntask + t];
+      if (T.dense_off >= 0) {
+        if (lane == (t & 31)) {
+          TaskVals tv;
+          eval_dense_task(P, T, fm.task_f[t], ws, s, nfr, des, tv);
+          for (int i = 0; i < 3; i++) { ev[T.row_off + i] = tv.jd[i] - tv.op[i]; wt[T.row_off + i] = wt_t; }
+        }
+      } else {
+#pragma unroll 1
+        for (int i = lane; i < T.dim; i += 32) {
+          int vi;
+          double perr, op;
+          eval_joint_row(P, T, i, ws, s, nq, des, vi, perr, op);
+          ev[T.row_off + i] = -op;
+          wt[T.row_off + i] = wt_t;
+        }
+      }
+    }
+    // stage the dense task Jacobian rows; clear the factor block and the linear term (dv = g0)
+#pragma unroll 1
+    for (int t = 0; t < P.ntask; t++) {
+      const DevTask& T = P.tasks[t];
+      if (T.dense_off < 0) continue;
+#pragma unroll 1
+      for (int i = 0; i < 3; i++) {
+        const double* src = dense_row_ptr(T, fm.task_f[t], ws, s, nfr, NV, i);
+        double* dst = Jd + (T.dense_off + i) * LDV;
+        for (int c = lane; c < NV; c += 32) dst[c] = src[c];
+      }
+    }
+#pragma unroll 1
+    for (int k = lane; k < NV * LDV; k += 32) Gm[k] = 0.0;
+    __syncwarp();
+
+    // ---- Hessian task block (lower triangle) = sum_t w_t J_t^T J_t + lambda_q_ddot M ----
+    {
+      const double* Mg = ws.M + s * NV * NV;
+      constexpr int nt = (NV + 1) >> 1, ntile = nt * (nt + 1) / 2;
+#pragma unroll 1
+      for (int idx = lane; idx < ntile; idx += 32) {
+        int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
+        while (ti * (ti + 1) / 2 > idx) ti--;
+        const int tj = idx - ti * (ti + 1) / 2;
+        const int r0 = 2 * ti, c0 = 2 * tj;
+        const bool r1ok = r0 + 1 < NV, c1ok = c0 + 1 < NV;
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+#pragma unroll 1
+        for (int t = 0; t < P.ntask; t++) {
+          const DevTask& T = P.tasks[t];
+          if (T.dense_off < 0) continue;
+          const double wk = wt[T.row_off];
+          if (wk == 0.0) continue;
+          double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            const double* row = Jd + (T.dense_off + i) * LDV;
+            const double ra = row[r0], rb = r1ok ? row[r0 + 1] : 0.0;
+            const double ca = row[c0], cb = c1ok ? row[c0 + 1] : 0.0;
+            t00 += ra * ca; t01 += ra * cb; t10 += rb * ca; t11 += rb * cb;
+          }
+          a00 += wk * t00; a01 += wk * t01; a10 += wk * t10; a11 += wk * t11;
+        }
+        const double lam = P.lambda_q_ddot;
+        Gm[r0 * LDV + c0] = a00 + lam * Mg[r0 * NV + c0];
+        if (c1ok && c0 + 1 <= r0) Gm[r0 * LDV + c0 + 1] = a01 + lam * Mg[r0 * NV + c0 + 1];
+        if (r1ok) {
+          Gm[(r0 + 1) * LDV + c0] = a10 + lam * Mg[(r0 + 1) * NV + c0];
+          if (c1ok) Gm[(r0 + 1) * LDV + c0 + 1] = a11 + lam * Mg[(r0 + 1) * NV + c0 + 1];
+        }
+      }
+#pragma unroll 1
+      for (int c = lane; c < NV; c += 32) {
+        double acc = 0.0;
+#pragma unroll 1
+        for (int t = 0; t < P.ntask; t++) {
+          const DevTask& T = P.tasks[t];
+          if (T.dense_off < 0) continue;
+          const double wk = wt[T.row_off];
+          if (wk == 0.0) continue;
+          double tt = 0.0;
+          for (int i = 0; i < 3; i++) tt += ev[T.row_off + i] * Jd[(T.dense_off + i) * LDV + c];
+          acc += wk * tt;
+        }
+        dv[c] = acc;
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int t = 0; t < P.ntask; t++) {  // one-hot rows of the joint tasks
+        const DevTask& T = P.tasks[t];
+        if (T.dense_off >= 0) continue;
+#pragma unroll 1
+        for (int i = lane; i < T.dim; i += 32) {
+          const int vi = T.type == PNC_TASK_JOINT ? 6 + i : P.joint_sel[T.joint_off + i];
+          const double wk = wt[T.row_off + i];
+          Gm[vi * LDV + vi] += wk;
+          dv[vi] += wk * ev[T.row_off + i];
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- constraint rows Arows = [M | -(Jc Ni)^T] (overwrites the staged Jacobians), cones ----
+    {
+      const double* Mg = ws.M + s * NV * NV;
+#pragma unroll 1
+      for (int rI = 0; rI < L.nrow; rI++) {
+        double* row = Ar + rI * lda;
+        if (rI >= 6 && rI < p) {
+          for (int c = lane; c < lda; c += 32) row[c] = c < NV ? P.ic_jac[rI - 6][c] : 0.0;
+          if (lane == 0) a0[rI] = 0.0;
+          continue;
+        }
+        if (has_ic && rI >= p) {
+          const double* src = ws.ic_tq + (s * nact + (rI - p)) * N;
+          for (int c = lane; c < lda; c += 32) row[c] = c < N ? src[c] : 0.0;
+          if (lane == 0) a0[rI] = ws.ic_tq0[s * nact + (rI - p)];
+          continue;
+        }
+        const int v = rI < 6 ? rI : P.act_idx[rI - p];
+        for (int c = lane; c < NV; c += 32) row[c] = Mg[v * NV + c];
+        for (int c = lane; c < lda - NV; c += 32) {
+          double val = 0.0;
+          if (c < NC) {
+            if (has_ic) {
+              val = ws.ic_jcni[(s * NC + c) * NV + v];
+            } else {
+              int ci = 0;
+              while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
+              val = contact_jac_row(P.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - P.contacts[ci].rf_off)[v];
+            }
+          }
+          row[NV + c] = -val;
+        }
+        if (lane == 0) a0[rI] = has_ic ? ws.ic_cg[s * NV + v] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
+      }
+#pragma unroll 1
+      for (int r = lane; r < nu; r += 32) {
+        const int ci = P.cone_contact[r];
+        const DevContact& Cc = P.contacts[ci];
+        const int lr = r - Cc.cone_off;
+        double u6[6];
+        cone_row_world(Cc, lr, ws.fr_iso + (s * nfr + fm.contact_f[ci]) * 12, u6);
+        for (int k = 0; k < 6; k++) Uf[r * 6 + k] = u6[k];
+        double rz = io.rfz[s * P.ncontact + ci];
+        if (rz <= 0.0) rz = 1e-3;  // contact.py:37-41
+        uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
+      }
+    }
+    __syncwarp();
+
+    // ---- Cholesky of the task block (QuadProg++.cc:705-730), left-looking, lanes = rows ----
+    double c1 = 0.0, c2 = 0.0;
+    {
+      double tr = 0.0;
+      for (int i = lane; i < NV; i += 32) tr += Gm[i * LDV + i];
+      c1 = wsum(tr) + NC * P.lambda_rf;
+    }
+    double* dl = vm;  // diagonal of L
+    bool pd = true;
+#pragma unroll 1
+    for (int j = 0; j < NV; j++) {
+      double t0 = 0.0, t1 = 0.0;
+      const double* rj = Gm + j * LDV;
+#pragma unroll
+      for (int rr = 0; rr < (NV > 32 ? 2 : 1); rr++) {
+        const int i = lane + 32 * rr;
+        if (i >= j && i < NV) {
+          const double* ri = Gm + i * LDV;
+          double sum = ri[j], sum2 = 0.0;
+          int k = 0;
+#pragma unroll 1
+          for (; k + 1 < j; k += 2) { sum -= ri[k] * rj[k]; sum2 -= ri[k + 1] * rj[k + 1]; }
+          if (k < j) sum -= ri[k] * rj[k];
+          if (rr == 0) t0 = sum + sum2; else t1 = sum + sum2;
+        }
+      }
+      const double piv = __shfl_sync(FULL, (j & 32) ? t1 : t0, j & 31);
+      if (!(piv > 0.0)) { pd = false; break; }
+      const double dj = sqrt(piv);
+      __syncwarp();
+      if (lane == (j & 31)) { Gm[j * LDV + j] = dj; dl[j] = dj; }
+      if (lane > j && lane < NV) Gm[lane * LDV + j] = t0 / dj;
+      if (NV > 32 && lane + 32 > j && lane + 32 < NV) Gm[(lane + 32) * LDV + j] = t1 / dj;
+      __syncwarp();
+    }
+    if (!pd || !(P.lambda_rf > 0.0 || NC == 0)) {
+      status = PNC_QP_NOT_PD;
+    } else if (status == PNC_QP_OK) {
+      // ---- J = L^-T in place (QuadProg++.cc:203-210): lane i forward-solves L z = e_i ----
+#pragma unroll 1
+      for (int j = 0; j < NV; j++) {
+        const double* Lj = Gm + j * LDV;
+        const double djj = dl[j];
+#pragma unroll
+        for (int rr = 0; rr < (NV > 32 ? 2 : 1); rr++) {
+          const int i = lane + 32 * rr;
+          if (i <= j && i < NV) {
+            double* zi = Gm + i * LDV;
+            double sum = i == j ? 1.0 : 0.0, sum2 = 0.0;
+            int k = i;
+#pragma unroll 1
+            for (; k + 1 < j; k += 2) { sum -= Lj[k] * zi[k]; sum2 -= Lj[k + 1] * zi[k + 1]; }
+            if (k < j) sum -= Lj[k] * zi[k];
+            zi[j] = (sum + sum2) / djj;
+          }
+        }
+        __syncwarp();
+      }
+      const double jrf = 1.0 / sqrt(P.lambda_rf > 0.0 ? P.lambda_rf : 1.0);
+      {
+        double tr = 0.0;
+        for (int i = lane; i < NV; i += 32) tr += Gm[i * LDV + i];
+        c2 = wsum(tr) + NC * jrf;
+      }
+      // ---- unconstrained minimiser x = -J (J^T g0)  (:222-224); J is upper triangular here ----
+#pragma unroll 1
+      for (int j = lane; j < NV; j += 32) {
+        double acc = 0.0;
+#pragma unroll 1
+        for (int k = 0; k <= j; k++) acc += Gm[k * LDV + j] * dv[k];
+        dm[j] = acc;
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int k = lane; k < NV; k += 32) {
+        double acc = 0.0;
+#pragma unroll 1
+        for (int j = k; j < NV; j++) acc += Gm[k * LDV + j] * dm[j];
+        x[k] = -acc;
+      }
+      // ---- move J into registers: row lane, and half rows 32.. in lane pairs ----
+#pragma unroll
+      for (int k = 0; k < NP; k++) {
+        double v = 0.0;
+        if (k < NV) { if (lane < NV && k >= lane) v = Gm[lane * LDV + k]; }
+        else if (k < N) { if (lane == k) v = jrf; }
+        Ja[k] = v;
+      }
+#pragma unroll
+      for (int c = 0; c < NB; c++) {
+        double v = 0.0;
+        if constexpr (EXT) {
+          const int col = eh * HW + c;
+          if (evalid && col < N) {
+            if (erow < NV) { if (col < NV && col >= erow) v = Gm[erow * LDV + col]; }
+            else if (col == erow) v = jrf;
+          }
+        }
+        Jb[c] = v;
+      }
+#pragma unroll 1
+      for (int k = lane; k < N + 2; k += 32) { uv[k] = 0.0; Aact[k] = 0; }
+#pragma unroll 1
+      for (int k = lane; k < NP; k += 32) { dm[k] = 0.0; dv[k] = 0.0; }
+      __syncwarp();  // Gm is dead from here: R and the scratch tile reuse the region
+
+      // ================= dual active-set iterations, equalities first (:232-500) =================
+      unsigned long long act0 = 0ull, act1 = 0ull;  // inequality currently in the active set
+      unsigned long long exc0 = 0ull, exc1 = 0ull;  // inequality excluded in this outer iteration
+      auto is_set = [](unsigned long long a, unsigned long long b, int i) {
+        return ((i < 64 ? a >> i : b >> (i - 64)) & 1ull) != 0ull;
+      };
+      auto set_bit = [](unsigned long long& a, unsigned long long& b, int i) {
+        if (i < 64) a |= 1ull << i; else b |= 1ull << (i - 64);
+      };
+      auto clr_bit = [](unsigned long long& a, unsigned long long& b, int i) {
+        if (i < 64) a &= ~(1ull << i); else b &= ~(1ull << (i - 64));
+      };
+      const double psi_tol = (double)m * QP_EPS * c1 * c2 * 100.0;  // QuadProg++.cc:306-312
+      const double psi_refine = psi_tol * 1e-6;                     // see ihwbc.cu / DESIGN.md 3.2
+      bool done = false, accepted = false, need_l1 = true;
+      int iq_acc = 0, ieq = 0;
+
+#pragma unroll 1
+      while (!done) {
+        const bool is_eq = ieq < p;
+        int ip = 0, k0 = 0, k1 = N;
+        double s_ip = 0.0;
+        if (is_eq) {
+          ip = ieq;
+        } else {
+          if (m <= 0) break;
+          if (need_l1) {
+            // l1: slacks of every inequality, termination test (:282-321)
+            need_l1 = false;
+            iter++;
+            act0 = act1 = exc0 = exc1 = 0ull;
+#pragma unroll 1
+            for (int i = p; i < iq; i++) set_bit(act0, act1, Aact[i]);
+            double psi = 0.0;
+            if (trq) {
+#pragma unroll 1
+              for (int a = lane; a < nact; a += 32) {
+                const double* row = Ar + (p + a) * lda;
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll 4
+                for (int k = 0; k < NP; k += 2) {
+                  const double2 rr = lds2(row + k), xx = lds2(x + k);
+                  t0 = fma(rr.x, xx.x, t0);
+                  t1 = fma(rr.y, xx.y, t1);
+                }
+                const double tau = t0 + t1 + a0[p + a];
+                const double slo = tau - P.trq_lo[a], shi = P.trq_hi[a] - tau;
+                sl[nu + a] = slo;
+                sl[nu + nact + a] = shi;
+                psi += fmin(0.0, slo) + fmin(0.0, shi);
+              }
+            }
+#pragma unroll 1
+            for (int r = lane; r < nu; r += 32) {
+              const DevContact& Cc = P.contacts[P.cone_contact[r]];
+              const double* xr = x + NV + Cc.rf_off;
+              double acc = 0.0;
+              for (int k = 0; k < Cc.dim; k++) acc = fma(Uf[r * 6 + k], xr[k], acc);
+              acc -= uf[r];
+              sl[r] = acc;
+              psi += fmin(0.0, acc);
+            }
+            psi = wsum(psi);
+            __syncwarp();
+            if (fabs(psi) <= psi_tol) {
+              if (fabs(psi) <= psi_refine) break;
+              if (!accepted) {
+                accepted = true;
+                iq_acc = iq;
+                for (int i = lane; i < NP; i += 32) xacc[i] = x[i];
+                for (int i = lane; i < iq; i += 32) Aacc[i] = Aact[i];
+                __syncwarp();
+              }
+            }
+            if (iter > 40 * (N + m)) { status = PNC_QP_MAX_ITER; break; }
+            for (int i = lane; i < iq; i += 32) { uold[i] = uv[i]; Aold[i] = Aact[i]; }
+            for (int i = lane; i < NP; i += 32) xold[i] = x[i];
+            __syncwarp();
+          }
+          // l2: most violated constraint, first index on ties (:323-334)
+          double ss = 0.0;
+          ip = 0x7fffffff;
+#pragma unroll 1
+          for (int i = lane; i < m; i += 32) {
+            const double v = sl[i];
+            if (v < ss && !is_set(act0, act1, i) && !is_set(exc0, exc1, i)) { ss = v; ip = i; }
+          }
+          wargmin(ss, ip);
+          if (ss >= 0.0) break;
+          s_ip = ss;
+        }
+        // ---- the constraint normal np and the rows [k0, k1) where it is non-zero ----
+        {
+          const double* row = nullptr;
+          double sg = 1.0;
+          if (is_eq) row = Ar + ip * lda;
+          else if (ip >= nu) {
+            const int a = (ip - nu) % nact;
+            sg = (ip - nu) >= nact ? -1.0 : 1.0;
+            row = Ar + (p + a) * lda;
+          }
+          if (row) {
+            double pnx = 0.0;
+#pragma unroll 1
+            for (int k = lane; k < NP; k += 32) { const double v = sg * row[k]; np[k] = v; pnx = fma(v, x[k], pnx); }
+            if (is_eq) s_ip = wsum(pnx) + a0[ip];
+          } else {
+            const DevContact& Cc = P.contacts[P.cone_contact[ip]];
+            k0 = NV + Cc.rf_off; k1 = k0 + Cc.dim;
+#pragma unroll 1
+            for (int k = lane; k < NP; k += 32) np[k] = (k >= k0 && k < k1) ? Uf[ip * 6 + (k - k0)] : 0.0;
+          }
+          if (lane == 0) { uv[iq] = 0.0; Aact[iq] = is_eq ? -ip - 1 : ip; }
+          __syncwarp();
+        }
+
+        // ---- l2a: step directions, step lengths, step; repeat while constraints are dropped ----
+#pragma unroll 1
+        for (;;) {
+          // d = J^T np through the scratch tile, six rows of J at a time (:504-516)
+          double dA = 0.0, dB = 0.0;
+#pragma unroll 1
+          for (int c0 = k0; c0 < k1; c0 += 6) {
+            const int dim = min(6, k1 - c0);
+            if (c0 < 32) {
+              const int r = lane - c0;
+              if (r >= 0 && r < dim) {
+                double* dst = Ts + r * LDT;
+#pragma unroll
+                for (int j = 0; j < NP; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(Ja[j], Ja[j + 1]);
+              }
+            }
+            if constexpr (EXT) {
+              if (c0 + dim > 32) {
+                const int r = erow - c0;
+                if (evalid && r >= 0 && r < dim) {
+                  double* dst = Ts + r * LDT + eh * HW;
+#pragma unroll
+                  for (int c = 0; c < HW; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(Jb[c], Jb[c + 1]);
+                }
+              }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int r = 0; r < dim; r++) {
+              const double nr = np[c0 + r];
+              dA = fma(nr, Ts[r * LDT + lane], dA);
+              if (NP > 32 && lane + 32 < NP) dB = fma(nr, Ts[r * LDT + lane + 32], dB);
+            }
+            __syncwarp();
+          }
+          if (lane < NP) { dv[lane] = dA; dm[lane] = lane >= iq ? dA : 0.0; }
+          if (NP > 32 && lane + 32 < NP) { dv[lane + 32] = dB; dm[lane + 32] = lane + 32 >= iq ? dB : 0.0; }
+          __syncwarp();
+
+          // z = J[:, iq:] d[iq:] (:518-528), z.z and z.np
+          double za, zb = 0.0, zz, znp;
+          {
+            double a0_ = 0.0, a1_ = 0.0;
+#pragma unroll
+            for (int j = 0; j < NP; j += 2) {
+              const double2 v = lds2(dm + j);
+              a0_ = fma(Ja[j], v.x, a0_);
+              a1_ = fma(Ja[j + 1], v.y, a1_);
+            }
+            za = a0_ + a1_;
+            if constexpr (EXT) {
+              double b0_ = 0.0, b1_ = 0.0;
+              const double* dh = dm + eh * HW;
+#pragma unroll
+              for (int c = 0; c < HW; c += 2) {
+                const double2 v = lds2(dh + c);
+                b0_ = fma(Jb[c], v.x, b0_);
+                b1_ = fma(Jb[c + 1], v.y, b1_);
+              }
+              zb = b0_ + b1_;
+              zb += __shfl_xor_sync(FULL, zb, 1);
+            }
+            double pzz = 0.0, pzn = 0.0;
+            if (lane < N) { zv[lane] = za; pzz = za * za; pzn = za * np[lane]; }
+            if (evalid && eh == 0) { zv[erow] = zb; pzz = fma(zb, zb, pzz); pzn = fma(zb, np[erow], pzn); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              pzz += __shfl_xor_sync(FULL, pzz, o);
+              pzn += __shfl_xor_sync(FULL, pzn, o);
+            }
+            zz = pzz; znp = pzn;
+          }
+          // r = R^-1 d[0:iq] (:530-542), column-oriented back substitution
+          {
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 1
+            for (int i = iq - 1; i >= 0; i--) {
+              const double* col = Rcol(i);
+              const double mine = (i & 32) ? acc1 : acc0;
+              double ri = (dv[i] - mine) * rinv[i];
+              ri = __shfl_sync(FULL, ri, i & 31);
+              if (lane == (i & 31)) rv[i] = ri;
+              if (lane < i) acc0 = fma(col[lane], ri, acc0);
+              if (lane + 32 < i) acc1 = fma(col[lane + 32], ri, acc1);
+            }
+          }
+          __syncwarp();
+          // step lengths (:366-393); equalities always take the full step (:246-258)
+          double t1 = INFINITY;
+          int kk = 0x7fffffff;
+          if (!is_eq) {
+#pragma unroll 1
+            for (int k = p + lane; k < iq; k += 32) {
+              const double rk = rv[k];
+              if (rk > 0.0) {
+                const double v = uv[k] / rk;
+                if (v < t1) { t1 = v; kk = k; }
+              }
+            }
+            wargmin(t1, kk);
+          }
+          const int l = kk != 0x7fffffff ? Aact[kk] : 0;
+          double t2;
+          if (fabs(zz) > QP_EPS) {
+            t2 = -s_ip / znp;
+            if (!is_eq && t2 < 0.0) t2 = INFINITY;
+          } else {
+            t2 = is_eq ? 0.0 : INFINITY;
+          }
+          const double t = fmin(t1, t2);
+          if (t >= INFINITY) { status = PNC_QP_INFEASIBLE; done = true; break; }  // :402-407
+          const bool dual_only = t2 >= INFINITY;
+          if (!dual_only)
+            for (int k = lane; k < N; k += 32) x[k] += t * zv[k];
+          for (int k = lane; k < iq; k += 32) uv[k] -= t * rv[k];
+          if (lane == 0) uv[iq] += t;
+          __syncwarp();
+
+          if (!dual_only && (is_eq || fabs(t - t2) < QP_EPS)) {
+            // ---- full step: add the constraint (:441-474), one Householder reflection of J2 ----
+            double part = 0.0;
+            for (int j = iq + lane; j < N; j += 32) part += dv[j] * dv[j];
+            const double sigma = sqrt(wsum(part));
+            if (sigma <= QP_EPS * R_norm) {  // linearly dependent on the active set
+              if (is_eq) { status = PNC_QP_EQ_DEPENDENT; done = true; break; }
+              set_bit(exc0, exc1, ip);
+              for (int i = p + lane; i < iq; i += 32) { Aact[i] = Aold[i]; uv[i] = uold[i]; }
+              for (int i = lane; i < NP; i += 32) x[i] = xold[i];
+              __syncwarp();
+              act0 = act1 = 0ull;
+#pragma unroll 1
+              for (int i = p; i < iq; i++) set_bit(act0, act1, Aact[i]);
+              break;  // back to l2
+            }
+            const double d0 = dv[iq];
+            const double alpha = d0 > 0.0 ? -sigma : sigma;
+            const double v0 = d0 - alpha;
+            const double beta = 1.0 / (sigma * (sigma + fabs(d0)));
+            double* col = Rcol(iq);
+            for (int i = lane; i < iq; i += 32) col[i] = dv[i];
+            if (lane == 0) { col[iq] = alpha; rinv[iq] = 1.0 / alpha; }
+            for (int j = lane; j < NP; j += 32) vm[j] = j > iq ? dv[j] : (j == iq ? v0 : 0.0);
+            const double ca = reg_pick(Ja, iq);  // old column iq of J
+            double hwb = 0.0;
+            if constexpr (EXT) {
+              const int hq = iq >= HW ? 1 : 0;
+              double cb = reg_pick(Jb, iq - hq * HW);
+              cb = __shfl_sync(FULL, cb, (lane & ~1) | hq);
+              hwb = beta * (zb - alpha * cb);
+            }
+            const double hwa = beta * (za - alpha * ca);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NP; j += 2) {
+              const double2 v = lds2(vm + j);
+              Ja[j] = fma(-hwa, v.x, Ja[j]);
+              Ja[j + 1] = fma(-hwa, v.y, Ja[j + 1]);
+            }
+            if constexpr (EXT) {
+              const double* vh = vm + eh * HW;
+#pragma unroll
+              for (int c = 0; c < HW; c += 2) {
+                const double2 v = lds2(vh + c);
+                Jb[c] = fma(-hwb, v.x, Jb[c]);
+                Jb[c + 1] = fma(-hwb, v.y, Jb[c + 1]);
+              }
+            }
+            iq++;
+            R_norm = fmax(R_norm, sigma);
+            if (is_eq) ieq++;
+            else { set_bit(act0, act1, ip); need_l1 = true; }
+            __syncwarp();
+            break;
+          }
+
+          // ---- drop constraint l at position kk (:409-423, :476-499; delete_constraint :610-679) ----
+          clr_bit(act0, act1, l);
+#pragma unroll 1
+          for (int i = kk; i < iq - 1; i++) {
+            const double* src = Rcol(i + 1);
+            double* dst = Rcol(i);
+            double v0 = 0.0, v1 = 0.0;
+            if (lane <= i + 1) v0 = src[lane];
+            if (lane + 32 <= i + 1) v1 = src[lane + 32];
+            const int ai = Aact[i + 1];
+            const double ui = uv[i + 1];
+            __syncwarp();
+            if (lane <= i + 1) dst[lane] = v0;
+            if (lane + 32 <= i + 1) dst[lane + 32] = v1;
+            if (lane == 0) { Aact[i] = ai; uv[i] = ui; }
+            __syncwarp();
+          }
+          if (lane == 0) {
+            Aact[iq - 1] = Aact[iq];
+            uv[iq - 1] = uv[iq];
+            Aact[iq] = 0;
+            uv[iq] = 0.0;
+          }
+          iq--;
+          __syncwarp();
+          if (iq > 0) {
+            // Givens on the rows of R; the coefficients go to the rotation table
+#pragma unroll 1
+            for (int j = kk; j < iq; j++) {
+              double* cj = Rcol(j);
+              double cc = cj[j], ss = cj[j + 1];
+              const double hh = qp_distance(cc, ss);
+              double xny = 0.0;
+              const bool skip = fabs(hh) < QP_EPS;
+              __syncwarp();
+              if (skip) {  // QuadProg++ leaves the pair untouched (:651)
+                if (lane == 0) { rot[3 * j] = 2.0; rot[3 * j + 1] = 0.0; rot[3 * j + 2] = 0.0; rinv[j] = 1.0 / cj[j]; }
+              } else {
+                cc = cc / hh;
+                ss = ss / hh;
+                double diag = hh;
+                if (cc < 0.0) { diag = -hh; cc = -cc; ss = -ss; }
+                xny = ss / (1.0 + cc);
+                if (lane == 0) {
+                  cj[j] = diag; cj[j + 1] = 0.0; rinv[j] = 1.0 / diag;
+                  rot[3 * j] = cc; rot[3 * j + 1] = ss; rot[3 * j + 2] = xny;
+                }
+#pragma unroll 1
+                for (int k = j + 1 + lane; k < iq; k += 32) {
+                  double* ck = Rcol(k);
+                  const double t1r = ck[j], t2r = ck[j + 1];
+                  const double nj = t1r * cc + t2r * ss;
+                  ck[j] = nj;
+                  ck[j + 1] = xny * (t1r + nj) - t2r;
+                }
+              }
+              __syncwarp();
+            }
+            // the same rotations on the columns of J (registers)
+            reg_rot_range(Ja, kk, iq, rot);
+            if constexpr (EXT) {
+              // half 0 holds columns [0, HW), half 1 columns [HW, 2 HW); pair (HW-1, HW) straddles
+              if (eh == 0) reg_rot_range(Jb, kk, min(iq, HW - 1), rot);
+              if (kk <= HW - 1 && iq > HW - 1) {
+                const double cc = rot[3 * (HW - 1)], ss = rot[3 * (HW - 1) + 1], xny = rot[3 * (HW - 1) + 2];
+                const double mine = eh == 0 ? Jb[HW - 1] : Jb[0];
+                const double other = __shfl_xor_sync(FULL, mine, 1);
+                const double t1r = eh == 0 ? mine : other, t2r = eh == 0 ? other : mine;
+                const double nj = t1r * cc + t2r * ss;
+                if (cc <= 1.5) {
+                  if (eh == 0) Jb[HW - 1] = nj;
+                  else Jb[0] = xny * (nj + t1r) - t2r;
+                }
+              }
+              if (eh == 1 && iq > HW) reg_rot_range(Jb, max(kk, HW) - HW, iq - HW, rot + 3 * HW);
+            }
+            __syncwarp();
+          }
+          if (!dual_only) {  // partial step: refresh the slack of ip (:494-499)
+            double acc = 0.0;
+            for (int k = lane; k < N; k += 32) acc = fma(np[k], x[k], acc);
+            acc = wsum(acc);
+            double ci0;
+            if (ip < nu) ci0 = -uf[ip];
+            else {
+              const int a = (ip - nu) % nact;
+              ci0 = (ip - nu) >= nact ? P.trq_hi[a] - a0[p + a] : a0[p + a] - P.trq_lo[a];
+            }
+            s_ip = acc + ci0;
+            if (lane == 0) sl[ip] = s_ip;
+            __syncwarp();
+          }
+        }
+      }
+      if (accepted && status != PNC_QP_OK) {  // refinement failed: fall back to the accepted iterate
+        status = PNC_QP_OK;
+        iq = iq_acc;
+        for (int i = lane; i < NP; i += 32) x[i] = xacc[i];
+        for (int i = lane; i < iq_acc; i += 32) Aact[i] = Aacc[i];
+        __syncwarp();
+      }
+    }
+
+    // ---- outputs: x = [qddot; rf], torque recovery (ihwbc.py:339-356) ----
+    const bool bad = status == PNC_QP_NOT_PD || status == PNC_QP_EQ_DEPENDENT || status == PNC_QP_INFEASIBLE;
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    if (io.qddot)
+      for (int k = lane; k < NV; k += 32) io.qddot[s * NV + k] = bad ? nanv : x[k];
+    if (io.rf)
+      for (int k = lane; k < NC; k += 32) io.rf[s * NC + k] = bad ? nanv : x[NV + k];
+    if (io.acc)
+      for (int a = lane; a < nact; a += 32) io.acc[s * nact + a] = bad ? nanv : x[P.act_idx[a]];
+    if (io.trq) {
+#pragma unroll 1
+      for (int a = lane; a < nact; a += 32) {
+        double tau = 0.0;
+        if (!bad) {
+          if (trq) {
+            const double* row = Ar + (p + a) * lda;
+            double t0 = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < N; k++) t0 += row[k] * x[k];
+            tau = t0 + a0[p + a];
+          } else if (has_ic) {
+            const double* row = ws.ic_tq + (s * nact + a) * N;
+            double t0 = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < N; k++) t0 += row[k] * x[k];
+            tau = t0 + ws.ic_tq0[s * nact + a];
+          } else {
+            const int v = P.act_idx[a];
+            const double* Mr = ws.M + (s * NV + v) * NV;
+            double t0 = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < NV; k++) t0 += Mr[k] * x[k];
+#pragma unroll 1
+            for (int ci = 0; ci < P.ncontact; ci++) {
+              const DevContact& Cc = P.contacts[ci];
+              for (int k = 0; k < Cc.dim; k++)
+                t0 -= contact_jac_row(Cc, fm.contact_f[ci], ws, s, nfr, NV, k)[v] * x[NV + Cc.rf_off + k];
+            }
+            tau = t0 + ws.cori[s * NV + v] + ws.grav[s * NV + v];
+          }
+        }
+        io.trq[s * nact + a] = bad ? nanv : tau;
+      }
+    }
+    if (io.active) {
+      const int mw = (m + 63) / 64 > 0 ? (m + 63) / 64 : 1;
+      for (int wdx = lane; wdx < mw; wdx += 32) {
+        unsigned long long bits = 0ull;
+        for (int i = p; i < iq; i++) {
+          const int c = Aact[i];
+          if (c >= 0 && (c >> 6) == wdx) bits |= 1ull << (c & 63);
+        }
+        io.active[s * mw + wdx] = bits;
+      }
+    }
+    if (lane == 0) {
+      io.status[s] = status;
+      if (io.iters) io.iters[s] = iter;
+    }
+    __syncwarp();
+  }
+}
+
+template <int NV, int NC>
+static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
+                       const SolveIO& io, int num_sms, cudaStream_t stream) {
+  if (hp.nv != NV || hp.nc != NC) return false;
+  using C = RCfg<NV, NC>;
+  if (hp.m > 128 || hp.nact > 64) return false;
+  for (int i = 0; i < hp.ncontact; i++)
+    if (hp.contacts[i].dim > 6) return false;
+  const RegLayout L = reg_layout<C>(hp);
+  const size_t smem = (size_t)L.per_state * sizeof(double);
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(k_ihwbc_reg<NV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return false;
+    configured = smem;
+  }
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC>, 32, smem);
+  if (per_sm < 1) return false;
+  int grid = num_sms * per_sm;
+  if (grid > B) grid = B;
+  k_ihwbc_reg<NV, NC><<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, B, io);
+  g_launch_count++;
+  return true;
+}
+
+// register-resident kernels exist for the QP shapes of the shipped robots; anything else takes
+// the generic shared-memory kernel of ihwbc.cu
+bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
+                            int B, const SolveIO& io, int num_sms, cudaStream_t stream) {
+  return try_launch<36, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Atlas
+         try_launch<18, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Laikago
+         try_launch<33, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3
+         try_launch<20, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3 lower body
+         try_launch<32, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream);    // Valkyrie
+}
+
+}  // namespace pnc

@@ -72,6 +72,8 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs
                           int num_sms, cudaStream_t stream);
 void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcLayout& L, const WsPtrs& ws,
                         const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream);
+bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
+                            int B, const SolveIO& io, int num_sms, cudaStream_t stream);
 void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
                        int B, int num_sms, cudaStream_t stream, int* counter);
 void launch_task_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int itask, int dim,

@@ -57,6 +57,9 @@ struct pnc_workspace {
   char* ic_slab;
   size_t ic_bytes;
   int ic_nc, ic_nact;
+  // task error terms written by k_task_prepare (allocated lazily, sized by the largest problem seen)
+  double* task_slab;
+  int task_rows;
   // staging buffers of pnc_wbc_tick_host
   char* stage;
   size_t stage_bytes;
@@ -230,6 +233,7 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
   memset(&ws->p, 0, sizeof(ws->p));
   ws->m = m; ws->cap = capacity; ws->nfr = nframes;
   ws->ic_slab = nullptr; ws->ic_bytes = 0; ws->ic_nc = ws->ic_nact = 0;
+  ws->task_slab = nullptr; ws->task_rows = 0;
   ws->stage = nullptr; ws->stage_bytes = 0; ws->tick_init = false;
   memset(&ws->hfr, 0, sizeof(ws->hfr));
   ws->hfr.nfr = nframes;
@@ -267,6 +271,7 @@ void pnc_workspace_destroy(pnc_workspace* ws) {
   cudaFree(ws->slab);
   cudaFree(ws->dfr);
   if (ws->ic_slab) cudaFree(ws->ic_slab);
+  if (ws->task_slab) cudaFree(ws->task_slab);
   if (ws->stage) cudaFree(ws->stage);
   if (ws->tick_init) {
     for (int i = 0; i < 2; i++) { cudaStreamDestroy(ws->tick_stream[i]); cudaEventDestroy(ws->tick_ev[i]); }
@@ -275,7 +280,7 @@ void pnc_workspace_destroy(pnc_workspace* ws) {
 }
 
 int64_t pnc_workspace_bytes(const pnc_workspace* ws) {
-  return ws ? (int64_t)(ws->bytes + ws->ic_bytes + ws->stage_bytes) : 0;
+  return ws ? (int64_t)(ws->bytes + ws->ic_bytes + ws->stage_bytes + (size_t)ws->cap * ws->task_rows * 8) : 0;
 }
 
 static int update_system_at(pnc_workspace* ws, int off, int32_t B, const double* bp, const double* bq,
@@ -334,6 +339,16 @@ static int resolve_frames(const pnc_problem* p, const pnc_workspace* ws, FrameMa
   return PNC_OK;
 }
 
+static int ensure_task_buf(pnc_workspace* ws, const pnc_problem* p) {
+  if (ws->task_slab && ws->task_rows >= p->h.ntaskrows) return PNC_OK;
+  if (ws->task_slab) { cudaFree(ws->task_slab); ws->task_slab = nullptr; }
+  const size_t bytes = (size_t)ws->cap * (p->h.ntaskrows > 0 ? p->h.ntaskrows : 1) * sizeof(double);
+  CK(cudaMalloc(&ws->task_slab, bytes));
+  ws->task_rows = p->h.ntaskrows;
+  ws->p.task_e = ws->task_slab;
+  return PNC_OK;
+}
+
 static int ensure_ic(pnc_workspace* ws, const pnc_problem* p) {
   if (p->h.n_ic == 0) return PNC_OK;
   if (ws->ic_slab && ws->ic_nc == p->h.nc && ws->ic_nact == p->h.nact) return PNC_OK;
@@ -364,7 +379,19 @@ static int solve_at(const pnc_problem* p, pnc_workspace* ws, int off, int32_t B,
   if (rc) return rc;
   rc = ensure_ic(ws, p);
   if (rc) return rc;
-  WsPtrs wsp = ws_offset(ws->p, off, ws->m->h.nq, p->h.nv, ws->nfr, p->h.nc, p->h.nact, p->h.n);
+  const bool use_reg = reg_kernel_available(p->h);
+  if (use_reg) {
+    rc = ensure_task_buf(ws, p);
+    if (rc) return rc;
+  } else {
+    ws->p.task_e = nullptr;  // the generic kernel evaluates the tasks itself
+  }
+  ws->p.task_e = use_reg ? ws->task_slab : nullptr;
+  WsPtrs wsp = ws_offset(ws->p, off, ws->m->h.nq, p->h.nv, ws->nfr, p->h.nc, p->h.nact, p->h.n, p->h.ntaskrows);
+  if (use_reg) {
+    launch_task_prepare(p->d, p->h, wsp, fm, ws->nfr, B, des, st);
+    CK(cudaGetLastError());
+  }
   if (p->h.n_ic > 0) {
     launch_ic_prepare(p->d, p->h, wsp, fm, ws->nfr, B, ws->m->num_sms, st, counter + 1);
     CK(cudaGetLastError());

@@ -271,7 +271,7 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
       __syncwarp();
       // ---- S [M | -(Jc Ni)^T] and S Ni^T (c+g), S = [0 | B] ----
       for (int a = 0; a < nact; a++) {
-        double* out = ws.ic_tq + (s * nact + a) * n;
+        double* out = ws.ic_tq + s * nact * n + a;  // stored transposed: [n][nact], lanes of the QP kernel = rows a
         for (int c = lane; c < n; c += 32) {
           double sum = 0.0;
           if (c < nv) {
@@ -284,7 +284,7 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
             const double* jr = ws.ic_jcni + (s * nc + (c - nv)) * nv;
             for (int j = 0; j < nj; j++) sum -= Bt[j * ldb + a] * jr[6 + j];
           }
-          out[c] = sum;
+          out[c * nact] = sum;
         }
         double part = 0.0;
         for (int j = lane; j < nj; j += 32) part += Bt[j * ldb + a] * ncg[6 + j];

@@ -376,8 +376,8 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
           continue;
         }
         if (has_ic && rI >= p) {  // S [M | -(Jc Ni)^T] from the projection kernel
-          const double* src = ws.ic_tq + (s * nact + (rI - p)) * n;
-          for (int c = lane; c < n; c += 32) row[c] = src[c];
+          const double* src = ws.ic_tq + s * nact * n + (rI - p);
+          for (int c = lane; c < n; c += 32) row[c] = src[c * nact];
           if (lane == 0) a0[rI] = ws.ic_tq0[s * nact + (rI - p)];
           continue;
         }
@@ -735,9 +735,9 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
           for (int k = 0; k < n; k++) t0 += row[k] * x[k];
           tau = t0 + a0[p + a];
         } else if (has_ic) {
-          const double* row = ws.ic_tq + (s * nact + a) * n;
+          const double* row = ws.ic_tq + s * nact * n + a;
           double t0 = 0.0;
-          for (int k = 0; k < n; k++) t0 += row[k] * x[k];
+          for (int k = 0; k < n; k++) t0 += row[k * nact] * x[k];
           tau = t0 + ws.ic_tq0[s * nact + a];
         } else {
           const int v = P.act_idx[a];
@@ -777,7 +777,7 @@ void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcL
                         const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream) {
   // register-resident kernel for the shipped QP shapes; PNC_SOLVER=smem forces the generic kernel
   static const bool force_smem = [] { const char* e = getenv("PNC_SOLVER"); return e && e[0] == 's'; }();
-  if (!force_smem && launch_ihwbc_solve_reg(dp, hp, ws, fm, nfr, B, io, num_sms, stream)) return;
+  if (!force_smem && ws.task_e && launch_ihwbc_solve_reg(dp, hp, ws, fm, nfr, B, io, num_sms, stream)) return;
   const size_t smem = (size_t)L.per_state * sizeof(double);
   static size_t configured = 0;
   if (smem > configured) {
@@ -791,6 +791,44 @@ void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcL
   if (grid > B) grid = B;
   const int nq = hp.nv + 1;
   k_ihwbc_solve<<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, nq, B, io);
+  g_launch_count++;
+}
+
+// ---------------------------------------------------------------------------------------
+// Task error terms e = Jdot qdot - xddot_cmd of every task row (basic_task.py:25-109), one thread
+// per (state, task): keeps the trigonometry of the orientation tasks out of the solve kernel.
+__global__ void __launch_bounds__(128)
+k_task_prepare(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int nq, int B,
+               const double* __restrict__ des_all) {
+  const DevProblem& P = *gp;
+  const size_t total = (size_t)B * P.ntask;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = idx / P.ntask;
+    const int t = (int)(idx % P.ntask);
+    const DevTask& T = P.tasks[t];
+    const double* des = des_all + s * P.ndes;
+    double* out = ws.task_e + s * P.ntaskrows + T.row_off;
+    if (T.dense_off >= 0) {
+      TaskVals tv;
+      eval_dense_task(P, T, fm.task_f[t], ws, s, nfr, des, tv);
+      for (int i = 0; i < 3; i++) out[i] = tv.jd[i] - tv.op[i];
+    } else {
+      for (int i = 0; i < T.dim; i++) {
+        int vi;
+        double perr, op;
+        eval_joint_row(P, T, i, ws, s, nq, des, vi, perr, op);
+        out[i] = -op;
+      }
+    }
+  }
+}
+
+void launch_task_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
+                         const double* des, cudaStream_t stream) {
+  const size_t total = (size_t)B * hp.ntask;
+  int grid = (int)((total + 127) / 128);
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_task_prepare<<<grid, 128, 0, stream>>>(dp, ws, fm, nfr, hp.nv + 1, B, des);
   g_launch_count++;
 }
 

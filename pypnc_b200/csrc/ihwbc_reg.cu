@@ -18,6 +18,8 @@
 //     through the same step code as inequalities -- and the only unrolled code is what register
 //     indexing forces.  Dynamic column indices (iq, the Givens pairs of a dropped constraint) are
 //     warp-uniform and go through switch statements (jump tables), never local memory.
+#include <stdlib.h>
+
 #include "ihwbc_common.cuh"
 
 namespace pnc {
@@ -30,15 +32,19 @@ struct RCfg {
   static constexpr int HW = EXT ? ((N + 3) / 4) * 2 : 0;      // half-row width (even)
   static constexpr int NP = EXT ? 2 * HW : ((N + 1) & ~1);    // padded vector length (even)
   static constexpr int NB = HW > 0 ? HW : 2;
-  static constexpr int LDV = NV | 1;                          // pitch of the nv x nv factor block
+  static constexpr int ldv_() { int l = (NV_ + 1) & ~1; while ((l & 15) != 6) l += 2; return l; }
+  static constexpr int LDV = ldv_();                          // pitch of the nv x nv block: even, 6 (mod 16) ->
+                                                              // rows 16-byte aligned, LDS.128 by row conflict-free
+  static constexpr int EV = NV_ > 32 ? NV_ - 32 : 0;          // Hessian rows beyond 32
+  static constexpr int EVP = EV <= 1 ? 1 : (EV <= 2 ? 2 : (EV <= 4 ? 4 : 8));
+  static constexpr int LPR = 32 / EVP;                        // lanes cooperating on one such row in the Cholesky
   static constexpr int LDT = NP + 2;                          // pitch of the d scratch tile
   static_assert(E <= 16, "rows beyond 32 must fit one lane pair each");
   static_assert(N <= 64, "n too large for the register kernel");
 };
 
 struct RegLayout {
-  int lda, nrow;
-  int oA, oa0, oRT, oT, orinv, oUf, ouf, ox, oz, odv, odm, ovm, onp, orr, ou, oxold, ouold, oxacc, osl, oev, owt, oint;
+  int oRT, oT, orinv, oBig, oUf, ouf, ox, oz, odv, odm, ovm, onp, orr, ou, oxold, ouold, oxacc, osl, oev, owt, oint;
   int per_state;
 };
 
@@ -46,20 +52,15 @@ template <class C>
 __host__ __device__ inline RegLayout reg_layout(const DevProblem& P) {
   RegLayout L;
   const int n = C::N, m = P.m > 0 ? P.m : 1;
-  int lda = C::NP;  // conflict-free LDS.128 by row needs lda = 2 (mod 16)
-  while ((lda & 15) != 2) lda++;
-  L.lda = lda;
-  L.nrow = P.p + (P.b_trq_limit ? P.nact : 0);
   int o = 0;
-  int asz = L.nrow * lda, jds = P.ndense * C::LDV;  // the staged task Jacobians borrow the Arows region
-  if (jds > asz) asz = jds;
-  L.oA = o; o += (asz + 1) & ~1;
-  L.oa0 = o; o += (L.nrow + 1) & ~1;
   const int rsz = (n * (n + 3) / 2 + 1) & ~1, tsz = 6 * C::LDT, gsz = C::NV * C::LDV;
   int reg = rsz + tsz;
   if (gsz > reg) reg = gsz;
   L.oRT = o; L.oT = o + rsz; o += (reg + 1) & ~1;
   L.orinv = o; o += C::NP;
+  // everything from here to osl is dead while the Hessian is assembled: the staged task
+  // Jacobian rows (ndense x LDV) borrow the space
+  L.oBig = o;
   L.oUf = o; o += (P.nu > 0 ? P.nu : 1) * 6;
   L.ouf = o; o += ((P.nu > 0 ? P.nu : 1) + 1) & ~1;
   L.ox = o; o += C::NP;
@@ -74,6 +75,8 @@ __host__ __device__ inline RegLayout reg_layout(const DevProblem& P) {
   L.ouold = o; o += C::NP + 2;
   L.oxacc = o; o += C::NP;
   L.osl = o; o += (m + 1) & ~1;
+  const int jds = (P.ndense * C::LDV + 1) & ~1;
+  if (o - L.oBig < jds) o = L.oBig + jds;
   const int tr = ((P.ntaskrows > 0 ? P.ntaskrows : 1) + 1) & ~1;
   L.oev = o; o += tr;
   L.owt = o; o += tr;
@@ -118,9 +121,53 @@ __device__ __forceinline__ void reg_rot_range(double (&A)[LEN], int j0, int j1, 
 
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
+// Torque of actuated row a at x = [qddot; rf] (ihwbc.py:344-354):  S (M qddot + Ni^T (c+g) - (Jc Ni)^T rf).
+// Called with lanes = rows: M is symmetric, so lane a reads column act_idx[a] of M -- consecutive
+// lanes touch consecutive addresses -- and the constraint rows never have to be copied anywhere.
+// One out-of-line copy serves the slack pass and the output pass.
+__device__ __noinline__ double torque_row(const DevProblem& P, const WsPtrs& ws, const FrameMap& fm, int nfr, size_t s,
+                                          int a, const double* __restrict__ x) {
+  const int nv = P.nv, nact = P.nact;
+  double t0 = 0.0, t1 = 0.0;
+  if (P.n_ic > 0) {
+    const int n = P.n;
+    const double* col = ws.ic_tq + s * n * nact + a;
+    const double* xe = x + (n & ~1);
+#pragma unroll 4
+    for (const double* xp = x; xp < xe; xp += 2, col += 2 * nact) {
+      const double2 xx = *reinterpret_cast<const double2*>(xp);
+      t0 = fma(col[0], xx.x, t0);
+      t1 = fma(col[nact], xx.y, t1);
+    }
+    if (n & 1) t0 = fma(col[0], xe[0], t0);
+    return t0 + t1 + ws.ic_tq0[s * nact + a];
+  }
+  const int v = P.act_idx[a];
+  const double* col = ws.M + s * nv * nv + v;  // column v of M == row v
+  const double* xe = x + (nv & ~1);
+#pragma unroll 6
+  for (const double* xp = x; xp < xe; xp += 2, col += 2 * nv) {
+    const double2 xx = *reinterpret_cast<const double2*>(xp);
+    t0 = fma(col[0], xx.x, t0);
+    t1 = fma(col[nv], xx.y, t1);
+  }
+  if (nv & 1) t0 = fma(col[0], xe[0], t0);
+  for (int ci = 0; ci < P.ncontact; ci++) {
+    const DevContact& Cc = P.contacts[ci];
+    const double* xr = x + nv + Cc.rf_off;
+    const double* jr = contact_jac_row(Cc, fm.contact_f[ci], ws, s, nfr, nv, 0) + v;
+#pragma unroll 3
+    for (int r = 0; r < Cc.dim; r++, jr += nv) t1 = fma(-jr[0], xr[r], t1);
+  }
+  return t0 + t1 + ws.cori[s * nv + v] + ws.grav[s * nv + v];
+}
+
 // =======================================================================================
 template <int NV, int NC>
-__global__ void __launch_bounds__(32)
+#ifndef PNC_REG_MINB
+#define PNC_REG_MINB 8
+#endif
+__global__ void __launch_bounds__(32, PNC_REG_MINB)
 k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap fm, int nfr, int B, SolveIO io) {
   using C = RCfg<NV, NC>;
   constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV;
@@ -128,12 +175,10 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
   extern __shared__ __align__(16) double smem[];
   const DevProblem& P = *gp;
   const int lane = threadIdx.x;
-  const int p = P.p, m = P.m, nu = P.nu, nact = P.nact, lda = L.lda, nq = NV + 1;
+  const int p = P.p, m = P.m, nu = P.nu, nact = P.nact;
   const bool trq = P.b_trq_limit != 0, has_ic = P.n_ic > 0;
   double* W = smem;
-  double* Ar = W + L.oA;
-  double* Jd = Ar;   // staged dense task Jacobian rows (dead before Arows is filled)
-  double* a0 = W + L.oa0;
+  double* Jd = W + L.oBig;  // staged dense task Jacobian rows (dead before the vectors below are used)
   double* Rp = W + L.oRT;
   double* Gm = Rp;   // nv x nv Hessian / factor / L^-T block (dead before R is written)
   double* Ts = W + L.oT;
@@ -176,33 +221,22 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
     si = __shfl_sync(FULL, si, 0);
     if (si >= B) break;
     const size_t s = (size_t)si;
-    const double* des = io.des + s * P.ndes;
     int status = PNC_QP_OK, iter = 0, iq = 0;
     double R_norm = 1.0;
     if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
 
     // ---- tasks: e = Jdot qdot - xddot_cmd, weights (ihwbc.py:159-172) ----
+    double* g0 = rinv;  // linear term while the Hessian is assembled (rinv is not live yet)
+    // task error terms e = Jdot qdot - xddot_cmd were evaluated by k_task_prepare (ihwbc.cu)
+    {
+      const double* te = ws.task_e + s * P.ntaskrows;
 #pragma unroll 1
-    for (int k = lane; k < NP; k += 32) { x[k] = 0.0; zv[k] = 0.0; dv[k] = 0.0; dm[k] = 0.0; vm[k] = 0.0; np[k] = 0.0; }
+      for (int k = lane; k < P.ntaskrows; k += 32) ev[k] = te[k];
 #pragma unroll 1
-    for (int t = 0; t < P.ntask; t++) {
-      const DevTask& T = P.tasks[t];
-      const double wt_t = io.w[s * P.ntask + t];
-      if (T.dense_off >= 0) {
-        if (lane == (t & 31)) {
-          TaskVals tv;
-          eval_dense_task(P, T, fm.task_f[t], ws, s, nfr, des, tv);
-          for (int i = 0; i < 3; i++) { ev[T.row_off + i] = tv.jd[i] - tv.op[i]; wt[T.row_off + i] = wt_t; }
-        }
-      } else {
-#pragma unroll 1
-        for (int i = lane; i < T.dim; i += 32) {
-          int vi;
-          double perr, op;
-          eval_joint_row(P, T, i, ws, s, nq, des, vi, perr, op);
-          ev[T.row_off + i] = -op;
-          wt[T.row_off + i] = wt_t;
-        }
+      for (int t = 0; t < P.ntask; t++) {
+        const DevTask& T = P.tasks[t];
+        const double wt_t = io.w[s * P.ntask + t];
+        for (int i = lane; i < T.dim; i += 32) wt[T.row_off + i] = wt_t;
       }
     }
     // stage the dense task Jacobian rows; clear the factor block and the linear term (dv = g0)
@@ -271,7 +305,7 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
           for (int i = 0; i < 3; i++) tt += ev[T.row_off + i] * Jd[(T.dense_off + i) * LDV + c];
           acc += wk * tt;
         }
-        dv[c] = acc;
+        g0[c] = acc;
       }
       __syncwarp();
 #pragma unroll 1
@@ -283,45 +317,27 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
           const int vi = T.type == PNC_TASK_JOINT ? 6 + i : P.joint_sel[T.joint_off + i];
           const double wk = wt[T.row_off + i];
           Gm[vi * LDV + vi] += wk;
-          dv[vi] += wk * ev[T.row_off + i];
+          g0[vi] += wk * ev[T.row_off + i];
         }
         __syncwarp();
       }
     }
 
-    // ---- constraint rows Arows = [M | -(Jc Ni)^T] (overwrites the staged Jacobians), cones ----
+    // ---- the staged Jacobians are dead: clear the work vectors, move g0, build the wrench cones ----
+    // (the constraint rows [M | -(Jc Ni)^T] are never copied: M is symmetric, so "row a for every
+    //  lane a" is a coalesced column read of the workspace M, see torque_row)
+    const double* Mg = ws.M + s * NV * NV;
+    auto row_jc = [&](int c, int v) -> double {  // (Jc Ni)[c][v]
+      if (has_ic) return ws.ic_jcni[(s * NC + c) * NV + v];
+      int ci = 0;
+      while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
+      return contact_jac_row(P.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - P.contacts[ci].rf_off)[v];
+    };
     {
-      const double* Mg = ws.M + s * NV * NV;
 #pragma unroll 1
-      for (int rI = 0; rI < L.nrow; rI++) {
-        double* row = Ar + rI * lda;
-        if (rI >= 6 && rI < p) {
-          for (int c = lane; c < lda; c += 32) row[c] = c < NV ? P.ic_jac[rI - 6][c] : 0.0;
-          if (lane == 0) a0[rI] = 0.0;
-          continue;
-        }
-        if (has_ic && rI >= p) {
-          const double* src = ws.ic_tq + (s * nact + (rI - p)) * N;
-          for (int c = lane; c < lda; c += 32) row[c] = c < N ? src[c] : 0.0;
-          if (lane == 0) a0[rI] = ws.ic_tq0[s * nact + (rI - p)];
-          continue;
-        }
-        const int v = rI < 6 ? rI : P.act_idx[rI - p];
-        for (int c = lane; c < NV; c += 32) row[c] = Mg[v * NV + c];
-        for (int c = lane; c < lda - NV; c += 32) {
-          double val = 0.0;
-          if (c < NC) {
-            if (has_ic) {
-              val = ws.ic_jcni[(s * NC + c) * NV + v];
-            } else {
-              int ci = 0;
-              while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
-              val = contact_jac_row(P.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - P.contacts[ci].rf_off)[v];
-            }
-          }
-          row[NV + c] = -val;
-        }
-        if (lane == 0) a0[rI] = has_ic ? ws.ic_cg[s * NV + v] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
+      for (int k = lane; k < NP; k += 32) {
+        x[k] = 0.0; zv[k] = 0.0; dm[k] = 0.0; vm[k] = 0.0; np[k] = 0.0;
+        dv[k] = k < NV ? g0[k] : 0.0;
       }
 #pragma unroll 1
       for (int r = lane; r < nu; r += 32) {
@@ -339,38 +355,53 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
     __syncwarp();
 
     // ---- Cholesky of the task block (QuadProg++.cc:705-730), left-looking, lanes = rows ----
+    // rows 32.. (Atlas has 4) are each shared by LPR lanes that split the dot product
     double c1 = 0.0, c2 = 0.0;
     {
       double tr = 0.0;
       for (int i = lane; i < NV; i += 32) tr += Gm[i * LDV + i];
       c1 = wsum(tr) + NC * P.lambda_rf;
     }
-    double* dl = vm;  // diagonal of L
+    double* dl = vm;  // reciprocal diagonal of L
     bool pd = true;
+    constexpr int EV = C::EV, LPR = C::LPR;
+    const int xrow = 32 + lane / LPR, xsl = lane % LPR;
 #pragma unroll 1
     for (int j = 0; j < NV; j++) {
       double t0 = 0.0, t1 = 0.0;
       const double* rj = Gm + j * LDV;
-#pragma unroll
-      for (int rr = 0; rr < (NV > 32 ? 2 : 1); rr++) {
-        const int i = lane + 32 * rr;
-        if (i >= j && i < NV) {
-          const double* ri = Gm + i * LDV;
-          double sum = ri[j], sum2 = 0.0;
-          int k = 0;
+      if (lane >= j && lane < NV) {
+        const double* ri = Gm + lane * LDV;
+        double s0 = ri[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int k = 0;
 #pragma unroll 1
-          for (; k + 1 < j; k += 2) { sum -= ri[k] * rj[k]; sum2 -= ri[k + 1] * rj[k + 1]; }
-          if (k < j) sum -= ri[k] * rj[k];
-          if (rr == 0) t0 = sum + sum2; else t1 = sum + sum2;
+        for (; k + 3 < j; k += 4) {
+          const double2 a0 = lds2(ri + k), a1 = lds2(ri + k + 2), b0 = lds2(rj + k), b1 = lds2(rj + k + 2);
+          s0 = fma(-a0.x, b0.x, s0); s1 = fma(-a0.y, b0.y, s1); s2 = fma(-a1.x, b1.x, s2); s3 = fma(-a1.y, b1.y, s3);
         }
+#pragma unroll 1
+        for (; k < j; k++) s0 = fma(-ri[k], rj[k], s0);
+        t0 = (s0 + s1) + (s2 + s3);
       }
-      const double piv = __shfl_sync(FULL, (j & 32) ? t1 : t0, j & 31);
+      if constexpr (EV > 0) {
+        const bool xact = xrow < NV && xrow >= j;
+        const double* ri = Gm + (xact ? xrow : 0) * LDV;
+        double part = 0.0;
+        if (xact) {
+#pragma unroll 1
+          for (int k = xsl; k < j; k += LPR) part = fma(ri[k], rj[k], part);
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+        if (xact) t1 = ri[j] - part;
+      }
+      const double piv = __shfl_sync(FULL, j < 32 ? t0 : t1, j < 32 ? j : (j - 32) * LPR);
       if (!(piv > 0.0)) { pd = false; break; }
-      const double dj = sqrt(piv);
+      const double dj = sqrt(piv), idj = 1.0 / dj;
       __syncwarp();
-      if (lane == (j & 31)) { Gm[j * LDV + j] = dj; dl[j] = dj; }
-      if (lane > j && lane < NV) Gm[lane * LDV + j] = t0 / dj;
-      if (NV > 32 && lane + 32 > j && lane + 32 < NV) Gm[(lane + 32) * LDV + j] = t1 / dj;
+      if (j < 32 ? lane == j : lane == (j - 32) * LPR) { Gm[j * LDV + j] = dj; dl[j] = idj; }
+      if (lane > j && lane < NV) Gm[lane * LDV + j] = t0 * idj;
+      if (EV > 0 && xsl == 0 && xrow > j && xrow < NV) Gm[xrow * LDV + j] = t1 * idj;
       __syncwarp();
     }
     if (!pd || !(P.lambda_rf > 0.0 || NC == 0)) {
@@ -380,18 +411,23 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
 #pragma unroll 1
       for (int j = 0; j < NV; j++) {
         const double* Lj = Gm + j * LDV;
-        const double djj = dl[j];
+        const double idjj = dl[j];
 #pragma unroll
         for (int rr = 0; rr < (NV > 32 ? 2 : 1); rr++) {
           const int i = lane + 32 * rr;
-          if (i <= j && i < NV) {
+          if ((rr == 0 || j >= 32) && i <= j && i < NV) {
             double* zi = Gm + i * LDV;
-            double sum = i == j ? 1.0 : 0.0, sum2 = 0.0;
+            double s0 = i == j ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int k = i;
+            if ((k & 1) && k < j) { s0 = fma(-Lj[k], zi[k], s0); k++; }
 #pragma unroll 1
-            for (; k + 1 < j; k += 2) { sum -= Lj[k] * zi[k]; sum2 -= Lj[k + 1] * zi[k + 1]; }
-            if (k < j) sum -= Lj[k] * zi[k];
-            zi[j] = (sum + sum2) / djj;
+            for (; k + 3 < j; k += 4) {
+              const double2 a0 = lds2(zi + k), a1 = lds2(zi + k + 2), b0 = lds2(Lj + k), b1 = lds2(Lj + k + 2);
+              s0 = fma(-a0.x, b0.x, s0); s1 = fma(-a0.y, b0.y, s1); s2 = fma(-a1.x, b1.x, s2); s3 = fma(-a1.y, b1.y, s3);
+            }
+#pragma unroll 1
+            for (; k < j; k++) s0 = fma(-Lj[k], zi[k], s0);
+            zi[j] = ((s0 + s1) + (s2 + s3)) * idjj;
           }
         }
         __syncwarp();
@@ -418,13 +454,66 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         for (int j = k; j < NV; j++) acc += Gm[k * LDV + j] * dm[j];
         x[k] = -acc;
       }
+      // ---- equality normals in the J basis, all at once while J = L^-T is still triangular in
+      //      shared memory: D[i] = J^T ce_i.  The active-set loop then never needs the dense
+      //      d = J^T n+ product for an equality: it reads D[i] and keeps the later rows current
+      //      with the Householder reflection of each added equality ----
+      double* Dt = dm;  // p rows of pitch NP over dm..sl (all dead here)
+      {
+        // floating-base rows i < 6: D[i][j] = sum_{k<=j} J[k][j] M[k][i] (M symmetric: the six
+        // coefficients of step k are contiguous), one column j per lane, six accumulators
+#pragma unroll
+        for (int pass = 0; pass < (NV > 32 ? 2 : 1); pass++) {
+          const int j = lane + 32 * pass;
+          double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, e4 = 0.0, e5 = 0.0;
+          const int kmax = NV < 32 * (pass + 1) ? NV : 32 * (pass + 1);
+          const double* gp_ = Gm + (j < NV ? j : 0);
+          const double* mk = Mg;
+#pragma unroll 2
+          for (int k = 0; k < kmax; k++, gp_ += LDV, mk += NV) {
+            const double g = (j < NV && k <= j) ? gp_[0] : 0.0;
+            e0 = fma(g, mk[0], e0); e1 = fma(g, mk[1], e1); e2 = fma(g, mk[2], e2);
+            e3 = fma(g, mk[3], e3); e4 = fma(g, mk[4], e4); e5 = fma(g, mk[5], e5);
+          }
+          if (j < NV) {
+            Dt[j] = e0; Dt[NP + j] = e1; Dt[2 * NP + j] = e2; Dt[3 * NP + j] = e3; Dt[4 * NP + j] = e4; Dt[5 * NP + j] = e5;
+          }
+        }
+#pragma unroll 1
+        for (int c = lane; c < NP - NV; c += 32)
+#pragma unroll 1
+          for (int i = 0; i < 6; i++) Dt[i * NP + NV + c] = c < NC ? -jrf * row_jc(c, i) : 0.0;
+      }
+#pragma unroll 1
+      for (int i = 6; i < p; i++) {  // internal-constraint rows [Ji | 0]
+#pragma unroll 1
+        for (int j = lane; j < NP; j += 32) {
+          double acc = 0.0;
+          if (j < NV) {
+#pragma unroll 1
+            for (int k = 0; k <= j; k++) acc = fma(Gm[k * LDV + j], P.ic_jac[i - 6][k], acc);
+          }
+          Dt[i * NP + j] = acc;
+        }
+      }
+      __syncwarp();
       // ---- move J into registers: row lane, and half rows 32.. in lane pairs ----
 #pragma unroll
-      for (int k = 0; k < NP; k++) {
-        double v = 0.0;
-        if (k < NV) { if (lane < NV && k >= lane) v = Gm[lane * LDV + k]; }
-        else if (k < N) { if (lane == k) v = jrf; }
-        Ja[k] = v;
+      for (int k = 0; k < NP; k += 2) {
+        double v0 = 0.0, v1 = 0.0;
+        if (k < NV) {
+          if (lane < NV) {
+            const double2 g = lds2(Gm + lane * LDV + k);
+            if (k >= lane) v0 = g.x;
+            if (k + 1 >= lane && k + 1 < NV) v1 = g.y;
+          }
+          if (k + 1 >= NV && k + 1 < N && lane == k + 1) v1 = jrf;
+        } else {
+          if (k < N && lane == k) v0 = jrf;
+          if (k + 1 < N && lane == k + 1) v1 = jrf;
+        }
+        Ja[k] = v0;
+        Ja[k + 1] = v1;
       }
 #pragma unroll
       for (int c = 0; c < NB; c++) {
@@ -438,11 +527,16 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         }
         Jb[c] = v;
       }
+      __syncwarp();  // Gm is dead from here: R, the scratch tile and the equality block reuse the region
+      double* Deq = Rp + 64;  // R only uses its first p columns (< 64 doubles) while Deq is live
+#pragma unroll 1
+      for (int k = lane; k < p * NP; k += 32) Deq[k] = Dt[k];
+      __syncwarp();
 #pragma unroll 1
       for (int k = lane; k < N + 2; k += 32) { uv[k] = 0.0; Aact[k] = 0; }
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) { dm[k] = 0.0; dv[k] = 0.0; }
-      __syncwarp();  // Gm is dead from here: R and the scratch tile reuse the region
+      __syncwarp();
 
       // ================= dual active-set iterations, equalities first (:232-500) =================
       unsigned long long act0 = 0ull, act1 = 0ull;  // inequality currently in the active set
@@ -474,22 +568,12 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
             // l1: slacks of every inequality, termination test (:282-321)
             need_l1 = false;
             iter++;
-            act0 = act1 = exc0 = exc1 = 0ull;
-#pragma unroll 1
-            for (int i = p; i < iq; i++) set_bit(act0, act1, Aact[i]);
+            exc0 = exc1 = 0ull;
             double psi = 0.0;
             if (trq) {
 #pragma unroll 1
               for (int a = lane; a < nact; a += 32) {
-                const double* row = Ar + (p + a) * lda;
-                double t0 = 0.0, t1 = 0.0;
-#pragma unroll 4
-                for (int k = 0; k < NP; k += 2) {
-                  const double2 rr = lds2(row + k), xx = lds2(x + k);
-                  t0 = fma(rr.x, xx.x, t0);
-                  t1 = fma(rr.y, xx.y, t1);
-                }
-                const double tau = t0 + t1 + a0[p + a];
+                const double tau = torque_row(P, ws, fm, nfr, s, a, x);
                 const double slo = tau - P.trq_lo[a], shi = P.trq_hi[a] - tau;
                 sl[nu + a] = slo;
                 sl[nu + nact + a] = shi;
@@ -500,9 +584,10 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
             for (int r = lane; r < nu; r += 32) {
               const DevContact& Cc = P.contacts[P.cone_contact[r]];
               const double* xr = x + NV + Cc.rf_off;
-              double acc = 0.0;
-              for (int k = 0; k < Cc.dim; k++) acc = fma(Uf[r * 6 + k], xr[k], acc);
-              acc -= uf[r];
+              const double* ur = Uf + r * 6;
+              double acc = -uf[r];
+#pragma unroll
+              for (int k = 0; k < 6; k++) acc = fma(ur[k], k < Cc.dim ? xr[k] : 0.0, acc);
               sl[r] = acc;
               psi += fmin(0.0, acc);
             }
@@ -537,19 +622,29 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         }
         // ---- the constraint normal np and the rows [k0, k1) where it is non-zero ----
         {
-          const double* row = nullptr;
-          double sg = 1.0;
-          if (is_eq) row = Ar + ip * lda;
-          else if (ip >= nu) {
-            const int a = (ip - nu) % nact;
-            sg = (ip - nu) >= nact ? -1.0 : 1.0;
-            row = Ar + (p + a) * lda;
-          }
-          if (row) {
+          if (is_eq || ip >= nu) {
+            int v = ip, a = 0;
+            double sg = 1.0;
+            const bool icrow = is_eq && ip >= 6, tq = !is_eq;
+            if (tq) { a = (ip - nu) % nact; sg = (ip - nu) >= nact ? -1.0 : 1.0; v = P.act_idx[a]; }
             double pnx = 0.0;
 #pragma unroll 1
-            for (int k = lane; k < NP; k += 32) { const double v = sg * row[k]; np[k] = v; pnx = fma(v, x[k], pnx); }
-            if (is_eq) s_ip = wsum(pnx) + a0[ip];
+            for (int k = lane; k < NP; k += 32) {
+              double val = 0.0;
+              if (k < N) {
+                if (icrow) val = k < NV ? P.ic_jac[ip - 6][k] : 0.0;
+                else if (tq && has_ic) val = ws.ic_tq[(s * N + k) * nact + a];
+                else if (k < NV) val = Mg[v * NV + k];
+                else val = -row_jc(k - NV, v);
+              }
+              val *= sg;
+              np[k] = val;
+              pnx = fma(val, x[k], pnx);
+            }
+            if (is_eq) {
+              const double a0v = icrow ? 0.0 : (has_ic ? ws.ic_cg[s * NV + v] : ws.cori[s * NV + v] + ws.grav[s * NV + v]);
+              s_ip = wsum(pnx) + a0v;
+            }
           } else {
             const DevContact& Cc = P.contacts[P.cone_contact[ip]];
             k0 = NV + Cc.rf_off; k1 = k0 + Cc.dim;
@@ -565,6 +660,10 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         for (;;) {
           // d = J^T np through the scratch tile, six rows of J at a time (:504-516)
           double dA = 0.0, dB = 0.0;
+          if (is_eq) {
+            if (lane < NP) dA = Deq[ip * NP + lane];
+            if (NP > 32 && lane + 32 < NP) dB = Deq[ip * NP + lane + 32];
+          } else
 #pragma unroll 1
           for (int c0 = k0; c0 < k1; c0 += 6) {
             const int dim = min(6, k1 - c0);
@@ -632,8 +731,20 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
             }
             zz = pzz; znp = pzn;
           }
-          // r = R^-1 d[0:iq] (:530-542), column-oriented back substitution
-          {
+          // r = R^-1 d[0:iq] (:530-542), column-oriented back substitution; lane i owns d[i], r[i]
+          if (iq <= 32) {
+            const double rinvA = lane < iq ? rinv[lane] : 0.0;
+            double acc = 0.0, rmine = 0.0;
+            const double* col = Rp + ((iq - 1) * (iq + 2)) / 2;
+#pragma unroll 1
+            for (int i = iq - 1; i >= 0; i--) {
+              const double ri = __shfl_sync(FULL, (dA - acc) * rinvA, i);
+              if (lane < i) acc = fma(col[lane], ri, acc);
+              if (lane == i) rmine = ri;
+              col -= i + 1;
+            }
+            if (lane < iq) rv[lane] = rmine;
+          } else {
             double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 1
             for (int i = iq - 1; i >= 0; i--) {
@@ -725,6 +836,18 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
                 const double2 v = lds2(vh + c);
                 Jb[c] = fma(-hwb, v.x, Jb[c]);
                 Jb[c + 1] = fma(-hwb, v.y, Jb[c + 1]);
+              }
+            }
+            if (is_eq) {  // D[i'] <- (I - beta v v^T) D[i'] for the equalities still to come
+#pragma unroll 1
+              for (int i2 = ieq + 1; i2 < p; i2++) {
+                double* Di = Deq + i2 * NP;
+                double e0 = 0.0, e1 = 0.0, w0 = 0.0, w1 = 0.0;
+                if (lane < NP) { e0 = Di[lane]; w0 = vm[lane]; }
+                if (NP > 32 && lane + 32 < NP) { e1 = Di[lane + 32]; w1 = vm[lane + 32]; }
+                const double g = beta * wsum(fma(e0, w0, e1 * w1));
+                if (lane < NP) Di[lane] = fma(-g, w0, e0);
+                if (NP > 32 && lane + 32 < NP) Di[lane + 32] = fma(-g, w1, e1);
               }
             }
             iq++;
@@ -820,8 +943,9 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
             double ci0;
             if (ip < nu) ci0 = -uf[ip];
             else {
-              const int a = (ip - nu) % nact;
-              ci0 = (ip - nu) >= nact ? P.trq_hi[a] - a0[p + a] : a0[p + a] - P.trq_lo[a];
+              const int a = (ip - nu) % nact, v = P.act_idx[a];
+              const double a0v = has_ic ? ws.ic_tq0[s * nact + a] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
+              ci0 = (ip - nu) >= nact ? P.trq_hi[a] - a0v : a0v - P.trq_lo[a];
             }
             s_ip = acc + ci0;
             if (lane == 0) sl[ip] = s_ip;
@@ -850,35 +974,7 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
     if (io.trq) {
 #pragma unroll 1
       for (int a = lane; a < nact; a += 32) {
-        double tau = 0.0;
-        if (!bad) {
-          if (trq) {
-            const double* row = Ar + (p + a) * lda;
-            double t0 = 0.0;
-#pragma unroll 1
-            for (int k = 0; k < N; k++) t0 += row[k] * x[k];
-            tau = t0 + a0[p + a];
-          } else if (has_ic) {
-            const double* row = ws.ic_tq + (s * nact + a) * N;
-            double t0 = 0.0;
-#pragma unroll 1
-            for (int k = 0; k < N; k++) t0 += row[k] * x[k];
-            tau = t0 + ws.ic_tq0[s * nact + a];
-          } else {
-            const int v = P.act_idx[a];
-            const double* Mr = ws.M + (s * NV + v) * NV;
-            double t0 = 0.0;
-#pragma unroll 1
-            for (int k = 0; k < NV; k++) t0 += Mr[k] * x[k];
-#pragma unroll 1
-            for (int ci = 0; ci < P.ncontact; ci++) {
-              const DevContact& Cc = P.contacts[ci];
-              for (int k = 0; k < Cc.dim; k++)
-                t0 -= contact_jac_row(Cc, fm.contact_f[ci], ws, s, nfr, NV, k)[v] * x[NV + Cc.rf_off + k];
-            }
-            tau = t0 + ws.cori[s * NV + v] + ws.grav[s * NV + v];
-          }
-        }
+        const double tau = bad ? nanv : torque_row(P, ws, fm, nfr, s, a, x);
         io.trq[s * nact + a] = bad ? nanv : tau;
       }
     }
@@ -902,13 +998,23 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
 }
 
 template <int NV, int NC>
-static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
-                       const SolveIO& io, int num_sms, cudaStream_t stream) {
+static bool shape_ok(const DevProblem& hp) {
   if (hp.nv != NV || hp.nc != NC) return false;
   using C = RCfg<NV, NC>;
   if (hp.m > 128 || hp.nact > 64) return false;
-  for (int i = 0; i < hp.ncontact; i++)
-    if (hp.contacts[i].dim > 6) return false;
+  const RegLayout L = reg_layout<C>(hp);
+  const int m_ = hp.m > 0 ? hp.m : 1, n_ = C::N;
+  // the equality block D needs p rows of NP doubles in the dm..sl span and behind the first R columns
+  if (hp.p * C::NP > L.osl + ((m_ + 1) & ~1) - L.odm) return false;
+  if (64 + hp.p * C::NP > n_ * (n_ + 3) / 2 || hp.p * (hp.p + 3) / 2 > 64) return false;
+  return true;
+}
+
+template <int NV, int NC>
+static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
+                       const SolveIO& io, int num_sms, cudaStream_t stream) {
+  if (!shape_ok<NV, NC>(hp)) return false;
+  using C = RCfg<NV, NC>;
   const RegLayout L = reg_layout<C>(hp);
   const size_t smem = (size_t)L.per_state * sizeof(double);
   static size_t configured = 0;
@@ -920,6 +1026,8 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC>, 32, smem);
   if (per_sm < 1) return false;
+  static const int cap = [] { const char* e = getenv("PNC_REG_WARPS"); return e ? atoi(e) : 0; }();
+  if (cap > 0 && per_sm > cap) per_sm = cap;
   int grid = num_sms * per_sm;
   if (grid > B) grid = B;
   k_ihwbc_reg<NV, NC><<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, B, io);
@@ -936,6 +1044,13 @@ bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const Ws
          try_launch<33, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3
          try_launch<20, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3 lower body
          try_launch<32, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream);    // Valkyrie
+}
+
+bool reg_kernel_available(const DevProblem& hp) {
+  static const bool force_smem = [] { const char* e = getenv("PNC_SOLVER"); return e && e[0] == 's'; }();
+  if (force_smem) return false;
+  return shape_ok<36, 12>(hp) || shape_ok<18, 12>(hp) || shape_ok<33, 12>(hp) || shape_ok<20, 12>(hp) ||
+         shape_ok<32, 12>(hp);
 }
 
 }  // namespace pnc

@@ -33,9 +33,10 @@ struct WsPtrs {
   // internal-constraint projection products (only when the problem has n_ic > 0)
   double *ic_cg;    // [B, nv]        Ni^T (c+g)
   double *ic_jcni;  // [B, nc, nv]    Jc Ni
-  double *ic_tq;    // [B, nact, n]   S [M | -(Jc Ni)^T]
+  double *ic_tq;    // [B, n, nact]   (S [M | -(Jc Ni)^T])^T, transposed for coalesced per-row reads
   double *ic_tq0;   // [B, nact]      S Ni^T (c+g)
   int* ic_status;   // [B]
+  double* task_e;   // [B, ntaskrows]  Jdot qdot - xddot_cmd of every task row (k_task_prepare)
 };
 
 // ---- WBC problem constants ----------------------------------------------------------

@@ -54,7 +54,7 @@ struct SolveIO {
 };
 
 // workspace pointers advanced by `off` states
-inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, int nc, int nact, int n) {
+inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, int nc, int nact, int n, int ntaskrows = 0) {
   WsPtrs w = a;
   w.q += off * nq; w.qdot += off * nv; w.M += off * nv * nv; w.grav += off * nv; w.cori += off * nv;
   w.com += off * 3; w.vcom += off * 3; w.jcom += off * 3 * nv; w.jcomdot += off * 3 * nv; w.jcomdot_qdot += off * 3;
@@ -63,6 +63,7 @@ inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, in
     w.ic_cg += off * nv; w.ic_jcni += off * nc * nv; w.ic_tq += off * nact * n; w.ic_tq0 += off * nact;
     w.ic_status += off;
   }
+  if (w.task_e) w.task_e += off * ntaskrows;
   return w;
 }
 
@@ -74,6 +75,9 @@ void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcL
                         const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream);
 bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
                             int B, const SolveIO& io, int num_sms, cudaStream_t stream);
+void launch_task_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
+                         const double* des, cudaStream_t stream);
+bool reg_kernel_available(const DevProblem& hp);
 void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
                        int B, int num_sms, cudaStream_t stream, int* counter);
 void launch_task_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int itask, int dim,

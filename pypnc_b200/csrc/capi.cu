@@ -60,6 +60,8 @@ struct pnc_workspace {
   // task error terms written by k_task_prepare (allocated lazily, sized by the largest problem seen)
   double* task_slab;
   int task_rows;
+  double* setup_slab;
+  int setup_stride;
   // staging buffers of pnc_wbc_tick_host
   char* stage;
   size_t stage_bytes;
@@ -234,6 +236,7 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
   ws->m = m; ws->cap = capacity; ws->nfr = nframes;
   ws->ic_slab = nullptr; ws->ic_bytes = 0; ws->ic_nc = ws->ic_nact = 0;
   ws->task_slab = nullptr; ws->task_rows = 0;
+  ws->setup_slab = nullptr; ws->setup_stride = 0;
   ws->stage = nullptr; ws->stage_bytes = 0; ws->tick_init = false;
   memset(&ws->hfr, 0, sizeof(ws->hfr));
   ws->hfr.nfr = nframes;
@@ -272,6 +275,7 @@ void pnc_workspace_destroy(pnc_workspace* ws) {
   cudaFree(ws->dfr);
   if (ws->ic_slab) cudaFree(ws->ic_slab);
   if (ws->task_slab) cudaFree(ws->task_slab);
+  if (ws->setup_slab) cudaFree(ws->setup_slab);
   if (ws->stage) cudaFree(ws->stage);
   if (ws->tick_init) {
     for (int i = 0; i < 2; i++) { cudaStreamDestroy(ws->tick_stream[i]); cudaEventDestroy(ws->tick_ev[i]); }
@@ -280,7 +284,7 @@ void pnc_workspace_destroy(pnc_workspace* ws) {
 }
 
 int64_t pnc_workspace_bytes(const pnc_workspace* ws) {
-  return ws ? (int64_t)(ws->bytes + ws->ic_bytes + ws->stage_bytes + (size_t)ws->cap * ws->task_rows * 8) : 0;
+  return ws ? (int64_t)(ws->bytes + ws->ic_bytes + ws->stage_bytes + (size_t)ws->cap * ((size_t)ws->task_rows + ws->setup_stride) * 8) : 0;
 }
 
 static int update_system_at(pnc_workspace* ws, int off, int32_t B, const double* bp, const double* bq,
@@ -349,6 +353,15 @@ static int ensure_task_buf(pnc_workspace* ws, const pnc_problem* p) {
   return PNC_OK;
 }
 
+static int ensure_setup_buf(pnc_workspace* ws, const pnc_problem* p) {
+  const int rec = reg_setup_record_doubles(p->h);
+  if (ws->setup_slab && ws->setup_stride == rec) return PNC_OK;
+  if (ws->setup_slab) { cudaFree(ws->setup_slab); ws->setup_slab = nullptr; }
+  CK(cudaMalloc(&ws->setup_slab, (size_t)ws->cap * rec * sizeof(double)));
+  ws->setup_stride = rec;
+  return PNC_OK;
+}
+
 static int ensure_ic(pnc_workspace* ws, const pnc_problem* p) {
   if (p->h.n_ic == 0) return PNC_OK;
   if (ws->ic_slab && ws->ic_nc == p->h.nc && ws->ic_nact == p->h.nact) return PNC_OK;
@@ -386,7 +399,13 @@ static int solve_at(const pnc_problem* p, pnc_workspace* ws, int off, int32_t B,
   } else {
     ws->p.task_e = nullptr;  // the generic kernel evaluates the tasks itself
   }
+  if (use_reg) {
+    rc = ensure_setup_buf(ws, p);
+    if (rc) return rc;
+  }
   ws->p.task_e = use_reg ? ws->task_slab : nullptr;
+  ws->p.setup_rec = use_reg ? ws->setup_slab : nullptr;
+  ws->p.setup_stride = use_reg ? ws->setup_stride : 0;
   WsPtrs wsp = ws_offset(ws->p, off, ws->m->h.nq, p->h.nv, ws->nfr, p->h.nc, p->h.nact, p->h.n, p->h.ntaskrows);
   if (use_reg) {
     launch_task_prepare(p->d, p->h, wsp, fm, ws->nfr, B, des, st);

@@ -53,13 +53,9 @@ __host__ __device__ inline RegLayout reg_layout(const DevProblem& P) {
   RegLayout L;
   const int n = C::N, m = P.m > 0 ? P.m : 1;
   int o = 0;
-  const int rsz = (n * (n + 3) / 2 + 1) & ~1, tsz = 6 * C::LDT, gsz = C::NV * C::LDV;
-  int reg = rsz + tsz;
-  if (gsz > reg) reg = gsz;
-  L.oRT = o; L.oT = o + rsz; o += (reg + 1) & ~1;
+  const int rsz = (n * (n + 3) / 2 + 1) & ~1, tsz = 6 * C::LDT;
+  L.oRT = o; L.oT = o + rsz; o += rsz + tsz;
   L.orinv = o; o += C::NP;
-  // everything from here to osl is dead while the Hessian is assembled: the staged task
-  // Jacobian rows (ndense x LDV) borrow the space
   L.oBig = o;
   L.oUf = o; o += (P.nu > 0 ? P.nu : 1) * 6;
   L.ouf = o; o += ((P.nu > 0 ? P.nu : 1) + 1) & ~1;
@@ -75,11 +71,7 @@ __host__ __device__ inline RegLayout reg_layout(const DevProblem& P) {
   L.ouold = o; o += C::NP + 2;
   L.oxacc = o; o += C::NP;
   L.osl = o; o += (m + 1) & ~1;
-  const int jds = (P.ndense * C::LDV + 1) & ~1;
-  if (o - L.oBig < jds) o = L.oBig + jds;
-  const int tr = ((P.ntaskrows > 0 ? P.ntaskrows : 1) + 1) & ~1;
-  L.oev = o; o += tr;
-  L.owt = o; o += tr;
+  L.oev = L.owt = o;
   L.oint = o; o += (3 * (n + 2) + 1) / 2 + 1;
   L.per_state = (o + 1) & ~1;
   return L;
@@ -125,108 +117,126 @@ __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_c
 // Called with lanes = rows: M is symmetric, so lane a reads column act_idx[a] of M -- consecutive
 // lanes touch consecutive addresses -- and the constraint rows never have to be copied anywhere.
 // One out-of-line copy serves the slack pass and the output pass.
-__device__ __noinline__ double torque_row(const DevProblem& P, const WsPtrs& ws, const FrameMap& fm, int nfr, size_t s,
+__device__ __noinline__ double torque_row(const DevProblem& P, const DevProblem& G, const WsPtrs& ws, const FrameMap& fm, int nfr, size_t s,
                                           int a, const double* __restrict__ x) {
   const int nv = P.nv, nact = P.nact;
-  double t0 = 0.0, t1 = 0.0;
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
   if (P.n_ic > 0) {
     const int n = P.n;
     const double* col = ws.ic_tq + s * n * nact + a;
-    const double* xe = x + (n & ~1);
-#pragma unroll 4
-    for (const double* xp = x; xp < xe; xp += 2, col += 2 * nact) {
-      const double2 xx = *reinterpret_cast<const double2*>(xp);
-      t0 = fma(col[0], xx.x, t0);
-      t1 = fma(col[nact], xx.y, t1);
+    int k = 0;
+#pragma unroll 2
+    for (; k + 3 < n; k += 4, col += 4 * nact) {
+      const double g0 = col[0], g1 = col[nact], g2 = col[2 * nact], g3 = col[3 * nact];
+      const double2 xa = *reinterpret_cast<const double2*>(x + k), xb = *reinterpret_cast<const double2*>(x + k + 2);
+      t0 = fma(g0, xa.x, t0); t1 = fma(g1, xa.y, t1); t2 = fma(g2, xb.x, t2); t3 = fma(g3, xb.y, t3);
     }
-    if (n & 1) t0 = fma(col[0], xe[0], t0);
-    return t0 + t1 + ws.ic_tq0[s * nact + a];
+    for (; k < n; k++, col += nact) t0 = fma(col[0], x[k], t0);
+    return (t0 + t1) + (t2 + t3) + ws.ic_tq0[s * nact + a];
   }
-  const int v = P.act_idx[a];
+  const int v = G.act_idx[a];
   const double* col = ws.M + s * nv * nv + v;  // column v of M == row v
-  const double* xe = x + (nv & ~1);
-#pragma unroll 6
-  for (const double* xp = x; xp < xe; xp += 2, col += 2 * nv) {
-    const double2 xx = *reinterpret_cast<const double2*>(xp);
-    t0 = fma(col[0], xx.x, t0);
-    t1 = fma(col[nv], xx.y, t1);
-  }
-  if (nv & 1) t0 = fma(col[0], xe[0], t0);
-  for (int ci = 0; ci < P.ncontact; ci++) {
-    const DevContact& Cc = P.contacts[ci];
-    const double* xr = x + nv + Cc.rf_off;
-    const double* jr = contact_jac_row(Cc, fm.contact_f[ci], ws, s, nfr, nv, 0) + v;
+  const double cg = ws.cori[s * nv + v] + ws.grav[s * nv + v];
+  int k = 0;
 #pragma unroll 3
-    for (int r = 0; r < Cc.dim; r++, jr += nv) t1 = fma(-jr[0], xr[r], t1);
+  for (; k + 3 < nv; k += 4, col += 4 * nv) {
+    const double g0 = col[0], g1 = col[nv], g2 = col[2 * nv], g3 = col[3 * nv];
+    const double2 xa = *reinterpret_cast<const double2*>(x + k), xb = *reinterpret_cast<const double2*>(x + k + 2);
+    t0 = fma(g0, xa.x, t0); t1 = fma(g1, xa.y, t1); t2 = fma(g2, xb.x, t2); t3 = fma(g3, xb.y, t3);
   }
-  return t0 + t1 + ws.cori[s * nv + v] + ws.grav[s * nv + v];
+  for (; k < nv; k++, col += nv) t0 = fma(col[0], x[k], t0);
+  const double* xr = x + nv;
+#pragma unroll 1
+  for (int ci = 0; ci < P.ncontact; ci++) {
+    const int dim = P.contacts[ci].dim;
+    const double* jr = ws.fr_jac + ((s * nfr + fm.contact_f[ci]) * 6 + (6 - dim)) * nv + v;  // point contacts: rows 3..5
+    if (dim == 6) {
+      const double j0 = jr[0], j1 = jr[nv], j2 = jr[2 * nv], j3 = jr[3 * nv], j4 = jr[4 * nv], j5 = jr[5 * nv];
+      t0 = fma(-j0, xr[0], t0); t1 = fma(-j1, xr[1], t1); t2 = fma(-j2, xr[2], t2);
+      t3 = fma(-j3, xr[3], t3); t0 = fma(-j4, xr[4], t0); t1 = fma(-j5, xr[5], t1);
+    } else {
+      const double j0 = jr[0], j1 = jr[nv], j2 = jr[2 * nv];
+      t0 = fma(-j0, xr[0], t0); t1 = fma(-j1, xr[1], t1); t2 = fma(-j2, xr[2], t2);
+    }
+    xr += dim;
+  }
+  return (t0 + t1) + (t2 + t3) + cg;
 }
 
 // =======================================================================================
+// Per-state setup, one state per warp, shared-memory resident and small enough to run at high
+// occupancy: Hessian task block, its Cholesky factor, J = L^-T, the unconstrained minimiser and
+// the equality normals in the J basis.  Results go to a per-state record in HBM that the
+// active-set kernel loads (one coalesced-by-sector read of ~14 KB per Atlas state).
+struct SetupLayout {
+  int oG, oJd, oev, owt, og0, odm, ozv, odl, oD, per_state;  // shared memory (doubles)
+  int rG, rX, rD, rS, rec;                                   // HBM record (doubles)
+};
+
+template <class C>
+__host__ __device__ inline SetupLayout setup_layout(const DevProblem& P) {
+  SetupLayout L;
+  int o = 0;
+  L.oG = o; o += (C::NV * C::LDV + 1) & ~1;
+  L.oJd = o; o += ((P.ndense > 0 ? P.ndense : 1) * C::LDV + 1) & ~1;
+  const int tr = ((P.ntaskrows > 0 ? P.ntaskrows : 1) + 1) & ~1;
+  L.oev = o; o += tr;
+  L.owt = o; o += tr;
+  L.og0 = o; o += C::NP;
+  L.odm = o; o += C::NP;
+  L.ozv = o; o += C::NP;
+  L.odl = o; o += C::NP;
+  L.oD = o; o += P.p * C::NP;
+  L.per_state = (o + 1) & ~1;
+  int r = 0;
+  L.rG = r; r += (C::NV * C::LDV + 1) & ~1;
+  L.rX = r; r += C::NP;
+  L.rD = r; r += P.p * C::NP;
+  L.rS = r; r += 4;
+  L.rec = (r + 1) & ~1;
+  return L;
+}
+
 template <int NV, int NC>
-#ifndef PNC_REG_MINB
-#define PNC_REG_MINB 8
-#endif
-__global__ void __launch_bounds__(32, PNC_REG_MINB)
-k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap fm, int nfr, int B, SolveIO io) {
+__global__ void __launch_bounds__(32)
+k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, SetupLayout SL, WsPtrs ws, FrameMap fm,
+              int nfr, int B, SolveIO io, double* __restrict__ rec_all, int* __restrict__ counter) {
   using C = RCfg<NV, NC>;
-  constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV;
-  constexpr bool EXT = C::EXT;
+  constexpr int N = C::N, NP = C::NP, LDV = C::LDV;
   extern __shared__ __align__(16) double smem[];
-  const DevProblem& P = *gp;
+  const DevProblem& G = *gp;
   const int lane = threadIdx.x;
-  const int p = P.p, m = P.m, nu = P.nu, nact = P.nact;
-  const bool trq = P.b_trq_limit != 0, has_ic = P.n_ic > 0;
-  double* W = smem;
-  double* Jd = W + L.oBig;  // staged dense task Jacobian rows (dead before the vectors below are used)
-  double* Rp = W + L.oRT;
-  double* Gm = Rp;   // nv x nv Hessian / factor / L^-T block (dead before R is written)
-  double* Ts = W + L.oT;
-  double* rinv = W + L.orinv;
-  double* Uf = W + L.oUf;
-  double* uf = W + L.ouf;
-  double* x = W + L.ox;
-  double* zv = W + L.oz;
-  double* dv = W + L.odv;
-  double* dm = W + L.odm;
-  double* vm = W + L.ovm;
-  double* np = W + L.onp;
-  double* rv = W + L.orr;
-  double* uv = W + L.ou;
-  double* xold = W + L.oxold;
-  double* uold = W + L.ouold;
-  double* xacc = W + L.oxacc;
-  double* sl = W + L.osl;
-  double* ev = W + L.oev;
-  double* wt = W + L.owt;
-  int* Aact = reinterpret_cast<int*>(W + L.oint);
-  int* Aold = Aact + (N + 2);
-  int* Aacc = Aold + (N + 2);
-  auto Rcol = [&](int c) { return Rp + (c * (c + 3)) / 2; };
-  double* rot = Ts;  // the d scratch tile doubles as the Givens coefficient table of a drop
-  static_assert(6 * LDT >= 3 * NP, "rotation table must fit the scratch tile");
-
-  // rows beyond 32: lane pair (2e, 2e+1) owns row 32+e, half eh of the columns
-  const int eh = lane & 1, epair = lane >> 1;
-  const int erow = 32 + epair;
-  const bool evalid = EXT && epair < E;
-
-  double Ja[NP];
-  double Jb[NB];
-
+  const int p = P.p;
+  const bool has_ic = P.n_ic > 0;
+  double* Gm = smem + SL.oG;
+  double* Jd = smem + SL.oJd;
+  double* ev = smem + SL.oev;
+  double* wt = smem + SL.owt;
+  double* g0 = smem + SL.og0;
+  double* dm = smem + SL.odm;
+  double* zv = smem + SL.ozv;
+  double* vm = smem + SL.odl;
+  double* Dt = smem + SL.oD;
+  double* dv = g0;
+  double* xs = zv;  // x0
 #pragma unroll 1
   for (;;) {
     int si = 0;
-    if (lane == 0) si = atomicAdd(io.counter, 1);
+    if (lane == 0) si = atomicAdd(counter, 1);
     si = __shfl_sync(FULL, si, 0);
     if (si >= B) break;
     const size_t s = (size_t)si;
-    int status = PNC_QP_OK, iter = 0, iq = 0;
-    double R_norm = 1.0;
+    double* rec = rec_all + s * SL.rec;
+    int status = PNC_QP_OK;
     if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
-
+    const double* Mg = ws.M + s * NV * NV;
+    auto row_jc = [&](int c, int v) -> double {  // (Jc Ni)[c][v]
+      if (has_ic) return ws.ic_jcni[(s * NC + c) * NV + v];
+      int ci = 0;
+      while (ci + 1 < P.ncontact && c >= G.contacts[ci + 1].rf_off) ci++;
+      return contact_jac_row(G.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - G.contacts[ci].rf_off)[v];
+    };
     // ---- tasks: e = Jdot qdot - xddot_cmd, weights (ihwbc.py:159-172) ----
-    double* g0 = rinv;  // linear term while the Hessian is assembled (rinv is not live yet)
     // task error terms e = Jdot qdot - xddot_cmd were evaluated by k_task_prepare (ihwbc.cu)
     {
       const double* te = ws.task_e + s * P.ntaskrows;
@@ -239,17 +249,25 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         for (int i = lane; i < T.dim; i += 32) wt[T.row_off + i] = wt_t;
       }
     }
-    // stage the dense task Jacobian rows; clear the factor block and the linear term (dv = g0)
+    // stage the dense task Jacobian rows (flattened copy: several independent loads in flight per
+    // lane instead of one row at a time); clear the factor block
+    {
+      // row -> source pointer table lives at the start of the factor block (cleared after the copy)
+      const double** rptr = reinterpret_cast<const double**>(Gm);  // Gm is cleared after the copy
 #pragma unroll 1
-    for (int t = 0; t < P.ntask; t++) {
-      const DevTask& T = P.tasks[t];
-      if (T.dense_off < 0) continue;
-#pragma unroll 1
-      for (int i = 0; i < 3; i++) {
-        const double* src = dense_row_ptr(T, fm.task_f[t], ws, s, nfr, NV, i);
-        double* dst = Jd + (T.dense_off + i) * LDV;
-        for (int c = lane; c < NV; c += 32) dst[c] = src[c];
+      for (int t = lane; t < P.ntask; t += 32) {
+        const DevTask& T = P.tasks[t];
+        if (T.dense_off >= 0)
+          for (int i = 0; i < 3; i++) rptr[T.dense_off + i] = dense_row_ptr(T, fm.task_f[t], ws, s, nfr, NV, i);
       }
+      __syncwarp();
+      const int total = P.ndense * NV;
+#pragma unroll 4
+      for (int e = lane; e < total; e += 32) {
+        const int r = e / NV, c = e - r * NV;
+        Jd[r * LDV + c] = rptr[r][c];
+      }
+      __syncwarp();
     }
 #pragma unroll 1
     for (int k = lane; k < NV * LDV; k += 32) Gm[k] = 0.0;
@@ -314,7 +332,7 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         if (T.dense_off >= 0) continue;
 #pragma unroll 1
         for (int i = lane; i < T.dim; i += 32) {
-          const int vi = T.type == PNC_TASK_JOINT ? 6 + i : P.joint_sel[T.joint_off + i];
+          const int vi = T.type == PNC_TASK_JOINT ? 6 + i : G.joint_sel[T.joint_off + i];
           const double wk = wt[T.row_off + i];
           Gm[vi * LDV + vi] += wk;
           g0[vi] += wk * ev[T.row_off + i];
@@ -322,37 +340,6 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         __syncwarp();
       }
     }
-
-    // ---- the staged Jacobians are dead: clear the work vectors, move g0, build the wrench cones ----
-    // (the constraint rows [M | -(Jc Ni)^T] are never copied: M is symmetric, so "row a for every
-    //  lane a" is a coalesced column read of the workspace M, see torque_row)
-    const double* Mg = ws.M + s * NV * NV;
-    auto row_jc = [&](int c, int v) -> double {  // (Jc Ni)[c][v]
-      if (has_ic) return ws.ic_jcni[(s * NC + c) * NV + v];
-      int ci = 0;
-      while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
-      return contact_jac_row(P.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - P.contacts[ci].rf_off)[v];
-    };
-    {
-#pragma unroll 1
-      for (int k = lane; k < NP; k += 32) {
-        x[k] = 0.0; zv[k] = 0.0; dm[k] = 0.0; vm[k] = 0.0; np[k] = 0.0;
-        dv[k] = k < NV ? g0[k] : 0.0;
-      }
-#pragma unroll 1
-      for (int r = lane; r < nu; r += 32) {
-        const int ci = P.cone_contact[r];
-        const DevContact& Cc = P.contacts[ci];
-        const int lr = r - Cc.cone_off;
-        double u6[6];
-        cone_row_world(Cc, lr, ws.fr_iso + (s * nfr + fm.contact_f[ci]) * 12, u6);
-        for (int k = 0; k < 6; k++) Uf[r * 6 + k] = u6[k];
-        double rz = io.rfz[s * P.ncontact + ci];
-        if (rz <= 0.0) rz = 1e-3;  // contact.py:37-41
-        uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
-      }
-    }
-    __syncwarp();
 
     // ---- Cholesky of the task block (QuadProg++.cc:705-730), left-looking, lanes = rows ----
     // rows 32.. (Atlas has 4) are each shared by LPR lanes that split the dot product
@@ -452,13 +439,12 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         double acc = 0.0;
 #pragma unroll 1
         for (int j = k; j < NV; j++) acc += Gm[k * LDV + j] * dm[j];
-        x[k] = -acc;
+        xs[k] = -acc;
       }
       // ---- equality normals in the J basis, all at once while J = L^-T is still triangular in
       //      shared memory: D[i] = J^T ce_i.  The active-set loop then never needs the dense
       //      d = J^T n+ product for an equality: it reads D[i] and keeps the later rows current
       //      with the Householder reflection of each added equality ----
-      double* Dt = dm;  // p rows of pitch NP over dm..sl (all dead here)
       {
         // floating-base rows i < 6: D[i][j] = sum_{k<=j} J[k][j] M[k][i] (M symmetric: the six
         // coefficients of step k are contiguous), one column j per lane, six accumulators
@@ -497,13 +483,123 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         }
       }
       __syncwarp();
+      __syncwarp();
+      // ---- record: factor block (J in its upper triangle), x0, D, scalars ----
+#pragma unroll 4
+      for (int k = lane; k < NV * LDV; k += 32) rec[SL.rG + k] = Gm[k];
+#pragma unroll 1
+      for (int k = lane; k < NP; k += 32) rec[SL.rX + k] = k < NV ? xs[k] : 0.0;
+#pragma unroll 1
+      for (int k = lane; k < p * NP; k += 32) rec[SL.rD + k] = Dt[k];
+      if (lane == 0) { rec[SL.rS] = c1; rec[SL.rS + 1] = c2; rec[SL.rS + 3] = jrf; }
+    }
+    if (lane == 0) rec[SL.rS + 2] = (double)status;
+    __syncwarp();
+  }
+}
+
+// =======================================================================================
+template <int NV, int NC>
+#ifndef PNC_REG_MINB
+#define PNC_REG_MINB 8
+#endif
+__global__ void __launch_bounds__(32, PNC_REG_MINB)
+k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, RegLayout L, SetupLayout SL, WsPtrs ws,
+            FrameMap fm, int nfr, int B, SolveIO io, const double* __restrict__ rec_all) {
+  // P (constant bank) serves warp-uniform reads; tables indexed per lane go through the global copy G
+  const DevProblem& G = *gp;
+  using C = RCfg<NV, NC>;
+  constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV;
+  constexpr bool EXT = C::EXT;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x;
+  const int p = P.p, m = P.m, nu = P.nu, nact = P.nact;
+  const bool trq = P.b_trq_limit != 0, has_ic = P.n_ic > 0;
+  double* W = smem;
+  double* Rp = W + L.oRT;
+  double* Ts = W + L.oT;
+  double* rinv = W + L.orinv;
+  double* Uf = W + L.oUf;
+  double* uf = W + L.ouf;
+  double* x = W + L.ox;
+  double* zv = W + L.oz;
+  double* dv = W + L.odv;
+  double* dm = W + L.odm;
+  double* vm = W + L.ovm;
+  double* np = W + L.onp;
+  double* rv = W + L.orr;
+  double* uv = W + L.ou;
+  double* xold = W + L.oxold;
+  double* uold = W + L.ouold;
+  double* xacc = W + L.oxacc;
+  double* sl = W + L.osl;
+  int* Aact = reinterpret_cast<int*>(W + L.oint);
+  int* Aold = Aact + (N + 2);
+  int* Aacc = Aold + (N + 2);
+  auto Rcol = [&](int c) { return Rp + (c * (c + 3)) / 2; };
+  double* rot = Ts;  // the d scratch tile doubles as the Givens coefficient table of a drop
+  static_assert(6 * LDT >= 3 * NP, "rotation table must fit the scratch tile");
+
+  // rows beyond 32: lane pair (2e, 2e+1) owns row 32+e, half eh of the columns
+  const int eh = lane & 1, epair = lane >> 1;
+  const int erow = 32 + epair;
+  const bool evalid = EXT && epair < E;
+
+  double Ja[NP];
+  double Jb[NB];
+
+#pragma unroll 1
+  for (;;) {
+    int si = 0;
+    if (lane == 0) si = atomicAdd(io.counter, 1);
+    si = __shfl_sync(FULL, si, 0);
+    if (si >= B) break;
+    const size_t s = (size_t)si;
+    int status = PNC_QP_OK, iter = 0, iq = 0;
+    double R_norm = 1.0;
+    if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
+
+    // ---- clear the work vectors, build the wrench cones ----
+    // (the constraint rows [M | -(Jc Ni)^T] are never copied: M is symmetric, so "row a for every
+    //  lane a" is a coalesced column read of the workspace M, see torque_row)
+    const double* Mg = ws.M + s * NV * NV;
+    auto row_jc = [&](int c, int v) -> double {  // (Jc Ni)[c][v]
+      if (has_ic) return ws.ic_jcni[(s * NC + c) * NV + v];
+      int ci = 0;
+      while (ci + 1 < P.ncontact && c >= G.contacts[ci + 1].rf_off) ci++;
+      return contact_jac_row(G.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - G.contacts[ci].rf_off)[v];
+    };
+    const double* rec = rec_all + s * SL.rec;  // written by k_ihwbc_setup
+    {
+#pragma unroll 1
+      for (int k = lane; k < NP; k += 32) {
+        x[k] = rec[SL.rX + k];
+        zv[k] = 0.0; dm[k] = 0.0; vm[k] = 0.0; np[k] = 0.0; dv[k] = 0.0;
+      }
+#pragma unroll 1
+      for (int r = lane; r < nu; r += 32) {
+        const int ci = G.cone_contact[r];
+        const DevContact& Cc = G.contacts[ci];
+        const int lr = r - Cc.cone_off;
+        double u6[6];
+        cone_row_world(Cc, lr, ws.fr_iso + (s * nfr + fm.contact_f[ci]) * 12, u6);
+        for (int k = 0; k < 6; k++) Uf[r * 6 + k] = u6[k];
+        double rz = io.rfz[s * P.ncontact + ci];
+        if (rz <= 0.0) rz = 1e-3;  // contact.py:37-41
+        uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
+      }
+    }
+    const double c1 = rec[SL.rS], c2 = rec[SL.rS + 1], jrf = rec[SL.rS + 3];
+    status = (int)rec[SL.rS + 2];
+    if (status == PNC_QP_OK) {
       // ---- move J into registers: row lane, and half rows 32.. in lane pairs ----
+      const double* Gg = rec + SL.rG;
 #pragma unroll
       for (int k = 0; k < NP; k += 2) {
         double v0 = 0.0, v1 = 0.0;
         if (k < NV) {
           if (lane < NV) {
-            const double2 g = lds2(Gm + lane * LDV + k);
+            const double2 g = *reinterpret_cast<const double2*>(Gg + lane * LDV + k);
             if (k >= lane) v0 = g.x;
             if (k + 1 >= lane && k + 1 < NV) v1 = g.y;
           }
@@ -521,21 +617,17 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
         if constexpr (EXT) {
           const int col = eh * HW + c;
           if (evalid && col < N) {
-            if (erow < NV) { if (col < NV && col >= erow) v = Gm[erow * LDV + col]; }
+            if (erow < NV) { if (col < NV && col >= erow) v = Gg[erow * LDV + col]; }
             else if (col == erow) v = jrf;
           }
         }
         Jb[c] = v;
       }
-      __syncwarp();  // Gm is dead from here: R, the scratch tile and the equality block reuse the region
       double* Deq = Rp + 64;  // R only uses its first p columns (< 64 doubles) while Deq is live
-#pragma unroll 1
-      for (int k = lane; k < p * NP; k += 32) Deq[k] = Dt[k];
-      __syncwarp();
+#pragma unroll 2
+      for (int k = lane; k < p * NP; k += 32) Deq[k] = rec[SL.rD + k];
 #pragma unroll 1
       for (int k = lane; k < N + 2; k += 32) { uv[k] = 0.0; Aact[k] = 0; }
-#pragma unroll 1
-      for (int k = lane; k < NP; k += 32) { dm[k] = 0.0; dv[k] = 0.0; }
       __syncwarp();
 
       // ================= dual active-set iterations, equalities first (:232-500) =================
@@ -573,8 +665,8 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
             if (trq) {
 #pragma unroll 1
               for (int a = lane; a < nact; a += 32) {
-                const double tau = torque_row(P, ws, fm, nfr, s, a, x);
-                const double slo = tau - P.trq_lo[a], shi = P.trq_hi[a] - tau;
+                const double tau = torque_row(P, G, ws, fm, nfr, s, a, x);
+                const double slo = tau - G.trq_lo[a], shi = G.trq_hi[a] - tau;
                 sl[nu + a] = slo;
                 sl[nu + nact + a] = shi;
                 psi += fmin(0.0, slo) + fmin(0.0, shi);
@@ -582,7 +674,7 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
             }
 #pragma unroll 1
             for (int r = lane; r < nu; r += 32) {
-              const DevContact& Cc = P.contacts[P.cone_contact[r]];
+              const DevContact& Cc = G.contacts[G.cone_contact[r]];
               const double* xr = x + NV + Cc.rf_off;
               const double* ur = Uf + r * 6;
               double acc = -uf[r];
@@ -632,7 +724,7 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
             for (int k = lane; k < NP; k += 32) {
               double val = 0.0;
               if (k < N) {
-                if (icrow) val = k < NV ? P.ic_jac[ip - 6][k] : 0.0;
+                if (icrow) val = k < NV ? G.ic_jac[ip - 6][k] : 0.0;
                 else if (tq && has_ic) val = ws.ic_tq[(s * N + k) * nact + a];
                 else if (k < NV) val = Mg[v * NV + k];
                 else val = -row_jc(k - NV, v);
@@ -970,11 +1062,11 @@ k_ihwbc_reg(const DevProblem* __restrict__ gp, RegLayout L, WsPtrs ws, FrameMap 
     if (io.rf)
       for (int k = lane; k < NC; k += 32) io.rf[s * NC + k] = bad ? nanv : x[NV + k];
     if (io.acc)
-      for (int a = lane; a < nact; a += 32) io.acc[s * nact + a] = bad ? nanv : x[P.act_idx[a]];
+      for (int a = lane; a < nact; a += 32) io.acc[s * nact + a] = bad ? nanv : x[G.act_idx[a]];
     if (io.trq) {
 #pragma unroll 1
       for (int a = lane; a < nact; a += 32) {
-        const double tau = bad ? nanv : torque_row(P, ws, fm, nfr, s, a, x);
+        const double tau = bad ? nanv : torque_row(P, G, ws, fm, nfr, s, a, x);
         io.trq[s * nact + a] = bad ? nanv : tau;
       }
     }
@@ -1004,8 +1096,8 @@ static bool shape_ok(const DevProblem& hp) {
   if (hp.m > 128 || hp.nact > 64) return false;
   const RegLayout L = reg_layout<C>(hp);
   const int m_ = hp.m > 0 ? hp.m : 1, n_ = C::N;
-  // the equality block D needs p rows of NP doubles in the dm..sl span and behind the first R columns
-  if (hp.p * C::NP > L.osl + ((m_ + 1) & ~1) - L.odm) return false;
+  (void)m_; (void)L;
+  // the equality block D sits behind the first R columns while the equalities are added
   if (64 + hp.p * C::NP > n_ * (n_ + 3) / 2 || hp.p * (hp.p + 3) / 2 > 64) return false;
   return true;
 }
@@ -1023,14 +1115,28 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
       return false;
     configured = smem;
   }
-  int per_sm = 0;
+  const SetupLayout SL = setup_layout<C>(hp);
+  if (!ws.setup_rec || ws.setup_stride != SL.rec) return false;
+  const size_t smem_s = (size_t)SL.per_state * sizeof(double);
+  static size_t configured_s = 0;
+  if (smem_s > configured_s) {
+    if (cudaFuncSetAttribute(k_ihwbc_setup<NV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess)
+      return false;
+    configured_s = smem_s;
+  }
+  int per_sm_s = 0, per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC>, 32, smem_s);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC>, 32, smem);
-  if (per_sm < 1) return false;
+  if (per_sm < 1 || per_sm_s < 1) return false;
   static const int cap = [] { const char* e = getenv("PNC_REG_WARPS"); return e ? atoi(e) : 0; }();
   if (cap > 0 && per_sm > cap) per_sm = cap;
-  int grid = num_sms * per_sm;
+  int grid_s = num_sms * per_sm_s, grid = num_sms * per_sm;
+  if (grid_s > B) grid_s = B;
   if (grid > B) grid = B;
-  k_ihwbc_reg<NV, NC><<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, B, io);
+  cudaMemsetAsync(io.counter + 2, 0, sizeof(int), stream);
+  k_ihwbc_setup<NV, NC><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
+  g_launch_count++;
+  k_ihwbc_reg<NV, NC><<<grid, 32, smem, stream>>>(hp, dp, L, SL, ws, fm, nfr, B, io, ws.setup_rec);
   g_launch_count++;
   return true;
 }
@@ -1044,6 +1150,20 @@ bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const Ws
          try_launch<33, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3
          try_launch<20, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3 lower body
          try_launch<32, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream);    // Valkyrie
+}
+
+template <int NV, int NC>
+static int rec_doubles(const DevProblem& hp) { return shape_ok<NV, NC>(hp) ? setup_layout<RCfg<NV, NC>>(hp).rec : 0; }
+
+// doubles per state of the setup record (0 when no register kernel matches the problem)
+int reg_setup_record_doubles(const DevProblem& hp) {
+  int r = 0;
+  if (!r) r = rec_doubles<36, 12>(hp);
+  if (!r) r = rec_doubles<18, 12>(hp);
+  if (!r) r = rec_doubles<33, 12>(hp);
+  if (!r) r = rec_doubles<20, 12>(hp);
+  if (!r) r = rec_doubles<32, 12>(hp);
+  return r;
 }
 
 bool reg_kernel_available(const DevProblem& hp) {

@@ -37,6 +37,8 @@ struct WsPtrs {
   double *ic_tq0;   // [B, nact]      S Ni^T (c+g)
   int* ic_status;   // [B]
   double* task_e;   // [B, ntaskrows]  Jdot qdot - xddot_cmd of every task row (k_task_prepare)
+  double* setup_rec;  // [B, setup_stride]  per-state record of k_ihwbc_setup (factor block, x0, D, scalars)
+  int setup_stride;
 };
 
 // ---- WBC problem constants ----------------------------------------------------------

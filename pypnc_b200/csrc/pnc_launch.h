@@ -64,6 +64,7 @@ inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, in
     w.ic_status += off;
   }
   if (w.task_e) w.task_e += off * ntaskrows;
+  if (w.setup_rec) w.setup_rec += off * (size_t)w.setup_stride;
   return w;
 }
 
@@ -78,6 +79,7 @@ bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const Ws
 void launch_task_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
                          const double* des, cudaStream_t stream);
 bool reg_kernel_available(const DevProblem& hp);
+int reg_setup_record_doubles(const DevProblem& hp);
 void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
                        int B, int num_sms, cudaStream_t stream, int* counter);
 void launch_task_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int itask, int dim,

@@ -42,6 +42,7 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=0, help='states in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--same-state', action='store_true', help='diagnostic: every state of the batch is state 0')
     return ap.parse_args()
 
 
@@ -194,11 +195,15 @@ def main():
 
     # ---- synthetic inputs, seed + rank per shard ----
     st = robots.synth_states(robot, spec, B, seed=1 + rank)
+    if args.same_state:
+        st = {k: np.ascontiguousarray(np.repeat(v[:1], B, axis=0)) for k, v in st.items()}
     keys = ('base_pos', 'base_quat', 'base_lin_vel', 'base_ang_vel', 'joint_pos', 'joint_vel')
     d_st = [torch.from_numpy(np.ascontiguousarray(st[k])).to(dev) for k in keys]
     ws.update_system(*d_st)
     torch.cuda.synchronize()
     des, w, rfz = robots.synth_desireds(robot, spec, st, engine.task_actuals_from_workspace(spec, ws), seed=1 + rank)
+    if args.same_state:
+        des, w, rfz = [np.ascontiguousarray(np.repeat(a[:1], B, axis=0)) for a in (des, w, rfz)]
     d_des, d_w, d_rfz = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (des, w, rfz)]
 
     nact, nc, nv, mw = spec.nact, pb.nc, spec.model.nv, pb.mw

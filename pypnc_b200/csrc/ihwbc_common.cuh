@@ -10,7 +10,7 @@ namespace pnc {
 #define FULL 0xffffffffu
 #define QP_EPS 2.220446049250313e-16
 
-__device__ __forceinline__ double wsum(double v) {
+static __device__ __noinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
@@ -21,7 +21,7 @@ __device__ __forceinline__ double wmax(double v) {
   return v;
 }
 // lexicographic (value, index) minimum over the warp; every lane gets the result
-__device__ __forceinline__ void wargmin(double& v, int& idx) {
+static __device__ __noinline__ void wargmin(double& v, int& idx) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double ov = __shfl_xor_sync(FULL, v, o);

@@ -117,9 +117,10 @@ __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_c
 // Called with lanes = rows: M is symmetric, so lane a reads column act_idx[a] of M -- consecutive
 // lanes touch consecutive addresses -- and the constraint rows never have to be copied anywhere.
 // One out-of-line copy serves the slack pass and the output pass.
-__device__ __noinline__ double torque_row(const DevProblem& P, const DevProblem& G, const WsPtrs& ws, const FrameMap& fm, int nfr, size_t s,
-                                          int a, const double* __restrict__ x) {
-  const int nv = P.nv, nact = P.nact;
+template <int NV>
+__device__ __noinline__ double torque_row(const DevProblem& P, const DevProblem& G, const WsPtrs& ws, const FrameMap& fm,
+                                          int nfr, size_t s, int a, const double* __restrict__ x) {
+  const int nact = P.nact;
   double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
   if (P.n_ic > 0) {
     const int n = P.n;
@@ -135,27 +136,27 @@ __device__ __noinline__ double torque_row(const DevProblem& P, const DevProblem&
     return (t0 + t1) + (t2 + t3) + ws.ic_tq0[s * nact + a];
   }
   const int v = G.act_idx[a];
-  const double* col = ws.M + s * nv * nv + v;  // column v of M == row v
-  const double cg = ws.cori[s * nv + v] + ws.grav[s * nv + v];
-  int k = 0;
-#pragma unroll 3
-  for (; k + 3 < nv; k += 4, col += 4 * nv) {
-    const double g0 = col[0], g1 = col[nv], g2 = col[2 * nv], g3 = col[3 * nv];
+  const double* col = ws.M + s * NV * NV + v;  // column v of M == row v
+  const double cg = ws.cori[s * NV + v] + ws.grav[s * NV + v];
+#pragma unroll
+  for (int k = 0; k + 3 < NV; k += 4) {
+    const double g0 = col[k * NV], g1 = col[(k + 1) * NV], g2 = col[(k + 2) * NV], g3 = col[(k + 3) * NV];
     const double2 xa = *reinterpret_cast<const double2*>(x + k), xb = *reinterpret_cast<const double2*>(x + k + 2);
     t0 = fma(g0, xa.x, t0); t1 = fma(g1, xa.y, t1); t2 = fma(g2, xb.x, t2); t3 = fma(g3, xb.y, t3);
   }
-  for (; k < nv; k++, col += nv) t0 = fma(col[0], x[k], t0);
-  const double* xr = x + nv;
+#pragma unroll
+  for (int k = NV & ~3; k < NV; k++) t0 = fma(col[k * NV], x[k], t0);
+  const double* xr = x + NV;
 #pragma unroll 1
   for (int ci = 0; ci < P.ncontact; ci++) {
     const int dim = P.contacts[ci].dim;
-    const double* jr = ws.fr_jac + ((s * nfr + fm.contact_f[ci]) * 6 + (6 - dim)) * nv + v;  // point contacts: rows 3..5
+    const double* jr = ws.fr_jac + ((s * nfr + fm.contact_f[ci]) * 6 + (6 - dim)) * NV + v;  // point contacts: rows 3..5
     if (dim == 6) {
-      const double j0 = jr[0], j1 = jr[nv], j2 = jr[2 * nv], j3 = jr[3 * nv], j4 = jr[4 * nv], j5 = jr[5 * nv];
+      const double j0 = jr[0], j1 = jr[NV], j2 = jr[2 * NV], j3 = jr[3 * NV], j4 = jr[4 * NV], j5 = jr[5 * NV];
       t0 = fma(-j0, xr[0], t0); t1 = fma(-j1, xr[1], t1); t2 = fma(-j2, xr[2], t2);
       t3 = fma(-j3, xr[3], t3); t0 = fma(-j4, xr[4], t0); t1 = fma(-j5, xr[5], t1);
     } else {
-      const double j0 = jr[0], j1 = jr[nv], j2 = jr[2 * nv];
+      const double j0 = jr[0], j1 = jr[NV], j2 = jr[2 * NV];
       t0 = fma(-j0, xr[0], t0); t1 = fma(-j1, xr[1], t1); t2 = fma(-j2, xr[2], t2);
     }
     xr += dim;
@@ -500,10 +501,10 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 
 // =======================================================================================
 template <int NV, int NC>
-#ifndef PNC_REG_MINB
-#define PNC_REG_MINB 8
+#ifndef PNC_REG_LB
+#define PNC_REG_LB __launch_bounds__(32)
 #endif
-__global__ void __launch_bounds__(32, PNC_REG_MINB)
+__global__ void PNC_REG_LB
 k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, RegLayout L, SetupLayout SL, WsPtrs ws,
             FrameMap fm, int nfr, int B, SolveIO io, const double* __restrict__ rec_all) {
   // P (constant bank) serves warp-uniform reads; tables indexed per lane go through the global copy G
@@ -665,7 +666,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             if (trq) {
 #pragma unroll 1
               for (int a = lane; a < nact; a += 32) {
-                const double tau = torque_row(P, G, ws, fm, nfr, s, a, x);
+                const double tau = torque_row<NV>(P, G, ws, fm, nfr, s, a, x);
                 const double slo = tau - G.trq_lo[a], shi = G.trq_hi[a] - tau;
                 sl[nu + a] = slo;
                 sl[nu + nact + a] = shi;
@@ -1066,7 +1067,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     if (io.trq) {
 #pragma unroll 1
       for (int a = lane; a < nact; a += 32) {
-        const double tau = bad ? nanv : torque_row(P, G, ws, fm, nfr, s, a, x);
+        const double tau = bad ? nanv : torque_row<NV>(P, G, ws, fm, nfr, s, a, x);
         io.trq[s * nact + a] = bad ? nanv : tau;
       }
     }

@@ -179,7 +179,11 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P) {
   SetupLayout L;
   int o = 0;
   L.oG = o; o += (C::NV * C::LDV + 1) & ~1;
-  L.oJd = o; o += ((P.ndense > 0 ? P.ndense : 1) * C::LDV + 1) & ~1;
+  {
+    int jd = (P.ndense > 0 ? P.ndense : 1) * C::LDV;
+    if (jd < 6 * C::NV) jd = 6 * C::NV;  // the D block stages six rows of M here
+    L.oJd = o; o += (jd + 1) & ~1;
+  }
   const int tr = ((P.ntaskrows > 0 ? P.ntaskrows : 1) + 1) & ~1;
   L.oev = o; o += tr;
   L.owt = o; o += tr;
@@ -263,10 +267,20 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       }
       __syncwarp();
       const int total = P.ndense * NV;
-#pragma unroll 4
-      for (int e = lane; e < total; e += 32) {
-        const int r = e / NV, c = e - r * NV;
-        Jd[r * LDV + c] = rptr[r][c];
+#pragma unroll 1
+      for (int e0 = lane; e0 < total; e0 += 32 * 9) {  // nine independent loads in flight per lane
+        double v[9];
+#pragma unroll
+        for (int u = 0; u < 9; u++) {
+          const int e = e0 + 32 * u;
+          const int r = e < total ? e / NV : 0, c = e < total ? e - r * NV : 0;
+          v[u] = rptr[r][c];
+        }
+#pragma unroll
+        for (int u = 0; u < 9; u++) {
+          const int e = e0 + 32 * u;
+          if (e < total) { const int r = e / NV, c = e - r * NV; Jd[r * LDV + c] = v[u]; }
+        }
       }
       __syncwarp();
     }
@@ -286,6 +300,8 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         const int tj = idx - ti * (ti + 1) / 2;
         const int r0 = 2 * ti, c0 = 2 * tj;
         const bool r1ok = r0 + 1 < NV, c1ok = c0 + 1 < NV;
+        const double m00 = Mg[r0 * NV + c0], m01 = c1ok ? Mg[r0 * NV + c0 + 1] : 0.0;
+        const double m10 = r1ok ? Mg[(r0 + 1) * NV + c0] : 0.0, m11 = (r1ok && c1ok) ? Mg[(r0 + 1) * NV + c0 + 1] : 0.0;
         double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
 #pragma unroll 1
         for (int t = 0; t < P.ntask; t++) {
@@ -304,11 +320,11 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           a00 += wk * t00; a01 += wk * t01; a10 += wk * t10; a11 += wk * t11;
         }
         const double lam = P.lambda_q_ddot;
-        Gm[r0 * LDV + c0] = a00 + lam * Mg[r0 * NV + c0];
-        if (c1ok && c0 + 1 <= r0) Gm[r0 * LDV + c0 + 1] = a01 + lam * Mg[r0 * NV + c0 + 1];
+        Gm[r0 * LDV + c0] = a00 + lam * m00;
+        if (c1ok && c0 + 1 <= r0) Gm[r0 * LDV + c0 + 1] = a01 + lam * m01;
         if (r1ok) {
-          Gm[(r0 + 1) * LDV + c0] = a10 + lam * Mg[(r0 + 1) * NV + c0];
-          if (c1ok) Gm[(r0 + 1) * LDV + c0 + 1] = a11 + lam * Mg[(r0 + 1) * NV + c0 + 1];
+          Gm[(r0 + 1) * LDV + c0] = a10 + lam * m10;
+          if (c1ok) Gm[(r0 + 1) * LDV + c0 + 1] = a11 + lam * m11;
         }
       }
 #pragma unroll 1
@@ -447,20 +463,30 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       //      d = J^T n+ product for an equality: it reads D[i] and keeps the later rows current
       //      with the Householder reflection of each added equality ----
       {
-        // floating-base rows i < 6: D[i][j] = sum_{k<=j} J[k][j] M[k][i] (M symmetric: the six
-        // coefficients of step k are contiguous), one column j per lane, six accumulators
+        // floating-base rows i < 6: D[i][j] = sum_{k<=j} J[k][j] M[i][k]; the six rows are staged in
+        // shared memory first (Jd is dead), one column j per lane, six accumulators
+        double* m6 = Jd;
+#pragma unroll 1
+        for (int e0 = lane; e0 < 6 * NV; e0 += 32 * 7) {
+          double v[7];
+#pragma unroll
+          for (int u = 0; u < 7; u++) v[u] = e0 + 32 * u < 6 * NV ? Mg[e0 + 32 * u] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 7; u++)
+            if (e0 + 32 * u < 6 * NV) m6[e0 + 32 * u] = v[u];
+        }
+        __syncwarp();
 #pragma unroll
         for (int pass = 0; pass < (NV > 32 ? 2 : 1); pass++) {
           const int j = lane + 32 * pass;
           double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, e4 = 0.0, e5 = 0.0;
           const int kmax = NV < 32 * (pass + 1) ? NV : 32 * (pass + 1);
           const double* gp_ = Gm + (j < NV ? j : 0);
-          const double* mk = Mg;
 #pragma unroll 2
-          for (int k = 0; k < kmax; k++, gp_ += LDV, mk += NV) {
+          for (int k = 0; k < kmax; k++, gp_ += LDV) {
             const double g = (j < NV && k <= j) ? gp_[0] : 0.0;
-            e0 = fma(g, mk[0], e0); e1 = fma(g, mk[1], e1); e2 = fma(g, mk[2], e2);
-            e3 = fma(g, mk[3], e3); e4 = fma(g, mk[4], e4); e5 = fma(g, mk[5], e5);
+            e0 = fma(g, m6[k], e0); e1 = fma(g, m6[NV + k], e1); e2 = fma(g, m6[2 * NV + k], e2);
+            e3 = fma(g, m6[3 * NV + k], e3); e4 = fma(g, m6[4 * NV + k], e4); e5 = fma(g, m6[5 * NV + k], e5);
           }
           if (j < NV) {
             Dt[j] = e0; Dt[NP + j] = e1; Dt[2 * NP + j] = e2; Dt[3 * NP + j] = e3; Dt[4 * NP + j] = e4; Dt[5 * NP + j] = e5;
@@ -792,16 +818,21 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           __syncwarp();
 
           // z = J[:, iq:] d[iq:] (:518-528), z.z and z.np
-          double za, zb = 0.0, zz, znp;
+          double za, zb = 0.0, zz, znp, sig2;
           {
-            double a0_ = 0.0, a1_ = 0.0;
+            double a0_ = 0.0, a1_ = 0.0, a2_ = 0.0, a3_ = 0.0;
 #pragma unroll
-            for (int j = 0; j < NP; j += 2) {
+            for (int j = 0; j < NP; j += 4) {
               const double2 v = lds2(dm + j);
               a0_ = fma(Ja[j], v.x, a0_);
               a1_ = fma(Ja[j + 1], v.y, a1_);
+              if (j + 2 < NP) {
+                const double2 w = lds2(dm + j + 2);
+                a2_ = fma(Ja[j + 2], w.x, a2_);
+                a3_ = fma(Ja[j + 3], w.y, a3_);
+              }
             }
-            za = a0_ + a1_;
+            za = (a0_ + a1_) + (a2_ + a3_);
             if constexpr (EXT) {
               double b0_ = 0.0, b1_ = 0.0;
               const double* dh = dm + eh * HW;
@@ -815,14 +846,17 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               zb += __shfl_xor_sync(FULL, zb, 1);
             }
             double pzz = 0.0, pzn = 0.0;
+            double psg = (lane >= iq && lane < N) ? dA * dA : 0.0;   // ||d[iq:]||^2 for the Householder step
+            if (lane + 32 >= iq && lane + 32 < N) psg = fma(dB, dB, psg);
             if (lane < N) { zv[lane] = za; pzz = za * za; pzn = za * np[lane]; }
             if (evalid && eh == 0) { zv[erow] = zb; pzz = fma(zb, zb, pzz); pzn = fma(zb, np[erow], pzn); }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
               pzz += __shfl_xor_sync(FULL, pzz, o);
               pzn += __shfl_xor_sync(FULL, pzn, o);
+              psg += __shfl_xor_sync(FULL, psg, o);
             }
-            zz = pzz; znp = pzn;
+            zz = pzz; znp = pzn; sig2 = psg;
           }
           // r = R^-1 d[0:iq] (:530-542), column-oriented back substitution; lane i owns d[i], r[i]
           if (iq <= 32) {
@@ -884,9 +918,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 
           if (!dual_only && (is_eq || fabs(t - t2) < QP_EPS)) {
             // ---- full step: add the constraint (:441-474), one Householder reflection of J2 ----
-            double part = 0.0;
-            for (int j = iq + lane; j < N; j += 32) part += dv[j] * dv[j];
-            const double sigma = sqrt(wsum(part));
+            const double sigma = sqrt(sig2);
             if (sigma <= QP_EPS * R_norm) {  // linearly dependent on the active set
               if (is_eq) { status = PNC_QP_EQ_DEPENDENT; done = true; break; }
               set_bit(exc0, exc1, ip);

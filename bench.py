@@ -348,7 +348,8 @@ def main():
     bytes_out = (2 * nact + nc) * 8 + 8 * mw + 8
     alg_bytes = bytes_in + bytes_out
     qp_tflops = B * mean_flops / (ms_qp * 1e-3) * 1e-12
-    roofline = {"bound": "fp64", "kernel": "k_ihwbc_solve", "achieved": qp_tflops, "peak": fp64_peak,
+    roofline = {"bound": "fp64", "kernel": "pnc_ihwbc_solve = k_task_prepare + k_ihwbc_setup + k_ihwbc_reg", "achieved": qp_tflops,
+                "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": qp_tflops / fp64_peak if fp64_peak else None, "traffic": None,
                 "peak_source": "measured in this run: DFMA-chain microbenchmark, all SMs (pnc_measure_fp64_peak)",
                 "flops_per_solve": mean_flops, "kernel_ms": ms_qp,
@@ -362,7 +363,7 @@ def main():
                        "global_batch": B * world, "qp_dims_n_p_m": list(spec.qp_dims),
                        "l2": "inputs + per-state workspace (%.2f GB per GPU) exceed the 126 MB L2" % (ws.nbytes / 1e9),
                        "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world},
-            "kernels_ms": {"k_update_system": ms_dyn, "k_ihwbc_solve": ms_qp},
+            "kernels_ms": {"pnc_update_system": ms_dyn, "pnc_ihwbc_solve": ms_qp},
             "solver": {"status_counts": [int(x) for x in stats[:5]], "mean_active_set_iterations": stats[5] / stats[6]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks}

@@ -116,10 +116,11 @@ __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_c
 // Torque of actuated row a at x = [qddot; rf] (ihwbc.py:344-354):  S (M qddot + Ni^T (c+g) - (Jc Ni)^T rf).
 // Called with lanes = rows: M is symmetric, so lane a reads column act_idx[a] of M -- consecutive
 // lanes touch consecutive addresses -- and the constraint rows never have to be copied anywhere.
-// One out-of-line copy serves the slack pass and the output pass.
+// Inlined (kernel parameters must not have their address taken: an out-of-line copy goes through
+// local memory and generic loads).
 template <int NV>
-__device__ __noinline__ double torque_row(const DevProblem& P, const DevProblem& G, const WsPtrs& ws, const FrameMap& fm,
-                                          int nfr, size_t s, int a, const double* __restrict__ x) {
+__device__ __forceinline__ double torque_row(const DevProblem& P, const DevProblem& G, const WsPtrs& ws, const FrameMap& fm,
+                                             int nfr, size_t s, int a, const double* __restrict__ x) {
   const int nact = P.nact;
   double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
   if (P.n_ic > 0) {

@@ -348,9 +348,17 @@ def main():
     bytes_out = (2 * nact + nc) * 8 + 8 * mw + 8
     alg_bytes = bytes_in + bytes_out
     qp_tflops = B * mean_flops / (ms_qp * 1e-3) * 1e-12
+    traffic = None  # DRAM bytes of the solve stage per launch, from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+            tj = json.load(f)
+        if tj.get('robot') == robot and tj.get('batch') == B:
+            traffic = tj['solve_stage_bytes']
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "kernel": "pnc_ihwbc_solve = k_task_prepare + k_ihwbc_setup + k_ihwbc_reg", "achieved": qp_tflops,
                 "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": qp_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": qp_tflops / fp64_peak if fp64_peak else None, "traffic": traffic,
                 "peak_source": "measured in this run: DFMA-chain microbenchmark, all SMs (pnc_measure_fp64_peak)",
                 "flops_per_solve": mean_flops, "kernel_ms": ms_qp,
                 "hbm": {"achieved": B * alg_bytes / (ms_per_step * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",

@@ -409,3 +409,41 @@ def test_reference_style_api_atlas(oracle_mod):
     assert list(cmd['joint_trq'].keys()) == list(robot.joint_id.keys())
     with pytest.raises(ValueError):
         BasicTask(robot, "NOT_A_TASK", 3)
+
+
+def test_generic_shared_memory_kernel_matches_oracle():
+    """PNC_SOLVER=smem forces the generic kernel of ihwbc.cu (the path any QP shape without a
+    register-resident instantiation takes); it must meet the same bar as the register kernel."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from pypnc_b200 import robots, engine
+from oracle import oracle
+for name in ("atlas", "draco3_lb"):
+    spec = robots.PROBLEMS[name]()
+    B = 48
+    st = robots.synth_states(name, spec, B, seed=3)
+    op = oracle.OracleProblem(spec)
+    des, w, rfz = robots.synth_desireds(name, spec, st, op.task_actuals(st), seed=3)
+    ref = op.tick_batch(st, des, w, rfz)
+    dm = engine.Model(spec.model, 0); pb = engine.Problem(dm, spec); ws = engine.Workspace(dm, B, spec.frames)
+    keys = ("base_pos", "base_quat", "base_lin_vel", "base_ang_vel", "joint_pos", "joint_vel")
+    ws.update_system(*[torch.from_numpy(np.ascontiguousarray(st[k])).cuda() for k in keys])
+    n0 = dm.lib.pnc_launch_count()
+    out = engine.ihwbc_solve(pb, ws, *[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (des, w, rfz)])
+    torch.cuda.synchronize()
+    assert dm.lib.pnc_launch_count() - n0 <= 2, "generic path is one kernel (+ the projection kernel)"
+    assert np.array_equal(out["status"].cpu().numpy(), ref["status"])
+    for k in ("trq", "acc", "rf"):
+        e = np.abs(out[k].cpu().numpy() - ref[k]).max(1) / np.abs(ref[k]).max(1)
+        assert e.max() < 1e-9, (name, k, e.max())
+print("ok")
+''' % ROOT_DIR
+    env = dict(os.environ, PNC_SOLVER='smem')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stdout + r.stderr
+
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

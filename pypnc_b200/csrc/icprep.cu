@@ -23,7 +23,7 @@ namespace pnc {
 
 struct IcLayout {
   int ld, ldz, ldb;
-  int oL, oZ, oV, oG, oBt, oY, oJb, oLam, odiag, ocg, oncg, oJcJb;
+  int oL, oZ, oV, oG, oBt, oY, oJb, oLam, odiag, ocg, oncg, oJcJb, oLdi, oGdi;
   int total;
 };
 
@@ -42,6 +42,8 @@ __host__ __device__ inline IcLayout ic_layout(int nv, int nact, int nc, int k) {
   L.ocg = o; o += nv;
   L.oncg = o; o += nv;
   L.oJcJb = o; o += (nc > 0 ? nc : 1) * k;
+  L.oLdi = o; o += nv;
+  L.oGdi = o; o += nact;
   L.oV = L.oZ;
   L.total = (o + 1) & ~1;
   return L;
@@ -65,6 +67,8 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
   double* cg = sm + L.ocg;
   double* ncg = sm + L.oncg;
   double* JcJb = sm + L.oJcJb;
+  double* Ldi = sm + L.oLdi;  // 1 / L[i][i]
+  double* Gdi = sm + L.oGdi;  // 1 / G-factor[i][i]
 
   for (;;) {
     int si = 0;
@@ -95,10 +99,11 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
       if (!(piv > 0.0)) { bad = 1; break; }
       const double dj = sqrt(piv);
       __syncwarp();
+      const double idj = 1.0 / dj;
       for (int rr = 0; rr < 2; rr++) {
         const int i = lane + 32 * rr;
-        if (i == j) Lm[j * ld + j] = dj;
-        else if (i > j && i < nv) Lm[i * ld + j] = t[rr] / dj;
+        if (i == j) { Lm[j * ld + j] = dj; Ldi[j] = idj; }
+        else if (i > j && i < nv) Lm[i * ld + j] = t[rr] * idj;
       }
       __syncwarp();
     }
@@ -108,7 +113,7 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
         for (int i = 0; i < nv; i++) {
           double sum = P.ic_jac[lane][i];
           for (int c = 0; c < i; c++) sum -= Lm[i * ld + c] * Y[c * k + lane];
-          Y[i * k + lane] = sum / Lm[i * ld + i];
+          Y[i * k + lane] = sum * Ldi[i];
         }
       }
       __syncwarp();
@@ -150,7 +155,7 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
           double sum = 0.0;
           for (int t = 0; t < k; t++) sum += Y[i * k + t] * Lam[t * k + lane];
           for (int c = i + 1; c < nv; c++) sum -= Lm[c * ld + i] * Jb[c * k + lane];
-          Jb[i * k + lane] = sum / Lm[i * ld + i];
+          Jb[i * k + lane] = sum * Ldi[i];
         }
       }
       __syncwarp();
@@ -200,8 +205,11 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
             sum = i == va ? 1.0 : 0.0;
             for (int t = 0; t < k; t++) sum -= Jb[va * k + t] * P.ic_jac[t][i];
           }
-          for (int c = 0; c < i; c++) sum -= Lm[i * ld + c] * Z[c * ldz + a];
-          Z[i * ldz + a] = sum / Lm[i * ld + i];
+          double sum2 = 0.0;
+          int c = 0;
+          for (; c + 1 < i; c += 2) { sum -= Lm[i * ld + c] * Z[c * ldz + a]; sum2 -= Lm[i * ld + c + 1] * Z[(c + 1) * ldz + a]; }
+          if (c < i) sum -= Lm[i * ld + c] * Z[c * ldz + a];
+          Z[i * ldz + a] = (sum + sum2) * Ldi[i];
         }
       }
       __syncwarp();
@@ -235,10 +243,11 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
         if (!(piv > 1e-13 * gmax)) { bad = 1; break; }
         const double dj = sqrt(piv);
         __syncwarp();
+        const double idj = 1.0 / dj;
         for (int rr = 0; rr < 2; rr++) {
           const int i = lane + 32 * rr;
-          if (i == j) G[j * ldz + j] = dj;
-          else if (i > j && i < nact) G[i * ldz + j] = t[rr] / dj;
+          if (i == j) { G[j * ldz + j] = dj; Gdi[j] = idj; }
+          else if (i > j && i < nact) G[i * ldz + j] = t[rr] * idj;
         }
         __syncwarp();
       }
@@ -247,9 +256,11 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
       // ---- V = L^-T Z in place (lane a back-substitutes column a); W A^T = rows 6.. of V ----
       for (int a = lane; a < nact; a += 32) {
         for (int i = nv - 1; i >= 0; i--) {
-          double sum = Z[i * ldz + a];
-          for (int c = i + 1; c < nv; c++) sum -= Lm[c * ld + i] * Z[c * ldz + a];
-          Z[i * ldz + a] = sum / Lm[i * ld + i];
+          double sum = Z[i * ldz + a], sum2 = 0.0;
+          int c = i + 1;
+          for (; c + 1 < nv; c += 2) { sum -= Lm[c * ld + i] * Z[c * ldz + a]; sum2 -= Lm[(c + 1) * ld + i] * Z[(c + 1) * ldz + a]; }
+          if (c < nv) sum -= Lm[c * ld + i] * Z[c * ldz + a];
+          Z[i * ldz + a] = (sum + sum2) * Ldi[i];
         }
       }
       __syncwarp();
@@ -260,36 +271,34 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
         for (int i = 0; i < nact; i++) {  // forward
           double sum = rhs[i];
           for (int c = 0; c < i; c++) sum -= G[i * ldz + c] * b[c];
-          b[i] = sum / G[i * ldz + i];
+          b[i] = sum * Gdi[i];
         }
         for (int i = nact - 1; i >= 0; i--) {  // backward
           double sum = b[i];
           for (int c = i + 1; c < nact; c++) sum -= G[c * ldz + i] * b[c];
-          b[i] = sum / G[i * ldz + i];
+          b[i] = sum * Gdi[i];
         }
       }
       __syncwarp();
-      // ---- S [M | -(Jc Ni)^T] and S Ni^T (c+g), S = [0 | B] ----
-      for (int a = 0; a < nact; a++) {
-        double* out = ws.ic_tq + s * nact * n + a;  // stored transposed: [n][nact], lanes of the QP kernel = rows a
-        for (int c = lane; c < n; c += 32) {
-          double sum = 0.0;
-          if (c < nv) {
-            for (int j = 0; j < nj; j++) {
-              const int r = 6 + j;
-              const double mv = r == c ? Mdiag[c] : (r < c ? Lm[r * ld + c] : Lm[c * ld + r]);
-              sum += Bt[j * ldb + a] * mv;
-            }
-          } else {
-            const double* jr = ws.ic_jcni + (s * nc + (c - nv)) * nv;
-            for (int j = 0; j < nj; j++) sum -= Bt[j * ldb + a] * jr[6 + j];
+      // ---- S [M | -(Jc Ni)^T] and S Ni^T (c+g), S = [0 | B]: lane = actuated row a, so the
+      //      transposed store [n][nact] is coalesced; M and Jc Ni are read warp-uniformly ----
+      for (int a = lane; a < nact; a += 32) {
+        double* out = ws.ic_tq + s * nact * n + a;
+        for (int c = 0; c < n; c++) {
+          const double* src = c < nv ? Mg + 6 * nv + c : ws.ic_jcni + (s * nc + (c - nv)) * nv + 6;
+          const int stride = c < nv ? nv : 1;
+          double s0 = 0.0, s1 = 0.0;
+          int j = 0;
+          for (; j + 1 < nj; j += 2) {
+            s0 += Bt[j * ldb + a] * src[j * stride];
+            s1 += Bt[(j + 1) * ldb + a] * src[(j + 1) * stride];
           }
-          out[c * nact] = sum;
+          if (j < nj) s0 += Bt[j * ldb + a] * src[j * stride];
+          out[c * nact] = c < nv ? (s0 + s1) : -(s0 + s1);
         }
         double part = 0.0;
-        for (int j = lane; j < nj; j += 32) part += Bt[j * ldb + a] * ncg[6 + j];
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-        if (lane == 0) ws.ic_tq0[s * nact + a] = part;
+        for (int j = 0; j < nj; j++) part += Bt[j * ldb + a] * ncg[6 + j];
+        ws.ic_tq0[s * nact + a] = part;
       }
     }
     if (lane == 0) ws.ic_status[s] = bad;

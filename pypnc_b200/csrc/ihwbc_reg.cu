@@ -39,43 +39,22 @@ struct RCfg {
   static constexpr int EVP = EV <= 1 ? 1 : (EV <= 2 ? 2 : (EV <= 4 ? 4 : 8));
   static constexpr int LPR = 32 / EVP;                        // lanes cooperating on one such row in the Cholesky
   static constexpr int LDT = NP + 2;                          // pitch of the d scratch tile
+  // ---- compile-time shared-memory layout of the active-set kernel (doubles).  Sizes that depend on
+  //      the problem (cone rows, inequalities, equalities) use their upper bounds, so every array
+  //      sits at an immediate offset from the shared-memory base: no address registers, nothing to
+  //      rematerialise under the register pressure of the resident J ----
+  static constexpr int NUMAX = PNC_MAX_CONE, MMAX = 128, PMAX = 10;
+  static constexpr int RSZ = (N * (N + 3) / 2 + 1) & ~1;
+  static constexpr int ORT = 0, OT = ORT + RSZ, ORINV = OT + 6 * LDT, OUF = ORINV + NP, OUFV = OUF + NUMAX * 6,
+                       OX = OUFV + NUMAX, OZ = OX + NP, ODV = OZ + NP, ODM = ODV + NP, OVM = ODM + NP, ONP = OVM + NP,
+                       ORR = ONP + NP, OU = ORR + NP + 2, OXOLD = OU + NP + 2, OUOLD = OXOLD + NP,
+                       OXACC = OUOLD + NP + 2, OSL = OXACC + NP, OINT = OSL + MMAX,
+                       SMEM_DOUBLES = (OINT + (3 * (N + 2) + 1) / 2 + 2) & ~1;
+  // ---- per-state HBM record written by the setup kernel (doubles) ----
+  static constexpr int RG = 0, RX = (NV * LDV + 1) & ~1, RD = RX + NP, RS = RD + PMAX * NP, REC = (RS + 4 + 1) & ~1;
   static_assert(E <= 16, "rows beyond 32 must fit one lane pair each");
   static_assert(N <= 64, "n too large for the register kernel");
 };
-
-struct RegLayout {
-  int oRT, oT, orinv, oBig, oUf, ouf, ox, oz, odv, odm, ovm, onp, orr, ou, oxold, ouold, oxacc, osl, oev, owt, oint;
-  int per_state;
-};
-
-template <class C>
-__host__ __device__ inline RegLayout reg_layout(const DevProblem& P) {
-  RegLayout L;
-  const int n = C::N, m = P.m > 0 ? P.m : 1;
-  int o = 0;
-  const int rsz = (n * (n + 3) / 2 + 1) & ~1, tsz = 6 * C::LDT;
-  L.oRT = o; L.oT = o + rsz; o += rsz + tsz;
-  L.orinv = o; o += C::NP;
-  L.oBig = o;
-  L.oUf = o; o += (P.nu > 0 ? P.nu : 1) * 6;
-  L.ouf = o; o += ((P.nu > 0 ? P.nu : 1) + 1) & ~1;
-  L.ox = o; o += C::NP;
-  L.oz = o; o += C::NP;
-  L.odv = o; o += C::NP;
-  L.odm = o; o += C::NP;
-  L.ovm = o; o += C::NP;
-  L.onp = o; o += C::NP;
-  L.orr = o; o += C::NP + 2;
-  L.ou = o; o += C::NP + 2;
-  L.oxold = o; o += C::NP;
-  L.ouold = o; o += C::NP + 2;
-  L.oxacc = o; o += C::NP;
-  L.osl = o; o += (m + 1) & ~1;
-  L.oev = L.owt = o;
-  L.oint = o; o += (3 * (n + 2) + 1) / 2 + 1;
-  L.per_state = (o + 1) & ~1;
-  return L;
-}
 
 // ---- register-array access by a warp-uniform dynamic index (jump table, no local memory) ----
 #define PNC_R8(M, B) M(B + 0) M(B + 1) M(B + 2) M(B + 3) M(B + 4) M(B + 5) M(B + 6) M(B + 7)
@@ -172,7 +151,6 @@ __device__ __forceinline__ double torque_row(const DevProblem& P, const DevProbl
 // active-set kernel loads (one coalesced-by-sector read of ~14 KB per Atlas state).
 struct SetupLayout {
   int oG, oJd, oev, owt, og0, odm, ozv, odl, oD, per_state;  // shared memory (doubles)
-  int rG, rX, rD, rS, rec;                                   // HBM record (doubles)
 };
 
 template <class C>
@@ -194,12 +172,6 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P) {
   L.odl = o; o += C::NP;
   L.oD = o; o += P.p * C::NP;
   L.per_state = (o + 1) & ~1;
-  int r = 0;
-  L.rG = r; r += (C::NV * C::LDV + 1) & ~1;
-  L.rX = r; r += C::NP;
-  L.rD = r; r += P.p * C::NP;
-  L.rS = r; r += 4;
-  L.rec = (r + 1) & ~1;
   return L;
 }
 
@@ -232,7 +204,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     si = __shfl_sync(FULL, si, 0);
     if (si >= B) break;
     const size_t s = (size_t)si;
-    double* rec = rec_all + s * SL.rec;
+    double* rec = rec_all + s * C::REC;
     int status = PNC_QP_OK;
     if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
     const double* Mg = ws.M + s * NV * NV;
@@ -514,14 +486,14 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       __syncwarp();
       // ---- record: factor block (J in its upper triangle), x0, D, scalars ----
 #pragma unroll 4
-      for (int k = lane; k < NV * LDV; k += 32) rec[SL.rG + k] = Gm[k];
+      for (int k = lane; k < NV * LDV; k += 32) rec[C::RG + k] = Gm[k];
 #pragma unroll 1
-      for (int k = lane; k < NP; k += 32) rec[SL.rX + k] = k < NV ? xs[k] : 0.0;
+      for (int k = lane; k < NP; k += 32) rec[C::RX + k] = k < NV ? xs[k] : 0.0;
 #pragma unroll 1
-      for (int k = lane; k < p * NP; k += 32) rec[SL.rD + k] = Dt[k];
-      if (lane == 0) { rec[SL.rS] = c1; rec[SL.rS + 1] = c2; rec[SL.rS + 3] = jrf; }
+      for (int k = lane; k < p * NP; k += 32) rec[C::RD + k] = Dt[k];
+      if (lane == 0) { rec[C::RS] = c1; rec[C::RS + 1] = c2; rec[C::RS + 3] = jrf; }
     }
-    if (lane == 0) rec[SL.rS + 2] = (double)status;
+    if (lane == 0) rec[C::RS + 2] = (double)status;
     __syncwarp();
   }
 }
@@ -532,39 +504,38 @@ template <int NV, int NC>
 #define PNC_REG_LB __launch_bounds__(32)
 #endif
 __global__ void PNC_REG_LB
-k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, RegLayout L, SetupLayout SL, WsPtrs ws,
-            FrameMap fm, int nfr, int B, SolveIO io, const double* __restrict__ rec_all) {
+k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B,
+            SolveIO io, const double* __restrict__ rec_all) {
   // P (constant bank) serves warp-uniform reads; tables indexed per lane go through the global copy G
   const DevProblem& G = *gp;
   using C = RCfg<NV, NC>;
   constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV;
   constexpr bool EXT = C::EXT;
-  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(16) double smem[C::SMEM_DOUBLES];  // static: addresses are immediates in the shared window
   const int lane = threadIdx.x;
   const int p = P.p, m = P.m, nu = P.nu, nact = P.nact;
   const bool trq = P.b_trq_limit != 0, has_ic = P.n_ic > 0;
-  double* W = smem;
-  double* Rp = W + L.oRT;
-  double* Ts = W + L.oT;
-  double* rinv = W + L.orinv;
-  double* Uf = W + L.oUf;
-  double* uf = W + L.ouf;
-  double* x = W + L.ox;
-  double* zv = W + L.oz;
-  double* dv = W + L.odv;
-  double* dm = W + L.odm;
-  double* vm = W + L.ovm;
-  double* np = W + L.onp;
-  double* rv = W + L.orr;
-  double* uv = W + L.ou;
-  double* xold = W + L.oxold;
-  double* uold = W + L.ouold;
-  double* xacc = W + L.oxacc;
-  double* sl = W + L.osl;
-  int* Aact = reinterpret_cast<int*>(W + L.oint);
+  double* const Rp = smem + C::ORT;
+  double* const Ts = smem + C::OT;
+  double* const rinv = smem + C::ORINV;
+  double* const Uf = smem + C::OUF;
+  double* const uf = smem + C::OUFV;
+  double* const x = smem + C::OX;
+  double* const zv = smem + C::OZ;
+  double* const dv = smem + C::ODV;
+  double* const dm = smem + C::ODM;
+  double* const vm = smem + C::OVM;
+  double* const np = smem + C::ONP;
+  double* const rv = smem + C::ORR;
+  double* const uv = smem + C::OU;
+  double* const xold = smem + C::OXOLD;
+  double* const uold = smem + C::OUOLD;
+  double* const xacc = smem + C::OXACC;
+  double* const sl = smem + C::OSL;
+  int* const Aact = reinterpret_cast<int*>(smem + C::OINT);
   int* Aold = Aact + (N + 2);
   int* Aacc = Aold + (N + 2);
-  auto Rcol = [&](int c) { return Rp + (c * (c + 3)) / 2; };
+#define Rcol(c) (Rp + ((c) * ((c) + 3)) / 2)
   double* rot = Ts;  // the d scratch tile doubles as the Givens coefficient table of a drop
   static_assert(6 * LDT >= 3 * NP, "rotation table must fit the scratch tile");
 
@@ -597,13 +568,15 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       while (ci + 1 < P.ncontact && c >= G.contacts[ci + 1].rf_off) ci++;
       return contact_jac_row(G.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - G.contacts[ci].rf_off)[v];
     };
-    const double* rec = rec_all + s * SL.rec;  // written by k_ihwbc_setup
+    const double* rec = rec_all + s * C::REC;  // written by k_ihwbc_setup
     {
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) {
-        x[k] = rec[SL.rX + k];
+        x[k] = rec[C::RX + k];
         zv[k] = 0.0; dm[k] = 0.0; vm[k] = 0.0; np[k] = 0.0; dv[k] = 0.0;
       }
+#pragma unroll 1
+      for (int k = lane; k < 6 * LDT; k += 32) Ts[k] = 0.0;
 #pragma unroll 1
       for (int r = lane; r < nu; r += 32) {
         const int ci = G.cone_contact[r];
@@ -617,11 +590,11 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
       }
     }
-    const double c1 = rec[SL.rS], c2 = rec[SL.rS + 1], jrf = rec[SL.rS + 3];
-    status = (int)rec[SL.rS + 2];
+    const double c1 = rec[C::RS], c2 = rec[C::RS + 1], jrf = rec[C::RS + 3];
+    status = (int)rec[C::RS + 2];
     if (status == PNC_QP_OK) {
       // ---- move J into registers: row lane, and half rows 32.. in lane pairs ----
-      const double* Gg = rec + SL.rG;
+      const double* Gg = rec + C::RG;
 #pragma unroll
       for (int k = 0; k < NP; k += 2) {
         double v0 = 0.0, v1 = 0.0;
@@ -653,7 +626,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       }
       double* Deq = Rp + 64;  // R only uses its first p columns (< 64 doubles) while Deq is live
 #pragma unroll 2
-      for (int k = lane; k < p * NP; k += 32) Deq[k] = rec[SL.rD + k];
+      for (int k = lane; k < p * NP; k += 32) Deq[k] = rec[C::RD + k];
 #pragma unroll 1
       for (int k = lane; k < N + 2; k += 32) { uv[k] = 0.0; Aact[k] = 0; }
       __syncwarp();
@@ -806,11 +779,15 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               }
             }
             __syncwarp();
-#pragma unroll 1
-            for (int r = 0; r < dim; r++) {
-              const double nr = np[c0 + r];
-              dA = fma(nr, Ts[r * LDT + lane], dA);
-              if (NP > 32 && lane + 32 < NP) dB = fma(nr, Ts[r * LDT + lane + 32], dB);
+            {
+              const double* npc = np + c0;
+              const double* tl = Ts + lane;
+#pragma unroll
+              for (int r = 0; r < 6; r++) {
+                const double nr = r < dim ? npc[r] : 0.0;
+                dA = fma(nr, tl[r * LDT], dA);
+                if (NP > 32 && lane + 32 < NP) dB = fma(nr, tl[r * LDT + 32], dB);
+              }
             }
             __syncwarp();
           }
@@ -1128,9 +1105,8 @@ static bool shape_ok(const DevProblem& hp) {
   if (hp.nv != NV || hp.nc != NC) return false;
   using C = RCfg<NV, NC>;
   if (hp.m > 128 || hp.nact > 64) return false;
-  const RegLayout L = reg_layout<C>(hp);
-  const int m_ = hp.m > 0 ? hp.m : 1, n_ = C::N;
-  (void)m_; (void)L;
+  const int n_ = C::N;
+  if (hp.nu > C::NUMAX || hp.m > C::MMAX || hp.p > C::PMAX) return false;
   // the equality block D sits behind the first R columns while the equalities are added
   if (64 + hp.p * C::NP > n_ * (n_ + 3) / 2 || hp.p * (hp.p + 3) / 2 > 64) return false;
   return true;
@@ -1141,16 +1117,10 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
                        const SolveIO& io, int num_sms, cudaStream_t stream) {
   if (!shape_ok<NV, NC>(hp)) return false;
   using C = RCfg<NV, NC>;
-  const RegLayout L = reg_layout<C>(hp);
-  const size_t smem = (size_t)L.per_state * sizeof(double);
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(k_ihwbc_reg<NV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return false;
-    configured = smem;
-  }
+  static_assert(C::SMEM_DOUBLES * sizeof(double) <= 48 * 1024, "static shared memory limit");
+  const size_t smem = 0;  // the active-set kernel's shared memory is static
   const SetupLayout SL = setup_layout<C>(hp);
-  if (!ws.setup_rec || ws.setup_stride != SL.rec) return false;
+  if (!ws.setup_rec || ws.setup_stride != C::REC) return false;
   const size_t smem_s = (size_t)SL.per_state * sizeof(double);
   static size_t configured_s = 0;
   if (smem_s > configured_s) {
@@ -1170,7 +1140,7 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   cudaMemsetAsync(io.counter + 2, 0, sizeof(int), stream);
   k_ihwbc_setup<NV, NC><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
   g_launch_count++;
-  k_ihwbc_reg<NV, NC><<<grid, 32, smem, stream>>>(hp, dp, L, SL, ws, fm, nfr, B, io, ws.setup_rec);
+  k_ihwbc_reg<NV, NC><<<grid, 32, smem, stream>>>(hp, dp, ws, fm, nfr, B, io, ws.setup_rec);
   g_launch_count++;
   return true;
 }
@@ -1187,7 +1157,7 @@ bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const Ws
 }
 
 template <int NV, int NC>
-static int rec_doubles(const DevProblem& hp) { return shape_ok<NV, NC>(hp) ? setup_layout<RCfg<NV, NC>>(hp).rec : 0; }
+static int rec_doubles(const DevProblem& hp) { return shape_ok<NV, NC>(hp) ? RCfg<NV, NC>::REC : 0; }
 
 // doubles per state of the setup record (0 when no register kernel matches the problem)
 int reg_setup_record_doubles(const DevProblem& hp) {

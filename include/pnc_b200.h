@@ -174,6 +174,16 @@ int pnc_update_system(pnc_workspace* ws, int32_t B, const double* d_base_pos, co
                       const double* d_base_lin_vel, const double* d_base_ang_vel,
                       const double* d_joint_pos, const double* d_joint_vel, void* stream);
 
+/* update_system(..., b_cent): additionally fills the centroidal quantities of
+ * PinocchioRobotSystem._update_centroidal_quantities (:181-194, pin.ccrba) when b_cent != 0:
+ * Ag [B,6,nv] and hg [B,6] with rows [angular; linear], Ig [B,6,6] (diagonal 3x3 blocks only). */
+int pnc_update_system_cent(pnc_workspace* ws, int32_t B, const double* d_base_pos, const double* d_base_quat,
+                           const double* d_base_lin_vel, const double* d_base_ang_vel,
+                           const double* d_joint_pos, const double* d_joint_vel, int32_t b_cent, void* stream);
+double* pnc_ws_centroidal_ag(pnc_workspace* ws);
+double* pnc_ws_centroidal_hg(pnc_workspace* ws);
+double* pnc_ws_centroidal_ig(pnc_workspace* ws);
+
 /* device pointers into the workspace, valid until the workspace is destroyed.
  * Shapes (row-major, batch first): q [B,nq], qdot [B,nv], M [B,nv,nv], grav [B,nv],
  * cori [B,nv], com [B,3], vcom [B,3], jcom [B,3,nv], jcomdot [B,3,nv], jcomdot_qdot [B,3],

@@ -124,6 +124,11 @@ def load_library():
     lib.pnc_workspace_bytes.argtypes = [vp]
     lib.pnc_workspace_bytes.restype = i64
     lib.pnc_update_system.argtypes = [vp, i32] + [vp] * 6 + [vp]
+    lib.pnc_update_system_cent.argtypes = [vp, i32] + [vp] * 6 + [i32, vp]
+    for name in ('ag', 'hg', 'ig'):
+        f = getattr(lib, 'pnc_ws_centroidal_' + name)
+        f.argtypes = [vp]
+        f.restype = vp
     for name in ('q', 'qdot', 'mass_matrix', 'gravity', 'coriolis', 'com_pos', 'com_vel', 'com_jac',
                  'com_jacdot', 'com_jdqd', 'frame_iso', 'frame_vel', 'frame_jac', 'frame_jdqd'):
         f = getattr(lib, 'pnc_ws_' + name)
@@ -147,7 +152,8 @@ def load_library():
 EXPORTED_SYMBOLS = [
     'pnc_model_create', 'pnc_model_destroy', 'pnc_problem_create', 'pnc_problem_destroy',
     'pnc_problem_dims', 'pnc_workspace_create', 'pnc_workspace_destroy', 'pnc_workspace_bytes',
-    'pnc_update_system', 'pnc_ws_q', 'pnc_ws_qdot', 'pnc_ws_mass_matrix', 'pnc_ws_gravity',
+    'pnc_update_system', 'pnc_update_system_cent', 'pnc_ws_centroidal_ag', 'pnc_ws_centroidal_hg',
+    'pnc_ws_centroidal_ig', 'pnc_ws_q', 'pnc_ws_qdot', 'pnc_ws_mass_matrix', 'pnc_ws_gravity',
     'pnc_ws_coriolis', 'pnc_ws_com_pos', 'pnc_ws_com_vel', 'pnc_ws_com_jac', 'pnc_ws_com_jacdot',
     'pnc_ws_com_jdqd', 'pnc_ws_frame_iso', 'pnc_ws_frame_vel', 'pnc_ws_frame_jac', 'pnc_ws_frame_jdqd',
     'pnc_ihwbc_solve', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_wbc_tick_host',

@@ -249,18 +249,18 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
     for (int k = 0; k < 3; k++) ws->hfr.p[f][k] = m->frame_p[3 * (size_t)mf + k];
   }
   const size_t B = capacity, nv = m->h.nv, nq = m->h.nq, nfr = nframes;
-  size_t sizes[14] = {B * nq, B * nv, B * nv * nv, B * nv, B * nv, B * 3, B * 3, B * 3 * nv, B * 3 * nv, B * 3,
-                      B * nfr * 12, B * nfr * 6, B * nfr * 6 * nv, B * nfr * 6};
-  size_t total = 0, off[14];
-  for (int i = 0; i < 14; i++) { off[i] = total; total += align_up(sizes[i] * sizeof(double)); }
+  size_t sizes[17] = {B * nq, B * nv, B * nv * nv, B * nv, B * nv, B * 3, B * 3, B * 3 * nv, B * 3 * nv, B * 3,
+                      B * nfr * 12, B * nfr * 6, B * nfr * 6 * nv, B * nfr * 6, B * 6 * nv, B * 6, B * 36};
+  size_t total = 0, off[17];
+  for (int i = 0; i < 17; i++) { off[i] = total; total += align_up(sizes[i] * sizeof(double)); }
   total += 256;  // counter
   CK(cudaMalloc(&ws->slab, total));
   CK(cudaMemset(ws->slab, 0, total));
   ws->bytes = total;
-  double** dst[14] = {&ws->p.q, &ws->p.qdot, &ws->p.M, &ws->p.grav, &ws->p.cori, &ws->p.com, &ws->p.vcom,
+  double** dst[17] = {&ws->p.q, &ws->p.qdot, &ws->p.M, &ws->p.grav, &ws->p.cori, &ws->p.com, &ws->p.vcom,
                       &ws->p.jcom, &ws->p.jcomdot, &ws->p.jcomdot_qdot, &ws->p.fr_iso, &ws->p.fr_vel,
-                      &ws->p.fr_jac, &ws->p.fr_jdqd};
-  for (int i = 0; i < 14; i++) *dst[i] = reinterpret_cast<double*>(ws->slab + off[i]);
+                      &ws->p.fr_jac, &ws->p.fr_jdqd, &ws->p.cent_ag, &ws->p.cent_hg, &ws->p.cent_ig};
+  for (int i = 0; i < 17; i++) *dst[i] = reinterpret_cast<double*>(ws->slab + off[i]);
   ws->counter = reinterpret_cast<int*>(ws->slab + total - 256);
   CK(cudaMalloc(&ws->dfr, sizeof(DevFrames)));
   CK(cudaMemcpy(ws->dfr, &ws->hfr, sizeof(DevFrames), cudaMemcpyHostToDevice));
@@ -289,11 +289,11 @@ int64_t pnc_workspace_bytes(const pnc_workspace* ws) {
 
 static int update_system_at(pnc_workspace* ws, int off, int32_t B, const double* bp, const double* bq,
                             const double* blv, const double* bav, const double* jp, const double* jv,
-                            cudaStream_t st) {
+                            cudaStream_t st, int b_cent = 0) {
   const pnc_model* m = ws->m;
   if (m->h.nfl && (!bp || !bq || !blv || !bav)) return PNC_E_ARG;
   WsPtrs w = ws_offset(ws->p, off, m->h.nq, m->h.nv, ws->nfr, 0, 0, 0);
-  launch_update_system(m->d, ws->dfr, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st);
+  launch_update_system(m->d, ws->dfr, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st, b_cent);
   CK(cudaGetLastError());
   return PNC_OK;
 }
@@ -308,6 +308,19 @@ int pnc_update_system(pnc_workspace* ws, int32_t B, const double* d_base_pos, co
                           d_joint_vel, (cudaStream_t)stream);
 }
 
+int pnc_update_system_cent(pnc_workspace* ws, int32_t B, const double* d_base_pos, const double* d_base_quat,
+                           const double* d_base_lin_vel, const double* d_base_ang_vel, const double* d_joint_pos,
+                           const double* d_joint_vel, int32_t b_cent, void* stream) {
+  if (!ws || B < 0 || B > ws->cap || !d_joint_pos || !d_joint_vel) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  return update_system_at(ws, 0, B, d_base_pos, d_base_quat, d_base_lin_vel, d_base_ang_vel, d_joint_pos,
+                          d_joint_vel, (cudaStream_t)stream, b_cent ? 1 : 0);
+}
+
+double* pnc_ws_centroidal_ag(pnc_workspace* ws) { return ws->p.cent_ag; }
+double* pnc_ws_centroidal_hg(pnc_workspace* ws) { return ws->p.cent_hg; }
+double* pnc_ws_centroidal_ig(pnc_workspace* ws) { return ws->p.cent_ig; }
 double* pnc_ws_q(pnc_workspace* ws) { return ws->p.q; }
 double* pnc_ws_qdot(pnc_workspace* ws) { return ws->p.qdot; }
 double* pnc_ws_mass_matrix(pnc_workspace* ws) { return ws->p.M; }

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(DYN_WARPS * 32)
 k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ gfr, WsPtrs ws, int B,
                 const double* __restrict__ base_pos, const double* __restrict__ base_quat,
                 const double* __restrict__ base_lin_vel, const double* __restrict__ base_ang_vel,
-                const double* __restrict__ joint_pos, const double* __restrict__ joint_vel) {
+                const double* __restrict__ joint_pos, const double* __restrict__ joint_vel, int b_cent) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* sm = reinterpret_cast<DevModel*>(smem_raw);
   DevFrames* sfr = reinterpret_cast<DevFrames*>(smem_raw + sizeof(DevModel));
@@ -251,6 +251,36 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
       o = ws.jcomdot_qdot + 3 * (size_t)s;  // (dAg_lin . qdot) / total_mass, basic_task.py:133-135
       o[0] = tfcl[0] * inv_mtot; o[1] = tfcl[1] * inv_mtot; o[2] = tfcl[2] * inv_mtot;
     }
+    // centroidal quantities (pinocchio_robot_system.py:181-194, pin.ccrba): optional
+    V3 crel = mk(0, 0, 0);  // centre of mass relative to the reference point
+    if (b_cent) {
+      double mt = 0.0, Iot[6] = {0, 0, 0, 0, 0, 0};
+      if (lane == 0) {
+        mt = acc[0];
+        for (int k = 0; k < 6; k++) Iot[k] = acc[4 + k];
+        for (int c = nsub; c < nb; c++) {
+          const double* row = sub + c * SUB_LD;
+          mt += row[0];
+          for (int k = 0; k < 6; k++) Iot[k] += row[4 + k];
+        }
+        crel = mk(tot[0] / mt, tot[1] / mt, tot[2] / mt);
+        // Ig: rotational inertia about the CoM (world axes) and m I3, off-diagonal blocks dropped (:192-194)
+        double* ig = ws.cent_ig + 36 * (size_t)s;
+        for (int k = 0; k < 36; k++) ig[k] = 0.0;
+        const double cc = dot(crel, crel);
+        const double cx[3] = {crel.x, crel.y, crel.z};
+        const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) {
+            ig[6 * r + c] = Iot[sym[r][c]] - mt * ((r == c ? cc : 0.0) - cx[r] * cx[c]);
+            ig[6 * (3 + r) + 3 + c] = r == c ? mt : 0.0;
+          }
+      }
+      crel.x = __shfl_sync(0xffffffffu, crel.x, 0);
+      crel.y = __shfl_sync(0xffffffffu, crel.y, 0);
+      crel.z = __shfl_sync(0xffffffffu, crel.z, 0);
+    }
+    double hgp[6] = {0, 0, 0, 0, 0, 0};
 
     // ---------------- phase 5: per-dof outputs: gravity, Coriolis, CoM Jacobians, F = Ic S
     if (active) {
@@ -287,6 +317,25 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
         V3 Fa = cross(hS, sl) + mulS(IS, sa);
         double* fr = isff ? (F0 + d * 6) : (Fs + i * SF_LD);
         st3(fr, Fl); st3(fr + 3, Fa);
+        if (b_cent) {  // Ag column = [moment about the CoM; force], rows [angular; linear]
+          const V3 ac = Fa - cross(crel, Fl);
+          double* ag = ws.cent_ag + (size_t)s * 6 * nv;
+          ag[iv + d] = ac.x; ag[nv + iv + d] = ac.y; ag[2 * nv + iv + d] = ac.z;
+          ag[3 * nv + iv + d] = Fl.x; ag[4 * nv + iv + d] = Fl.y; ag[5 * nv + iv + d] = Fl.z;
+          const double qdd = isff ? (d < 3 ? (d == 0 ? vloc_lin.x : d == 1 ? vloc_lin.y : vloc_lin.z)
+                                           : (d == 3 ? vloc_ang.x : d == 4 ? vloc_ang.y : vloc_ang.z))
+                                  : qd;
+          hgp[0] += ac.x * qdd; hgp[1] += ac.y * qdd; hgp[2] += ac.z * qdd;
+          hgp[3] += Fl.x * qdd; hgp[4] += Fl.y * qdd; hgp[5] += Fl.z * qdd;
+        }
+      }
+    }
+    if (b_cent) {  // hg = Ag qdot
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        double v = hgp[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) ws.cent_hg[6 * (size_t)s + k] = v;
       }
     }
     __syncwarp();
@@ -373,7 +422,7 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
 void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs& ws, int B, int nv,
                           const double* base_pos, const double* base_quat, const double* base_lin_vel,
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
-                          int num_sms, cudaStream_t stream) {
+                          int num_sms, cudaStream_t stream, int b_cent) {
   size_t smem = dyn_smem_bytes(nv);
   static size_t configured = 0;
   if (smem > configured) {
@@ -388,7 +437,7 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   k_update_system<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, ws, B, base_pos, base_quat, base_lin_vel,
-                                                          base_ang_vel, joint_pos, joint_vel);
+                                                          base_ang_vel, joint_pos, joint_vel, b_cent);
   g_launch_count++;
 }
 

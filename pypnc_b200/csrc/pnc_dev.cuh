@@ -30,6 +30,7 @@ struct DevFrames {
 struct WsPtrs {
   double *q, *qdot, *M, *grav, *cori, *com, *vcom, *jcom, *jcomdot, *jcomdot_qdot;
   double *fr_iso, *fr_vel, *fr_jac, *fr_jdqd;
+  double *cent_ag, *cent_hg, *cent_ig;  // centroidal momentum matrix [B,6,nv], momentum [B,6], inertia [B,36]
   // internal-constraint projection products (only when the problem has n_ic > 0)
   double *ic_cg;    // [B, nv]        Ni^T (c+g)
   double *ic_jcni;  // [B, nc, nv]    Jc Ni

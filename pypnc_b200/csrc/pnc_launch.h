@@ -58,6 +58,7 @@ inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, in
   WsPtrs w = a;
   w.q += off * nq; w.qdot += off * nv; w.M += off * nv * nv; w.grav += off * nv; w.cori += off * nv;
   w.com += off * 3; w.vcom += off * 3; w.jcom += off * 3 * nv; w.jcomdot += off * 3 * nv; w.jcomdot_qdot += off * 3;
+  w.cent_ag += off * 6 * nv; w.cent_hg += off * 6; w.cent_ig += off * 36;
   w.fr_iso += off * nfr * 12; w.fr_vel += off * nfr * 6; w.fr_jac += off * nfr * 6 * nv; w.fr_jdqd += off * nfr * 6;
   if (w.ic_cg) {
     w.ic_cg += off * nv; w.ic_jcni += off * nc * nv; w.ic_tq += off * nact * n; w.ic_tq0 += off * nact;
@@ -71,7 +72,7 @@ inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, in
 void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs& ws, int B, int nv,
                           const double* base_pos, const double* base_quat, const double* base_lin_vel,
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
-                          int num_sms, cudaStream_t stream);
+                          int num_sms, cudaStream_t stream, int b_cent = 0);
 void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcLayout& L, const WsPtrs& ws,
                         const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream);
 bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,

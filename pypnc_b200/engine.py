@@ -103,12 +103,20 @@ class Workspace:
     def nbytes(self):
         return int(self.lib.pnc_workspace_bytes(self.h))
 
-    def update_system(self, base_pos, base_quat, base_lin_vel, base_ang_vel, joint_pos, joint_vel):
+    def update_system(self, base_pos, base_quat, base_lin_vel, base_ang_vel, joint_pos, joint_vel, b_cent=False):
         B = joint_pos.shape[0]
-        _check(self.lib.pnc_update_system(self.h, B, _ptr(base_pos), _ptr(base_quat), _ptr(base_lin_vel),
-                                          _ptr(base_ang_vel), _ptr(joint_pos), _ptr(joint_vel), _stream()),
-               'pnc_update_system')
+        _check(self.lib.pnc_update_system_cent(self.h, B, _ptr(base_pos), _ptr(base_quat), _ptr(base_lin_vel),
+                                               _ptr(base_ang_vel), _ptr(joint_pos), _ptr(joint_vel),
+                                               1 if b_cent else 0, _stream()), 'pnc_update_system_cent')
         self.B = B
+
+    def centroidal(self, B=None):
+        """(Ag [B,6,nv], hg [B,6], Ig [B,6,6]) views; valid after update_system(..., b_cent=True)."""
+        B = self.B if B is None else B
+        nv, dev = self.dev_model.model.nv, self.dev_model.device
+        return (_from_ptr(self.lib.pnc_ws_centroidal_ag(self.h), (B, 6, nv), dev),
+                _from_ptr(self.lib.pnc_ws_centroidal_hg(self.h), (B, 6), dev),
+                _from_ptr(self.lib.pnc_ws_centroidal_ig(self.h), (B, 6, 6), dev))
 
     def view(self, name, B=None):
         """A torch view (no copy) of one workspace array for the first B states."""

@@ -70,6 +70,14 @@ class BatchedRobotSystem:
     dev_model = property(lambda s: s._dev_model)
     batch = property(lambda s: 0 if s._ws is None else s._ws.B)
 
+    def _cent(self, k):
+        assert getattr(self, '_b_cent', False), "call update_system(..., b_cent=True) first"
+        return self._ws.centroidal()[k].clone()
+
+    Ag = property(lambda s: s._cent(0))  # [B, 6, nv]  rows [angular; linear]  (:188-190)
+    hg = property(lambda s: s._cent(1))  # [B, 6]                              (:184-186)
+    Ig = property(lambda s: s._cent(2))  # [B, 6, 6]   diagonal blocks only    (:192-194)
+
     def get_q_idx(self, joint_id):  # :95-100
         if isinstance(joint_id, (list, tuple)):
             return [self._model.get_q_idx(j) for j in joint_id]
@@ -104,7 +112,7 @@ class BatchedRobotSystem:
             self._frames = want
             self._ws = engine.Workspace(self._dev_model, self._capacity, self._frames)
             if self._inputs is not None:
-                self._ws.update_system(*self._inputs)
+                self._ws.update_system(*self._inputs, b_cent=getattr(self, '_b_cent', False))
         return self._ws
 
     def _t(self, a, width):
@@ -135,10 +143,9 @@ class BatchedRobotSystem:
                     self._t(base_joint_ang_vel, 3)]
         self._inputs = base + [jp, jv]
         self._joint_positions, self._joint_velocities = jp, jv
+        self._b_cent = bool(b_cent)
         ws = self.workspace()
-        ws.update_system(*self._inputs)
-        if b_cent:
-            raise NotImplementedError("centroidal quantities (Ag, hg, Ig) are SURVEY.md 8(f) rank 3: next round")
+        ws.update_system(*self._inputs, b_cent=self._b_cent)
 
     # ---- getters (:197-278); every one returns a fresh tensor like the reference's np.copy --
     def _get(self, name):

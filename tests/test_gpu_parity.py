@@ -191,6 +191,24 @@ def test_golden_vectors_from_reference_python(name):
     assert rel(ws.view('grav').cpu().numpy(), z['out_grav']) < 1e-13
 
 
+@pytest.mark.parametrize("ctx", ['atlas', 'laikago', 'draco3'], indirect=True)
+def test_centroidal_quantities_match_oracle(ctx):
+    """update_system(..., b_cent=True): Ag, hg, Ig of pinocchio_robot_system.py:181-194."""
+    ws = ctx.ws
+    M0 = ws.view('M').clone()
+    ws.update_system(*ctx.d_st, b_cent=True)
+    ctx.torch.cuda.synchronize()
+    Ag, hg, Ig = [t.cpu().numpy() for t in ws.centroidal()]
+    rel = lambda a, b: np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+    for b in range(0, ctx.B, 6):
+        q, v = ctx.qv(b)
+        rAg, rhg, rIg = ctx.op.om.centroidal(q, v)
+        assert rel(Ag[b], rAg) < 1e-12
+        assert rel(hg[b], rhg) < 1e-11
+        assert rel(Ig[b], rIg) < 1e-12
+    assert ctx.torch.equal(ws.view('M'), M0)  # the other outputs are untouched by the flag
+
+
 def test_tick_host_equals_device_path(oracle_mod):
     """pnc_wbc_tick_host (host buffers, chunked over two streams) == the device-resident calls."""
     import torch

@@ -237,6 +237,14 @@ int pnc_joint_integrate(int32_t B, int32_t na, const double* d_acc, const double
                         const double* d_vel_limit, double alpha_vel, double alpha_pos, double dt,
                         void* stream);
 
+/* Operational-space control step of the fixed-base manipulator, ManipulatorInterface._compute_osc_command
+ * (pnc/manipulator_pnc/manipulator_interface.py:77-114), for B states after pnc_update_system:
+ * xddot = kp (pos_des - pos) + kd (vel_des - vel) on the LINEAR rows of frame `frame` (a model frame index
+ * the workspace materialises), qddot = smooth * pinv(J, rcond = 1e-3) xddot, trq = M qddot + c + g.
+ * d_pos_des / d_vel_des [B,3], d_kp / d_kd [3] (device), outputs d_trq [B,nv], d_qddot [B,nv] (may be NULL). */
+int pnc_osc_step(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_pos_des, const double* d_vel_des,
+                 const double* d_kp, const double* d_kd, double smooth, double* d_trq, double* d_qddot, void* stream);
+
 /* Whole controller tick with HOST buffers: H2D of the inputs, update_system, solve,
  * D2H of the outputs; synchronous.  Any output may be NULL. */
 int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,

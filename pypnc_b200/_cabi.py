@@ -137,6 +137,7 @@ def load_library():
     lib.pnc_ihwbc_solve.argtypes = [vp, vp, i32] + [vp] * 10 + [vp]
     lib.pnc_task_eval.argtypes = [vp, vp, i32, i32] + [vp] * 5 + [vp]
     lib.pnc_contact_eval.argtypes = [vp, vp, i32, i32] + [vp] * 4 + [vp]
+    lib.pnc_osc_step.argtypes = [vp, i32, i32] + [vp] * 4 + [dbl, vp, vp, vp]
     lib.pnc_joint_integrate.argtypes = [i32, i32] + [vp] * 6 + [dbl, dbl, dbl, vp]
     lib.pnc_wbc_tick_host.argtypes = [vp, vp, i32] + [vp] * 15
     lib.pnc_launch_count.argtypes = []
@@ -156,6 +157,6 @@ EXPORTED_SYMBOLS = [
     'pnc_ws_centroidal_ig', 'pnc_ws_q', 'pnc_ws_qdot', 'pnc_ws_mass_matrix', 'pnc_ws_gravity',
     'pnc_ws_coriolis', 'pnc_ws_com_pos', 'pnc_ws_com_vel', 'pnc_ws_com_jac', 'pnc_ws_com_jacdot',
     'pnc_ws_com_jdqd', 'pnc_ws_frame_iso', 'pnc_ws_frame_vel', 'pnc_ws_frame_jac', 'pnc_ws_frame_jdqd',
-    'pnc_ihwbc_solve', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_wbc_tick_host',
+    'pnc_ihwbc_solve', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_osc_step', 'pnc_wbc_tick_host',
     'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version', 'pnc_debug_set_dump',
 ]

@@ -492,6 +492,23 @@ int pnc_joint_integrate(int32_t B, int32_t na, const double* d_acc, const double
   return PNC_OK;
 }
 
+// Operational-space control step of a fixed-base arm (manipulator_interface.py:77-114) for B states.
+// `frame` is a MODEL frame index that the workspace materialises; d_kp / d_kd are 3 device doubles.
+int pnc_osc_step(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_pos_des, const double* d_vel_des,
+                 const double* d_kp, const double* d_kd, double smooth, double* d_trq, double* d_qddot, void* stream) {
+  if (!ws || B < 0 || B > ws->cap || !d_pos_des || !d_vel_des || !d_kp || !d_kd || !d_trq) return PNC_E_ARG;
+  int slot = -1;
+  for (int f = 0; f < ws->nfr; f++)
+    if (ws->hfr.model_frame[f] == frame) slot = f;
+  if (slot < 0) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  launch_osc_step(ws->p, ws->nfr, slot, ws->m->h.nv, B, d_pos_des, d_vel_des, d_kp, d_kd, smooth, 1e-3, d_trq, d_qddot,
+                  (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // Whole tick with host buffers.  The batch is cut into chunks that ping-pong over two
 // streams so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels

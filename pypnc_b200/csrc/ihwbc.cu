@@ -939,6 +939,86 @@ void launch_joint_integrate(int B, int na, const double* acc, const double* join
 }
 
 // ---------------------------------------------------------------------------------------
+// Operational-space control step of the fixed-base manipulator
+// (pnc/manipulator_pnc/manipulator_interface.py:77-114): xddot = kp (pos_des - pos) + kd (vel_des - vel),
+// qddot = smooth * pinv(J_lin, rcond = 1e-3) xddot, trq = M qddot + c + g.  One thread per state.
+// pinv of the 3 x nv Jacobian through the eigen-decomposition of J J^T (cyclic Jacobi, 3 x 3):
+// singular values sigma_i = sqrt(lambda_i), kept when sigma_i > rcond * sigma_max as numpy does.
+__global__ void k_osc_step(WsPtrs ws, int nfr, int slot, int nv, int B, const double* __restrict__ pos_des,
+                           const double* __restrict__ vel_des, const double* __restrict__ kp,
+                           const double* __restrict__ kd, double smooth, double rcond, double* trq, double* qddot) {
+  for (size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x; s < (size_t)B; s += (size_t)gridDim.x * blockDim.x) {
+    const double* J = ws.fr_jac + ((s * nfr + slot) * 6 + 3) * nv;  // linear rows
+    const double* iso = ws.fr_iso + (s * nfr + slot) * 12;
+    const double* fv = ws.fr_vel + (s * nfr + slot) * 6;
+    double xdd[3];
+    for (int i = 0; i < 3; i++) xdd[i] = kp[i] * (pos_des[3 * s + i] - iso[9 + i]) + kd[i] * (vel_des[3 * s + i] - fv[3 + i]);
+    double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        double acc = 0.0;
+        for (int k = 0; k < nv; k++) acc += J[r * nv + k] * J[c * nv + k];
+        A[r][c] = acc;
+      }
+    for (int sweep = 0; sweep < 12; sweep++) {
+      const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+      if (off <= 1e-300) break;
+      for (int p = 0; p < 2; p++)
+        for (int q = p + 1; q < 3; q++) {
+          if (A[p][q] == 0.0) continue;
+          const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+          for (int k = 0; k < 3; k++) {  // A <- A G
+            const double akp = A[k][p], akq = A[k][q];
+            A[k][p] = c * akp - sn * akq;
+            A[k][q] = sn * akp + c * akq;
+          }
+          for (int k = 0; k < 3; k++) {  // A <- G^T A
+            const double apk = A[p][k], aqk = A[q][k];
+            A[p][k] = c * apk - sn * aqk;
+            A[q][k] = sn * apk + c * aqk;
+          }
+          for (int k = 0; k < 3; k++) {
+            const double vkp = V[k][p], vkq = V[k][q];
+            V[k][p] = c * vkp - sn * vkq;
+            V[k][q] = sn * vkp + c * vkq;
+          }
+        }
+    }
+    double lmax = fmax(fmax(A[0][0], A[1][1]), A[2][2]);
+    if (lmax < 0.0) lmax = 0.0;
+    // y = V diag(1/lambda_i | kept) V^T xdd ;  qddot = J^T y
+    double y[3] = {0, 0, 0};
+    for (int i = 0; i < 3; i++) {
+      const double lam = A[i][i];
+      if (lam > 0.0 && sqrt(lam) > rcond * sqrt(lmax)) {
+        const double coef = (V[0][i] * xdd[0] + V[1][i] * xdd[1] + V[2][i] * xdd[2]) / lam;
+        for (int r = 0; r < 3; r++) y[r] += V[r][i] * coef;
+      }
+    }
+    const double* M = ws.M + s * nv * nv;
+    for (int i = 0; i < nv; i++) {
+      double acc = ws.cori[s * nv + i] + ws.grav[s * nv + i];
+      for (int j = 0; j < nv; j++) {
+        const double qj = smooth * (J[j] * y[0] + J[nv + j] * y[1] + J[2 * nv + j] * y[2]);
+        acc += M[i * nv + j] * qj;
+      }
+      trq[s * nv + i] = acc;
+      if (qddot) qddot[s * nv + i] = smooth * (J[i] * y[0] + J[nv + i] * y[1] + J[2 * nv + i] * y[2]);
+    }
+  }
+}
+
+void launch_osc_step(const WsPtrs& ws, int nfr, int slot, int nv, int B, const double* pos_des, const double* vel_des,
+                     const double* kp, const double* kd, double smooth, double rcond, double* trq, double* qddot,
+                     cudaStream_t stream) {
+  int grid = (B + 127) / 128;
+  k_osc_step<<<grid, 128, 0, stream>>>(ws, nfr, slot, nv, B, pos_des, vel_des, kp, kd, smooth, rcond, trq, qddot);
+  g_launch_count++;
+}
+
+// ---------------------------------------------------------------------------------------
 // DFMA-chain microbenchmark: the fp64 roofline denominator (MEASURED_PEAKS.json has none)
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

@@ -92,6 +92,9 @@ void launch_contact_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap&
 void launch_joint_integrate(int B, int na, const double* acc, const double* joint_pos, double* vel_state,
                             double* pos_state, const double* pos_limit, const double* vel_limit, double alpha_vel,
                             double alpha_pos, double dt, cudaStream_t stream);
+void launch_osc_step(const WsPtrs& ws, int nfr, int slot, int nv, int B, const double* pos_des, const double* vel_des,
+                     const double* kp, const double* kd, double smooth, double rcond, double* trq, double* qddot,
+                     cudaStream_t stream);
 int measure_fp64_peak(int num_sms, double* tflops);
 
 }  // namespace pnc

@@ -465,3 +465,43 @@ print("ok")
 
 
 ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_manipulator_osc_step_1k(oracle_mod):
+    """BASELINE config 1: three-link manipulator OSC control step (manipulator_interface.py:77-114),
+    batch of 1 K random joint states, fixed base."""
+    import torch
+    from pypnc_b200 import engine, _cabi
+    lib = _cabi.load_library()
+    m = robots.load_model('three_link_manipulator')
+    assert m.n_floating == 0 and m.nv == 3
+    B = 1024
+    rng = np.random.default_rng(11)
+    jp, jv = rng.uniform(-1.5, 1.5, (B, 3)), rng.normal(0, 1.0, (B, 3))
+    pos_des, vel_des = rng.uniform(-2, 2, (B, 3)), rng.normal(0, 0.3, (B, 3))
+    pos_des[:, 2] = 0.0
+    kp, kd = np.array([10., 10., 10.]), np.array([1., 1., 1.])
+    ee = m.frame_id('ee')
+    dm = engine.Model(m, 0)
+    ws = engine.Workspace(dm, B, [ee])
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d_jp, d_jv = d(jp), d(jv)
+    ws.update_system(None, None, None, None, d_jp, d_jv)
+    trq = torch.zeros((B, 3), dtype=torch.float64, device='cuda')
+    qdd = torch.zeros((B, 3), dtype=torch.float64, device='cuda')
+    P = lambda t: C.c_void_p(t.data_ptr())
+    d_pd, d_vd, d_kp, d_kd = d(pos_des), d(vel_des), d(kp), d(kd)
+    assert lib.pnc_osc_step(ws.h, B, ee, P(d_pd), P(d_vd), P(d_kp), P(d_kd), 1.0, P(trq), P(qdd), None) == 0
+    torch.cuda.synchronize()
+    om = oracle_mod.OracleModel(m)
+    # closed-form fixture of the reference (test/pinocchio_frame_test.py:14-16): q = [pi/2, 0, 0] -> ee at (0, 3, 0)
+    ws1 = engine.Workspace(dm, 1, [ee])
+    ws1.update_system(None, None, None, None, d(np.array([[np.pi / 2, 0., 0.]])), d(np.zeros((1, 3))))
+    np.testing.assert_allclose(ws1.view('frame_iso')[0, 0, 9:12].cpu().numpy(), [0., 3., 0.], atol=1e-12)
+    worst = 0.0
+    for b in range(0, B, 7):
+        t_ref, qdd_ref = om.osc_step(ee, jp[b], jv[b], pos_des[b], vel_des[b], np.zeros(3), kp, kd)
+        e = np.abs(trq[b].cpu().numpy() - t_ref).max() / max(1e-12, np.abs(t_ref).max())
+        worst = max(worst, e)
+        assert e < 1e-9, (b, e)
+        assert np.abs(qdd[b].cpu().numpy() - qdd_ref).max() / max(1e-12, np.abs(qdd_ref).max()) < 1e-9

@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.01)
 
     def finish(self):
         self._stop_evt.set()

@@ -20,14 +20,21 @@ __device__ __forceinline__ double wmax(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
   return v;
 }
-// lexicographic (value, index) minimum over the warp; every lane gets the result
-static __device__ __noinline__ void wargmin(double& v, int& idx) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_xor_sync(FULL, v, o);
-    int oi = __shfl_xor_sync(FULL, idx, o);
-    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-  }
+// lexicographic (value, index) minimum over the warp; every lane gets the result.
+// Three REDUX (integer warp reductions) on an order-preserving 64-bit key instead of five
+// shuffle rounds: the latency of this chain sits on the critical path of every iteration.
+static __device__ __forceinline__ void wargmin(double& v, int& idx) {
+  const long long bits = __double_as_longlong(v);
+  const unsigned long long key = bits < 0 ? ~(unsigned long long)bits : ((unsigned long long)bits | 0x8000000000000000ull);
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mh = __reduce_min_sync(FULL, hi);
+  const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+  const bool win = hi == mh && lo == ml;
+  const unsigned mi = __reduce_min_sync(FULL, win ? (unsigned)idx : 0xffffffffu);
+  const unsigned long long mk = ((unsigned long long)mh << 32) | ml;
+  const long long mb = (mk & 0x8000000000000000ull) ? (long long)(mk & 0x7fffffffffffffffull) : (long long)~mk;
+  v = __longlong_as_double(mb);
+  idx = (int)mi;
 }
 
 __device__ __forceinline__ double qp_distance(double a, double b) {  // QuadProg++.cc:681-692

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(32)
 k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, SetupLayout SL, WsPtrs ws, FrameMap fm,
               int nfr, int B, SolveIO io, double* __restrict__ rec_all, int* __restrict__ counter) {
   using C = RCfg<NV, NC>;
-  constexpr int N = C::N, NP = C::NP, LDV = C::LDV;
+  constexpr int NP = C::NP, LDV = C::LDV;
   extern __shared__ __align__(16) double smem[];
   const DevProblem& G = *gp;
   const int lane = threadIdx.x;
@@ -836,31 +836,21 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             }
             zz = pzz; znp = pzn; sig2 = psg;
           }
-          // r = R^-1 d[0:iq] (:530-542), column-oriented back substitution; lane i owns d[i], r[i]
-          if (iq <= 32) {
-            const double rinvA = lane < iq ? rinv[lane] : 0.0;
-            double acc = 0.0, rmine = 0.0;
-            const double* col = Rp + ((iq - 1) * (iq + 2)) / 2;
-#pragma unroll 1
-            for (int i = iq - 1; i >= 0; i--) {
-              const double ri = __shfl_sync(FULL, (dA - acc) * rinvA, i);
-              if (lane < i) acc = fma(col[lane], ri, acc);
-              if (lane == i) rmine = ri;
-              col -= i + 1;
-            }
-            if (lane < iq) rv[lane] = rmine;
-          } else {
+          // r = R^-1 d[0:iq] (:530-542).  The kernel keeps S = R^-1 (upper triangular, packed by
+          // columns) instead of R: r = S d is a matrix-vector product -- lane i owns row i -- not a
+          // back substitution with its dependent chain of iq steps
+          {
             double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 1
-            for (int i = iq - 1; i >= 0; i--) {
-              const double* col = Rcol(i);
-              const double mine = (i & 32) ? acc1 : acc0;
-              double ri = (dv[i] - mine) * rinv[i];
-              ri = __shfl_sync(FULL, ri, i & 31);
-              if (lane == (i & 31)) rv[i] = ri;
-              if (lane < i) acc0 = fma(col[lane], ri, acc0);
-              if (lane + 32 < i) acc1 = fma(col[lane + 32], ri, acc1);
+            const double* col = Rp;
+#pragma unroll 2
+            for (int j = 0; j < iq; j++) {
+              const double dj = dv[j];
+              if (lane <= j) acc0 = fma(col[lane], dj, acc0);
+              if (N > 32 && lane + 32 <= j) acc1 = fma(col[lane + 32], dj, acc1);
+              col += j + 2;
             }
+            if (lane < iq) rv[lane] = acc0;
+            if (N > 32 && lane + 32 < iq) rv[lane + 32] = acc1;
           }
           __syncwarp();
           // step lengths (:366-393); equalities always take the full step (:246-258)
@@ -912,9 +902,11 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             const double alpha = d0 > 0.0 ? -sigma : sigma;
             const double v0 = d0 - alpha;
             const double beta = 1.0 / (sigma * (sigma + fabs(d0)));
+            // R gains the column [d1; alpha]  <=>  S = R^-1 gains the column [-S d1 / alpha; 1 / alpha]
             double* col = Rcol(iq);
-            for (int i = lane; i < iq; i += 32) col[i] = dv[i];
-            if (lane == 0) { col[iq] = alpha; rinv[iq] = 1.0 / alpha; }
+            const double ialpha = 1.0 / alpha;
+            for (int i = lane; i < iq; i += 32) col[i] = -rv[i] * ialpha;
+            if (lane == 0) col[iq] = ialpha;
             for (int j = lane; j < NP; j += 32) vm[j] = j > iq ? dv[j] : (j == iq ? v0 : 0.0);
             const double ca = reg_pick(Ja, iq);  // old column iq of J
             double hwb = 0.0;
@@ -962,63 +954,62 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           }
 
           // ---- drop constraint l at position kk (:409-423, :476-499; delete_constraint :610-679) ----
+          // With S = R^-1 the Givens sweep is driven by row kk of S: rotating the column pairs
+          // (j, j+1), j = kk .. iq-2, so that this row ends up in the last column makes
+          // S Q^T (minus row kk and the last column) the inverse of the re-triangularised R, with the
+          // same Q that QuadProg++ applies to the columns of J.
           clr_bit(act0, act1, l);
+          {
+            double carry = Rcol(kk)[kk];
 #pragma unroll 1
-          for (int i = kk; i < iq - 1; i++) {
-            const double* src = Rcol(i + 1);
-            double* dst = Rcol(i);
-            double v0 = 0.0, v1 = 0.0;
-            if (lane <= i + 1) v0 = src[lane];
-            if (lane + 32 <= i + 1) v1 = src[lane + 32];
-            const int ai = Aact[i + 1];
-            const double ui = uv[i + 1];
-            __syncwarp();
-            if (lane <= i + 1) dst[lane] = v0;
-            if (lane + 32 <= i + 1) dst[lane + 32] = v1;
-            if (lane == 0) { Aact[i] = ai; uv[i] = ui; }
-            __syncwarp();
+            for (int j = kk; j < iq - 1; j++) {
+              double* cj = Rcol(j);
+              double* cn = Rcol(j + 1);
+              const double a = carry, b = cn[kk];
+              const double hh = qp_distance(a, b);
+              const bool skip = fabs(hh) < QP_EPS;
+              double cc = 1.0, ss = 0.0, xny = 0.0;
+              if (!skip) {
+                const double sgn = b >= 0.0 ? 1.0 : -1.0;
+                cc = sgn * b / hh;
+                ss = -sgn * a / hh;
+                xny = ss / (1.0 + cc);
+                carry = -sgn * hh;
+              } else {
+                carry = b;
+              }
+              const double t1a = lane <= j ? cj[lane] : 0.0, t2a = lane <= j + 1 ? cn[lane] : 0.0;
+              double t1b = 0.0, t2b = 0.0;
+              if (N > 32) { t1b = lane + 32 <= j ? cj[lane + 32] : 0.0; t2b = lane + 32 <= j + 1 ? cn[lane + 32] : 0.0; }
+              __syncwarp();
+              const double nja = skip ? t1a : t1a * cc + t2a * ss, nna = skip ? t2a : xny * (t1a + nja) - t2a;
+              // column j is final: store it without row kk; column j+1 keeps its rows until its turn
+              if (lane <= j + 1 && lane != kk) cj[lane - (lane > kk ? 1 : 0)] = nja;
+              if (lane <= j + 1) cn[lane] = nna;
+              if (N > 32) {
+                const double njb = skip ? t1b : t1b * cc + t2b * ss, nnb = skip ? t2b : xny * (t1b + njb) - t2b;
+                const int i = lane + 32;
+                if (i <= j + 1 && i != kk) cj[i - (i > kk ? 1 : 0)] = njb;
+                if (i <= j + 1) cn[i] = nnb;
+              }
+              if (lane == 0) { rot[3 * j] = skip ? 2.0 : cc; rot[3 * j + 1] = ss; rot[3 * j + 2] = xny; }
+              __syncwarp();
+            }
           }
-          if (lane == 0) {
-            Aact[iq - 1] = Aact[iq];
-            uv[iq - 1] = uv[iq];
-            Aact[iq] = 0;
-            uv[iq] = 0.0;
+          {  // A[i], u[i] <- A[i+1], u[i+1] for i = kk .. iq-1 (the candidate at iq moves down too)
+            int a0_ = 0, a1_ = 0;
+            double u0_ = 0.0, u1_ = 0.0;
+            const bool m0 = lane >= kk && lane < iq, m1 = lane + 32 >= kk && lane + 32 < iq;
+            if (m0) { a0_ = Aact[lane + 1]; u0_ = uv[lane + 1]; }
+            if (m1) { a1_ = Aact[lane + 33]; u1_ = uv[lane + 33]; }
+            __syncwarp();
+            if (m0) { Aact[lane] = a0_; uv[lane] = u0_; }
+            if (m1) { Aact[lane + 32] = a1_; uv[lane + 32] = u1_; }
+            if (lane == 0) { Aact[iq] = 0; uv[iq] = 0.0; }
           }
           iq--;
           __syncwarp();
-          if (iq > 0) {
-            // Givens on the rows of R; the coefficients go to the rotation table
-#pragma unroll 1
-            for (int j = kk; j < iq; j++) {
-              double* cj = Rcol(j);
-              double cc = cj[j], ss = cj[j + 1];
-              const double hh = qp_distance(cc, ss);
-              double xny = 0.0;
-              const bool skip = fabs(hh) < QP_EPS;
-              __syncwarp();
-              if (skip) {  // QuadProg++ leaves the pair untouched (:651)
-                if (lane == 0) { rot[3 * j] = 2.0; rot[3 * j + 1] = 0.0; rot[3 * j + 2] = 0.0; rinv[j] = 1.0 / cj[j]; }
-              } else {
-                cc = cc / hh;
-                ss = ss / hh;
-                double diag = hh;
-                if (cc < 0.0) { diag = -hh; cc = -cc; ss = -ss; }
-                xny = ss / (1.0 + cc);
-                if (lane == 0) {
-                  cj[j] = diag; cj[j + 1] = 0.0; rinv[j] = 1.0 / diag;
-                  rot[3 * j] = cc; rot[3 * j + 1] = ss; rot[3 * j + 2] = xny;
-                }
-#pragma unroll 1
-                for (int k = j + 1 + lane; k < iq; k += 32) {
-                  double* ck = Rcol(k);
-                  const double t1r = ck[j], t2r = ck[j + 1];
-                  const double nj = t1r * cc + t2r * ss;
-                  ck[j] = nj;
-                  ck[j + 1] = xny * (t1r + nj) - t2r;
-                }
-              }
-              __syncwarp();
-            }
+          if (iq > kk) {
             // the same rotations on the columns of J (registers)
             reg_rot_range(Ja, kk, iq, rot);
             if constexpr (EXT) {

@@ -428,10 +428,10 @@ static int solve_at(const pnc_problem* p, pnc_workspace* ws, int off, int32_t B,
     launch_ic_prepare(p->d, p->h, wsp, fm, ws->nfr, B, ws->m->num_sms, st, counter + 1);
     CK(cudaGetLastError());
   }
-  CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(counter, 0, 4 * sizeof(int), st));  // work counters of the stage + the overflow flag
   SolveIO io;
   io.des = des; io.w = w; io.rfz = rfz; io.trq = trq; io.acc = acc; io.rf = rf; io.qddot = qddot;
-  io.status = status; io.iters = iters; io.active = reinterpret_cast<unsigned long long*>(active); io.counter = counter;
+  io.status = status; io.iters = iters; io.active = reinterpret_cast<unsigned long long*>(active); io.counter = counter; io.overflow = counter + 3;
   launch_ihwbc_solve(p->d, p->h, p->lay, wsp, fm, ws->nfr, B, io, ws->m->num_sms, st);
   CK(cudaGetLastError());
   return PNC_OK;

@@ -222,7 +222,10 @@ struct DebugDump {
 __device__ DebugDump g_dump = {nullptr, -1};
 
 __global__ void __launch_bounds__(32)
-k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, FrameMap fm, int nfr, int nq, int B, SolveIO io) {
+k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, FrameMap fm, int nfr, int nq, int B, SolveIO io,
+              const int* __restrict__ only_flag) {
+  // only_flag != NULL: second pass after the register kernel -- nothing to do unless it flagged states
+  if (only_flag && *only_flag == 0) return;
   extern __shared__ __align__(16) double smem[];
   const DevProblem& P = *gp;
   const int lane = threadIdx.x;
@@ -261,6 +264,7 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
     si = __shfl_sync(FULL, si, 0);
     if (si >= B) break;
     const size_t s = (size_t)si;
+    if (only_flag && io.status[s] != PNC_QP_OVERFLOW) continue;
     const double* des = io.des + s * P.ndes;
     int status = PNC_QP_OK, iter = 0;
     if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;  // rank-deficient projection (icprep.cu)
@@ -777,7 +781,10 @@ void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcL
                         const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream) {
   // register-resident kernel for the shipped QP shapes; PNC_SOLVER=smem forces the generic kernel
   static const bool force_smem = [] { const char* e = getenv("PNC_SOLVER"); return e && e[0] == 's'; }();
-  if (!force_smem && ws.task_e && launch_ihwbc_solve_reg(dp, hp, ws, fm, nfr, B, io, num_sms, stream)) return;
+  const bool fast = !force_smem && ws.task_e && launch_ihwbc_solve_reg(dp, hp, ws, fm, nfr, B, io, num_sms, stream);
+  // after the register kernel the generic kernel runs as a (normally empty) second pass over the
+  // states it could not finish (more than 32 active constraints)
+  if (fast) cudaMemsetAsync(io.counter, 0, sizeof(int), stream);
   const size_t smem = (size_t)L.per_state * sizeof(double);
   static size_t configured = 0;
   if (smem > configured) {
@@ -790,7 +797,7 @@ void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcL
   int grid = num_sms * per_sm;
   if (grid > B) grid = B;
   const int nq = hp.nv + 1;
-  k_ihwbc_solve<<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, nq, B, io);
+  k_ihwbc_solve<<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, nq, B, io, fast ? io.overflow : nullptr);
   g_launch_count++;
 }
 

@@ -39,21 +39,33 @@ struct RCfg {
   static constexpr int EVP = EV <= 1 ? 1 : (EV <= 2 ? 2 : (EV <= 4 ? 4 : 8));
   static constexpr int LPR = 32 / EVP;                        // lanes cooperating on one such row in the Cholesky
   static constexpr int LDT = NP + 2;                          // pitch of the d scratch tile
-  // ---- compile-time shared-memory layout of the active-set kernel (doubles).  Sizes that depend on
-  //      the problem (cone rows, inequalities, equalities) use their upper bounds, so every array
-  //      sits at an immediate offset from the shared-memory base: no address registers, nothing to
-  //      rematerialise under the register pressure of the resident J ----
-  static constexpr int NUMAX = PNC_MAX_CONE, MMAX = 128, PMAX = 10;
-  static constexpr int RSZ = (N * (N + 3) / 2 + 1) & ~1;
-  static constexpr int ORT = 0, OT = ORT + RSZ, ORINV = OT + 6 * LDT, OUF = ORINV + NP, OUFV = OUF + NUMAX * 6,
-                       OX = OUFV + NUMAX, OZ = OX + NP, ODV = OZ + NP, ODM = ODV + NP, OVM = ODM + NP, ONP = OVM + NP,
-                       ORR = ONP + NP, OU = ORR + NP + 2, OXOLD = OU + NP + 2, OUOLD = OXOLD + NP,
-                       OXACC = OUOLD + NP + 2, OSL = OXACC + NP, OINT = OSL + MMAX,
-                       SMEM_DOUBLES = (OINT + (3 * (N + 2) + 1) / 2 + 2) & ~1;
   // ---- per-state HBM record written by the setup kernel (doubles) ----
+  static constexpr int PMAX = 10;
   static constexpr int RG = 0, RX = (NV * LDV + 1) & ~1, RD = RX + NP, RS = RD + PMAX * NP, REC = (RS + 4 + 1) & ~1;
   static_assert(E <= 16, "rows beyond 32 must fit one lane pair each");
   static_assert(N <= 64, "n too large for the register kernel");
+};
+
+// Compile-time shared-memory layout of the active-set kernel (doubles).  NU = wrench-cone rows,
+// NT = torque-limit rows (0 without torque limits).  Every array sits at an immediate offset from
+// the shared-memory base: no address registers, nothing to rematerialise under the register
+// pressure of the resident J.  S = R^-1 is capped at RC = 32 columns (active constraints incl.
+// equalities); a state that would need more is handed to the generic kernel (status OVERFLOW).
+template <int NV_, int NC_, int NU_, int NT_>
+struct MCfg : RCfg<NV_, NC_> {
+  using R = RCfg<NV_, NC_>;
+  static constexpr int NU = NU_, NT = NT_, M = NU_ + 2 * NT_;
+  static constexpr int RC = R::N < 32 ? R::N : 32;
+  static constexpr int RSZ = (RC * (RC + 3) / 2 + 1) & ~1;
+  static constexpr int lda_() { int l = R::NP; while ((l & 15) != 2) l += 2; return l; }
+  static constexpr int LDA = lda_();  // torque rows: LDS.128 by row is conflict free at 2 (mod 16)
+  static constexpr int ORT = 0, OT = ORT + RSZ, OAR = OT + 6 * R::LDT, OA0 = OAR + NT * LDA, OUF = OA0 + ((NT + 1) & ~1),
+                       OUFV = OUF + (NU > 0 ? NU : 1) * 6, OX = OUFV + (((NU > 0 ? NU : 1) + 1) & ~1), OZ = OX + R::NP,
+                       ODV = OZ + R::NP, ODM = ODV + R::NP, OVM = ODM + R::NP, ONP = OVM + R::NP, ORR = ONP + R::NP,
+                       OU = ORR + R::NP + 2, OXOLD = OU + R::NP + 2, OUOLD = OXOLD + R::NP, OXACC = OUOLD + R::NP + 2,
+                       OSL = OXACC + R::NP, OINT = OSL + (((M > 0 ? M : 1) + 1) & ~1),
+                       SMEM_DOUBLES = (OINT + (3 * (R::N + 2) + 1) / 2 + 2) & ~1;
+  static_assert(64 + R::PMAX * R::NP <= RSZ || R::N < 20, "equality block must fit behind the first S columns");
 };
 
 // ---- register-array access by a warp-uniform dynamic index (jump table, no local memory) ----
@@ -499,25 +511,27 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 }
 
 // =======================================================================================
-template <int NV, int NC>
+template <int NV, int NC, int NU, int NT>
 #ifndef PNC_REG_LB
 #define PNC_REG_LB __launch_bounds__(32)
 #endif
 __global__ void PNC_REG_LB
 k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B,
-            SolveIO io, const double* __restrict__ rec_all) {
+            SolveIO io, const double* __restrict__ rec_all, int rc_cap) {
   // P (constant bank) serves warp-uniform reads; tables indexed per lane go through the global copy G
   const DevProblem& G = *gp;
-  using C = RCfg<NV, NC>;
-  constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV;
+  using C = MCfg<NV, NC, NU, NT>;
+  constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV, LDA = C::LDA;
   constexpr bool EXT = C::EXT;
   __shared__ __align__(16) double smem[C::SMEM_DOUBLES];  // static: addresses are immediates in the shared window
   const int lane = threadIdx.x;
-  const int p = P.p, m = P.m, nu = P.nu, nact = P.nact;
-  const bool trq = P.b_trq_limit != 0, has_ic = P.n_ic > 0;
+  const int p = P.p, m = C::M, nu = NU, nact = P.nact;
+  constexpr bool trq = NT > 0;
+  const bool has_ic = P.n_ic > 0;
   double* const Rp = smem + C::ORT;
   double* const Ts = smem + C::OT;
-  double* const rinv = smem + C::ORINV;
+  double* const Ar = smem + C::OAR;   // torque-limit rows S [M | -(Jc Ni)^T], pitch LDA
+  double* const a0 = smem + C::OA0;   // their offsets S Ni^T (c + g)
   double* const Uf = smem + C::OUF;
   double* const uf = smem + C::OUFV;
   double* const x = smem + C::OX;
@@ -588,6 +602,38 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         double rz = io.rfz[s * P.ncontact + ci];
         if (rz <= 0.0) rz = 1e-3;  // contact.py:37-41
         uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
+      }
+    }
+    if constexpr (NT > 0) {
+      // torque-limit rows S [M | -(Jc Ni)^T] (nact x n) and their offsets, staged once per state:
+      // the slack pass of every outer iteration then reads shared memory instead of waiting on L2.
+      // Flattened copy with several independent loads in flight; M is symmetric, so row act_idx[a]
+      // is read as column act_idx[a] with consecutive lanes on consecutive addresses.
+#pragma unroll 1
+      for (int e0 = lane; e0 < N * 32; e0 += 32 * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int e = e0 + 32 * u, k = e >> 5, a = e & 31;  // element (row a, column k), a fastest
+          double val = 0.0;
+          if (k < N && a < nact) {
+            if (has_ic) val = ws.ic_tq[(s * N + k) * nact + a];
+            else if (k < NV) val = Mg[k * NV + G.act_idx[a]];
+            else val = -row_jc(k - NV, G.act_idx[a]);
+          }
+          v[u] = val;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int e = e0 + 32 * u, k = e >> 5, a = e & 31;
+          if (k < N && a < nact) Ar[a * LDA + k] = v[u];
+        }
+      }
+      for (int a = lane; a < nact; a += 32) {
+        const int v = G.act_idx[a];
+        a0[a] = has_ic ? ws.ic_tq0[s * nact + a] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
+#pragma unroll 1
+        for (int k = N; k < LDA; k++) Ar[a * LDA + k] = 0.0;
       }
     }
     const double c1 = rec[C::RS], c2 = rec[C::RS + 1], jrf = rec[C::RS + 3];
@@ -666,7 +712,18 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             if (trq) {
 #pragma unroll 1
               for (int a = lane; a < nact; a += 32) {
-                const double tau = torque_row<NV>(P, G, ws, fm, nfr, s, a, x);
+                const double* row = Ar + a * LDA;
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < NP; k += 4) {
+                  const double2 r0 = lds2(row + k), x0 = lds2(x + k);
+                  t0 = fma(r0.x, x0.x, t0); t1 = fma(r0.y, x0.y, t1);
+                  if (k + 2 < NP) {
+                    const double2 r1 = lds2(row + k + 2), x1 = lds2(x + k + 2);
+                    t2 = fma(r1.x, x1.x, t2); t3 = fma(r1.y, x1.y, t3);
+                  }
+                }
+                const double tau = (t0 + t1) + (t2 + t3) + a0[a];
                 const double slo = tau - G.trq_lo[a], shi = G.trq_hi[a] - tau;
                 sl[nu + a] = slo;
                 sl[nu + nact + a] = shi;
@@ -726,7 +783,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               double val = 0.0;
               if (k < N) {
                 if (icrow) val = k < NV ? G.ic_jac[ip - 6][k] : 0.0;
-                else if (tq && has_ic) val = ws.ic_tq[(s * N + k) * nact + a];
+                else if (tq) val = Ar[a * LDA + k];
                 else if (k < NV) val = Mg[v * NV + k];
                 else val = -row_jc(k - NV, v);
               }
@@ -898,6 +955,12 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               for (int i = p; i < iq; i++) set_bit(act0, act1, Aact[i]);
               break;  // back to l2
             }
+            if (iq >= rc_cap) {  // S is capped at RC columns: hand the state to the generic kernel
+              status = PNC_QP_OVERFLOW;
+              if (lane == 0) *io.overflow = 1;
+              done = true;
+              break;
+            }
             const double d0 = dv[iq];
             const double alpha = d0 > 0.0 ? -sigma : sigma;
             const double v0 = d0 - alpha;
@@ -1037,8 +1100,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             double ci0;
             if (ip < nu) ci0 = -uf[ip];
             else {
-              const int a = (ip - nu) % nact, v = P.act_idx[a];
-              const double a0v = has_ic ? ws.ic_tq0[s * nact + a] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
+              const int a = (ip - nu) % nact;
+              const double a0v = a0[a];
               ci0 = (ip - nu) >= nact ? P.trq_hi[a] - a0v : a0v - P.trq_lo[a];
             }
             s_ip = acc + ci0;
@@ -1057,7 +1120,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     }
 
     // ---- outputs: x = [qddot; rf], torque recovery (ihwbc.py:339-356) ----
-    const bool bad = status == PNC_QP_NOT_PD || status == PNC_QP_EQ_DEPENDENT || status == PNC_QP_INFEASIBLE;
+    const bool bad = status == PNC_QP_NOT_PD || status == PNC_QP_EQ_DEPENDENT || status == PNC_QP_INFEASIBLE ||
+                     status == PNC_QP_OVERFLOW;
     const double nanv = __longlong_as_double(0x7ff8000000000000LL);
     if (io.qddot)
       for (int k = lane; k < NV; k += 32) io.qddot[s * NV + k] = bad ? nanv : x[k];
@@ -1068,7 +1132,18 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     if (io.trq) {
 #pragma unroll 1
       for (int a = lane; a < nact; a += 32) {
-        const double tau = bad ? nanv : torque_row<NV>(P, G, ws, fm, nfr, s, a, x);
+        double tau = nanv;
+        if (!bad) {
+          if constexpr (NT > 0) {
+            const double* row = Ar + a * LDA;
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < NP; k += 2) { const double2 r0 = lds2(row + k), x0 = lds2(x + k); t0 = fma(r0.x, x0.x, t0); t1 = fma(r0.y, x0.y, t1); }
+            tau = t0 + t1 + a0[a];
+          } else {
+            tau = torque_row<NV>(P, G, ws, fm, nfr, s, a, x);
+          }
+        }
         io.trq[s * nact + a] = bad ? nanv : tau;
       }
     }
@@ -1091,26 +1166,24 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   }
 }
 
-template <int NV, int NC>
+template <int NV, int NC, int NU, int NT>
 static bool shape_ok(const DevProblem& hp) {
-  if (hp.nv != NV || hp.nc != NC) return false;
-  using C = RCfg<NV, NC>;
-  if (hp.m > 128 || hp.nact > 64) return false;
-  const int n_ = C::N;
-  if (hp.nu > C::NUMAX || hp.m > C::MMAX || hp.p > C::PMAX) return false;
-  // the equality block D sits behind the first R columns while the equalities are added
-  if (64 + hp.p * C::NP > n_ * (n_ + 3) / 2 || hp.p * (hp.p + 3) / 2 > 64) return false;
+  using C = MCfg<NV, NC, NU, NT>;
+  if (hp.nv != NV || hp.nc != NC || hp.nu != NU || hp.m != C::M) return false;
+  if ((hp.b_trq_limit ? hp.nact : 0) != NT || hp.nact > 32 || hp.m > 128 || hp.p > C::PMAX) return false;
+  // the equality block D sits behind the first S columns while the equalities are added
+  if (64 + hp.p * C::NP > C::RSZ || hp.p * (hp.p + 3) / 2 > 64 || hp.p >= C::RC) return false;
   return true;
 }
 
-template <int NV, int NC>
+template <int NV, int NC, int NU, int NT>
 static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
                        const SolveIO& io, int num_sms, cudaStream_t stream) {
-  if (!shape_ok<NV, NC>(hp)) return false;
-  using C = RCfg<NV, NC>;
+  if (!shape_ok<NV, NC, NU, NT>(hp)) return false;
+  using C = MCfg<NV, NC, NU, NT>;
   static_assert(C::SMEM_DOUBLES * sizeof(double) <= 48 * 1024, "static shared memory limit");
   const size_t smem = 0;  // the active-set kernel's shared memory is static
-  const SetupLayout SL = setup_layout<C>(hp);
+  const SetupLayout SL = setup_layout<RCfg<NV, NC>>(hp);
   if (!ws.setup_rec || ws.setup_stride != C::REC) return false;
   const size_t smem_s = (size_t)SL.per_state * sizeof(double);
   static size_t configured_s = 0;
@@ -1121,7 +1194,7 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   }
   int per_sm_s = 0, per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC>, 32, smem_s);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC>, 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT>, 32, smem);
   if (per_sm < 1 || per_sm_s < 1) return false;
   static const int cap = [] { const char* e = getenv("PNC_REG_WARPS"); return e ? atoi(e) : 0; }();
   if (cap > 0 && per_sm > cap) per_sm = cap;
@@ -1131,7 +1204,10 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   cudaMemsetAsync(io.counter + 2, 0, sizeof(int), stream);
   k_ihwbc_setup<NV, NC><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
   g_launch_count++;
-  k_ihwbc_reg<NV, NC><<<grid, 32, smem, stream>>>(hp, dp, ws, fm, nfr, B, io, ws.setup_rec);
+  // PNC_DEBUG_RC lowers the cap on active constraints so the tests can exercise the hand-over
+  static const int rc_dbg = [] { const char* e = getenv("PNC_DEBUG_RC"); return e ? atoi(e) : 0; }();
+  const int rc_cap = (rc_dbg > hp.p && rc_dbg < C::RC) ? rc_dbg : C::RC;
+  k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32, smem, stream>>>(hp, dp, ws, fm, nfr, B, io, ws.setup_rec, rc_cap);
   g_launch_count++;
   return true;
 }
@@ -1140,32 +1216,32 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
 // the generic shared-memory kernel of ihwbc.cu
 bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
                             int B, const SolveIO& io, int num_sms, cudaStream_t stream) {
-  return try_launch<36, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Atlas
-         try_launch<18, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Laikago
-         try_launch<33, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3
-         try_launch<20, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3 lower body
-         try_launch<32, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream);    // Valkyrie
+  // <nv, nc, cone rows, torque-limit rows>
+  return try_launch<36, 12, 36, 30>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Atlas
+         try_launch<18, 12, 24, 0>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||   // Laikago
+         try_launch<33, 12, 36, 0>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||   // Draco3
+         try_launch<20, 12, 36, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3 lower body
+         try_launch<32, 12, 36, 26>(dp, hp, ws, fm, nfr, B, io, num_sms, stream);    // Valkyrie
 }
 
-template <int NV, int NC>
-static int rec_doubles(const DevProblem& hp) { return shape_ok<NV, NC>(hp) ? RCfg<NV, NC>::REC : 0; }
+template <int NV, int NC, int NU, int NT>
+static int rec_doubles(const DevProblem& hp) { return shape_ok<NV, NC, NU, NT>(hp) ? RCfg<NV, NC>::REC : 0; }
 
 // doubles per state of the setup record (0 when no register kernel matches the problem)
 int reg_setup_record_doubles(const DevProblem& hp) {
   int r = 0;
-  if (!r) r = rec_doubles<36, 12>(hp);
-  if (!r) r = rec_doubles<18, 12>(hp);
-  if (!r) r = rec_doubles<33, 12>(hp);
-  if (!r) r = rec_doubles<20, 12>(hp);
-  if (!r) r = rec_doubles<32, 12>(hp);
+  if (!r) r = rec_doubles<36, 12, 36, 30>(hp);
+  if (!r) r = rec_doubles<18, 12, 24, 0>(hp);
+  if (!r) r = rec_doubles<33, 12, 36, 0>(hp);
+  if (!r) r = rec_doubles<20, 12, 36, 12>(hp);
+  if (!r) r = rec_doubles<32, 12, 36, 26>(hp);
   return r;
 }
 
 bool reg_kernel_available(const DevProblem& hp) {
   static const bool force_smem = [] { const char* e = getenv("PNC_SOLVER"); return e && e[0] == 's'; }();
   if (force_smem) return false;
-  return shape_ok<36, 12>(hp) || shape_ok<18, 12>(hp) || shape_ok<33, 12>(hp) || shape_ok<20, 12>(hp) ||
-         shape_ok<32, 12>(hp);
+  return reg_setup_record_doubles(hp) > 0;
 }
 
 }  // namespace pnc

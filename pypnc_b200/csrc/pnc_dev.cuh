@@ -5,6 +5,8 @@
 
 #include "../../include/pnc_b200.h"
 
+#define PNC_QP_OVERFLOW 5  /* internal status: the register kernel hands the state to the generic kernel */
+
 namespace pnc {
 
 // ---- model tables (one copy in HBM, staged into shared memory by each CTA) ----------

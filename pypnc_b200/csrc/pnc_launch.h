@@ -51,6 +51,7 @@ struct SolveIO {
   int *status, *iters;
   unsigned long long* active;
   int* counter;
+  int* overflow;  // set by the register kernel when a state needs the generic kernel
 };
 
 // workspace pointers advanced by `off` states

@@ -464,6 +464,40 @@ print("ok")
     assert r.returncode == 0 and 'ok' in r.stdout, r.stdout + r.stderr
 
 
+def test_overflow_states_are_handed_to_the_generic_kernel():
+    """The register kernel keeps at most 32 active constraints; states that need more are re-solved
+    by the generic kernel in a second pass.  PNC_DEBUG_RC=9 lowers the cap so that most Atlas states
+    take that path; the result must still match the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from pypnc_b200 import robots, engine
+from oracle import oracle
+name, B = "atlas", 64
+spec = robots.PROBLEMS[name]()
+st = robots.synth_states(name, spec, B, seed=5)
+op = oracle.OracleProblem(spec)
+des, w, rfz = robots.synth_desireds(name, spec, st, op.task_actuals(st), seed=5)
+ref = op.tick_batch(st, des, w, rfz)
+dm = engine.Model(spec.model, 0); pb = engine.Problem(dm, spec); ws = engine.Workspace(dm, B, spec.frames)
+keys = ("base_pos", "base_quat", "base_lin_vel", "base_ang_vel", "joint_pos", "joint_vel")
+ws.update_system(*[torch.from_numpy(np.ascontiguousarray(st[k])).cuda() for k in keys])
+out = engine.ihwbc_solve(pb, ws, *[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (des, w, rfz)])
+torch.cuda.synchronize()
+assert (ref["active"].sum(1) + 6 > 9).sum() > B // 2, "the cap must bite on most states"
+assert np.array_equal(out["status"].cpu().numpy(), ref["status"])
+for k in ("trq", "acc", "rf"):
+    e = np.abs(out[k].cpu().numpy() - ref[k]).max(1) / np.abs(ref[k]).max(1)
+    assert e.max() < 1e-9, (k, e.max())
+print("ok")
+''' % ROOT_DIR
+    env = dict(os.environ, PNC_DEBUG_RC='9')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stdout + r.stderr
+
+
 ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

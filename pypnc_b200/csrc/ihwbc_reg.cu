@@ -104,6 +104,15 @@ __device__ __forceinline__ void reg_rot_range(double (&A)[LEN], int j0, int j1, 
 
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
+// CTA barrier over the `nthr` threads still iterating; returns how many of them stay (every
+// arriving thread votes `stay`).  A warp that runs out of states votes false once and leaves.
+__device__ __forceinline__ int slot_barrier(int nthr, bool stay) {
+  int n;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tbarrier.cta.red.popc.u32 %0, 0, %1, p;\n\t}"
+               : "=r"(n) : "r"(nthr), "r"((int)stay) : "memory");
+  return n;
+}
+
 // Torque of actuated row a at x = [qddot; rf] (ihwbc.py:344-354):  S (M qddot + Ni^T (c+g) - (Jc Ni)^T rf).
 // Called with lanes = rows: M is symmetric, so lane a reads column act_idx[a] of M -- consecutive
 // lanes touch consecutive addresses -- and the constraint rows never have to be copied anywhere.
@@ -513,7 +522,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 // =======================================================================================
 template <int NV, int NC, int NU, int NT>
 #ifndef PNC_REG_LB
-#define PNC_REG_LB __launch_bounds__(32)
+#define PNC_REG_LB __launch_bounds__(256, 1)
 #endif
 __global__ void PNC_REG_LB
 k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B,
@@ -523,8 +532,16 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   using C = MCfg<NV, NC, NU, NT>;
   constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV, LDA = C::LDA;
   constexpr bool EXT = C::EXT;
-  __shared__ __align__(16) double smem[C::SMEM_DOUBLES];  // static: addresses are immediates in the shared window
-  const int lane = threadIdx.x;
+  // One warp per state, each with its own slice of shared memory.  The launcher uses one-warp CTAs;
+  // with PNC_REG_WARPS=w the w warps of a CTA meet at a barrier at the top of every step-direction
+  // pass, which makes them walk the ~31 KB hot loop together (the SM's 32 KB instruction cache
+  // thrashes when eight warps wander through it independently, scripts/icache_probe.cu).  Measured
+  // on Atlas 64K the wait for the slowest warp costs more than the shared fetch saves (w = 1/2/4/8:
+  // 15.3 / 16.2 / 17.3 / 21.4 ms), so this stays a diagnostic knob.
+  extern __shared__ __align__(16) double smem_all[];
+  const int lane = threadIdx.x & 31;
+  double* const smem = smem_all + (threadIdx.x >> 5) * C::SMEM_DOUBLES;
+  int nthr = blockDim.x;  // threads still taking part in the slot barrier
   const int p = P.p, m = C::M, nu = NU, nact = P.nact;
   constexpr bool trq = NT > 0;
   const bool has_ic = P.n_ic > 0;
@@ -566,7 +583,10 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     int si = 0;
     if (lane == 0) si = atomicAdd(io.counter, 1);
     si = __shfl_sync(FULL, si, 0);
-    if (si >= B) break;
+    if (si >= B) {  // no work left: leave the barrier group
+      slot_barrier(nthr, false);
+      break;
+    }
     const size_t s = (size_t)si;
     int status = PNC_QP_OK, iter = 0, iq = 0;
     double R_norm = 1.0;
@@ -808,6 +828,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         // ---- l2a: step directions, step lengths, step; repeat while constraints are dropped ----
 #pragma unroll 1
         for (;;) {
+          nthr = slot_barrier(nthr, true);
           // d = J^T np through the scratch tile, six rows of J at a time (:504-516)
           double dA = 0.0, dB = 0.0;
           if (is_eq) {
@@ -1181,8 +1202,16 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
                        const SolveIO& io, int num_sms, cudaStream_t stream) {
   if (!shape_ok<NV, NC, NU, NT>(hp)) return false;
   using C = MCfg<NV, NC, NU, NT>;
-  static_assert(C::SMEM_DOUBLES * sizeof(double) <= 48 * 1024, "static shared memory limit");
-  const size_t smem = 0;  // the active-set kernel's shared memory is static
+  static const int warps_env = [] { const char* e = getenv("PNC_REG_WARPS"); return e ? atoi(e) : 0; }();
+  int warps = warps_env >= 1 && warps_env <= 8 ? warps_env : 1;  // warps (= states in flight) per CTA
+  while (warps > 1 && (size_t)warps * C::SMEM_DOUBLES * sizeof(double) > 227 * 1024) warps--;
+  const size_t smem = (size_t)warps * C::SMEM_DOUBLES * sizeof(double);
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(k_ihwbc_reg<NV, NC, NU, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return false;
+    configured = smem;
+  }
   const SetupLayout SL = setup_layout<RCfg<NV, NC>>(hp);
   if (!ws.setup_rec || ws.setup_stride != C::REC) return false;
   const size_t smem_s = (size_t)SL.per_state * sizeof(double);
@@ -1194,20 +1223,20 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   }
   int per_sm_s = 0, per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC>, 32, smem_s);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT>, 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT>, 32 * warps, smem);
   if (per_sm < 1 || per_sm_s < 1) return false;
-  static const int cap = [] { const char* e = getenv("PNC_REG_WARPS"); return e ? atoi(e) : 0; }();
+  static const int cap = [] { const char* e = getenv("PNC_REG_CTAS"); return e ? atoi(e) : 0; }();
   if (cap > 0 && per_sm > cap) per_sm = cap;
   int grid_s = num_sms * per_sm_s, grid = num_sms * per_sm;
   if (grid_s > B) grid_s = B;
-  if (grid > B) grid = B;
+  if (grid * warps > B) grid = (B + warps - 1) / warps;
   cudaMemsetAsync(io.counter + 2, 0, sizeof(int), stream);
   k_ihwbc_setup<NV, NC><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
   g_launch_count++;
   // PNC_DEBUG_RC lowers the cap on active constraints so the tests can exercise the hand-over
   static const int rc_dbg = [] { const char* e = getenv("PNC_DEBUG_RC"); return e ? atoi(e) : 0; }();
   const int rc_cap = (rc_dbg > hp.p && rc_dbg < C::RC) ? rc_dbg : C::RC;
-  k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32, smem, stream>>>(hp, dp, ws, fm, nfr, B, io, ws.setup_rec, rc_cap);
+  k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32 * warps, smem, stream>>>(hp, dp, ws, fm, nfr, B, io, ws.setup_rec, rc_cap);
   g_launch_count++;
   return true;
 }

@@ -39,9 +39,7 @@ struct RCfg {
   static constexpr int EVP = EV <= 1 ? 1 : (EV <= 2 ? 2 : (EV <= 4 ? 4 : 8));
   static constexpr int LPR = 32 / EVP;                        // lanes cooperating on one such row in the Cholesky
   static constexpr int LDT = NP + 2;                          // pitch of the d scratch tile
-  // ---- per-state HBM record written by the setup kernel (doubles) ----
-  static constexpr int PMAX = 10;
-  static constexpr int RG = 0, RX = (NV * LDV + 1) & ~1, RD = RX + NP, RS = RD + PMAX * NP, REC = (RS + 4 + 1) & ~1;
+  static constexpr int PMAX = 10;                             // equality rows the record holds
   static_assert(E <= 16, "rows beyond 32 must fit one lane pair each");
   static_assert(N <= 64, "n too large for the register kernel");
 };
@@ -66,6 +64,21 @@ struct MCfg : RCfg<NV_, NC_> {
                        OSL = OXACC + R::NP, OINT = OSL + (((M > 0 ? M : 1) + 1) & ~1),
                        SMEM_DOUBLES = (OINT + (3 * (R::N + 2) + 1) / 2 + 2) & ~1;
   static_assert(64 + R::PMAX * R::NP <= RSZ || R::N < 20, "equality block must fit behind the first S columns");
+  // ---- per-state HBM record (doubles): written by k_ihwbc_setup, consumed by k_ihwbc_reg, whose
+  //      result goes back into it for k_ihwbc_finish.  Everything the active-set kernel needs is
+  //      here in the layout it is used in, so that kernel holds no staging code at all ----
+  static constexpr int IMG = OX - OAR;                      // shared-memory image: Ar, a0, Uf, uf
+  static constexpr int RJ = 0;                              // J rows as register chunks: [NP/2][32 lanes][2]
+  static constexpr int RJB = RJ + 32 * R::NP;               // half rows 32..: [NB/2][32 lanes][2]
+  static constexpr int RX = RJB + (R::EXT ? 32 * R::NB : 0);  // x0
+  static constexpr int RD = RX + R::NP;                     // D = J^T CE^T, one row per equality
+  static constexpr int RE = RD + R::PMAX * R::NP;           // equality normals
+  static constexpr int RE0 = RE + R::PMAX * R::NP;          // equality offsets
+  static constexpr int RS = RE0 + ((R::PMAX + 1) & ~1);     // c1, c2, status, jrf
+  static constexpr int RI = RS + 4;                         // the image
+  static constexpr int RO = RI + ((IMG + 1) & ~1);          // result: x[NP], then ints iq, iter, status, A[N+2]
+  static constexpr int REC = (RO + R::NP + (R::N + 6 + 1) / 2 + 1) & ~1;
+  static_assert((OAR & 1) == 0 && (IMG & 1) == 0, "image is copied in 16-byte pieces");
 };
 
 // ---- register-array access by a warp-uniform dynamic index (jump table, no local memory) ----
@@ -175,7 +188,7 @@ struct SetupLayout {
 };
 
 template <class C>
-__host__ __device__ inline SetupLayout setup_layout(const DevProblem& P) {
+__host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min_doubles) {
   SetupLayout L;
   int o = 0;
   L.oG = o; o += (C::NV * C::LDV + 1) & ~1;
@@ -192,16 +205,18 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P) {
   L.ozv = o; o += C::NP;
   L.odl = o; o += C::NP;
   L.oD = o; o += P.p * C::NP;
+  if (o < min_doubles) o = min_doubles;  // the image of the active-set kernel's arrays is assembled here at the end
   L.per_state = (o + 1) & ~1;
   return L;
 }
 
-template <int NV, int NC>
+template <int NV, int NC, int NU, int NT>
 __global__ void __launch_bounds__(32)
 k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, SetupLayout SL, WsPtrs ws, FrameMap fm,
               int nfr, int B, SolveIO io, double* __restrict__ rec_all, int* __restrict__ counter) {
-  using C = RCfg<NV, NC>;
-  constexpr int NP = C::NP, LDV = C::LDV;
+  using C = MCfg<NV, NC, NU, NT>;
+  constexpr int N = C::N, NP = C::NP, LDV = C::LDV, HW = C::HW, NB = C::NB, LDA = C::LDA, E = C::E;
+  constexpr bool EXT = C::EXT;
   extern __shared__ __align__(16) double smem[];
   const DevProblem& G = *gp;
   const int lane = threadIdx.x;
@@ -504,15 +519,125 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         }
       }
       __syncwarp();
-      __syncwarp();
-      // ---- record: factor block (J in its upper triangle), x0, D, scalars ----
-#pragma unroll 4
-      for (int k = lane; k < NV * LDV; k += 32) rec[C::RG + k] = Gm[k];
+      // ---- record, part 1: J = L^-T as the register chunks of the active-set kernel (lane = row,
+      //      two columns per 16-byte piece, rows 32.. as half rows of lane pairs), x0, D, scalars ----
+      {
+        const int eh = lane & 1, erow = 32 + (lane >> 1);
+        const bool evalid = EXT && (lane >> 1) < E;
+        double2* rj = reinterpret_cast<double2*>(rec + C::RJ);
+#pragma unroll 2
+        for (int k = 0; k < NP; k += 2) {
+          double v0 = 0.0, v1 = 0.0;
+          if (k < NV) {
+            if (lane < NV) {
+              const double2 g = lds2(Gm + lane * LDV + k);
+              if (k >= lane) v0 = g.x;
+              if (k + 1 >= lane && k + 1 < NV) v1 = g.y;
+            }
+            if (k + 1 >= NV && k + 1 < N && lane == k + 1) v1 = jrf;
+          } else {
+            if (k < N && lane == k) v0 = jrf;
+            if (k + 1 < N && lane == k + 1) v1 = jrf;
+          }
+          rj[(k >> 1) * 32 + lane] = make_double2(v0, v1);
+        }
+        if constexpr (EXT) {
+          double2* rb = reinterpret_cast<double2*>(rec + C::RJB);
+#pragma unroll 2
+          for (int c = 0; c < NB; c += 2) {
+            double v[2] = {0.0, 0.0};
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+              const int col = eh * HW + c + u;
+              if (evalid && col < N) {
+                if (erow < NV) { if (col < NV && col >= erow) v[u] = Gm[erow * LDV + col]; }
+                else if (col == erow) v[u] = jrf;
+              }
+            }
+            rb[(c >> 1) * 32 + lane] = make_double2(v[0], v[1]);
+          }
+        }
+      }
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) rec[C::RX + k] = k < NV ? xs[k] : 0.0;
 #pragma unroll 1
       for (int k = lane; k < p * NP; k += 32) rec[C::RD + k] = Dt[k];
       if (lane == 0) { rec[C::RS] = c1; rec[C::RS + 1] = c2; rec[C::RS + 3] = jrf; }
+      // equality normals [M | -(Jc Ni)^T] rows 0..5, then the internal-constraint rows, and offsets
+#pragma unroll 1
+      for (int i = 0; i < p; i++) {
+#pragma unroll 1
+        for (int k = lane; k < NP; k += 32) {
+          double val = 0.0;
+          if (k < N) {
+            if (i >= 6) val = k < NV ? G.ic_jac[i - 6][k] : 0.0;
+            else if (k < NV) val = Mg[i * NV + k];
+            else val = -row_jc(k - NV, i);
+          }
+          rec[C::RE + i * NP + k] = val;
+        }
+      }
+      for (int i = lane; i < p; i += 32)
+        rec[C::RE0 + i] = i >= 6 ? 0.0 : (has_ic ? ws.ic_cg[s * NV + i] : ws.cori[s * NV + i] + ws.grav[s * NV + i]);
+      __syncwarp();
+      // ---- record, part 2: the image of the active-set kernel's constant arrays (torque-limit rows
+      //      S [M | -(Jc Ni)^T] with their offsets, wrench cones), assembled in shared memory over the
+      //      dead factor block and written out in one coalesced copy ----
+      {
+        double* img = smem;
+        double* Ar = img + (C::OAR - C::OAR);
+        double* a0 = img + (C::OA0 - C::OAR);
+        double* Uf = img + (C::OUF - C::OAR);
+        double* uf = img + (C::OUFV - C::OAR);
+        const int nact = P.nact;
+#pragma unroll 1
+        for (int k = lane; k < C::IMG; k += 32) img[k] = 0.0;
+        __syncwarp();
+#pragma unroll 1
+        for (int r = lane; r < NU; r += 32) {
+          const int ci = G.cone_contact[r];
+          const DevContact& Cc = G.contacts[ci];
+          const int lr = r - Cc.cone_off;
+          double u6[6];
+          cone_row_world(Cc, lr, ws.fr_iso + (s * nfr + fm.contact_f[ci]) * 12, u6);
+          for (int k = 0; k < 6; k++) Uf[r * 6 + k] = u6[k];
+          double rz = io.rfz[s * P.ncontact + ci];
+          if (rz <= 0.0) rz = 1e-3;  // contact.py:37-41
+          uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
+        }
+        if constexpr (NT > 0) {
+          // flattened copy with several independent loads in flight; M is symmetric, so row
+          // act_idx[a] is read as column act_idx[a] with consecutive lanes on consecutive addresses
+#pragma unroll 1
+          for (int e0 = lane; e0 < N * 32; e0 += 32 * 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const int e = e0 + 32 * u, k = e >> 5, a = e & 31;  // element (row a, column k), a fastest
+              double val = 0.0;
+              if (k < N && a < nact) {
+                if (has_ic) val = ws.ic_tq[(s * N + k) * nact + a];
+                else if (k < NV) val = Mg[k * NV + G.act_idx[a]];
+                else val = -row_jc(k - NV, G.act_idx[a]);
+              }
+              v[u] = val;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const int e = e0 + 32 * u, k = e >> 5, a = e & 31;
+              if (k < N && a < nact) Ar[a * LDA + k] = v[u];
+            }
+          }
+          for (int a = lane; a < nact; a += 32) {
+            const int v = G.act_idx[a];
+            a0[a] = has_ic ? ws.ic_tq0[s * nact + a] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
+          }
+        }
+        __syncwarp();
+        double2* ri = reinterpret_cast<double2*>(rec + C::RI);
+#pragma unroll 4
+        for (int k = lane; k < C::IMG / 2; k += 32) ri[k] = lds2(img + 2 * k);
+      }
     }
     if (lane == 0) rec[C::RS + 2] = (double)status;
     __syncwarp();
@@ -525,12 +650,12 @@ template <int NV, int NC, int NU, int NT>
 #define PNC_REG_LB __launch_bounds__(256, 1)
 #endif
 __global__ void PNC_REG_LB
-k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B,
-            SolveIO io, const double* __restrict__ rec_all, int rc_cap) {
+k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, int B, int* __restrict__ counter,
+            int* __restrict__ overflow, double* __restrict__ rec_all, int rc_cap) {
   // P (constant bank) serves warp-uniform reads; tables indexed per lane go through the global copy G
   const DevProblem& G = *gp;
   using C = MCfg<NV, NC, NU, NT>;
-  constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDV = C::LDV, LDA = C::LDA;
+  constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDA = C::LDA;
   constexpr bool EXT = C::EXT;
   // One warp per state, each with its own slice of shared memory.  The launcher uses one-warp CTAs;
   // with PNC_REG_WARPS=w the w warps of a CTA meet at a barrier at the top of every step-direction
@@ -544,7 +669,6 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   int nthr = blockDim.x;  // threads still taking part in the slot barrier
   const int p = P.p, m = C::M, nu = NU, nact = P.nact;
   constexpr bool trq = NT > 0;
-  const bool has_ic = P.n_ic > 0;
   double* const Rp = smem + C::ORT;
   double* const Ts = smem + C::OT;
   double* const Ar = smem + C::OAR;   // torque-limit rows S [M | -(Jc Ni)^T], pitch LDA
@@ -581,7 +705,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 #pragma unroll 1
   for (;;) {
     int si = 0;
-    if (lane == 0) si = atomicAdd(io.counter, 1);
+    if (lane == 0) si = atomicAdd(counter, 1);
     si = __shfl_sync(FULL, si, 0);
     if (si >= B) {  // no work left: leave the barrier group
       slot_barrier(nthr, false);
@@ -590,20 +714,13 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     const size_t s = (size_t)si;
     int status = PNC_QP_OK, iter = 0, iq = 0;
     double R_norm = 1.0;
-    if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
-
-    // ---- clear the work vectors, build the wrench cones ----
-    // (the constraint rows [M | -(Jc Ni)^T] are never copied: M is symmetric, so "row a for every
-    //  lane a" is a coalesced column read of the workspace M, see torque_row)
-    const double* Mg = ws.M + s * NV * NV;
-    auto row_jc = [&](int c, int v) -> double {  // (Jc Ni)[c][v]
-      if (has_ic) return ws.ic_jcni[(s * NC + c) * NV + v];
-      int ci = 0;
-      while (ci + 1 < P.ncontact && c >= G.contacts[ci + 1].rf_off) ci++;
-      return contact_jac_row(G.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - G.contacts[ci].rf_off)[v];
-    };
-    const double* rec = rec_all + s * C::REC;  // written by k_ihwbc_setup
+    double* rec = rec_all + s * C::REC;  // written by k_ihwbc_setup
     {
+      // torque-limit rows, their offsets and the wrench cones arrive in their final layout
+      const double2* src = reinterpret_cast<const double2*>(rec + C::RI);
+      double2* dst = reinterpret_cast<double2*>(smem + C::OAR);
+#pragma unroll 4
+      for (int k = lane; k < C::IMG / 2; k += 32) dst[k] = __ldg(src + k);
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) {
         x[k] = rec[C::RX + k];
@@ -611,84 +728,31 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       }
 #pragma unroll 1
       for (int k = lane; k < 6 * LDT; k += 32) Ts[k] = 0.0;
-#pragma unroll 1
-      for (int r = lane; r < nu; r += 32) {
-        const int ci = G.cone_contact[r];
-        const DevContact& Cc = G.contacts[ci];
-        const int lr = r - Cc.cone_off;
-        double u6[6];
-        cone_row_world(Cc, lr, ws.fr_iso + (s * nfr + fm.contact_f[ci]) * 12, u6);
-        for (int k = 0; k < 6; k++) Uf[r * 6 + k] = u6[k];
-        double rz = io.rfz[s * P.ncontact + ci];
-        if (rz <= 0.0) rz = 1e-3;  // contact.py:37-41
-        uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
-      }
-    }
-    if constexpr (NT > 0) {
-      // torque-limit rows S [M | -(Jc Ni)^T] (nact x n) and their offsets, staged once per state:
-      // the slack pass of every outer iteration then reads shared memory instead of waiting on L2.
-      // Flattened copy with several independent loads in flight; M is symmetric, so row act_idx[a]
-      // is read as column act_idx[a] with consecutive lanes on consecutive addresses.
-#pragma unroll 1
-      for (int e0 = lane; e0 < N * 32; e0 += 32 * 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int e = e0 + 32 * u, k = e >> 5, a = e & 31;  // element (row a, column k), a fastest
-          double val = 0.0;
-          if (k < N && a < nact) {
-            if (has_ic) val = ws.ic_tq[(s * N + k) * nact + a];
-            else if (k < NV) val = Mg[k * NV + G.act_idx[a]];
-            else val = -row_jc(k - NV, G.act_idx[a]);
-          }
-          v[u] = val;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int e = e0 + 32 * u, k = e >> 5, a = e & 31;
-          if (k < N && a < nact) Ar[a * LDA + k] = v[u];
-        }
-      }
-      for (int a = lane; a < nact; a += 32) {
-        const int v = G.act_idx[a];
-        a0[a] = has_ic ? ws.ic_tq0[s * nact + a] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
-#pragma unroll 1
-        for (int k = N; k < LDA; k++) Ar[a * LDA + k] = 0.0;
-      }
     }
     const double c1 = rec[C::RS], c2 = rec[C::RS + 1], jrf = rec[C::RS + 3];
     status = (int)rec[C::RS + 2];
     if (status == PNC_QP_OK) {
       // ---- move J into registers: row lane, and half rows 32.. in lane pairs ----
-      const double* Gg = rec + C::RG;
+      {
+        const double2* rj = reinterpret_cast<const double2*>(rec + C::RJ) + lane;
 #pragma unroll
-      for (int k = 0; k < NP; k += 2) {
-        double v0 = 0.0, v1 = 0.0;
-        if (k < NV) {
-          if (lane < NV) {
-            const double2 g = *reinterpret_cast<const double2*>(Gg + lane * LDV + k);
-            if (k >= lane) v0 = g.x;
-            if (k + 1 >= lane && k + 1 < NV) v1 = g.y;
-          }
-          if (k + 1 >= NV && k + 1 < N && lane == k + 1) v1 = jrf;
-        } else {
-          if (k < N && lane == k) v0 = jrf;
-          if (k + 1 < N && lane == k + 1) v1 = jrf;
+        for (int k = 0; k < NP; k += 2) {
+          const double2 g = __ldg(rj + (k >> 1) * 32);
+          Ja[k] = g.x;
+          Ja[k + 1] = g.y;
         }
-        Ja[k] = v0;
-        Ja[k + 1] = v1;
-      }
-#pragma unroll
-      for (int c = 0; c < NB; c++) {
-        double v = 0.0;
         if constexpr (EXT) {
-          const int col = eh * HW + c;
-          if (evalid && col < N) {
-            if (erow < NV) { if (col < NV && col >= erow) v = Gg[erow * LDV + col]; }
-            else if (col == erow) v = jrf;
+          const double2* rb = reinterpret_cast<const double2*>(rec + C::RJB) + lane;
+#pragma unroll
+          for (int c = 0; c < NB; c += 2) {
+            const double2 g = __ldg(rb + (c >> 1) * 32);
+            Jb[c] = g.x;
+            Jb[c + 1] = g.y;
           }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NB; c++) Jb[c] = 0.0;
         }
-        Jb[c] = v;
       }
       double* Deq = Rp + 64;  // R only uses its first p columns (< 64 doubles) while Deq is live
 #pragma unroll 2
@@ -793,28 +857,19 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         // ---- the constraint normal np and the rows [k0, k1) where it is non-zero ----
         {
           if (is_eq || ip >= nu) {
-            int v = ip, a = 0;
+            int a = 0;
             double sg = 1.0;
-            const bool icrow = is_eq && ip >= 6, tq = !is_eq;
-            if (tq) { a = (ip - nu) % nact; sg = (ip - nu) >= nact ? -1.0 : 1.0; v = P.act_idx[a]; }
+            const bool tq = !is_eq;
+            if (tq) { a = (ip - nu) % nact; sg = (ip - nu) >= nact ? -1.0 : 1.0; }
+            const double* row = tq ? Ar + a * LDA : rec + C::RE + ip * NP;  // shared or global
             double pnx = 0.0;
 #pragma unroll 1
             for (int k = lane; k < NP; k += 32) {
-              double val = 0.0;
-              if (k < N) {
-                if (icrow) val = k < NV ? G.ic_jac[ip - 6][k] : 0.0;
-                else if (tq) val = Ar[a * LDA + k];
-                else if (k < NV) val = Mg[v * NV + k];
-                else val = -row_jc(k - NV, v);
-              }
-              val *= sg;
+              const double val = k < N ? sg * row[k] : 0.0;
               np[k] = val;
               pnx = fma(val, x[k], pnx);
             }
-            if (is_eq) {
-              const double a0v = icrow ? 0.0 : (has_ic ? ws.ic_cg[s * NV + v] : ws.cori[s * NV + v] + ws.grav[s * NV + v]);
-              s_ip = wsum(pnx) + a0v;
-            }
+            if (is_eq) s_ip = wsum(pnx) + rec[C::RE0 + ip];
           } else {
             const DevContact& Cc = P.contacts[P.cone_contact[ip]];
             k0 = NV + Cc.rf_off; k1 = k0 + Cc.dim;
@@ -978,7 +1033,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             }
             if (iq >= rc_cap) {  // S is capped at RC columns: hand the state to the generic kernel
               status = PNC_QP_OVERFLOW;
-              if (lane == 0) *io.overflow = 1;
+              if (lane == 0) *overflow = 1;
               done = true;
               break;
             }
@@ -1140,50 +1195,88 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       }
     }
 
-    // ---- outputs: x = [qddot; rf], torque recovery (ihwbc.py:339-356) ----
-    const bool bad = status == PNC_QP_NOT_PD || status == PNC_QP_EQ_DEPENDENT || status == PNC_QP_INFEASIBLE ||
-                     status == PNC_QP_OVERFLOW;
-    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-    if (io.qddot)
-      for (int k = lane; k < NV; k += 32) io.qddot[s * NV + k] = bad ? nanv : x[k];
-    if (io.rf)
-      for (int k = lane; k < NC; k += 32) io.rf[s * NC + k] = bad ? nanv : x[NV + k];
-    if (io.acc)
-      for (int a = lane; a < nact; a += 32) io.acc[s * nact + a] = bad ? nanv : x[G.act_idx[a]];
-    if (io.trq) {
+    // ---- result back into the record; k_ihwbc_finish turns it into the outputs ----
+    {
+      int* ro = reinterpret_cast<int*>(rec + C::RO + NP);
 #pragma unroll 1
-      for (int a = lane; a < nact; a += 32) {
-        double tau = nanv;
-        if (!bad) {
-          if constexpr (NT > 0) {
-            const double* row = Ar + a * LDA;
-            double t0 = 0.0, t1 = 0.0;
-#pragma unroll 4
-            for (int k = 0; k < NP; k += 2) { const double2 r0 = lds2(row + k), x0 = lds2(x + k); t0 = fma(r0.x, x0.x, t0); t1 = fma(r0.y, x0.y, t1); }
-            tau = t0 + t1 + a0[a];
-          } else {
-            tau = torque_row<NV>(P, G, ws, fm, nfr, s, a, x);
-          }
-        }
-        io.trq[s * nact + a] = bad ? nanv : tau;
-      }
-    }
-    if (io.active) {
-      const int mw = (m + 63) / 64 > 0 ? (m + 63) / 64 : 1;
-      for (int wdx = lane; wdx < mw; wdx += 32) {
-        unsigned long long bits = 0ull;
-        for (int i = p; i < iq; i++) {
-          const int c = Aact[i];
-          if (c >= 0 && (c >> 6) == wdx) bits |= 1ull << (c & 63);
-        }
-        io.active[s * mw + wdx] = bits;
-      }
-    }
-    if (lane == 0) {
-      io.status[s] = status;
-      if (io.iters) io.iters[s] = iter;
+      for (int k = lane; k < NP; k += 32) rec[C::RO + k] = x[k];
+#pragma unroll 1
+      for (int i = lane; i < iq; i += 32) ro[3 + i] = Aact[i];
+      if (lane == 0) { ro[0] = iq; ro[1] = iter; ro[2] = status; }
     }
     __syncwarp();
+  }
+}
+
+// Outputs of one state from the result the active-set kernel left in its record: x = [qddot; rf],
+// the actuated accelerations, the torque recovery tau = S (M qddot + Ni^T (c + g) - (Jc Ni)^T rf)
+// (ihwbc.py:339-356), status, iteration count and the active-set bit mask.  One warp per state,
+// lanes = actuated rows: M is symmetric, so lane a reads column act_idx[a] of M and consecutive
+// lanes touch consecutive addresses.  States the register kernel handed over (OVERFLOW) keep that
+// status here; the generic kernel's second pass overwrites them.
+__global__ void __launch_bounds__(256)
+k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B, SolveIO io,
+               const double* __restrict__ rec_all, int rec_stride, int ro_off, int np_pad) {
+  const DevProblem& G = *gp;
+  const int lane = threadIdx.x & 31;
+  const size_t s = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= (size_t)B) return;
+  const int nv = G.nv, nc = G.nc, n = nv + nc, nact = G.nact, p = G.p, m = G.m;
+  const double* x = rec_all + s * rec_stride + ro_off;
+  const int* ro = reinterpret_cast<const int*>(x + np_pad);
+  const int iq = ro[0], iter = ro[1], status = ro[2];
+  const bool bad = status != PNC_QP_OK && status != PNC_QP_MAX_ITER;
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  if (io.qddot)
+    for (int k = lane; k < nv; k += 32) io.qddot[s * nv + k] = bad ? nanv : x[k];
+  if (io.rf)
+    for (int k = lane; k < nc; k += 32) io.rf[s * nc + k] = bad ? nanv : x[nv + k];
+  if (io.acc)
+    for (int a = lane; a < nact; a += 32) io.acc[s * nact + a] = bad ? nanv : x[G.act_idx[a]];
+  if (io.trq) {
+    for (int a = lane; a < nact; a += 32) {
+      double tau = nanv;
+      if (!bad) {
+        double t0 = 0.0, t1 = 0.0;
+        if (G.n_ic > 0) {
+          const double* col = ws.ic_tq + s * n * nact + a;
+          int k = 0;
+          for (; k + 1 < n; k += 2) { t0 = fma(col[k * nact], x[k], t0); t1 = fma(col[(k + 1) * nact], x[k + 1], t1); }
+          if (k < n) t0 = fma(col[k * nact], x[k], t0);
+          tau = t0 + t1 + ws.ic_tq0[s * nact + a];
+        } else {
+          const int v = G.act_idx[a];
+          const double* col = ws.M + s * nv * nv + v;  // column v of M == row v
+          int k = 0;
+          for (; k + 1 < nv; k += 2) { t0 = fma(col[k * nv], x[k], t0); t1 = fma(col[(k + 1) * nv], x[k + 1], t1); }
+          if (k < nv) t0 = fma(col[k * nv], x[k], t0);
+          const double* xr = x + nv;
+          for (int ci = 0; ci < G.ncontact; ci++) {
+            const int dim = G.contacts[ci].dim;
+            const double* jr = ws.fr_jac + ((s * nfr + fm.contact_f[ci]) * 6 + (6 - dim)) * nv + v;  // point contacts: rows 3..5
+            for (int r = 0; r < dim; r++) t1 = fma(-jr[r * nv], xr[r], t1);
+            xr += dim;
+          }
+          tau = t0 + t1 + ws.cori[s * nv + v] + ws.grav[s * nv + v];
+        }
+      }
+      io.trq[s * nact + a] = tau;
+    }
+  }
+  if (io.active) {
+    const int mw = (m + 63) / 64 > 0 ? (m + 63) / 64 : 1;
+    for (int wdx = lane; wdx < mw; wdx += 32) {
+      unsigned long long bits = 0ull;
+      for (int i = p; i < iq; i++) {
+        const int c = ro[3 + i];
+        if (c >= 0 && (c >> 6) == wdx) bits |= 1ull << (c & 63);
+      }
+      io.active[s * mw + wdx] = bits;
+    }
+  }
+  if (lane == 0) {
+    io.status[s] = status;
+    if (io.iters) io.iters[s] = iter;
   }
 }
 
@@ -1212,17 +1305,17 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
       return false;
     configured = smem;
   }
-  const SetupLayout SL = setup_layout<RCfg<NV, NC>>(hp);
+  const SetupLayout SL = setup_layout<C>(hp, C::IMG);
   if (!ws.setup_rec || ws.setup_stride != C::REC) return false;
   const size_t smem_s = (size_t)SL.per_state * sizeof(double);
   static size_t configured_s = 0;
   if (smem_s > configured_s) {
-    if (cudaFuncSetAttribute(k_ihwbc_setup<NV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_ihwbc_setup<NV, NC, NU, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess)
       return false;
     configured_s = smem_s;
   }
   int per_sm_s = 0, per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC>, 32, smem_s);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC, NU, NT>, 32, smem_s);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT>, 32 * warps, smem);
   if (per_sm < 1 || per_sm_s < 1) return false;
   static const int cap = [] { const char* e = getenv("PNC_REG_CTAS"); return e ? atoi(e) : 0; }();
@@ -1231,12 +1324,14 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   if (grid_s > B) grid_s = B;
   if (grid * warps > B) grid = (B + warps - 1) / warps;
   cudaMemsetAsync(io.counter + 2, 0, sizeof(int), stream);
-  k_ihwbc_setup<NV, NC><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
+  k_ihwbc_setup<NV, NC, NU, NT><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
   g_launch_count++;
   // PNC_DEBUG_RC lowers the cap on active constraints so the tests can exercise the hand-over
   static const int rc_dbg = [] { const char* e = getenv("PNC_DEBUG_RC"); return e ? atoi(e) : 0; }();
   const int rc_cap = (rc_dbg > hp.p && rc_dbg < C::RC) ? rc_dbg : C::RC;
-  k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32 * warps, smem, stream>>>(hp, dp, ws, fm, nfr, B, io, ws.setup_rec, rc_cap);
+  k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32 * warps, smem, stream>>>(hp, dp, B, io.counter, io.overflow, ws.setup_rec, rc_cap);
+  g_launch_count++;
+  k_ihwbc_finish<<<(B + 7) / 8, 256, 0, stream>>>(dp, ws, fm, nfr, B, io, ws.setup_rec, C::REC, C::RO, C::NP);
   g_launch_count++;
   return true;
 }
@@ -1254,7 +1349,7 @@ bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const Ws
 }
 
 template <int NV, int NC, int NU, int NT>
-static int rec_doubles(const DevProblem& hp) { return shape_ok<NV, NC, NU, NT>(hp) ? RCfg<NV, NC>::REC : 0; }
+static int rec_doubles(const DevProblem& hp) { return shape_ok<NV, NC, NU, NT>(hp) ? MCfg<NV, NC, NU, NT>::REC : 0; }
 
 // doubles per state of the setup record (0 when no register kernel matches the problem)
 int reg_setup_record_doubles(const DevProblem& hp) {

@@ -2,7 +2,8 @@
 import csv, subprocess, sys
 rep, nstates = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 1
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv'], capture_output=True, text=True).stdout
+KFILTER = ['-k', 'regex:' + sys.argv[4]] if len(sys.argv) > 4 else []  # optional kernel-name filter
+txt = subprocess.run(['ncu', '-i', rep] + KFILTER + [ '--page', 'source', '--print-source', 'cuda,sass', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 hdr = None; out = []
 for r in rows:

@@ -3,7 +3,8 @@ import csv, subprocess, sys, re, bisect
 rep, srcfile, nstates = sys.argv[1], sys.argv[2], int(sys.argv[3])
 src = open(srcfile).read().split('\n')
 marks = [(i + 1, l.strip()[:70]) for i, l in enumerate(src) if re.match(r'\s*// (----|====)', l)]
-txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv'], capture_output=True, text=True).stdout
+KFILTER = ['-k', 'regex:' + sys.argv[4]] if len(sys.argv) > 4 else []  # optional kernel-name filter
+txt = subprocess.run(['ncu', '-i', rep] + KFILTER + [ '--page', 'source', '--print-source', 'cuda,sass', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 hdr = None; cur_file = None
 agg = {}

@@ -184,27 +184,35 @@ __device__ __forceinline__ double torque_row(const DevProblem& P, const DevProbl
 // the equality normals in the J basis.  Results go to a per-state record in HBM that the
 // active-set kernel loads (one coalesced-by-sector read of ~14 KB per Atlas state).
 struct SetupLayout {
-  int oG, oJd, oev, owt, og0, odm, ozv, odl, oD, per_state;  // shared memory (doubles)
+  int oG, oJd, oev, owt, og0, odm, ozv, odl, oD, om6, per_state;  // shared memory (doubles)
 };
 
 template <class C>
 __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min_doubles) {
   SetupLayout L;
   int o = 0;
-  L.oG = o; o += (C::NV * C::LDV + 1) & ~1;
-  {
-    int jd = (P.ndense > 0 ? P.ndense : 1) * C::LDV;
-    if (jd < 6 * C::NV) jd = 6 * C::NV;  // the D block stages six rows of M here
-    L.oJd = o; o += (jd + 1) & ~1;
-  }
+  // the staged task Jacobians share the factor block: the Hessian tiles are accumulated in
+  // registers and only written once every lane is done reading the Jacobians
+  int blk = (C::NV * C::LDV + 1) & ~1;
+  const int jd = (((P.ndense > 0 ? P.ndense : 1) * C::LDV) + 1) & ~1;
+  if (blk < jd) blk = jd;
+  L.oG = o; L.oJd = o; o += blk;
   const int tr = ((P.ntaskrows > 0 ? P.ntaskrows : 1) + 1) & ~1;
+  // task errors, weights, g0, dm and the reciprocal diagonal are all dead when the D block is
+  // built: the six floating-base rows of M it needs are staged over them
+  L.om6 = o;
   L.oev = o; o += tr;
   L.owt = o; o += tr;
   L.og0 = o; o += C::NP;
   L.odm = o; o += C::NP;
-  L.ozv = o; o += C::NP;
   L.odl = o; o += C::NP;
-  L.oD = o; o += P.p * C::NP;
+  if (o - L.om6 < ((6 * C::NV + 1) & ~1)) o = L.om6 + ((6 * C::NV + 1) & ~1);
+  L.ozv = o; o += C::NP;  // x0 stays live until the record is written
+  {
+    int d = P.p * C::NP;  // D; before that, the row-pointer table of the Jacobian copy
+    if (d < PNC_MAX_TASK_ROWS) d = PNC_MAX_TASK_ROWS;
+    L.oD = o; o += (d + 1) & ~1;
+  }
   if (o < min_doubles) o = min_doubles;  // the image of the active-set kernel's arrays is assembled here at the end
   L.per_state = (o + 1) & ~1;
   return L;
@@ -266,8 +274,8 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     // stage the dense task Jacobian rows (flattened copy: several independent loads in flight per
     // lane instead of one row at a time); clear the factor block
     {
-      // row -> source pointer table lives at the start of the factor block (cleared after the copy)
-      const double** rptr = reinterpret_cast<const double**>(Gm);  // Gm is cleared after the copy
+      // row -> source pointer table borrows the D block (not live yet)
+      const double** rptr = reinterpret_cast<const double**>(Dt);
 #pragma unroll 1
       for (int t = lane; t < P.ntask; t += 32) {
         const DevTask& T = P.tasks[t];
@@ -293,16 +301,19 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       }
       __syncwarp();
     }
-#pragma unroll 1
-    for (int k = lane; k < NV * LDV; k += 32) Gm[k] = 0.0;
-    __syncwarp();
 
     // ---- Hessian task block (lower triangle) = sum_t w_t J_t^T J_t + lambda_q_ddot M ----
+    // 2x2 tiles, accumulated in registers: the factor block shares its shared memory with the
+    // staged Jacobians and is only written once every lane is done reading them
     {
       const double* Mg = ws.M + s * NV * NV;
-      constexpr int nt = (NV + 1) >> 1, ntile = nt * (nt + 1) / 2;
-#pragma unroll 1
-      for (int idx = lane; idx < ntile; idx += 32) {
+      constexpr int nt = (NV + 1) >> 1, ntile = nt * (nt + 1) / 2, TPL = (ntile + 31) / 32;
+      double h[TPL][4];
+#pragma unroll
+      for (int u = 0; u < TPL; u++) {
+        const int idx = lane + 32 * u;
+        h[u][0] = h[u][1] = h[u][2] = h[u][3] = 0.0;
+        if (idx >= ntile) continue;
         int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
         while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
         while (ti * (ti + 1) / 2 > idx) ti--;
@@ -329,12 +340,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           a00 += wk * t00; a01 += wk * t01; a10 += wk * t10; a11 += wk * t11;
         }
         const double lam = P.lambda_q_ddot;
-        Gm[r0 * LDV + c0] = a00 + lam * m00;
-        if (c1ok && c0 + 1 <= r0) Gm[r0 * LDV + c0 + 1] = a01 + lam * m01;
-        if (r1ok) {
-          Gm[(r0 + 1) * LDV + c0] = a10 + lam * m10;
-          if (c1ok) Gm[(r0 + 1) * LDV + c0 + 1] = a11 + lam * m11;
-        }
+        h[u][0] = a00 + lam * m00; h[u][1] = a01 + lam * m01; h[u][2] = a10 + lam * m10; h[u][3] = a11 + lam * m11;
       }
 #pragma unroll 1
       for (int c = lane; c < NV; c += 32) {
@@ -350,6 +356,28 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           acc += wk * tt;
         }
         g0[c] = acc;
+      }
+      __syncwarp();
+      // the Jacobians are dead: clear the factor block and store the tiles
+#pragma unroll 1
+      for (int k = lane; k < NV * LDV; k += 32) Gm[k] = 0.0;
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < TPL; u++) {
+        const int idx = lane + 32 * u;
+        if (idx >= ntile) continue;
+        int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
+        while (ti * (ti + 1) / 2 > idx) ti--;
+        const int tj = idx - ti * (ti + 1) / 2;
+        const int r0 = 2 * ti, c0 = 2 * tj;
+        const bool r1ok = r0 + 1 < NV, c1ok = c0 + 1 < NV;
+        Gm[r0 * LDV + c0] = h[u][0];
+        if (c1ok && c0 + 1 <= r0) Gm[r0 * LDV + c0 + 1] = h[u][1];
+        if (r1ok) {
+          Gm[(r0 + 1) * LDV + c0] = h[u][2];
+          if (c1ok) Gm[(r0 + 1) * LDV + c0 + 1] = h[u][3];
+        }
       }
       __syncwarp();
 #pragma unroll 1
@@ -474,7 +502,8 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       {
         // floating-base rows i < 6: D[i][j] = sum_{k<=j} J[k][j] M[i][k]; the six rows are staged in
         // shared memory first (Jd is dead), one column j per lane, six accumulators
-        double* m6 = Jd;
+        double* m6 = smem + SL.om6;
+        __syncwarp();  // x0 is done with the vectors m6 overlays
 #pragma unroll 1
         for (int e0 = lane; e0 < 6 * NV; e0 += 32 * 7) {
           double v[7];

@@ -83,6 +83,8 @@ extern "C" {
 #define PNC_MAX_TASKS 16
 #define PNC_MAX_CONTACTS 4
 #define PNC_MAX_IC 4        /* internal-constraint rows */
+#define PNC_SWING_REC 26    /* doubles per state of a swing-foot trajectory record (pnc_swing_init) */
+#define PNC_FB_REC 14       /* doubles per state of a floating-base trajectory record (pnc_floating_base_init) */
 
 /* ---- model ------------------------------------------------------------- */
 typedef struct {
@@ -244,6 +246,58 @@ int pnc_joint_integrate(int32_t B, int32_t na, const double* d_acc, const double
  * d_pos_des / d_vel_des [B,3], d_kp / d_kd [3] (device), outputs d_trq [B,nv], d_qddot [B,nv] (may be NULL). */
 int pnc_osc_step(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_pos_des, const double* d_vel_des,
                  const double* d_kp, const double* d_kd, double smooth, double* d_trq, double* d_qddot, void* stream);
+
+/* ---- the reference generators that feed the tasks each tick ----
+ * All pointers are device pointers, fp64, batch first; `frame` is a model frame index the
+ * workspace materialises; quaternions scalar-last.  Outputs go straight into
+ * BasicTask.update_desired(pos, vel, acc) / the w and rf_z_max arrays of pnc_ihwbc_solve. */
+
+/* TaskHierarchyManager.update_ramp_to_{min,max} (pnc/wbc/manager/task_hierarchy_manager.py:23-35) and
+ * ReactionForceManager.update_ramp_to_{min,max} (reaction_force_manager.py:23-35):
+ * out = (target - start_value) / duration * (clip(t, t0, t0 + duration) - t0) + start_value.  Arrays [B]. */
+int pnc_ramp_update(int32_t B, const double* d_start_value, double target, const double* d_start_time,
+                    const double* d_duration, double current_time, double* d_out, void* stream);
+
+/* FootTrajectoryManager.use_current (pnc/wbc/manager/foot_trajectory_manager.py:41-52): desireds of the
+ * LINK_XYZ / LINK_ORI task pair of `frame` = its current pose and velocity, zero acceleration.
+ * pos/vel/acc/angvel/angacc [B,3], quat [B,4]. */
+int pnc_foot_use_current(pnc_workspace* ws, int32_t B, int32_t frame, double* d_pos, double* d_vel, double* d_acc,
+                         double* d_quat, double* d_angvel, double* d_angacc, void* stream);
+
+/* FootTrajectoryManager.initialize_swing_foot_trajectory (:54-84): from the current pose of `frame`
+ * and the landing foot (d_land_pos [B,3], d_land_quat [B,4]) build the two Hermite position
+ * segments through the raised mid foot (footstep.py:64-69 interpolate, swing_height) and the
+ * HermiteCurveQuat (util/interpolation.py:104-134) into d_rec [B, PNC_SWING_REC]. */
+int pnc_swing_init(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_land_pos, const double* d_land_quat,
+                   const double* d_swing_duration, double swing_height, double* d_rec, void* stream);
+
+/* FootTrajectoryManager.update_swing_foot_desired (:86-110).  Derivatives are with respect to the
+ * segment parameter, exactly as the reference passes them on. */
+int pnc_swing_eval(int32_t B, const double* d_rec, const double* d_start_time, const double* d_swing_duration,
+                   double current_time, double* d_pos, double* d_vel, double* d_acc, double* d_quat, double* d_angvel,
+                   double* d_angacc, void* stream);
+
+/* FloatingBaseTrajectoryManager.initialize_floating_base_interpolation_trajectory
+ * (pnc/wbc/manager/floating_base_trajectory_manager.py:35-54): record of the current CoM, the target,
+ * the current orientation of `base_frame` and the exponential-coordinate error, [B, PNC_FB_REC]. */
+int pnc_floating_base_init(pnc_workspace* ws, int32_t B, int32_t base_frame, const double* d_target_com,
+                           const double* d_target_quat, double* d_rec, void* stream);
+
+/* update_floating_base_desired, interpolation branch (:81-115; util/interpolation.py:8-32). */
+int pnc_floating_base_eval(int32_t B, const double* d_rec, const double* d_start_time, const double* d_duration,
+                           double current_time, double* d_pos, double* d_vel, double* d_acc, double* d_quat,
+                           double* d_angvel, double* d_angacc, void* stream);
+
+/* util.get_sinusoid_trajectory (util/util.py:98-107), the swaying branch (:76-80): d_mid [B,3],
+ * amp / freq are 3 HOST doubles. */
+int pnc_sinusoid_eval(int32_t B, const double* d_mid, const double* d_start_time, const double* amp3, const double* freq3,
+                      double current_time, double* d_pos, double* d_vel, double* d_acc, void* stream);
+
+/* AtlasStateEstimator._update_dcm (pnc/atlas_pnc/atlas_state_estimator.py:35-44) from the workspace CoM
+ * and CoM velocity: d_dcm [B,3] is state (in: last dcm, out: new dcm), d_prev_dcm / d_dcm_vel [B,3] out.
+ * As executed by the reference: dcm_vel = alpha (dcm - prev) / dt (its low-pass term is a no-op statement). */
+int pnc_dcm_update(pnc_workspace* ws, int32_t B, double dt, double alpha, double* d_dcm, double* d_prev_dcm,
+                   double* d_dcm_vel, void* stream);
 
 /* Whole controller tick with HOST buffers: H2D of the inputs, update_system, solve,
  * D2H of the outputs; synchronous.  Any output may be NULL. */

@@ -510,6 +510,104 @@ int pnc_osc_step(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_po
 }
 
 // ---------------------------------------------------------------------------------------
+// The reference generators that feed the tasks (managers.cu).
+static int frame_slot(const pnc_workspace* ws, int32_t frame) {
+  for (int f = 0; f < ws->nfr; f++)
+    if (ws->hfr.model_frame[f] == frame) return f;
+  return -1;
+}
+
+int pnc_ramp_update(int32_t B, const double* d_start_value, double target, const double* d_start_time,
+                    const double* d_duration, double current_time, double* d_out, void* stream) {
+  if (B < 0 || !d_start_value || !d_start_time || !d_duration || !d_out) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  launch_ramp_update(B, d_start_value, target, d_start_time, d_duration, current_time, d_out, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_foot_use_current(pnc_workspace* ws, int32_t B, int32_t frame, double* d_pos, double* d_vel, double* d_acc,
+                         double* d_quat, double* d_angvel, double* d_angacc, void* stream) {
+  if (!ws || B < 0 || B > ws->cap || !d_pos || !d_vel || !d_acc || !d_quat || !d_angvel || !d_angacc) return PNC_E_ARG;
+  const int slot = frame_slot(ws, frame);
+  if (slot < 0) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  launch_foot_use_current(ws->p, ws->nfr, slot, B, d_pos, d_vel, d_acc, d_quat, d_angvel, d_angacc, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_swing_init(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_land_pos, const double* d_land_quat,
+                   const double* d_swing_duration, double swing_height, double* d_rec, void* stream) {
+  if (!ws || B < 0 || B > ws->cap || !d_land_pos || !d_land_quat || !d_swing_duration || !d_rec) return PNC_E_ARG;
+  const int slot = frame_slot(ws, frame);
+  if (slot < 0) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  launch_swing_init(ws->p, ws->nfr, slot, B, d_land_pos, d_land_quat, d_swing_duration, swing_height, d_rec,
+                    (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_swing_eval(int32_t B, const double* d_rec, const double* d_start_time, const double* d_swing_duration,
+                   double current_time, double* d_pos, double* d_vel, double* d_acc, double* d_quat, double* d_angvel,
+                   double* d_angacc, void* stream) {
+  if (B < 0 || !d_rec || !d_start_time || !d_swing_duration || !d_pos || !d_vel || !d_acc || !d_quat || !d_angvel ||
+      !d_angacc)
+    return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  launch_swing_eval(B, d_rec, d_start_time, d_swing_duration, current_time, d_pos, d_vel, d_acc, d_quat, d_angvel, d_angacc,
+                    (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_floating_base_init(pnc_workspace* ws, int32_t B, int32_t base_frame, const double* d_target_com,
+                           const double* d_target_quat, double* d_rec, void* stream) {
+  if (!ws || B < 0 || B > ws->cap || !d_target_com || !d_target_quat || !d_rec) return PNC_E_ARG;
+  const int slot = frame_slot(ws, base_frame);
+  if (slot < 0) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  launch_floating_base_init(ws->p, ws->nfr, slot, B, d_target_com, d_target_quat, d_rec, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_floating_base_eval(int32_t B, const double* d_rec, const double* d_start_time, const double* d_duration,
+                           double current_time, double* d_pos, double* d_vel, double* d_acc, double* d_quat,
+                           double* d_angvel, double* d_angacc, void* stream) {
+  if (B < 0 || !d_rec || !d_start_time || !d_duration || !d_pos || !d_vel || !d_acc || !d_quat || !d_angvel || !d_angacc)
+    return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  launch_floating_base_eval(B, d_rec, d_start_time, d_duration, current_time, d_pos, d_vel, d_acc, d_quat, d_angvel,
+                            d_angacc, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_sinusoid_eval(int32_t B, const double* d_mid, const double* d_start_time, const double* amp3, const double* freq3,
+                      double current_time, double* d_pos, double* d_vel, double* d_acc, void* stream) {
+  if (B < 0 || !d_mid || !d_start_time || !amp3 || !freq3 || !d_pos || !d_vel || !d_acc) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  launch_sinusoid_eval(B, d_mid, d_start_time, amp3, freq3, current_time, d_pos, d_vel, d_acc, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_dcm_update(pnc_workspace* ws, int32_t B, double dt, double alpha, double* d_dcm, double* d_prev_dcm,
+                   double* d_dcm_vel, void* stream) {
+  if (!ws || B < 0 || B > ws->cap || !(dt > 0.0) || !d_dcm || !d_prev_dcm || !d_dcm_vel) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  launch_dcm_update(ws->p, B, dt, alpha, d_dcm, d_prev_dcm, d_dcm_vel, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Whole tick with host buffers.  The batch is cut into chunks that ping-pong over two
 // streams so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels
 // of chunk k.  Chunks own disjoint slices of the workspace, so they never alias.

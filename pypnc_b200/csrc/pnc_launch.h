@@ -93,6 +93,24 @@ void launch_contact_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap&
 void launch_joint_integrate(int B, int na, const double* acc, const double* joint_pos, double* vel_state,
                             double* pos_state, const double* pos_limit, const double* vel_limit, double alpha_vel,
                             double alpha_pos, double dt, cudaStream_t stream);
+// managers.cu
+void launch_ramp_update(int B, const double* sv, double target, const double* st, const double* dur, double t, double* out,
+                        cudaStream_t stream);
+void launch_foot_use_current(const WsPtrs& ws, int nfr, int slot, int B, double* pos, double* vel, double* acc, double* quat,
+                             double* angvel, double* angacc, cudaStream_t stream);
+void launch_swing_init(const WsPtrs& ws, int nfr, int slot, int B, const double* land_pos, const double* land_quat,
+                       const double* duration, double height, double* rec, cudaStream_t stream);
+void launch_swing_eval(int B, const double* rec, const double* st, const double* dur, double t, double* pos, double* vel,
+                       double* acc, double* quat, double* angvel, double* angacc, cudaStream_t stream);
+void launch_floating_base_init(const WsPtrs& ws, int nfr, int slot, int B, const double* tcom, const double* tquat,
+                               double* rec, cudaStream_t stream);
+void launch_floating_base_eval(int B, const double* rec, const double* st, const double* dur, double t, double* pos,
+                               double* vel, double* acc, double* quat, double* angvel, double* angacc,
+                               cudaStream_t stream);
+void launch_sinusoid_eval(int B, const double* mid, const double* st, const double* amp3, const double* freq3, double t,
+                          double* pos, double* vel, double* acc, cudaStream_t stream);
+void launch_dcm_update(const WsPtrs& ws, int B, double dt, double alpha, double* dcm, double* prev, double* dcm_vel,
+                       cudaStream_t stream);
 void launch_osc_step(const WsPtrs& ws, int nfr, int slot, int nv, int B, const double* pos_des, const double* vel_des,
                      const double* kp, const double* kd, double smooth, double rcond, double* trq, double* qddot,
                      cudaStream_t stream);

@@ -122,3 +122,11 @@ def test_stats_gather_over_gloo_world_size_2():
     for rank, st, mx, full in res:
         assert st == full          # every rank sees the whole-job stats
         assert mx == 11.0          # max over ranks
+
+
+def test_manager_record_sizes_match_header():
+    import re
+    from pypnc_b200 import managers
+    hdr = open(os.path.join(ROOT, 'include', 'pnc_b200.h')).read()
+    assert int(re.search(r'#define PNC_SWING_REC (\d+)', hdr).group(1)) == managers.SWING_REC
+    assert int(re.search(r'#define PNC_FB_REC (\d+)', hdr).group(1)) == managers.FB_REC

@@ -247,6 +247,21 @@ int pnc_joint_integrate(int32_t B, int32_t na, const double* d_acc, const double
 int pnc_osc_step(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_pos_des, const double* d_vel_des,
                  const double* d_kp, const double* d_kd, double smooth, double* d_trq, double* d_qddot, void* stream);
 
+/* Batched dense QP: B independent problems of one shape, each
+ *   min 1/2 x^T G x + g0^T x   s.t.  CE^T x + ce0 = 0,  CI^T x + ci0 >= 0
+ * -- the reference's own C++ entry point solve_quadprog(G, g0, CE, ce0, CI, ci0, x)
+ * (external_source/Goldfarb/QuadProg++.hh:70, QuadProg++.cc:115-502; its in-repo caller is the
+ * wrench-distribution QP of towr_plus/src/dcm_planner.cpp:752-855, n = 12, p = 6, m = 36).
+ * Layout as QuadProg++'s Matrix<double>: row-major d_G [B,n,n], d_CE [B,n,p], d_CI [B,n,m] (one
+ * COLUMN per constraint), d_g0 [B,n], d_ce0 [B,p], d_ci0 [B,m].  Outputs d_x [B,n], d_f [B] (the
+ * cost; +inf for an infeasible problem as in :402-407), d_status [B] (PNC_QP_*), d_iters [B],
+ * d_active [B, ceil(m/64)] bit mask of the active inequalities; any output but d_x may be NULL.
+ * n <= 64; returns PNC_E_SIZE when the shape does not fit shared memory.  `device` is the CUDA
+ * device the pointers live on. */
+int pnc_quadprog_batch(int32_t device, int32_t B, int32_t n, int32_t p, int32_t m, const double* d_G, const double* d_g0,
+                       const double* d_CE, const double* d_ce0, const double* d_CI, const double* d_ci0, double* d_x,
+                       double* d_f, int32_t* d_status, int32_t* d_iters, uint64_t* d_active, void* stream);
+
 /* ---- the reference generators that feed the tasks each tick ----
  * All pointers are device pointers, fp64, batch first; `frame` is a model frame index the
  * workspace materialises; quaternions scalar-last.  Outputs go straight into

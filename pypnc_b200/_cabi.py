@@ -139,6 +139,7 @@ def load_library():
     lib.pnc_contact_eval.argtypes = [vp, vp, i32, i32] + [vp] * 4 + [vp]
     lib.pnc_osc_step.argtypes = [vp, i32, i32] + [vp] * 4 + [dbl, vp, vp, vp]
     lib.pnc_joint_integrate.argtypes = [i32, i32] + [vp] * 6 + [dbl, dbl, dbl, vp]
+    lib.pnc_quadprog_batch.argtypes = [i32] * 5 + [vp] * 11 + [vp]
     lib.pnc_ramp_update.argtypes = [i32, vp, dbl, vp, vp, dbl, vp, vp]
     lib.pnc_foot_use_current.argtypes = [vp, i32, i32] + [vp] * 6 + [vp]
     lib.pnc_swing_init.argtypes = [vp, i32, i32, vp, vp, vp, dbl, vp, vp]
@@ -166,7 +167,7 @@ EXPORTED_SYMBOLS = [
     'pnc_ws_coriolis', 'pnc_ws_com_pos', 'pnc_ws_com_vel', 'pnc_ws_com_jac', 'pnc_ws_com_jacdot',
     'pnc_ws_com_jdqd', 'pnc_ws_frame_iso', 'pnc_ws_frame_vel', 'pnc_ws_frame_jac', 'pnc_ws_frame_jdqd',
     'pnc_ihwbc_solve', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_osc_step', 'pnc_wbc_tick_host',
-    'pnc_ramp_update', 'pnc_foot_use_current', 'pnc_swing_init', 'pnc_swing_eval', 'pnc_floating_base_init',
+    'pnc_quadprog_batch', 'pnc_ramp_update', 'pnc_foot_use_current', 'pnc_swing_init', 'pnc_swing_eval', 'pnc_floating_base_init',
     'pnc_floating_base_eval', 'pnc_sinusoid_eval', 'pnc_dcm_update',
     'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version', 'pnc_debug_set_dump',
 ]

@@ -510,6 +510,29 @@ int pnc_osc_step(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_po
 }
 
 // ---------------------------------------------------------------------------------------
+// Batched dense QP (ihwbc.cu: k_quadprog_dense)
+int pnc_quadprog_batch(int32_t device, int32_t B, int32_t n, int32_t p, int32_t m, const double* d_G, const double* d_g0,
+                       const double* d_CE, const double* d_ce0, const double* d_CI, const double* d_ci0, double* d_x,
+                       double* d_f, int32_t* d_status, int32_t* d_iters, uint64_t* d_active, void* stream) {
+  if (B < 0 || n < 1 || p < 0 || m < 0 || !d_G || !d_g0 || !d_x || (p > 0 && (!d_CE || !d_ce0)) ||
+      (m > 0 && (!d_CI || !d_ci0)))
+    return PNC_E_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return PNC_E_NOGPU; }
+  if (device < 0 || device >= ndev) return PNC_E_ARG;
+  if (n > 64 || p > n) return PNC_E_SIZE;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(device));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (!launch_quadprog_dense(n, p, m, B, d_G, d_g0, d_CE, d_ce0, d_CI, d_ci0, d_x, d_f, d_status, d_iters,
+                             reinterpret_cast<unsigned long long*>(d_active), sms, (cudaStream_t)stream))
+    return PNC_E_SIZE;
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // The reference generators that feed the tasks (managers.cu).
 static int frame_slot(const pnc_workspace* ws, int32_t frame) {
   for (int f = 0; f < ws->nfr; f++)

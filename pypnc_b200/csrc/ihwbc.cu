@@ -830,6 +830,357 @@ k_task_prepare(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nf
   }
 }
 
+// =======================================================================================
+// Batched dense QP -- the drop-in for the reference's own C++ entry point
+//   solve_quadprog(G, g0, CE, ce0, CI, ci0, x)   external_source/Goldfarb/QuadProg++.hh:70,
+//   QuadProg++.cc:115-502:  min 1/2 x^T G x + g0^T x   s.t.  CE^T x + ce0 = 0,  CI^T x + ci0 >= 0
+// for B independent problems of one shape (n, p, m), e.g. the wrench-distribution QP of the
+// DCM planner (towr_plus/src/dcm_planner.cpp:752-855: n = 12, p = 6, m = 36).  Matrices are laid
+// out as QuadProg++'s Matrix<double>: row-major, CE is n x p and CI is n x m (one COLUMN per
+// constraint).  One problem per warp, everything in shared memory, the same routines as
+// k_ihwbc_solve (Householder add, Givens drop, refined termination -- see DESIGN.md 3.2).
+struct QpDenseLayout {
+  int ld, oJ, oR, oC, oc0, ox, og0, oz, od, onp, ohw, orr, ou, oxold, ouold, os, oxacc, oint, total;
+};
+
+__host__ __device__ inline QpDenseLayout qpd_layout(int n, int p, int m) {
+  QpDenseLayout L;
+  L.ld = n | 1;
+  int o = 0;
+  auto take = [&](int cnt) { const int at = o; o += (cnt + 1) & ~1; return at; };
+  L.oJ = take(n * L.ld);
+  L.oR = take(n * (n + 3) / 2 + 2);
+  L.oC = take((p + m > 0 ? p + m : 1) * L.ld);
+  L.oc0 = take(p + m + 1);
+  L.ox = take(n); L.og0 = take(n); L.oz = take(n); L.od = take(n); L.onp = take(n); L.ohw = take(n);
+  L.orr = take(n + 1); L.ou = take(n + 1); L.oxold = take(n); L.ouold = take(n + 1); L.os = take(m + 1);
+  L.oxacc = take(n);
+  L.oint = take((3 * (n + 1) + 2 * (m + 1) + 1) / 2 + 1);
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(32)
+k_quadprog_dense(int n, int p, int m, QpDenseLayout L, int B, const double* __restrict__ Gall, const double* __restrict__ g0all,
+                 const double* __restrict__ CEall, const double* __restrict__ ce0all, const double* __restrict__ CIall,
+                 const double* __restrict__ ci0all, double* __restrict__ xout, double* __restrict__ fout,
+                 int* __restrict__ status_out, int* __restrict__ iters_out, unsigned long long* __restrict__ active_out) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x, ld = L.ld;
+  double* W = smem;
+  double* Jm = W + L.oJ;
+  double* Cr = W + L.oC;   // constraint normals by rows: p equalities, then m inequalities
+  double* c0 = W + L.oc0;
+  double* x = W + L.ox;
+  double* g0 = W + L.og0;
+  double* xold = W + L.oxold;
+  double* uold = W + L.ouold;
+  double* sl = W + L.os;
+  double* xacc = W + L.oxacc;
+  int* Aact = reinterpret_cast<int*>(W + L.oint);
+  int* Aold = Aact + (n + 1);
+  int* Aacc = Aold + (n + 1);
+  int* iai = Aacc + (n + 1);
+  int* iaexcl = iai + (m + 1);
+  QP q;
+  q.lane = lane; q.n = n; q.ld = ld; q.p = p; q.m = m;
+  q.J = Jm; q.R = W + L.oR; q.x = x; q.z = W + L.oz; q.d = W + L.od; q.np = W + L.onp; q.hw = W + L.ohw;
+  q.r = W + L.orr; q.u = W + L.ou;
+
+  // problems are dealt round-robin: no device-side counter, so the entry point needs no handle and
+  // concurrent calls on different streams cannot interfere
+  for (int si = blockIdx.x; si < B; si += gridDim.x) {
+    const size_t s = (size_t)si;
+    int status = PNC_QP_OK, iter = 0;
+    q.iq = 0;
+    q.R_norm = 1.0;
+    double f = 0.0;
+    {
+      const double* G = Gall + s * n * n;
+      for (int e = lane; e < n * n; e += 32) { const int r = e / n, c = e - r * n; Jm[r * ld + c] = G[e]; }
+      for (int k = lane; k < n; k += 32) g0[k] = g0all[s * n + k];
+      const double* CE = CEall + s * n * p;
+      for (int e = lane; e < n * p; e += 32) { const int k = e / p, c = e - k * p; Cr[c * ld + k] = CE[e]; }
+      const double* CI = CIall + s * n * m;
+      for (int e = lane; e < n * m; e += 32) { const int k = e / m, c = e - k * m; Cr[(p + c) * ld + k] = CI[e]; }
+      for (int c = lane; c < p; c += 32) c0[c] = ce0all[s * p + c];
+      for (int c = lane; c < m; c += 32) c0[p + c] = ci0all[s * m + c];
+      __syncwarp();
+    }
+    // ---- Cholesky (QuadProg++.cc:705-730), left-looking, lanes = rows (two rows per lane) ----
+    double c1 = 0.0, c2 = 0.0;
+    {
+      double tr = 0.0;
+      for (int i = lane; i < n; i += 32) tr += Jm[i * ld + i];
+      c1 = wsum(tr);
+    }
+    double* dl = q.hw;
+    bool pd = true;
+    for (int j = 0; j < n; j++) {
+      double tt[2] = {0.0, 0.0};
+      const double* rj = Jm + j * ld;
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+        const int i = lane + 32 * rr;
+        if (i >= j && i < n) {
+          const double* ri = Jm + i * ld;
+          double sum = ri[j], sum2 = 0.0;
+          int k = 0;
+          for (; k + 1 < j; k += 2) { sum -= ri[k] * rj[k]; sum2 -= ri[k + 1] * rj[k + 1]; }
+          if (k < j) sum -= ri[k] * rj[k];
+          tt[rr] = sum + sum2;
+        }
+      }
+      const double piv = __shfl_sync(FULL, (j & 32) ? tt[1] : tt[0], j & 31);
+      if (!(piv > 0.0)) { pd = false; break; }
+      const double dj = sqrt(piv);
+      __syncwarp();
+      if (lane == (j & 31)) { Jm[j * ld + j] = dj; dl[j] = dj; }
+      if (lane > j && lane < n) Jm[lane * ld + j] = tt[0] / dj;
+      if (lane + 32 > j && lane + 32 < n) Jm[(lane + 32) * ld + j] = tt[1] / dj;
+      __syncwarp();
+    }
+    if (!pd) {
+      status = PNC_QP_NOT_PD;
+    } else {
+      // ---- J = L^-T in place (:203-210) ----
+      for (int j = 0; j < n; j++) {
+        const double* Lj = Jm + j * ld;
+        const double djj = dl[j];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+          const int i = lane + 32 * rr;
+          if (i <= j && i < n) {
+            double* zi = Jm + i * ld;
+            double sum = i == j ? 1.0 : 0.0, sum2 = 0.0;
+            int k = i;
+            for (; k + 1 < j; k += 2) { sum -= Lj[k] * zi[k]; sum2 -= Lj[k + 1] * zi[k + 1]; }
+            if (k < j) sum -= Lj[k] * zi[k];
+            zi[j] = (sum + sum2) / djj;
+          }
+        }
+        __syncwarp();
+      }
+      for (int i = 1; i < n; i++)
+        for (int k = lane; k < i; k += 32) Jm[i * ld + k] = 0.0;
+      __syncwarp();
+      {
+        double tr = 0.0;
+        for (int i = lane; i < n; i += 32) tr += Jm[i * ld + i];
+        c2 = wsum(tr);
+      }
+      // ---- unconstrained minimiser x = -J J^T g0, f = 1/2 g0.x (:222-226) ----
+      for (int k = lane; k < n; k += 32) q.np[k] = g0[k];
+      __syncwarp();
+      qp_compute_d(q, 0, n);
+      double zz, znp;
+      qp_compute_z(q, zz, znp);
+      {
+        double part = 0.0;
+        for (int k = lane; k < n; k += 32) { const double xv = -q.z[k]; x[k] = xv; part += g0[k] * xv; }
+        f = 0.5 * wsum(part);
+      }
+      for (int k = lane; k <= n; k += 32) { q.u[k] = 0.0; Aact[k] = 0; }
+      __syncwarp();
+      // ---- equality constraints (:232-272) ----
+      for (int i = 0; i < p && status == PNC_QP_OK; i++) {
+        const double* row = Cr + i * ld;
+        double pnx = 0.0;
+        for (int k = lane; k < n; k += 32) { const double v = row[k]; q.np[k] = v; pnx += v * x[k]; }
+        pnx = wsum(pnx);
+        __syncwarp();
+        qp_compute_d(q, 0, n);
+        qp_compute_z(q, zz, znp);
+        qp_compute_r(q);
+        double t2 = 0.0;
+        if (fabs(zz) > QP_EPS) t2 = (-pnx - c0[i]) / znp;
+        for (int k = lane; k < n; k += 32) x[k] += t2 * q.z[k];
+        for (int k = lane; k < q.iq; k += 32) q.u[k] -= t2 * q.r[k];
+        if (lane == 0) { q.u[q.iq] = t2; Aact[i] = -i - 1; }
+        f += 0.5 * (t2 * t2) * znp;
+        __syncwarp();
+        if (!qp_add_constraint(q)) status = PNC_QP_EQ_DEPENDENT;
+      }
+      // ---- active-set loop (:274-500) ----
+      if (status == PNC_QP_OK && m > 0) {
+        for (int i = lane; i < m; i += 32) iai[i] = i;
+        __syncwarp();
+        const double psi_tol = (double)m * QP_EPS * c1 * c2 * 100.0;  // :306-312
+        const double psi_refine = psi_tol * 1e-6;
+        bool done = false, accepted = false;
+        int iq_acc = 0;
+        double f_acc = 0.0;
+        while (!done) {
+          iter++;
+          for (int i = p + lane; i < q.iq; i += 32) iai[Aact[i]] = -1;
+          double psi = 0.0;
+          for (int c = lane; c < m; c += 32) {  // slacks s = CI^T x + ci0 (:293-301)
+            const double* row = Cr + (p + c) * ld;
+            double t0 = 0.0, t1 = 0.0;
+            int k = 0;
+            for (; k + 1 < n; k += 2) { t0 += row[k] * x[k]; t1 += row[k + 1] * x[k + 1]; }
+            if (k < n) t0 += row[k] * x[k];
+            const double v = t0 + t1 + c0[p + c];
+            sl[c] = v;
+            psi += fmin(0.0, v);
+            iaexcl[c] = 1;
+          }
+          psi = wsum(psi);
+          __syncwarp();
+          if (fabs(psi) <= psi_tol) {
+            if (fabs(psi) <= psi_refine) break;
+            if (!accepted) {
+              accepted = true;
+              iq_acc = q.iq;
+              f_acc = f;
+              for (int i = lane; i < n; i += 32) xacc[i] = x[i];
+              for (int i = lane; i < q.iq; i += 32) Aacc[i] = Aact[i];
+              __syncwarp();
+            }
+          }
+          if (iter > 40 * (n + m)) { status = PNC_QP_MAX_ITER; break; }
+          for (int i = lane; i < q.iq; i += 32) { uold[i] = q.u[i]; Aold[i] = Aact[i]; }
+          for (int i = lane; i < n; i += 32) xold[i] = x[i];
+          __syncwarp();
+          bool next_l1 = false;
+          while (!next_l1 && !done) {
+            double ss = 0.0;  // l2 (:323-334)
+            int ip = 0x7fffffff;
+            for (int i = lane; i < m; i += 32) {
+              const double v = sl[i];
+              if (v < ss && iai[i] != -1 && iaexcl[i]) { ss = v; ip = i; }
+            }
+            wargmin(ss, ip);
+            if (ss >= 0.0) { done = true; break; }
+            {
+              const double* row = Cr + (p + ip) * ld;
+              for (int k = lane; k < n; k += 32) q.np[k] = row[k];
+            }
+            if (lane == 0) { q.u[q.iq] = 0.0; Aact[q.iq] = ip; }
+            __syncwarp();
+            for (;;) {  // l2a
+              qp_compute_d(q, 0, n);
+              qp_compute_z(q, zz, znp);
+              qp_compute_r(q);
+              double t1 = INFINITY;
+              int kk = 0x7fffffff;
+              for (int k = p + lane; k < q.iq; k += 32) {
+                const double rk = q.r[k];
+                if (rk > 0.0) {
+                  const double v = q.u[k] / rk;
+                  if (v < t1) { t1 = v; kk = k; }
+                }
+              }
+              wargmin(t1, kk);
+              const int l = kk != 0x7fffffff ? Aact[kk] : 0;
+              double t2 = INFINITY;
+              if (fabs(zz) > QP_EPS) {
+                t2 = -sl[ip] / znp;
+                if (t2 < 0.0) t2 = INFINITY;
+              }
+              const double t = fmin(t1, t2);
+              if (t >= INFINITY) { status = PNC_QP_INFEASIBLE; done = true; break; }  // :402-407
+              if (t2 >= INFINITY) {  // dual step only, drop l (:409-423)
+                for (int k = lane; k < q.iq; k += 32) q.u[k] -= t * q.r[k];
+                if (lane == 0) { q.u[q.iq] += t; iai[l] = l; }
+                __syncwarp();
+                qp_delete_constraint(q, Aact, kk);
+                continue;
+              }
+              const double uq = q.u[q.iq];
+              for (int k = lane; k < n; k += 32) x[k] += t * q.z[k];  // :425-434
+              f += t * znp * (0.5 * t + uq);
+              __syncwarp();
+              for (int k = lane; k < q.iq; k += 32) q.u[k] -= t * q.r[k];
+              if (lane == 0) q.u[q.iq] += t;
+              __syncwarp();
+              if (fabs(t - t2) < QP_EPS) {  // full step (:441-474)
+                if (!qp_add_constraint(q)) {
+                  if (lane == 0) iaexcl[ip] = 0;
+                  for (int i = lane; i < m; i += 32) iai[i] = i;
+                  __syncwarp();
+                  for (int i = p + lane; i < q.iq; i += 32) {
+                    Aact[i] = Aold[i];
+                    q.u[i] = uold[i];
+                    iai[Aold[i]] = -1;
+                  }
+                  for (int i = lane; i < n; i += 32) x[i] = xold[i];
+                  __syncwarp();
+                  break;
+                }
+                if (lane == 0) iai[ip] = -1;
+                __syncwarp();
+                next_l1 = true;
+                break;
+              }
+              if (lane == 0) iai[l] = l;  // partial step (:476-499)
+              __syncwarp();
+              qp_delete_constraint(q, Aact, kk);
+              double acc = 0.0;
+              for (int k = lane; k < n; k += 32) acc += q.np[k] * x[k];
+              acc = wsum(acc);
+              if (lane == 0) sl[ip] = acc + c0[p + ip];
+              __syncwarp();
+            }
+          }
+        }
+        if (accepted && status != PNC_QP_OK) {
+          status = PNC_QP_OK;
+          q.iq = iq_acc;
+          f = f_acc;
+          for (int i = lane; i < n; i += 32) x[i] = xacc[i];
+          for (int i = lane; i < iq_acc; i += 32) Aact[i] = Aacc[i];
+          __syncwarp();
+        }
+      }
+    }
+    const bool bad = status == PNC_QP_NOT_PD || status == PNC_QP_EQ_DEPENDENT || status == PNC_QP_INFEASIBLE;
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    for (int k = lane; k < n; k += 32) xout[s * n + k] = bad ? nanv : x[k];
+    if (active_out) {
+      const int mw = (m + 63) / 64 > 0 ? (m + 63) / 64 : 1;
+      for (int wd = lane; wd < mw; wd += 32) {
+        unsigned long long bits = 0ull;
+        for (int i = p; i < q.iq; i++) {
+          const int c = Aact[i];
+          if (c >= 0 && (c >> 6) == wd) bits |= 1ull << (c & 63);
+        }
+        active_out[s * mw + wd] = bits;
+      }
+    }
+    if (lane == 0) {
+      // QuadProg++ returns +inf for an infeasible problem (:402-407)
+      if (fout) fout[s] = status == PNC_QP_INFEASIBLE ? INFINITY : (bad ? nanv : f);
+      if (status_out) status_out[s] = status;
+      if (iters_out) iters_out[s] = iter;
+    }
+    __syncwarp();
+  }
+}
+
+// returns false when the shape does not fit shared memory
+bool launch_quadprog_dense(int n, int p, int m, int B, const double* G, const double* g0, const double* CE, const double* ce0,
+                           const double* CI, const double* ci0, double* x, double* f, int* status, int* iters,
+                           unsigned long long* active, int num_sms, cudaStream_t stream) {
+  if (n < 1 || n > 64 || p < 0 || p > n || m < 0) return false;
+  const QpDenseLayout L = qpd_layout(n, p, m);
+  const size_t smem = (size_t)L.total * sizeof(double);
+  if (smem > 200 * 1024) return false;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(k_quadprog_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    configured = smem;
+  }
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_quadprog_dense, 32, smem);
+  if (per_sm < 1) return false;
+  int grid = num_sms * per_sm;
+  if (grid > B) grid = B;
+  k_quadprog_dense<<<grid, 32, smem, stream>>>(n, p, m, L, B, G, g0, CE, ce0, CI, ci0, x, f, status, iters, active);
+  g_launch_count++;
+  return true;
+}
+
 void launch_task_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
                          const double* des, cudaStream_t stream) {
   const size_t total = (size_t)B * hp.ntask;

@@ -198,3 +198,30 @@ def task_actuals_from_workspace(spec, ws):
                 list(range(6, 6 + t['dim']))
             pos.append(q[:, [i + 1 for i in idx]].copy()); vl.append(v[:, idx].copy())
     return dict(task_pos=pos, task_vel=vl)
+
+
+def quadprog_batch(G, g0, CE=None, ce0=None, CI=None, ci0=None, want_active=False):
+    """Batched ``solve_quadprog(G, g0, CE, ce0, CI, ci0, x)`` (reference external_source/Goldfarb/
+    QuadProg++.hh:70): min 1/2 x'Gx + g0'x  s.t. CE'x + ce0 = 0, CI'x + ci0 >= 0 for B problems.
+    CUDA fp64 tensors: G [B,n,n], g0 [B,n], CE [B,n,p], ce0 [B,p], CI [B,n,m], ci0 [B,m] (one COLUMN
+    per constraint, as QuadProg++'s matrices).  Returns (x [B,n], f [B], status [B] int32, iters [B]
+    int32[, active [B, ceil(m/64)] int64 bit mask])."""
+    lib = _cabi.load_library()
+    assert G.is_cuda and G.dtype == torch.float64
+    B, n = G.shape[0], G.shape[1]
+    dev = G.device
+    p = 0 if CE is None else CE.shape[2]
+    m = 0 if CI is None else CI.shape[2]
+    c = lambda t: None if t is None else t.contiguous()
+    G, g0, CE, ce0, CI, ci0 = c(G), c(g0), c(CE), c(ce0), c(CI), c(ci0)
+    x = torch.empty((B, n), dtype=torch.float64, device=dev)
+    f = torch.empty((B,), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    iters = torch.empty((B,), dtype=torch.int32, device=dev)
+    mw = max(1, (m + 63) // 64)
+    active = torch.zeros((B, mw), dtype=torch.int64, device=dev) if want_active else None
+    P = lambda t: None if t is None else _ptr(t)
+    stream = vp(torch.cuda.current_stream(dev).cuda_stream)
+    _check(lib.pnc_quadprog_batch(dev.index or 0, B, n, p, m, P(G), P(g0), P(CE), P(ce0), P(CI), P(ci0), P(x), P(f),
+                                  P(status), P(iters), P(active), stream), 'pnc_quadprog_batch')
+    return (x, f, status, iters, active) if want_active else (x, f, status, iters)

@@ -78,8 +78,16 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
     const size_t s = (size_t)si;
     int bad = 0;
     const double* Mg = ws.M + s * nv * nv;
-    for (int i = 0; i < nv; i++)
-      for (int c = lane; c < nv; c += 32) Lm[i * ld + c] = Mg[i * nv + c];
+    for (int e0 = lane; e0 < nv * nv; e0 += 32 * 8) {  // flattened: eight independent loads in flight per lane
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = e0 + 32 * u < nv * nv ? Mg[e0 + 32 * u] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + 32 * u;
+        if (e < nv * nv) { const int i = e / nv; Lm[i * ld + (e - i * nv)] = v[u]; }
+      }
+    }
     for (int c = lane; c < nv; c += 32) { Mdiag[c] = Mg[c * nv + c]; cg[c] = ws.cori[s * nv + c] + ws.grav[s * nv + c]; }
     __syncwarp();
     // ---- M = L L^T (lower triangle of Lm; the strict upper triangle keeps M) ----
@@ -176,12 +184,28 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
         }
       }
       // ---- Jc Ni = Jc - (Jc Jibar) Ji ----
+      // the contact Jacobian rows are staged in shared memory first (Z is not live yet): coalesced
+      // loads instead of one strided row walk per lane
+      const bool stage_jc = nc * ld <= nv * ldz;
+      double* Jcs = Z;
+      if (stage_jc) {
+        for (int c = 0; c < nc; c++) {
+          int ci = 0;
+          while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
+          const DevContact& C = P.contacts[ci];
+          const double* Jrow = ws.fr_jac + (s * nfr + fm.contact_f[ci]) * 6 * nv +
+                               (C.type == PNC_CONTACT_POINT ? 3 + (c - C.rf_off) : (c - C.rf_off)) * nv;
+          for (int i = lane; i < nv; i += 32) Jcs[c * ld + i] = Jrow[i];
+        }
+        __syncwarp();
+      }
       for (int c = lane; c < nc; c += 32) {
         int ci = 0;
         while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
         const DevContact& C = P.contacts[ci];
-        const double* Jrow = ws.fr_jac + (s * nfr + fm.contact_f[ci]) * 6 * nv +
-                             (C.type == PNC_CONTACT_POINT ? 3 + (c - C.rf_off) : (c - C.rf_off)) * nv;
+        const double* Jrow = stage_jc ? Jcs + c * ld
+                                      : ws.fr_jac + (s * nfr + fm.contact_f[ci]) * 6 * nv +
+                                            (C.type == PNC_CONTACT_POINT ? 3 + (c - C.rf_off) : (c - C.rf_off)) * nv;
         double acc[PNC_MAX_IC];
         for (int t = 0; t < k; t++) acc[t] = 0.0;
         for (int i = 0; i < nv; i++) {
@@ -281,20 +305,60 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
       }
       __syncwarp();
       // ---- S [M | -(Jc Ni)^T] and S Ni^T (c+g), S = [0 | B]: lane = actuated row a, so the
-      //      transposed store [n][nact] is coalesced; M and Jc Ni are read warp-uniformly ----
+      //      transposed store [n][nact] is coalesced.  The right factor X = [M[6:, :] | (Jc Ni)[:, 6:]^T]
+      //      (nj x n) is staged over the dead factor L and Z, then read as shared-memory broadcasts ----
+      const int ldx = n | 1;
+      const bool stage_x = nj * ldx <= nv * ld + nv * ldz;
+      double* X = Lm;
+      if (stage_x) {
+        for (int e0 = lane; e0 < nj * nv; e0 += 32 * 8) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = e0 + 32 * u < nj * nv ? Mg[6 * nv + e0 + 32 * u] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int e = e0 + 32 * u;
+            if (e < nj * nv) { const int j = e / nv; X[j * ldx + (e - j * nv)] = v[u]; }
+          }
+        }
+        for (int e = lane; e < nc * nj; e += 32) {
+          const int cc = e / nj, j = e - cc * nj;
+          X[j * ldx + nv + cc] = ws.ic_jcni[(s * nc + cc) * nv + 6 + j];
+        }
+        __syncwarp();
+      }
       for (int a = lane; a < nact; a += 32) {
         double* out = ws.ic_tq + s * nact * n + a;
-        for (int c = 0; c < n; c++) {
-          const double* src = c < nv ? Mg + 6 * nv + c : ws.ic_jcni + (s * nc + (c - nv)) * nv + 6;
-          const int stride = c < nv ? nv : 1;
-          double s0 = 0.0, s1 = 0.0;
-          int j = 0;
-          for (; j + 1 < nj; j += 2) {
-            s0 += Bt[j * ldb + a] * src[j * stride];
-            s1 += Bt[(j + 1) * ldb + a] * src[(j + 1) * stride];
+        if (stage_x) {
+          for (int c = 0; c < n; c += 4) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            const double* xc = X + c;
+            const bool ok1 = c + 1 < n, ok2 = c + 2 < n, ok3 = c + 3 < n;
+            for (int j = 0; j < nj; j++, xc += ldx) {
+              const double b = Bt[j * ldb + a];
+              s0 = fma(b, xc[0], s0);
+              if (ok1) s1 = fma(b, xc[1], s1);
+              if (ok2) s2 = fma(b, xc[2], s2);
+              if (ok3) s3 = fma(b, xc[3], s3);
+            }
+            out[c * nact] = c < nv ? s0 : -s0;
+            if (ok1) out[(c + 1) * nact] = c + 1 < nv ? s1 : -s1;
+            if (ok2) out[(c + 2) * nact] = c + 2 < nv ? s2 : -s2;
+            if (ok3) out[(c + 3) * nact] = c + 3 < nv ? s3 : -s3;
           }
-          if (j < nj) s0 += Bt[j * ldb + a] * src[j * stride];
-          out[c * nact] = c < nv ? (s0 + s1) : -(s0 + s1);
+        } else {
+          for (int c = 0; c < n; c++) {
+            const double* src = c < nv ? Mg + 6 * nv + c : ws.ic_jcni + (s * nc + (c - nv)) * nv + 6;
+            const int stride = c < nv ? nv : 1;
+            double s0 = 0.0, s1 = 0.0;
+            int j = 0;
+            for (; j + 1 < nj; j += 2) {
+              s0 += Bt[j * ldb + a] * src[j * stride];
+              s1 += Bt[(j + 1) * ldb + a] * src[(j + 1) * stride];
+            }
+            if (j < nj) s0 += Bt[j * ldb + a] * src[j * stride];
+            out[c * nact] = c < nv ? (s0 + s1) : -(s0 + s1);
+          }
         }
         double part = 0.0;
         for (int j = 0; j < nj; j++) part += Bt[j * ldb + a] * ncg[6 + j];

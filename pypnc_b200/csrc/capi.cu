@@ -37,6 +37,7 @@ struct pnc_model {
 
 struct pnc_problem {
   const pnc_model* m;
+  int device;  // copy of m->device (see pnc_workspace)
   DevProblem h;
   DevProblem* d;
   int task_model_frame[PNC_MAX_TASKS];
@@ -46,6 +47,7 @@ struct pnc_problem {
 
 struct pnc_workspace {
   const pnc_model* m;
+  int device;  // copy of m->device: destroy must not touch the model, which may already be gone
   int cap, nfr;
   DevFrames hfr;
   DevFrames* dfr;
@@ -126,6 +128,7 @@ void pnc_model_destroy(pnc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaFree(m->d);
+  cudaGetLastError();
   delete m;
 }
 
@@ -139,6 +142,7 @@ int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* dsc, pnc_prob
   CK(cudaSetDevice(m->device));
   pnc_problem* p = new pnc_problem();
   p->m = m;
+  p->device = m->device;
   DevProblem& h = p->h;
   memset(&h, 0, sizeof(h));
   h.ntask = dsc->ntask; h.ncontact = dsc->ncontact; h.n_ic = dsc->n_ic; h.nact = dsc->nact;
@@ -208,8 +212,9 @@ int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* dsc, pnc_prob
 
 void pnc_problem_destroy(pnc_problem* p) {
   if (!p) return;
-  cudaSetDevice(p->m->device);
+  cudaSetDevice(p->device);
   cudaFree(p->d);
+  cudaGetLastError();  // a destroy during interpreter teardown must not leave a stale error behind
   delete p;
 }
 
@@ -233,7 +238,7 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
   CK(cudaSetDevice(m->device));
   pnc_workspace* ws = new pnc_workspace();
   memset(&ws->p, 0, sizeof(ws->p));
-  ws->m = m; ws->cap = capacity; ws->nfr = nframes;
+  ws->m = m; ws->device = m->device; ws->cap = capacity; ws->nfr = nframes;
   ws->ic_slab = nullptr; ws->ic_bytes = 0; ws->ic_nc = ws->ic_nact = 0;
   ws->task_slab = nullptr; ws->task_rows = 0;
   ws->setup_slab = nullptr; ws->setup_stride = 0;
@@ -270,7 +275,7 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
 
 void pnc_workspace_destroy(pnc_workspace* ws) {
   if (!ws) return;
-  cudaSetDevice(ws->m->device);
+  cudaSetDevice(ws->device);
   cudaFree(ws->slab);
   cudaFree(ws->dfr);
   if (ws->ic_slab) cudaFree(ws->ic_slab);
@@ -280,6 +285,7 @@ void pnc_workspace_destroy(pnc_workspace* ws) {
   if (ws->tick_init) {
     for (int i = 0; i < 2; i++) { cudaStreamDestroy(ws->tick_stream[i]); cudaEventDestroy(ws->tick_ev[i]); }
   }
+  cudaGetLastError();
   delete ws;
 }
 

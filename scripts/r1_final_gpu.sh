@@ -9,5 +9,5 @@ timeout 600 python bench.py --steps 5 --warmup 3 > $O/bench_full.json 2> $O/benc
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err
 for r in laikago valkyrie draco3 draco3_lb; do timeout 300 python bench.py --robot $r --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/bench_$r.json 2>/dev/null; done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_launches.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_ihwbc_reg|k_ihwbc_setup|k_update_system|k_ihwbc_finish|k_task_prepare" -c 5 -o $O/r1_full -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $O/ncu_full.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_ihwbc_reg|k_ihwbc_setup|k_update_system|k_ihwbc_finish|k_task_prepare" -c 8 -o $O/r1_full -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $O/ncu_full.log 2>&1
 ls -la $O

@@ -690,13 +690,29 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
   int32_t* d_status = (int32_t*)take(C * 4);
   int32_t* d_iters = (int32_t*)take(C * 4);
   uint64_t* d_active = (uint64_t*)take(C * mw * 8);
-  int* counters = (int*)take(256);
+  int* counters = (int*)take(1024);  // 8 ints per chunk, up to 16 chunks
 
-  int nchunk = B >= 8192 ? 4 : 1;
-  int chunk = (B + nchunk - 1) / nchunk;
+  // chunk schedule: a short first chunk gets the kernels going early (its H2D copy is the only
+  // one nothing overlaps), the rest are equal.  PNC_TICK_CHUNKS / PNC_TICK_FIRST (fraction) override.
+  static const int env_chunks = [] { const char* e = getenv("PNC_TICK_CHUNKS"); return e ? atoi(e) : 0; }();
+  static const double env_first = [] { const char* e = getenv("PNC_TICK_FIRST"); return e ? atof(e) : 0.0; }();
+  int nchunk = B >= 8192 ? (env_chunks > 0 && env_chunks <= 16 ? env_chunks : 4) : 1;
+  int bounds[17];
+  {
+    // default: first chunk = B/8, then three equal chunks (measured on Atlas 64 K, scripts/e2e_sweep.sh:
+    // 13.3 ms per step against 14.3 ms for four equal chunks)
+    int first = env_chunks > 0 ? (B + nchunk - 1) / nchunk : B / 8;
+    if (nchunk > 1 && env_first > 0.0 && env_first < 1.0) first = (int)(env_first * B);
+    if (first < 1) first = 1;
+    bounds[0] = 0;
+    const int rest = B - first;
+    for (int c = 1; c <= nchunk; c++)
+      bounds[c] = c == nchunk ? B : first + (int)((long long)rest * (c - 1) / (nchunk - 1 > 0 ? nchunk - 1 : 1));
+    if (nchunk == 1) bounds[1] = B;
+  }
   for (int c = 0; c < nchunk; c++) {
-    int o = c * chunk, nb = B - o < chunk ? B - o : chunk;
-    if (nb <= 0) break;
+    int o = bounds[c], nb = bounds[c + 1] - bounds[c];
+    if (nb <= 0) continue;
     cudaStream_t st = ws->tick_stream[c & 1];
 #define H2D(dst, src, per) CK(cudaMemcpyAsync((dst) + (size_t)o * (per), (src) + (size_t)o * (per), (size_t)nb * (per) * 8, cudaMemcpyHostToDevice, st))
     H2D(d_bp, h_base_pos, 3); H2D(d_bq, h_base_quat, 4); H2D(d_blv, h_base_lin_vel, 3); H2D(d_bav, h_base_ang_vel, 3);

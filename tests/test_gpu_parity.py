@@ -567,3 +567,58 @@ def test_large_sample_tick_parity(name, B, oracle_mod):
         assert _active_sets_equivalent(c, b, act[b], ref['active'][b]), (b, np.where(act[b])[0], np.where(ref['active'][b])[0])
     if name == 'laikago':
         assert not differing
+
+
+@pytest.mark.parametrize("name", ['atlas', 'draco3'])
+def test_controller_get_command(name, oracle_mod):
+    """controller.Controller.get_command (AtlasController / Draco3Controller mirror): torques and
+    accelerations scattered back through Sa[:, 6:]^T, integrated joint commands, ordered dict."""
+    import torch
+    from pypnc_b200.robot_system import BatchedRobotSystem
+    from pypnc_b200.wbc import BasicTask, SurfaceContact, RollingJointConstraint
+    from pypnc_b200.controller import Controller, TCIContainer
+    ctx = _CTX.get(name) or Ctx(name, oracle_mod)
+    spec, B = ctx.spec, ctx.B
+    robot = BatchedRobotSystem(spec.model, None, False, False, capacity=B)
+    d = dict(zip(KEYS, ctx.d_st))
+    robot.update_system(None, None, None, None, d['base_pos'], d['base_quat'], d['base_lin_vel'], d['base_ang_vel'],
+                        d['joint_pos'], d['joint_vel'])
+    tasks, des = [], ctx.d_in[0]
+    for i, t in enumerate(spec.tasks):
+        ttype = [k for k, v in robots.TASK_TYPE_NAMES.items() if v == t['type']][0]
+        task = BasicTask(robot, ttype, t['dim'], t['target'] if ttype != 'COM' else None)
+        task.kp = np.array(spec.kp[t['gain_off']:t['gain_off'] + t['dim']])
+        task.kd = np.array(spec.kd[t['gain_off']:t['gain_off'] + t['dim']])
+        task.w_hierarchy = ctx.d_in[1][:, i]
+        npos = 4 if t['type'] == 3 else t['dim']
+        o = t['des_off']
+        task.update_desired(des[:, o:o + npos], des[:, o + npos:o + npos + t['dim']],
+                            des[:, o + npos + t['dim']:o + npos + 2 * t['dim']])
+        tasks.append(task)
+    contacts = []
+    for i, c in enumerate(spec.contacts):
+        sc = SurfaceContact(robot, c['link'], c['x'], c['y'], c['mu'])
+        sc.rf_z_max = ctx.d_in[2][:, i]
+        contacts.append(sc)
+    passive = ('l_knee_fe_jd', 'r_knee_fe_jd') if name == 'draco3' else ()
+    ics = [RollingJointConstraint(robot)] if name == 'draco3' else []
+    ctrl = Controller(TCIContainer(tasks, contacts, ics), robot, passive_joints=passive, b_trq_limit=bool(spec.b_trq_limit),
+                      lambda_q_ddot=spec.lambda_q_ddot, lambda_rf=spec.lambda_rf)
+    cmd = ctrl.get_command()
+    torch.cuda.synchronize()
+    names = list(robot.joint_id.keys())
+    assert list(cmd['joint_trq'].keys()) == names and list(cmd['joint_pos'].keys()) == names
+    trq = torch.stack([cmd['joint_trq'][k] for k in names], dim=1).cpu().numpy()
+    ok = ctx.ref['status'] == 0
+    act = np.array(spec.act_idx) - 6
+    tol = 5e-9 if spec.n_ic else RTOL
+    assert per_state_rel(trq[ok][:, act], ctx.ref['trq'][ok]).max() < tol
+    passive_cols = [i for i in range(robot.n_a) if i not in set(act.tolist())]
+    assert len(passive_cols) == len(passive) and np.all(trq[:, passive_cols] == 0.0)
+    # first tick of the integrator (joint_integrator.py:73-82): vel = alpha_v-filtered 0 + acc dt, clipped
+    ji = ctrl.joint_integrator
+    acc_full = np.zeros((B, robot.n_a)); acc_full[:, act] = ctx.ref['acc']
+    vel_ref = np.clip((1.0 - ji._alpha_vel) * 0.0 + acc_full * 0.001, spec.model.joint_vel_limit[:, 0], spec.model.joint_vel_limit[:, 1])
+    vel = torch.stack([cmd['joint_vel'][k] for k in names], dim=1).cpu().numpy()
+    assert np.abs(vel[ok] - vel_ref[ok]).max() < 1e-9 * max(1.0, np.abs(vel_ref[ok]).max())
+    assert torch.equal(ctrl.rf_cmd, ctrl.ihwbc.solve(tasks, contacts, ics)[2])

@@ -13,6 +13,7 @@
 // sum become masked loops over lanes through shared memory -- no per-level transforms on the
 // way back up the tree.  Joint tables are staged once per CTA in shared memory.
 #include "pnc_dev.cuh"
+#include "pnc_launch.h"
 
 namespace pnc {
 
@@ -424,11 +425,8 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
                           int num_sms, cudaStream_t stream, int b_cent) {
   size_t smem = dyn_smem_bytes(nv);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_update_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  optin.ensure(k_update_system, smem);
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 4) ctas_per_sm = 4;

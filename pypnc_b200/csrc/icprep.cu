@@ -430,11 +430,8 @@ void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
                        int B, int num_sms, cudaStream_t stream, int* counter) {
   IcLayout L = ic_layout(hp.nv, hp.nact, hp.nc, hp.n_ic);
   const size_t smem = (size_t)L.total * sizeof(double);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_ic_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  optin.ensure(k_ic_prepare, smem);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 16) per_sm = 16;

@@ -786,11 +786,8 @@ void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcL
   // states it could not finish (more than 32 active constraints)
   if (fast) cudaMemsetAsync(io.counter, 0, sizeof(int), stream);
   const size_t smem = (size_t)L.per_state * sizeof(double);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_ihwbc_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  optin.ensure(k_ihwbc_solve, smem);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 16) per_sm = 16;
@@ -1166,11 +1163,8 @@ bool launch_quadprog_dense(int n, int p, int m, int B, const double* G, const do
   const QpDenseLayout L = qpd_layout(n, p, m);
   const size_t smem = (size_t)L.total * sizeof(double);
   if (smem > 200 * 1024) return false;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(k_quadprog_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (!optin.ensure(k_quadprog_dense, smem)) return false;
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_quadprog_dense, 32, smem);
   if (per_sm < 1) return false;

@@ -1328,21 +1328,13 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   int warps = warps_env >= 1 && warps_env <= 8 ? warps_env : 1;  // warps (= states in flight) per CTA
   while (warps > 1 && (size_t)warps * C::SMEM_DOUBLES * sizeof(double) > 227 * 1024) warps--;
   const size_t smem = (size_t)warps * C::SMEM_DOUBLES * sizeof(double);
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(k_ihwbc_reg<NV, NC, NU, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return false;
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (!optin.ensure(k_ihwbc_reg<NV, NC, NU, NT>, smem)) return false;
   const SetupLayout SL = setup_layout<C>(hp, C::IMG);
   if (!ws.setup_rec || ws.setup_stride != C::REC) return false;
   const size_t smem_s = (size_t)SL.per_state * sizeof(double);
-  static size_t configured_s = 0;
-  if (smem_s > configured_s) {
-    if (cudaFuncSetAttribute(k_ihwbc_setup<NV, NC, NU, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess)
-      return false;
-    configured_s = smem_s;
-  }
+  static SmemOptIn optin_s;
+  if (!optin_s.ensure(k_ihwbc_setup<NV, NC, NU, NT>, smem_s)) return false;
   int per_sm_s = 0, per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC, NU, NT>, 32, smem_s);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT>, 32 * warps, smem);

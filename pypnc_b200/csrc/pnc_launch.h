@@ -96,6 +96,22 @@ void launch_joint_integrate(int B, int na, const double* acc, const double* join
 bool launch_quadprog_dense(int n, int p, int m, int B, const double* G, const double* g0, const double* CE, const double* ce0,
                            const double* CI, const double* ci0, double* x, double* f, int* status, int* iters,
                            unsigned long long* active, int num_sms, cudaStream_t stream);
+// The opt-in dynamic shared-memory limit of a kernel is a per-device attribute: one process may
+// drive several GPUs, so the high-water mark is remembered per device.
+struct SmemOptIn {
+  size_t bytes[64] = {};
+  template <class K>
+  bool ensure(K kernel, size_t smem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (smem > bytes[dev]) {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+      bytes[dev] = smem;
+    }
+    return true;
+  }
+};
+
 // managers.cu
 void launch_ramp_update(int B, const double* sv, double target, const double* st, const double* dur, double t, double* out,
                         cudaStream_t stream);

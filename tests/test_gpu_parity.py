@@ -622,3 +622,33 @@ def test_controller_get_command(name, oracle_mod):
     vel = torch.stack([cmd['joint_vel'][k] for k in names], dim=1).cpu().numpy()
     assert np.abs(vel[ok] - vel_ref[ok]).max() < 1e-9 * max(1.0, np.abs(vel_ref[ok]).max())
     assert torch.equal(ctrl.rf_cmd, ctrl.ihwbc.solve(tasks, contacts, ics)[2])
+
+
+def test_second_device_in_one_process(oracle_mod):
+    """One process driving two GPUs: the handles carry their device, kernel attributes are set per
+    device, and the same states give the same bits on either GPU.  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from pypnc_b200 import engine
+    ctx = _CTX.get('atlas') or Ctx('atlas', oracle_mod)
+    spec, B = ctx.spec, ctx.B
+    with torch.cuda.device(1):
+        dm = engine.Model(spec.model, 1)
+        pb = engine.Problem(dm, spec)
+        ws = engine.Workspace(dm, B, spec.frames)
+        ws.update_system(*[t.to('cuda:1') for t in ctx.d_st])
+        out = engine.ihwbc_solve(pb, ws, *[t.to('cuda:1') for t in ctx.d_in])
+        torch.cuda.synchronize()
+    for k in ('trq', 'acc', 'rf'):
+        assert torch.equal(out[k].cpu(), ctx.out[k].cpu()), k
+    assert torch.equal(out['status'].cpu(), ctx.out['status'].cpu())
+    # the generic shared-memory kernel needs the 48 KB+ opt-in on the second device too
+    G = torch.eye(40, dtype=torch.float64, device='cuda:1').repeat(4, 1, 1)
+    g0 = torch.ones((4, 40), dtype=torch.float64, device='cuda:1')
+    CI = torch.eye(40, dtype=torch.float64, device='cuda:1').repeat(4, 1, 1).contiguous()
+    ci0 = torch.zeros((4, 40), dtype=torch.float64, device='cuda:1')
+    with torch.cuda.device(1):
+        x, f, st, it = engine.quadprog_batch(G, g0, None, None, CI, ci0)
+        torch.cuda.synchronize()
+    assert (st == 0).all() and float(x.abs().max()) == 0.0  # min 1/2|x|^2 + 1.x s.t. x >= 0  ->  x = 0

@@ -217,3 +217,48 @@ class DCMEstimator:
             self.prev_dcm, self.dcm_vel = torch.zeros_like(self.dcm), torch.zeros_like(self.dcm)
         engine._check(self._lib.pnc_dcm_update(ws.h, B, self._dt, self._alpha, _P(self.dcm), _P(self.prev_dcm),
                                                _P(self.dcm_vel), None), 'pnc_dcm_update')
+
+
+class PointFootTrajectoryManager(FootTrajectoryManager):
+    """point_foot_trajectory_manager.py:10-99 (Laikago toes): the position half of
+    ``FootTrajectoryManager`` -- same swing record (the raised mid foot still uses the interpolated
+    orientation, :54-70), only the LINK_XYZ task is written."""
+
+    def __init__(self, pos_task, robot):
+        self._pos_task, self._ori_task, self._robot = pos_task, None, robot
+        self._target_id = pos_task.target_id
+        self._lib = load_library()
+        self._swing_start_time = self._swing_duration = self._rec = None
+        self._swing_height = 0.05
+
+    def use_current(self):  # :37-45
+        ws, frame = self._ws()
+        B = ws.B
+        pos, vel, acc, quat, w, wd = _outputs(B, ws.view('com').device)
+        engine._check(self._lib.pnc_foot_use_current(ws.h, B, frame, _P(pos), _P(vel), _P(acc), _P(quat), _P(w), _P(wd), None),
+                      'pnc_foot_use_current')
+        self._pos_task.update_desired(pos, vel, acc)
+
+    def update_swing_foot_desired(self, curr_time):  # :73-89
+        B, dev = self._rec.shape[0], self._rec.device
+        pos, vel, acc, quat, w, wd = _outputs(B, dev)
+        engine._check(self._lib.pnc_swing_eval(B, _P(self._rec), _P(self._swing_start_time), _P(self._swing_duration),
+                                               float(curr_time), _P(pos), _P(vel), _P(acc), _P(quat), _P(w), _P(wd), None),
+                      'pnc_swing_eval')
+        self._pos_task.update_desired(pos, vel, acc)
+
+
+class UpperBodyTrajectoryManager:
+    """upper_body_trajectory_manager.py:6-28: hold the SELECTED_JOINT task at the nominal pose."""
+
+    def __init__(self, upper_body_task, robot):
+        self._upper_body_task, self._robot = upper_body_task, robot
+
+    task = property(lambda s: s._upper_body_task)
+
+    def use_nominal_upper_body_joint_pos(self, nominal_joint_pos):
+        """nominal_joint_pos: {joint name: float or [B] tensor}."""
+        vals = [torch.as_tensor(nominal_joint_pos[k], dtype=torch.float64).reshape(-1) for k in self._upper_body_task.target_id]
+        B = max(v.numel() for v in vals)
+        pos = torch.stack([v.expand(B) for v in vals], dim=-1).cuda()
+        self._upper_body_task.update_desired(pos, torch.zeros_like(pos), torch.zeros_like(pos))

@@ -3,7 +3,7 @@
     python tests/golden/make_golden_managers.py      (needs /root/reference; run in the build container)
 
 Runs unmodified from /root/reference: pnc/wbc/manager/{task_hierarchy_manager, reaction_force_manager,
-foot_trajectory_manager, floating_base_trajectory_manager}.py, util/interpolation.py, util/util.py,
+foot_trajectory_manager, point_foot_trajectory_manager, floating_base_trajectory_manager}.py, util/interpolation.py, util/util.py,
 pnc/planner/locomotion/dcm_planner/footstep.py, and the DCM update of
 pnc/atlas_pnc/atlas_state_estimator.py:35-44 (re-typed below because the module imports the
 simulator config; the arithmetic is the three lines cited).  The robot is a stub that returns the
@@ -22,6 +22,7 @@ from scipy.spatial.transform import Rotation as R  # noqa: E402
 from pnc.wbc.manager.task_hierarchy_manager import TaskHierarchyManager  # noqa: E402
 from pnc.wbc.manager.reaction_force_manager import ReactionForceManager  # noqa: E402
 from pnc.wbc.manager.foot_trajectory_manager import FootTrajectoryManager  # noqa: E402
+from pnc.wbc.manager.point_foot_trajectory_manager import PointFootTrajectoryManager  # noqa: E402
 from pnc.wbc.manager.floating_base_trajectory_manager import FloatingBaseTrajectoryManager  # noqa: E402
 from pnc.planner.locomotion.dcm_planner.footstep import Footstep  # noqa: E402
 
@@ -100,6 +101,7 @@ def main(n=96, seed=7):
     height = 0.05
     uc = {k: [] for k in ('pos', 'vel', 'acc', 'quat', 'angvel', 'angacc')}
     sw = {k: [] for k in ('pos', 'vel', 'acc', 'quat', 'angvel', 'angacc')}
+    pf = {k: [] for k in ('uc_pos', 'uc_vel', 'uc_acc', 'sw_pos', 'sw_vel', 'sw_acc')}
     land_quat = np.zeros((n, 4))
     for i in range(n):
         robot = StubRobot()
@@ -122,6 +124,18 @@ def main(n=96, seed=7):
             sw[k].append(v)
         for k, v in zip(('quat', 'angvel', 'angacc'), ot.des):
             sw[k].append(v)
+        # the point-foot manager (Laikago toes): positions only, same landing foot
+        pt2 = StubTask('foot')
+        m2 = PointFootTrajectoryManager(pt2, robot)
+        m2.use_current()
+        for k, v in zip(('uc_pos', 'uc_vel', 'uc_acc'), pt2.des):
+            pf[k].append(v)
+        m2.swing_height = height
+        m2.initialize_swing_foot_trajectory(sw_t0[i], sw_dur[i], land)
+        m2.update_swing_foot_desired(sw_t0[i] + sw_frac[i] * sw_dur[i])
+        for k, v in zip(('sw_pos', 'sw_vel', 'sw_acc'), pt2.des):
+            pf[k].append(v)
+    out.update(**{'pf_' + k: np.array(v) for k, v in pf.items()})
     out.update(foot_iso=iso, foot_vel=vel, land_pos=land_iso[:, :3, 3], land_quat=land_quat, sw_t0=sw_t0, sw_dur=sw_dur,
                sw_frac=sw_frac, sw_height=height, **{'uc_' + k: np.array(v) for k, v in uc.items()},
                **{'sw_' + k: np.array(v) for k, v in sw.items()})

@@ -213,3 +213,63 @@ def test_manager_classes_closed_loop_vs_oracle():
     vcom = robot.get_com_lin_vel().cpu().numpy()
     ref = [MO.dcm_update(cpos[i], vcom[i], np.zeros(3), 0.001) for i in range(B)]
     close(est.dcm, np.array([r[0] for r in ref])); close(est.dcm_vel, np.array([r[2] for r in ref]), 1e-9)
+
+
+def test_point_foot_and_upper_body_managers(rig):
+    """PointFootTrajectoryManager / UpperBodyTrajectoryManager through the reference-style classes, against
+    the golden vectors of the reference's PointFootTrajectoryManager."""
+    from pypnc_b200 import managers, wbc
+
+    class Rob:  # just enough of BatchedRobotSystem for the managers: the rigged workspace and its frame ids
+        def __init__(self, spec, ws):
+            self._ws, self.model, self._spec = ws, spec.model, spec
+
+        def _slot(self, target):
+            f = self.model.frame_id(target) if isinstance(target, str) else int(target)
+            return self._ws, self._ws.frames.index(f)
+
+    spec, dm, ws = rig
+    slot = 3
+    put_frame(ws, slot, G['foot_iso'], G['foot_vel'])
+    rob = Rob(spec, ws)
+    target = spec.frames[slot]
+
+    class T:  # records update_desired like the reference's Task
+        target_id = target
+
+        def update_desired(self, p, v, a):
+            self.des = (p, v, a)
+
+    class Model2:
+        def __init__(self, m):
+            self._m = m
+
+        def frame_id(self, t):
+            return int(t)
+
+    rob.model = Model2(spec.model)
+    task = T()
+    m = managers.PointFootTrajectoryManager(task, rob)
+    m.use_current()
+    for k, t in zip(('uc_pos', 'uc_vel', 'uc_acc'), task.des):
+        close(t, G['pf_' + k])
+    m.swing_height = float(G['sw_height'])
+    m.initialize_swing_foot_trajectory(dev(G['sw_t0']), dev(G['sw_dur']), dev(G['land_pos']), dev(G['land_quat']))
+    got = {k: np.zeros((N, 3)) for k in ('sw_pos', 'sw_vel', 'sw_acc')}
+    for i in range(N):
+        m.update_swing_foot_desired(float(G['sw_t0'][i] + G['sw_frac'][i] * G['sw_dur'][i]))
+        for k, t in zip(('sw_pos', 'sw_vel', 'sw_acc'), task.des):
+            got[k][i] = t[i].cpu().numpy()
+    for k in got:
+        close(got[k], G['pf_' + k])
+    # upper body: desired = nominal, zero velocity / acceleration
+    class JT:
+        target_id = ['a', 'b', 'c']
+
+        def update_desired(self, p, v, a):
+            self.des = (p, v, a)
+
+    jt = JT()
+    ub = managers.UpperBodyTrajectoryManager(jt, rob)
+    ub.use_nominal_upper_body_joint_pos({'a': 0.1, 'b': torch.tensor([0.2, 0.3], dtype=torch.float64), 'c': -0.4, 'unused': 9.0})
+    assert jt.des[0].shape == (2, 3) and jt.des[0][1].tolist() == [0.1, 0.3, -0.4] and float(jt.des[1].abs().max()) == 0.0

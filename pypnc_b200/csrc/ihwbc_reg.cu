@@ -698,6 +698,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   int nthr = blockDim.x;  // threads still taking part in the slot barrier
   const int p = P.p, m = C::M, nu = NU, nact = P.nact;
   constexpr bool trq = NT > 0;
+  constexpr bool S2 = C::RC > 32;  // S = R^-1 never has rows beyond 32 (RC caps the active set): second-half code is dead
   double* const Rp = smem + C::ORT;
   double* const Ts = smem + C::OT;
   double* const Ar = smem + C::OAR;   // torque-limit rows S [M | -(Jc Ni)^T], pitch LDA
@@ -1008,11 +1009,11 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             for (int j = 0; j < iq; j++) {
               const double dj = dv[j];
               if (lane <= j) acc0 = fma(col[lane], dj, acc0);
-              if (N > 32 && lane + 32 <= j) acc1 = fma(col[lane + 32], dj, acc1);
+              if (S2 && lane + 32 <= j) acc1 = fma(col[lane + 32], dj, acc1);
               col += j + 2;
             }
             if (lane < iq) rv[lane] = acc0;
-            if (N > 32 && lane + 32 < iq) rv[lane + 32] = acc1;
+            if (S2 && lane + 32 < iq) rv[lane + 32] = acc1;
           }
           __syncwarp();
           // step lengths (:366-393); equalities always take the full step (:246-258)
@@ -1148,13 +1149,13 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               }
               const double t1a = lane <= j ? cj[lane] : 0.0, t2a = lane <= j + 1 ? cn[lane] : 0.0;
               double t1b = 0.0, t2b = 0.0;
-              if (N > 32) { t1b = lane + 32 <= j ? cj[lane + 32] : 0.0; t2b = lane + 32 <= j + 1 ? cn[lane + 32] : 0.0; }
+              if (S2) { t1b = lane + 32 <= j ? cj[lane + 32] : 0.0; t2b = lane + 32 <= j + 1 ? cn[lane + 32] : 0.0; }
               __syncwarp();
               const double nja = skip ? t1a : t1a * cc + t2a * ss, nna = skip ? t2a : xny * (t1a + nja) - t2a;
               // column j is final: store it without row kk; column j+1 keeps its rows until its turn
               if (lane <= j + 1 && lane != kk) cj[lane - (lane > kk ? 1 : 0)] = nja;
               if (lane <= j + 1) cn[lane] = nna;
-              if (N > 32) {
+              if (S2) {
                 const double njb = skip ? t1b : t1b * cc + t2b * ss, nnb = skip ? t2b : xny * (t1b + njb) - t2b;
                 const int i = lane + 32;
                 if (i <= j + 1 && i != kk) cj[i - (i > kk ? 1 : 0)] = njb;
@@ -1167,7 +1168,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           {  // A[i], u[i] <- A[i+1], u[i+1] for i = kk .. iq-1 (the candidate at iq moves down too)
             int a0_ = 0, a1_ = 0;
             double u0_ = 0.0, u1_ = 0.0;
-            const bool m0 = lane >= kk && lane < iq, m1 = lane + 32 >= kk && lane + 32 < iq;
+            const bool m0 = lane >= kk && lane < iq, m1 = S2 && lane + 32 >= kk && lane + 32 < iq;
             if (m0) { a0_ = Aact[lane + 1]; u0_ = uv[lane + 1]; }
             if (m1) { a1_ = Aact[lane + 33]; u1_ = uv[lane + 33]; }
             __syncwarp();

@@ -62,7 +62,7 @@ struct MCfg : RCfg<NV_, NC_> {
                        ODV = OZ + R::NP, ODM = ODV + R::NP, OVM = ODM + R::NP, ONP = OVM + R::NP, ORR = ONP + R::NP,
                        OU = ORR + R::NP + 2, OXOLD = OU + R::NP + 2, OUOLD = OXOLD + R::NP, OXACC = OUOLD + R::NP + 2,
                        OSL = OXACC + R::NP, OINT = OSL + (((M > 0 ? M : 1) + 1) & ~1),
-                       SMEM_DOUBLES = (OINT + (3 * (R::N + 2) + 1) / 2 + 2) & ~1;
+                       SMEM_DOUBLES = (OINT + (((3 * (R::N + 2) + 1) & ~1) + 2 * NU) / 2 + 2) & ~1;  // A, Aold, Aacc, cone-row table
   static_assert(64 + R::PMAX * R::NP <= RSZ || R::N < 20, "equality block must fit behind the first S columns");
   // ---- per-state HBM record (doubles): written by k_ihwbc_setup, consumed by k_ihwbc_reg, whose
   //      result goes back into it for k_ihwbc_finish.  Everything the active-set kernel needs is
@@ -696,7 +696,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   const int lane = threadIdx.x & 31;
   double* const smem = smem_all + (threadIdx.x >> 5) * C::SMEM_DOUBLES;
   int nthr = blockDim.x;  // threads still taking part in the slot barrier
-  const int p = P.p, m = C::M, nu = NU, nact = P.nact;
+  const int p = P.p, m = C::M, nu = NU;
+  constexpr int nact = NT;  // torque-limit rows = actuated joints (shape_ok); only used when NT > 0
   constexpr bool trq = NT > 0;
   constexpr bool S2 = C::RC > 32;  // S = R^-1 never has rows beyond 32 (RC caps the active set): second-half code is dead
   double* const Rp = smem + C::ORT;
@@ -720,6 +721,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   int* const Aact = reinterpret_cast<int*>(smem + C::OINT);
   int* Aold = Aact + (N + 2);
   int* Aacc = Aold + (N + 2);
+  int* const Cm = Aact + ((3 * (N + 2) + 1) & ~1);  // per cone row: first variable, number of variables (8-byte aligned pairs)
 #define Rcol(c) (Rp + ((c) * ((c) + 3)) / 2)
   double* rot = Ts;  // the d scratch tile doubles as the Givens coefficient table of a drop
   static_assert(6 * LDT >= 3 * NP, "rotation table must fit the scratch tile");
@@ -731,6 +733,13 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 
   double Ja[NP];
   double Jb[NB];
+#pragma unroll 1
+  for (int r = lane; r < NU; r += 32) {
+    const DevContact& Cc = G.contacts[G.cone_contact[r]];
+    Cm[2 * r] = NV + Cc.rf_off;
+    Cm[2 * r + 1] = Cc.dim;
+  }
+  __syncwarp();
 
 #pragma unroll 1
   for (;;) {
@@ -846,12 +855,12 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             }
 #pragma unroll 1
             for (int r = lane; r < nu; r += 32) {
-              const DevContact& Cc = G.contacts[G.cone_contact[r]];
-              const double* xr = x + NV + Cc.rf_off;
+              const int2 cm = *reinterpret_cast<const int2*>(Cm + 2 * r);
+              const double* xr = x + cm.x;
               const double* ur = Uf + r * 6;
               double acc = -uf[r];
 #pragma unroll
-              for (int k = 0; k < 6; k++) acc = fma(ur[k], k < Cc.dim ? xr[k] : 0.0, acc);
+              for (int k = 0; k < 6; k++) acc = fma(ur[k], k < cm.y ? xr[k] : 0.0, acc);
               sl[r] = acc;
               psi += fmin(0.0, acc);
             }
@@ -890,7 +899,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             int a = 0;
             double sg = 1.0;
             const bool tq = !is_eq;
-            if (tq) { a = (ip - nu) % nact; sg = (ip - nu) >= nact ? -1.0 : 1.0; }
+            if (tq) { const int tr = ip - nu; a = tr >= nact ? tr - nact : tr; sg = tr >= nact ? -1.0 : 1.0; }
             const double* row = tq ? Ar + a * LDA : rec + C::RE + ip * NP;  // shared or global
             double pnx = 0.0;
 #pragma unroll 1
@@ -901,8 +910,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             }
             if (is_eq) s_ip = wsum(pnx) + rec[C::RE0 + ip];
           } else {
-            const DevContact& Cc = P.contacts[P.cone_contact[ip]];
-            k0 = NV + Cc.rf_off; k1 = k0 + Cc.dim;
+            k0 = Cm[2 * ip]; k1 = k0 + Cm[2 * ip + 1];
 #pragma unroll 1
             for (int k = lane; k < NP; k += 32) np[k] = (k >= k0 && k < k1) ? Uf[ip * 6 + (k - k0)] : 0.0;
           }
@@ -1206,7 +1214,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             double ci0;
             if (ip < nu) ci0 = -uf[ip];
             else {
-              const int a = (ip - nu) % nact;
+              const int tr = ip - nu, a = tr >= nact ? tr - nact : tr;
               const double a0v = a0[a];
               ci0 = (ip - nu) >= nact ? P.trq_hi[a] - a0v : a0v - P.trq_lo[a];
             }

@@ -57,7 +57,7 @@ struct MCfg : RCfg<NV_, NC_> {
   static constexpr int RSZ = (RC * (RC + 3) / 2 + 1) & ~1;
   static constexpr int lda_() { int l = R::NP; while ((l & 15) != 2) l += 2; return l; }
   static constexpr int LDA = lda_();  // torque rows: LDS.128 by row is conflict free at 2 (mod 16)
-  static constexpr int ORT = 0, OT = ORT + RSZ, OAR = OT + 6 * R::LDT, OA0 = OAR + NT * LDA, OUF = OA0 + ((NT + 1) & ~1),
+  static constexpr int ORT = 0, OT = ORT + RSZ, OAR = OT + 6 * R::LDT, OA0 = OAR + NT * LDA, OUF = OA0 + ((2 * NT + 1) & ~1),
                        OUFV = OUF + (NU > 0 ? NU : 1) * 6, OX = OUFV + (((NU > 0 ? NU : 1) + 1) & ~1), OZ = OX + R::NP,
                        ODV = OZ + R::NP, ODM = ODV + R::NP, OVM = ODM + R::NP, ONP = OVM + R::NP, ORR = ONP + R::NP,
                        OU = ORR + R::NP + 2, OXOLD = OU + R::NP + 2, OUOLD = OXOLD + R::NP, OXACC = OUOLD + R::NP + 2,
@@ -67,7 +67,7 @@ struct MCfg : RCfg<NV_, NC_> {
   // ---- per-state HBM record (doubles): written by k_ihwbc_setup, consumed by k_ihwbc_reg, whose
   //      result goes back into it for k_ihwbc_finish.  Everything the active-set kernel needs is
   //      here in the layout it is used in, so that kernel holds no staging code at all ----
-  static constexpr int IMG = OX - OAR;                      // shared-memory image: Ar, a0, Uf, uf
+  static constexpr int IMG = OX - OAR;                      // shared-memory image: Ar, ci0 of the torque rows, Uf, uf
   static constexpr int RJ = 0;                              // J rows as register chunks: [NP/2][32 lanes][2]
   static constexpr int RJB = RJ + 32 * R::NP;               // half rows 32..: [NB/2][32 lanes][2]
   static constexpr int RX = RJB + (R::EXT ? 32 * R::NB : 0);  // x0
@@ -659,7 +659,10 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           }
           for (int a = lane; a < nact; a += 32) {
             const int v = G.act_idx[a];
-            a0[a] = has_ic ? ws.ic_tq0[s * nact + a] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
+            // ci0 of the two torque-limit rows of joint a (ihwbc.py:266-296): S Ni^T (c+g) - trq_lo, trq_hi - S Ni^T (c+g)
+            const double a0v = has_ic ? ws.ic_tq0[s * nact + a] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
+            a0[a] = a0v - G.trq_lo[a];
+            a0[NT + a] = G.trq_hi[a] - a0v;
           }
         }
         __syncwarp();
@@ -703,7 +706,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   double* const Rp = smem + C::ORT;
   double* const Ts = smem + C::OT;
   double* const Ar = smem + C::OAR;   // torque-limit rows S [M | -(Jc Ni)^T], pitch LDA
-  double* const a0 = smem + C::OA0;   // their offsets S Ni^T (c + g)
+  double* const a0 = smem + C::OA0;   // ci0 of the torque-limit rows: [0, NT) lower limits, [NT, 2 NT) upper limits
   double* const Uf = smem + C::OUF;
   double* const uf = smem + C::OUFV;
   double* const x = smem + C::OX;
@@ -846,8 +849,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
                     t2 = fma(r1.x, x1.x, t2); t3 = fma(r1.y, x1.y, t3);
                   }
                 }
-                const double tau = (t0 + t1) + (t2 + t3) + a0[a];
-                const double slo = tau - G.trq_lo[a], shi = G.trq_hi[a] - tau;
+                const double dot = (t0 + t1) + (t2 + t3);
+                const double slo = dot + a0[a], shi = a0[NT + a] - dot;  // CI^T x + ci0 (QuadProg++.cc:293-301)
                 sl[nu + a] = slo;
                 sl[nu + nact + a] = shi;
                 psi += fmin(0.0, slo) + fmin(0.0, shi);
@@ -1213,11 +1216,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             acc = wsum(acc);
             double ci0;
             if (ip < nu) ci0 = -uf[ip];
-            else {
-              const int tr = ip - nu, a = tr >= nact ? tr - nact : tr;
-              const double a0v = a0[a];
-              ci0 = (ip - nu) >= nact ? P.trq_hi[a] - a0v : a0v - P.trq_lo[a];
-            }
+            else ci0 = a0[ip - nu];  // lower-limit rows first, then upper-limit rows, as in sl[]
             s_ip = acc + ci0;
             if (lane == 0) sl[ip] = s_ip;
             __syncwarp();

@@ -184,7 +184,7 @@ __device__ __forceinline__ double torque_row(const DevProblem& P, const DevProbl
 // the equality normals in the J basis.  Results go to a per-state record in HBM that the
 // active-set kernel loads (one coalesced-by-sector read of ~14 KB per Atlas state).
 struct SetupLayout {
-  int oG, oJd, oev, owt, og0, odm, ozv, odl, oD, om6, per_state;  // shared memory (doubles)
+  int oG, oJd, oev, owt, og0, odm, ozv, odl, oD, om6, ojc, per_state;  // shared memory (doubles)
 };
 
 template <class C>
@@ -214,6 +214,7 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min
     L.oD = o; o += (d + 1) & ~1;
   }
   if (o < min_doubles) o = min_doubles;  // the image of the active-set kernel's arrays is assembled here at the end
+  L.ojc = o; o += C::NC > 0 ? C::NC : 1;  // row pointers of Jc Ni, behind the image: they are used while it is built
   L.per_state = (o + 1) & ~1;
   return L;
 }
@@ -252,12 +253,23 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     int status = PNC_QP_OK;
     if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
     const double* Mg = ws.M + s * NV * NV;
-    auto row_jc = [&](int c, int v) -> double {  // (Jc Ni)[c][v]
-      if (has_ic) return ws.ic_jcni[(s * NC + c) * NV + v];
-      int ci = 0;
-      while (ci + 1 < P.ncontact && c >= G.contacts[ci + 1].rf_off) ci++;
-      return contact_jac_row(G.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - G.contacts[ci].rf_off)[v];
-    };
+    // rows of Jc Ni: the pointer of each row is looked up once per state (contact table, frame
+    // slot), so the element reads below are single loads instead of dependent chains
+    const double** jcrow = reinterpret_cast<const double**>(smem + SL.ojc);
+    if (lane < NC) {
+      const int c = lane;
+      const double* ptr;
+      if (has_ic) {
+        ptr = ws.ic_jcni + (s * NC + c) * NV;
+      } else {
+        int ci = 0;
+        while (ci + 1 < P.ncontact && c >= G.contacts[ci + 1].rf_off) ci++;
+        ptr = contact_jac_row(G.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - G.contacts[ci].rf_off);
+      }
+      jcrow[c] = ptr;
+    }
+    __syncwarp();
+    auto row_jc = [&](int c, int v) -> double { return jcrow[c][v]; };  // (Jc Ni)[c][v]
     // ---- tasks: e = Jdot qdot - xddot_cmd, weights (ihwbc.py:159-172) ----
     // task error terms e = Jdot qdot - xddot_cmd were evaluated by k_task_prepare (ihwbc.cu)
     {

@@ -650,16 +650,18 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           // flattened copy with several independent loads in flight; M is symmetric, so row
           // act_idx[a] is read as column act_idx[a] with consecutive lanes on consecutive addresses
 #pragma unroll 1
+          // element (row a, column k) with a fastest: a == lane throughout, so its joint index is loaded once
+          const int va = lane < nact ? G.act_idx[lane] : 0;
           for (int e0 = lane; e0 < N * 32; e0 += 32 * 8) {
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-              const int e = e0 + 32 * u, k = e >> 5, a = e & 31;  // element (row a, column k), a fastest
+              const int e = e0 + 32 * u, k = e >> 5, a = e & 31;
               double val = 0.0;
               if (k < N && a < nact) {
                 if (has_ic) val = ws.ic_tq[(s * N + k) * nact + a];
-                else if (k < NV) val = Mg[k * NV + G.act_idx[a]];
-                else val = -row_jc(k - NV, G.act_idx[a]);
+                else if (k < NV) val = Mg[k * NV + va];
+                else val = -row_jc(k - NV, va);
               }
               v[u] = val;
             }

@@ -818,16 +818,16 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       __syncwarp();
 
       // ================= dual active-set iterations, equalities first (:232-500) =================
-      unsigned long long act0 = 0ull, act1 = 0ull;  // inequality currently in the active set
-      unsigned long long exc0 = 0ull, exc1 = 0ull;  // inequality excluded in this outer iteration
-      auto is_set = [](unsigned long long a, unsigned long long b, int i) {
-        return ((i < 64 ? a >> i : b >> (i - 64)) & 1ull) != 0ull;
+      // Per-lane bit masks: lane l owns the inequalities l, l + 32, l + 64, l + 96 (the ones it scans in
+      // l2), bit t of its mask speaks for inequality l + 32 t.
+      static_assert(C::M <= 128, "four inequalities per lane");
+      unsigned actm = 0u;  // in the active set
+      unsigned excm = 0u;  // excluded in this outer iteration
+      auto set_bit = [&](unsigned& msk, int i) {
+        if (lane == (i & 31)) msk |= 1u << (i >> 5);
       };
-      auto set_bit = [](unsigned long long& a, unsigned long long& b, int i) {
-        if (i < 64) a |= 1ull << i; else b |= 1ull << (i - 64);
-      };
-      auto clr_bit = [](unsigned long long& a, unsigned long long& b, int i) {
-        if (i < 64) a &= ~(1ull << i); else b &= ~(1ull << (i - 64));
+      auto clr_bit = [&](unsigned& msk, int i) {
+        if (lane == (i & 31)) msk &= ~(1u << (i >> 5));
       };
       const double psi_tol = (double)m * QP_EPS * c1 * c2 * 100.0;  // QuadProg++.cc:306-312
       const double psi_refine = psi_tol * 1e-6;                     // see ihwbc.cu / DESIGN.md 3.2
@@ -847,7 +847,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             // l1: slacks of every inequality, termination test (:282-321)
             need_l1 = false;
             iter++;
-            exc0 = exc1 = 0ull;
+            excm = 0u;
             double psi = 0.0;
             if (trq) {
 #pragma unroll 1
@@ -901,10 +901,13 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           // l2: most violated constraint, first index on ties (:323-334)
           double ss = 0.0;
           ip = 0x7fffffff;
+          {
+            unsigned blocked = actm | excm;
 #pragma unroll 1
-          for (int i = lane; i < m; i += 32) {
-            const double v = sl[i];
-            if (v < ss && !is_set(act0, act1, i) && !is_set(exc0, exc1, i)) { ss = v; ip = i; }
+            for (int i = lane; i < m; i += 32, blocked >>= 1) {
+              const double v = sl[i];
+              if (v < ss && !(blocked & 1u)) { ss = v; ip = i; }
+            }
           }
           wargmin(ss, ip);
           if (ss >= 0.0) break;
@@ -1077,13 +1080,13 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             const double sigma = sqrt(sig2);
             if (sigma <= QP_EPS * R_norm) {  // linearly dependent on the active set
               if (is_eq) { status = PNC_QP_EQ_DEPENDENT; done = true; break; }
-              set_bit(exc0, exc1, ip);
+              set_bit(excm, ip);
               for (int i = p + lane; i < iq; i += 32) { Aact[i] = Aold[i]; uv[i] = uold[i]; }
               for (int i = lane; i < NP; i += 32) x[i] = xold[i];
               __syncwarp();
-              act0 = act1 = 0ull;
+              actm = 0u;
 #pragma unroll 1
-              for (int i = p; i < iq; i++) set_bit(act0, act1, Aact[i]);
+              for (int i = p; i < iq; i++) set_bit(actm, Aact[i]);
               break;  // back to l2
             }
             if (iq >= rc_cap) {  // S is capped at RC columns: hand the state to the generic kernel
@@ -1142,7 +1145,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             iq++;
             R_norm = fmax(R_norm, sigma);
             if (is_eq) ieq++;
-            else { set_bit(act0, act1, ip); need_l1 = true; }
+            else { set_bit(actm, ip); need_l1 = true; }
             __syncwarp();
             break;
           }
@@ -1152,7 +1155,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           // (j, j+1), j = kk .. iq-2, so that this row ends up in the last column makes
           // S Q^T (minus row kk and the last column) the inverse of the re-triangularised R, with the
           // same Q that QuadProg++ applies to the columns of J.
-          clr_bit(act0, act1, l);
+          clr_bit(actm, l);
           {
             double carry = Rcol(kk)[kk];
 #pragma unroll 1

@@ -649,9 +649,9 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         if constexpr (NT > 0) {
           // flattened copy with several independent loads in flight; M is symmetric, so row
           // act_idx[a] is read as column act_idx[a] with consecutive lanes on consecutive addresses
-#pragma unroll 1
           // element (row a, column k) with a fastest: a == lane throughout, so its joint index is loaded once
           const int va = lane < nact ? G.act_idx[lane] : 0;
+#pragma unroll 1
           for (int e0 = lane; e0 < N * 32; e0 += 32 * 8) {
             double v[8];
 #pragma unroll
@@ -889,12 +889,12 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
                 accepted = true;
                 iq_acc = iq;
                 for (int i = lane; i < NP; i += 32) xacc[i] = x[i];
-                for (int i = lane; i < iq; i += 32) Aacc[i] = Aact[i];
+                if (lane < iq) Aacc[lane] = Aact[lane];
                 __syncwarp();
               }
             }
             if (iter > 40 * (N + m)) { status = PNC_QP_MAX_ITER; break; }
-            for (int i = lane; i < iq; i += 32) { uold[i] = uv[i]; Aold[i] = Aact[i]; }
+            if (lane < iq) { uold[lane] = uv[lane]; Aold[lane] = Aact[lane]; }  // iq <= RC = 32
             for (int i = lane; i < NP; i += 32) xold[i] = x[i];
             __syncwarp();
           }
@@ -1048,13 +1048,9 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           double t1 = INFINITY;
           int kk = 0x7fffffff;
           if (!is_eq) {
-#pragma unroll 1
-            for (int k = p + lane; k < iq; k += 32) {
-              const double rk = rv[k];
-              if (rk > 0.0) {
-                const double v = uv[k] / rk;
-                if (v < t1) { t1 = v; kk = k; }
-              }
+            if (lane >= p && lane < iq) {  // iq <= RC = 32: one candidate per lane
+              const double rk = rv[lane];
+              if (rk > 0.0) { t1 = uv[lane] / rk; kk = lane; }
             }
             wargmin(t1, kk);
           }
@@ -1071,7 +1067,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           const bool dual_only = t2 >= INFINITY;
           if (!dual_only)
             for (int k = lane; k < N; k += 32) x[k] += t * zv[k];
-          for (int k = lane; k < iq; k += 32) uv[k] -= t * rv[k];
+          if (lane < iq) uv[lane] -= t * rv[lane];
           if (lane == 0) uv[iq] += t;
           __syncwarp();
 
@@ -1081,7 +1077,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             if (sigma <= QP_EPS * R_norm) {  // linearly dependent on the active set
               if (is_eq) { status = PNC_QP_EQ_DEPENDENT; done = true; break; }
               set_bit(excm, ip);
-              for (int i = p + lane; i < iq; i += 32) { Aact[i] = Aold[i]; uv[i] = uold[i]; }
+              if (lane >= p && lane < iq) { Aact[lane] = Aold[lane]; uv[lane] = uold[lane]; }
               for (int i = lane; i < NP; i += 32) x[i] = xold[i];
               __syncwarp();
               actm = 0u;
@@ -1102,7 +1098,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             // R gains the column [d1; alpha]  <=>  S = R^-1 gains the column [-S d1 / alpha; 1 / alpha]
             double* col = Rcol(iq);
             const double ialpha = 1.0 / alpha;
-            for (int i = lane; i < iq; i += 32) col[i] = -rv[i] * ialpha;
+            if (lane < iq) col[lane] = -rv[lane] * ialpha;
             if (lane == 0) col[iq] = ialpha;
             for (int j = lane; j < NP; j += 32) vm[j] = j > iq ? dv[j] : (j == iq ? v0 : 0.0);
             const double ca = reg_pick(Ja, iq);  // old column iq of J
@@ -1244,7 +1240,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         status = PNC_QP_OK;
         iq = iq_acc;
         for (int i = lane; i < NP; i += 32) x[i] = xacc[i];
-        for (int i = lane; i < iq_acc; i += 32) Aact[i] = Aacc[i];
+        if (lane < iq_acc) Aact[lane] = Aacc[lane];
         __syncwarp();
       }
     }
@@ -1254,8 +1250,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       int* ro = reinterpret_cast<int*>(rec + C::RO + NP);
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) rec[C::RO + k] = x[k];
-#pragma unroll 1
-      for (int i = lane; i < iq; i += 32) ro[3 + i] = Aact[i];
+      if (lane < iq) ro[3 + lane] = Aact[lane];
       if (lane == 0) { ro[0] = iq; ro[1] = iter; ro[2] = status; }
     }
     __syncwarp();

@@ -1031,17 +1031,20 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           // columns) instead of R: r = S d is a matrix-vector product -- lane i owns row i -- not a
           // back substitution with its dependent chain of iq steps
           {
-            double acc0 = 0.0, acc1 = 0.0;
+            static_assert(!S2, "rows of S beyond 32 are not implemented");
+            double acc0 = 0.0, acc1 = 0.0;  // even / odd columns: two independent FMA chains
             const double* col = Rp;
-#pragma unroll 2
-            for (int j = 0; j < iq; j++) {
-              const double dj = dv[j];
-              if (lane <= j) acc0 = fma(col[lane], dj, acc0);
-              if (S2 && lane + 32 <= j) acc1 = fma(col[lane + 32], dj, acc1);
-              col += j + 2;
+            int j = 0;
+#pragma unroll 1
+            for (; j + 1 < iq; j += 2) {
+              const double2 dj = lds2(dv + j);
+              const double* cn = col + j + 2;
+              if (lane <= j) acc0 = fma(col[lane], dj.x, acc0);
+              if (lane <= j + 1) acc1 = fma(cn[lane], dj.y, acc1);
+              col = cn + j + 3;
             }
-            if (lane < iq) rv[lane] = acc0;
-            if (S2 && lane + 32 < iq) rv[lane + 32] = acc1;
+            if (j < iq && lane <= j) acc0 = fma(col[lane], dv[j], acc0);
+            if (lane < iq) rv[lane] = acc0 + acc1;
           }
           __syncwarp();
           // step lengths (:366-393); equalities always take the full step (:246-258)

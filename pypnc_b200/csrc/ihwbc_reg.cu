@@ -59,7 +59,7 @@ struct MCfg : RCfg<NV_, NC_> {
   static constexpr int LDA = lda_();  // torque rows: LDS.128 by row is conflict free at 2 (mod 16)
   static constexpr int ORT = 0, OT = ORT + RSZ, OAR = OT + 6 * R::LDT, OA0 = OAR + NT * LDA, OUF = OA0 + ((2 * NT + 1) & ~1),
                        OUFV = OUF + (NU > 0 ? NU : 1) * 6, OX = OUFV + (((NU > 0 ? NU : 1) + 1) & ~1), OZ = OX + R::NP,
-                       ODV = OZ + R::NP, ODM = ODV + R::NP, OVM = ODM + R::NP, ONP = OVM + R::NP, ORR = ONP + R::NP,
+                       ODV = OZ + R::NP, ODM = ODV + R::NP, OVM = ODM + R::NP, ONP = OVM + R::NP, ORR = ONP + R::NP + 6 /* zero pad: the d tile reads np six at a time */,
                        OU = ORR + R::NP + 2, OXOLD = OU + R::NP + 2, OUOLD = OXOLD + R::NP, OXACC = OUOLD + R::NP + 2,
                        OSL = OXACC + R::NP, OINT = OSL + (((M > 0 ? M : 1) + 1) & ~1),
                        SMEM_DOUBLES = (OINT + (((3 * (R::N + 2) + 1) & ~1) + 2 * NU) / 2 + 2) & ~1;  // A, Aold, Aacc, cone-row table
@@ -756,6 +756,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     Cm[2 * r] = NV + Cc.rf_off;
     Cm[2 * r + 1] = Cc.dim;
   }
+  if (lane < 6) np[NP + lane] = 0.0;  // never written again
   __syncwarp();
 
 #pragma unroll 1
@@ -877,7 +878,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               const double* ur = Uf + r * 6;
               double acc = -uf[r];
 #pragma unroll
-              for (int k = 0; k < 6; k++) acc = fma(ur[k], k < cm.y ? xr[k] : 0.0, acc);
+              for (int k = 0; k < 6; k++) acc = fma(ur[k], xr[k], acc);  // ur is zero beyond the contact's dimension
               sl[r] = acc;
               psi += fmin(0.0, acc);
             }
@@ -975,7 +976,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               const double* tl = Ts + lane;
 #pragma unroll
               for (int r = 0; r < 6; r++) {
-                const double nr = r < dim ? npc[r] : 0.0;
+                const double nr = npc[r];  // rows beyond the normal's support are zero (np is zero-padded)
                 dA = fma(nr, tl[r * LDT], dA);
                 if (NP > 32 && lane + 32 < NP) dB = fma(nr, tl[r * LDT + 32], dB);
               }

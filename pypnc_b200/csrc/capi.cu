@@ -67,8 +67,9 @@ struct pnc_workspace {
   // staging buffers of pnc_wbc_tick_host
   char* stage;
   size_t stage_bytes;
-  cudaStream_t tick_stream[2];
-  cudaEvent_t tick_ev[2];
+  cudaStream_t tick_stream[2];          // compute, chunks alternate
+  cudaStream_t tick_in, tick_out;       // host -> device and device -> host copies
+  cudaEvent_t tick_ev_in[16], tick_ev_done[16];  // per chunk: inputs landed, kernels finished
   bool tick_init;
 };
 
@@ -283,7 +284,9 @@ void pnc_workspace_destroy(pnc_workspace* ws) {
   if (ws->setup_slab) cudaFree(ws->setup_slab);
   if (ws->stage) cudaFree(ws->stage);
   if (ws->tick_init) {
-    for (int i = 0; i < 2; i++) { cudaStreamDestroy(ws->tick_stream[i]); cudaEventDestroy(ws->tick_ev[i]); }
+    for (int i = 0; i < 2; i++) cudaStreamDestroy(ws->tick_stream[i]);
+    cudaStreamDestroy(ws->tick_in); cudaStreamDestroy(ws->tick_out);
+    for (int i = 0; i < 16; i++) { cudaEventDestroy(ws->tick_ev_in[i]); cudaEventDestroy(ws->tick_ev_done[i]); }
   }
   cudaGetLastError();
   delete ws;
@@ -665,9 +668,12 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
     ws->stage_bytes = need;
   }
   if (!ws->tick_init) {
-    for (int i = 0; i < 2; i++) {
-      CK(cudaStreamCreateWithFlags(&ws->tick_stream[i], cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&ws->tick_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&ws->tick_stream[i], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ws->tick_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ws->tick_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; i++) {
+      CK(cudaEventCreateWithFlags(&ws->tick_ev_in[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ws->tick_ev_done[i], cudaEventDisableTiming));
     }
     ws->tick_init = true;
   }
@@ -699,9 +705,9 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
   int nchunk = B >= 8192 ? (env_chunks > 0 && env_chunks <= 16 ? env_chunks : 4) : 1;
   int bounds[17];
   {
-    // default: first chunk = B/8, then three equal chunks (measured on Atlas 64 K, scripts/e2e_sweep.sh:
-    // 13.3 ms per step against 14.3 ms for four equal chunks)
-    int first = env_chunks > 0 ? (B + nchunk - 1) / nchunk : B / 8;
+    // default: first chunk = B/16, then three equal chunks (Atlas 64 K, scripts/e2e_sweep.sh: 12.0 ms per step;
+    // every schedule between 2 and 8 chunks lands within 5 % of that with the three-role stream layout below)
+    int first = env_chunks > 0 ? (B + nchunk - 1) / nchunk : B / 16;
     if (nchunk > 1 && env_first > 0.0 && env_first < 1.0) first = (int)(env_first * B);
     if (first < 1) first = 1;
     bounds[0] = 0;
@@ -710,15 +716,26 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
       bounds[c] = c == nchunk ? B : first + (int)((long long)rest * (c - 1) / (nchunk - 1 > 0 ? nchunk - 1 : 1));
     if (nchunk == 1) bounds[1] = B;
   }
+  // Three roles: one stream feeds the inputs of every chunk as fast as the link takes them, the
+  // kernels of the chunks alternate over two streams (the tail of one chunk overlaps the start of
+  // the next), one stream drains the outputs.  Events tie a chunk's kernels to its inputs and its
+  // output copies to its kernels.
   for (int c = 0; c < nchunk; c++) {
     int o = bounds[c], nb = bounds[c + 1] - bounds[c];
     if (nb <= 0) continue;
-    cudaStream_t st = ws->tick_stream[c & 1];
+    cudaStream_t st = ws->tick_in;
 #define H2D(dst, src, per) CK(cudaMemcpyAsync((dst) + (size_t)o * (per), (src) + (size_t)o * (per), (size_t)nb * (per) * 8, cudaMemcpyHostToDevice, st))
     H2D(d_bp, h_base_pos, 3); H2D(d_bq, h_base_quat, 4); H2D(d_blv, h_base_lin_vel, 3); H2D(d_bav, h_base_ang_vel, 3);
     H2D(d_jp, h_joint_pos, na); H2D(d_jv, h_joint_vel, na); H2D(d_des, h_des, P.ndes); H2D(d_w, h_w, P.ntask);
     if (P.ncontact) H2D(d_rfz, h_rf_z_max, P.ncontact);
 #undef H2D
+    CK(cudaEventRecord(ws->tick_ev_in[c], st));
+  }
+  for (int c = 0; c < nchunk; c++) {
+    int o = bounds[c], nb = bounds[c + 1] - bounds[c];
+    if (nb <= 0) continue;
+    cudaStream_t st = ws->tick_stream[c & 1];
+    CK(cudaStreamWaitEvent(st, ws->tick_ev_in[c], 0));
     int rc = update_system_at(ws, o, nb, d_bp + (size_t)o * 3, d_bq + (size_t)o * 4, d_blv + (size_t)o * 3,
                               d_bav + (size_t)o * 3, d_jp + (size_t)o * na, d_jv + (size_t)o * na, st);
     if (rc) return rc;
@@ -727,11 +744,15 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
                   d_rf + (size_t)o * P.nc, nullptr, d_status + o, d_iters + o, d_active + (size_t)o * mw, st,
                   counters + 8 * c);
     if (rc) return rc;
-#define D2H(dst, src, per, esz) if (dst) CK(cudaMemcpyAsync((char*)(dst) + (size_t)o * (per) * (esz), (const char*)(src) + (size_t)o * (per) * (esz), (size_t)nb * (per) * (esz), cudaMemcpyDeviceToHost, st))
+    CK(cudaEventRecord(ws->tick_ev_done[c], st));
+    cudaStream_t so = ws->tick_out;
+    CK(cudaStreamWaitEvent(so, ws->tick_ev_done[c], 0));
+#define D2H(dst, src, per, esz) if (dst) CK(cudaMemcpyAsync((char*)(dst) + (size_t)o * (per) * (esz), (const char*)(src) + (size_t)o * (per) * (esz), (size_t)nb * (per) * (esz), cudaMemcpyDeviceToHost, so))
     D2H(h_trq, d_trq, P.nact, 8); D2H(h_acc, d_acc, P.nact, 8); D2H(h_rf, d_rf, P.nc, 8);
     D2H(h_status, d_status, 1, 4); D2H(h_iters, d_iters, 1, 4); D2H(h_active, d_active, mw, 8);
 #undef D2H
   }
+  CK(cudaStreamSynchronize(ws->tick_out));
   CK(cudaStreamSynchronize(ws->tick_stream[0]));
   CK(cudaStreamSynchronize(ws->tick_stream[1]));
   return PNC_OK;

@@ -220,15 +220,22 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
     __syncwarp();
 
     // ---------------- phase 4: subtree sums (composite inertia, bias force, momentum) ---
-    double acc[SUB_LD];
-    for (int k = 0; k < SUB_LD; k++) acc[k] = 0.0;
-    if (active) {
-      for (int c = 0; c < nsub; c++) {
-        const double* row = sub + (i + c) * SUB_LD;
-#pragma unroll
-        for (int k = 0; k < SUB_LD; k++) acc[k] += row[k];
+    // Reverse scan over the bodies with lanes = components: every body adds its (already complete)
+    // row to its parent's.  Depth-first numbering puts children after their parent, so a row is
+    // complete when its turn comes; lane k only ever touches column k, so no synchronisation is
+    // needed inside the loop.  (Lanes = bodies would make the root lane walk all 31 rows while the
+    // leaf lanes idle.)
+    if (lane < SUB_LD) {
+#pragma unroll 1
+      for (int b = nb - 1; b > 0; b--) {
+        const int pb = sm->parent[b];
+        if (pb >= 0) sub[pb * SUB_LD + lane] += sub[b * SUB_LD + lane];
       }
     }
+    __syncwarp();
+    double acc[SUB_LD];
+#pragma unroll
+    for (int k = 0; k < SUB_LD; k++) acc[k] = active ? sub[i * SUB_LD + k] : 0.0;
     const double mS = acc[0];
     const V3 hS = mk(acc[1], acc[2], acc[3]);
     const double* IS = acc + 4;
@@ -240,7 +247,8 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
     if (lane == 0) {
       tot[0] = acc[1]; tot[1] = acc[2]; tot[2] = acc[3]; tot[3] = acc[16]; tot[4] = acc[17]; tot[5] = acc[18];
       tfcl[0] = acc[10]; tfcl[1] = acc[11]; tfcl[2] = acc[12];
-      for (int c = nsub; c < nb; c++) {  // forest (several bodies hang off the universe)
+      for (int c = nsub; c < nb; c++) {  // forest (several bodies hang off the universe): add the other roots' subtrees
+        if (sm->parent[c] >= 0) continue;
         const double* row = sub + c * SUB_LD;
         tot[0] += row[1]; tot[1] += row[2]; tot[2] += row[3]; tot[3] += row[16]; tot[4] += row[17]; tot[5] += row[18];
         tfcl[0] += row[10]; tfcl[1] += row[11]; tfcl[2] += row[12];
@@ -260,6 +268,7 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
         mt = acc[0];
         for (int k = 0; k < 6; k++) Iot[k] = acc[4 + k];
         for (int c = nsub; c < nb; c++) {
+          if (sm->parent[c] >= 0) continue;
           const double* row = sub + c * SUB_LD;
           mt += row[0];
           for (int k = 0; k < 6; k++) Iot[k] += row[4 + k];

@@ -727,7 +727,6 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   double* const zv = smem + C::OZ;
   double* const dv = smem + C::ODV;
   double* const dm = smem + C::ODM;
-  double* const vm = smem + C::OVM;
   double* const np = smem + C::ONP;
   double* const rv = smem + C::ORR;
   double* const uv = smem + C::OU;
@@ -781,7 +780,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) {
         x[k] = rec[C::RX + k];
-        zv[k] = 0.0; dm[k] = 0.0; vm[k] = 0.0; np[k] = 0.0; dv[k] = 0.0;
+        zv[k] = 0.0; dm[k] = 0.0; np[k] = 0.0; dv[k] = 0.0;
       }
 #pragma unroll 1
       for (int k = lane; k < 6 * LDT; k += 32) Ts[k] = 0.0;
@@ -1104,7 +1103,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             const double ialpha = 1.0 / alpha;
             if (lane < iq) col[lane] = -rv[lane] * ialpha;
             if (lane == 0) col[iq] = ialpha;
-            for (int j = lane; j < NP; j += 32) vm[j] = j > iq ? dv[j] : (j == iq ? v0 : 0.0);
+            // the Householder vector v = [0 .. 0, v0, d[iq+1:]] is the masked d with one entry patched
+            if (lane == 0) dm[iq] = v0;
             const double ca = reg_pick(Ja, iq);  // old column iq of J
             double hwb = 0.0;
             if constexpr (EXT) {
@@ -1117,12 +1117,12 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < NP; j += 2) {
-              const double2 v = lds2(vm + j);
+              const double2 v = lds2(dm + j);
               Ja[j] = fma(-hwa, v.x, Ja[j]);
               Ja[j + 1] = fma(-hwa, v.y, Ja[j + 1]);
             }
             if constexpr (EXT) {
-              const double* vh = vm + eh * HW;
+              const double* vh = dm + eh * HW;
 #pragma unroll
               for (int c = 0; c < HW; c += 2) {
                 const double2 v = lds2(vh + c);
@@ -1135,8 +1135,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               for (int i2 = ieq + 1; i2 < p; i2++) {
                 double* Di = Deq + i2 * NP;
                 double e0 = 0.0, e1 = 0.0, w0 = 0.0, w1 = 0.0;
-                if (lane < NP) { e0 = Di[lane]; w0 = vm[lane]; }
-                if (NP > 32 && lane + 32 < NP) { e1 = Di[lane + 32]; w1 = vm[lane + 32]; }
+                if (lane < NP) { e0 = Di[lane]; w0 = dm[lane]; }
+                if (NP > 32 && lane + 32 < NP) { e1 = Di[lane + 32]; w1 = dm[lane + 32]; }
                 const double g = beta * wsum(fma(e0, w0, e1 * w1));
                 if (lane < NP) Di[lane] = fma(-g, w0, e0);
                 if (NP > 32 && lane + 32 < NP) Di[lane + 32] = fma(-g, w1, e1);

@@ -850,8 +850,9 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             excm = 0u;
             double psi = 0.0;
             if (trq) {
-#pragma unroll 1
-              for (int a = lane; a < nact; a += 32) {
+              static_assert(NT <= 32, "one torque-limit row per lane");
+              if (lane < nact) {
+                const int a = lane;
                 const double* row = Ar + a * LDA;
                 double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
@@ -903,10 +904,13 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           ip = 0x7fffffff;
           {
             unsigned blocked = actm | excm;
-#pragma unroll 1
-            for (int i = lane; i < m; i += 32, blocked >>= 1) {
-              const double v = sl[i];
-              if (v < ss && !(blocked & 1u)) { ss = v; ip = i; }
+#pragma unroll
+            for (int t4 = 0; t4 < (C::M + 31) / 32; t4++) {  // at most four inequalities per lane
+              const int i = lane + 32 * t4;
+              if (i < m) {
+                const double v = sl[i];
+                if (v < ss && !((blocked >> t4) & 1u)) { ss = v; ip = i; }
+              }
             }
           }
           wargmin(ss, ip);

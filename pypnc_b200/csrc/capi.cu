@@ -705,16 +705,38 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
   int nchunk = B >= 8192 ? (env_chunks > 0 && env_chunks <= 16 ? env_chunks : 4) : 1;
   int bounds[17];
   {
-    // default: first chunk = B/16, then three equal chunks (Atlas 64 K, scripts/e2e_sweep.sh: 12.0 ms per step;
-    // every schedule between 2 and 8 chunks lands within 5 % of that with the three-role stream layout below)
-    int first = env_chunks > 0 ? (B + nchunk - 1) / nchunk : B / 16;
-    if (nchunk > 1 && env_first > 0.0 && env_first < 1.0) first = (int)(env_first * B);
-    if (first < 1) first = 1;
+    // default: B/16, 2 x 0.4 B, the rest (0.14 B): the first chunk's input copy and the last chunk's output
+    // copy are the transfers nothing overlaps, so both are kept small (Atlas 64 K, scripts/e2e_split_sweep.sh:
+    // 11.75 ms per step against 11.86 ms with three equal chunks after the first)
     bounds[0] = 0;
-    const int rest = B - first;
-    for (int c = 1; c <= nchunk; c++)
-      bounds[c] = c == nchunk ? B : first + (int)((long long)rest * (c - 1) / (nchunk - 1 > 0 ? nchunk - 1 : 1));
+    if (env_chunks > 0 || (env_first > 0.0 && env_first < 1.0)) {
+      int first = env_chunks > 0 ? (B + nchunk - 1) / nchunk : B / 16;
+      if (nchunk > 1 && env_first > 0.0 && env_first < 1.0) first = (int)(env_first * B);
+      if (first < 1) first = 1;
+      const int rest = B - first;
+      for (int c = 1; c <= nchunk; c++)
+        bounds[c] = c == nchunk ? B : first + (int)((long long)rest * (c - 1) / (nchunk - 1 > 0 ? nchunk - 1 : 1));
+    } else if (nchunk == 4) {
+      bounds[1] = B / 16;
+      bounds[2] = bounds[1] + (int)(0.4 * B);
+      bounds[3] = bounds[2] + (int)(0.4 * B);
+      bounds[4] = B;
+    }
     if (nchunk == 1) bounds[1] = B;
+    // PNC_TICK_SPLIT="f0,f1,..." (fractions of the batch, diagnostic) overrides everything above
+    static const char* env_split = getenv("PNC_TICK_SPLIT");
+    if (env_split && B >= 8192) {
+      double f[16];
+      int nf = 0;
+      for (const char* q = env_split; *q && nf < 16;) {
+        f[nf++] = atof(q);
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+      }
+      double acc = 0.0;
+      for (int c = 0; c < nf; c++) { acc += f[c]; bounds[c + 1] = c == nf - 1 ? B : (int)(acc * B); }
+      if (nf > 0) nchunk = nf;
+    }
   }
   // Three roles: one stream feeds the inputs of every chunk as fast as the link takes them, the
   // kernels of the chunks alternate over two streams (the tail of one chunk overlaps the start of

@@ -208,11 +208,7 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min
   L.odl = o; o += C::NP;
   if (o - L.om6 < ((6 * C::NV + 1) & ~1)) o = L.om6 + ((6 * C::NV + 1) & ~1);
   L.ozv = o; o += C::NP;  // x0 stays live until the record is written
-  {
-    int d = P.p * C::NP;  // D; before that, the row-pointer table of the Jacobian copy
-    if (d < PNC_MAX_TASK_ROWS) d = PNC_MAX_TASK_ROWS;
-    L.oD = o; o += (d + 1) & ~1;
-  }
+  L.oD = 0;  // D goes straight to the record in HBM (coalesced by construction): no shared-memory copy
   if (o < min_doubles) o = min_doubles;  // the image of the active-set kernel's arrays is assembled here at the end
   L.ojc = o; o += C::NC > 0 ? C::NC : 1;  // row pointers of Jc Ni, behind the image: they are used while it is built
   L.per_state = (o + 1) & ~1;
@@ -239,7 +235,6 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
   double* dm = smem + SL.odm;
   double* zv = smem + SL.ozv;
   double* vm = smem + SL.odl;
-  double* Dt = smem + SL.oD;
   double* dv = g0;
   double* xs = zv;  // x0
 #pragma unroll 1
@@ -250,6 +245,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     if (si >= B) break;
     const size_t s = (size_t)si;
     double* rec = rec_all + s * C::REC;
+    double* Dt = rec + C::RD;  // equality normals in the J basis, written in place
     int status = PNC_QP_OK;
     if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
     const double* Mg = ws.M + s * NV * NV;
@@ -286,8 +282,9 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     // stage the dense task Jacobian rows (flattened copy: several independent loads in flight per
     // lane instead of one row at a time); clear the factor block
     {
-      // row -> source pointer table borrows the D block (not live yet)
-      const double** rptr = reinterpret_cast<const double**>(Dt);
+      // row -> source pointer table borrows g0 (written later, by the Hessian phase)
+      // (shape_ok checks ndense <= NP)
+      const double** rptr = reinterpret_cast<const double**>(g0);
 #pragma unroll 1
       for (int t = lane; t < P.ntask; t += 32) {
         const DevTask& T = P.tasks[t];
@@ -601,8 +598,6 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       }
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) rec[C::RX + k] = k < NV ? xs[k] : 0.0;
-#pragma unroll 1
-      for (int k = lane; k < p * NP; k += 32) rec[C::RD + k] = Dt[k];
       if (lane == 0) { rec[C::RS] = c1; rec[C::RS + 1] = c2; rec[C::RS + 3] = jrf; }
       // equality normals [M | -(Jc Ni)^T] rows 0..5, then the internal-constraint rows, and offsets
 #pragma unroll 1
@@ -1344,6 +1339,7 @@ static bool shape_ok(const DevProblem& hp) {
   if ((hp.b_trq_limit ? hp.nact : 0) != NT || hp.nact > 32 || hp.m > 128 || hp.p > C::PMAX) return false;
   // the equality block D sits behind the first S columns while the equalities are added
   if (64 + hp.p * C::NP > C::RSZ || hp.p * (hp.p + 3) / 2 > 64 || hp.p >= C::RC) return false;
+  if (hp.ndense > C::NP) return false;  // the setup kernel keeps one row pointer per dense task row in an NP-sized vector
   return true;
 }
 

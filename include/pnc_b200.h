@@ -315,7 +315,9 @@ int pnc_dcm_update(pnc_workspace* ws, int32_t B, double dt, double alpha, double
                    double* d_dcm_vel, void* stream);
 
 /* Whole controller tick with HOST buffers: H2D of the inputs, update_system, solve,
- * D2H of the outputs; synchronous.  Any output may be NULL. */
+ * D2H of the outputs, pipelined over chunks of the batch on the library's own streams;
+ * synchronous (returns when every output has landed).  Pinned host buffers let the copies
+ * overlap the kernels.  Any output may be NULL. */
 int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,
                       const double* h_base_quat, const double* h_base_lin_vel,
                       const double* h_base_ang_vel, const double* h_joint_pos, const double* h_joint_vel,

@@ -640,9 +640,10 @@ int pnc_dcm_update(pnc_workspace* ws, int32_t B, double dt, double alpha, double
 }
 
 // ---------------------------------------------------------------------------------------
-// Whole tick with host buffers.  The batch is cut into chunks that ping-pong over two
-// streams so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels
-// of chunk k.  Chunks own disjoint slices of the workspace, so they never alias.
+// Whole tick with host buffers.  The batch is cut into chunks; one stream copies the inputs of
+// every chunk in, the kernels of the chunks alternate over two streams, one stream copies the
+// outputs out, and per-chunk events order them (see below).  Chunks own disjoint slices of the
+// workspace and of the staging slab, so they never alias.  Host buffers should be pinned.
 int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,
                       const double* h_base_quat, const double* h_base_lin_vel, const double* h_base_ang_vel,
                       const double* h_joint_pos, const double* h_joint_vel, const double* h_des, const double* h_w,

@@ -57,7 +57,7 @@ struct MCfg : RCfg<NV_, NC_> {
   static constexpr int RSZ = (RC * (RC + 3) / 2 + 1) & ~1;
   static constexpr int lda_() { int l = R::NP; while ((l & 15) != 2) l += 2; return l; }
   static constexpr int LDA = lda_();  // torque rows: LDS.128 by row is conflict free at 2 (mod 16)
-  static constexpr int ORT = 0, OT = ORT + RSZ, OAR = OT + 6 * R::LDT, OA0 = OAR + NT * LDA, OUF = OA0 + ((2 * NT + 1) & ~1),
+  static constexpr int ORT = 0, OT = ORT + RSZ, OAR = OT + 6 * R::LDT, OA0 = OAR + NT * LDA, OUF = OA0 + ((3 * NT + 1) & ~1),
                        OUFV = OUF + (NU > 0 ? NU : 1) * 6, OX = OUFV + (((NU > 0 ? NU : 1) + 1) & ~1), OZ = OX + R::NP,
                        ODV = OZ + R::NP, ODM = ODV + R::NP, OVM = ODM + R::NP, ONP = OVM + R::NP, ORR = ONP + R::NP + 6 /* zero pad: the d tile reads np six at a time */,
                        OU = ORR + R::NP + 2, OXOLD = OU + R::NP + 2, OUOLD = OXOLD + R::NP, OXACC = OUOLD + R::NP + 2,
@@ -77,7 +77,8 @@ struct MCfg : RCfg<NV_, NC_> {
   static constexpr int RS = RE0 + ((R::PMAX + 1) & ~1);     // c1, c2, status, jrf
   static constexpr int RI = RS + 4;                         // the image
   static constexpr int RO = RI + ((IMG + 1) & ~1);          // result: x[NP], then ints iq, iter, status, A[N+2]
-  static constexpr int REC = (RO + R::NP + (R::N + 6 + 1) / 2 + 1) & ~1;
+  static constexpr int RT = (RO + R::NP + (R::N + 6 + 1) / 2 + 1) & ~1;  // joint torques (robots with torque-limit rows)
+  static constexpr int REC = RT + (NT > 0 ? 32 : 0);
   static_assert((OAR & 1) == 0 && (IMG & 1) == 0, "image is copied in 16-byte pieces");
 };
 
@@ -672,6 +673,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
             const double a0v = has_ic ? ws.ic_tq0[s * nact + a] : ws.cori[s * NV + v] + ws.grav[s * NV + v];
             a0[a] = a0v - G.trq_lo[a];
             a0[NT + a] = G.trq_hi[a] - a0v;
+            a0[2 * NT + a] = a0v;  // for the torque recovery at the end of the active-set kernel
           }
         }
         __syncwarp();
@@ -715,7 +717,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   double* const Rp = smem + C::ORT;
   double* const Ts = smem + C::OT;
   double* const Ar = smem + C::OAR;   // torque-limit rows S [M | -(Jc Ni)^T], pitch LDA
-  double* const a0 = smem + C::OA0;   // ci0 of the torque-limit rows: [0, NT) lower limits, [NT, 2 NT) upper limits
+  double* const a0 = smem + C::OA0;   // ci0 of the torque-limit rows: [0, NT) lower limits, [NT, 2 NT) upper limits; [2 NT, 3 NT) S Ni^T (c+g)
   double* const Uf = smem + C::OUF;
   double* const uf = smem + C::OUFV;
   double* const x = smem + C::OX;
@@ -1255,6 +1257,21 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       for (int k = lane; k < NP; k += 32) rec[C::RO + k] = x[k];
       if (lane < iq) ro[3 + lane] = Aact[lane];
       if (lane == 0) { ro[0] = iq; ro[1] = iter; ro[2] = status; }
+      if constexpr (NT > 0) {
+        // torque recovery tau = S (M qddot + Ni^T (c+g) - (Jc Ni)^T rf) (ihwbc.py:344-354): the rows
+        // S [M | -(Jc Ni)^T] are the torque-limit rows already in shared memory
+        if (lane < nact) {
+          const double* row = Ar + lane * LDA;
+          double t0 = 0.0, t1 = 0.0;
+#pragma unroll 1
+          for (int k = 0; k < NP; k += 2) {
+            const double2 r0 = lds2(row + k), x0 = lds2(x + k);
+            t0 = fma(r0.x, x0.x, t0);
+            t1 = fma(r0.y, x0.y, t1);
+          }
+          rec[C::RT + lane] = (t0 + t1) + a0[2 * NT + lane];
+        }
+      }
     }
     __syncwarp();
   }
@@ -1268,7 +1285,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 // status here; the generic kernel's second pass overwrites them.
 __global__ void __launch_bounds__(256)
 k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B, SolveIO io,
-               const double* __restrict__ rec_all, int rec_stride, int ro_off, int np_pad) {
+               const double* __restrict__ rec_all, int rec_stride, int ro_off, int np_pad, int rt_off) {
   const DevProblem& G = *gp;
   const int lane = threadIdx.x & 31;
   const size_t s = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1288,7 +1305,9 @@ k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nf
   if (io.trq) {
     for (int a = lane; a < nact; a += 32) {
       double tau = nanv;
-      if (!bad) {
+      if (!bad && rt_off >= 0) {
+        tau = rec_all[s * rec_stride + rt_off + a];  // recovered by the active-set kernel from its torque-limit rows
+      } else if (!bad) {
         double t0 = 0.0, t1 = 0.0;
         if (G.n_ic > 0) {
           const double* col = ws.ic_tq + s * n * nact + a;
@@ -1376,7 +1395,7 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   const int rc_cap = (rc_dbg > hp.p && rc_dbg < C::RC) ? rc_dbg : C::RC;
   k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32 * warps, smem, stream>>>(hp, dp, B, io.counter, io.overflow, ws.setup_rec, rc_cap);
   g_launch_count++;
-  k_ihwbc_finish<<<(B + 7) / 8, 256, 0, stream>>>(dp, ws, fm, nfr, B, io, ws.setup_rec, C::REC, C::RO, C::NP);
+  k_ihwbc_finish<<<(B + 7) / 8, 256, 0, stream>>>(dp, ws, fm, nfr, B, io, ws.setup_rec, C::REC, C::RO, C::NP, NT > 0 ? C::RT : -1);
   g_launch_count++;
   return true;
 }

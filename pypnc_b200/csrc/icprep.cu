@@ -69,12 +69,16 @@ __host__ __device__ inline IcLayout ic_layout(int nv, int nact, int nc, int k) {
   return L;
 }
 
+// NV_ / NACT_ / NC_ / K_ > 0 fix the dimensions at compile time (the shipped robots); 0 = read them
+// from the problem (any other shape).  Same code either way.
+template <int NV_, int NACT_, int NC_, int K_>
 __global__ void __launch_bounds__(32)
 k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap fm, int nfr, int B, int* counter) {
   extern __shared__ __align__(16) double sm[];
   const DevProblem& P = *gp;
   const int lane = threadIdx.x;
-  const int nv = P.nv, k = P.n_ic, nact = P.nact, nc = P.nc, n = P.n, ld = L.ld, ldz = L.ldz, ldb = L.ldb;
+  const int nv = NV_ ? NV_ : P.nv, k = K_ ? K_ : P.n_ic, nact = NACT_ ? NACT_ : P.nact, nc = NV_ ? NC_ : P.nc;
+  const int n = nv + nc, ld = nv | 1, ldz = nact | 1, ldb = nact | 1;
   const int nj = nv - 6;
   double* Lm = sm + L.oL;
   double* Z = sm + L.oZ;
@@ -430,15 +434,20 @@ void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
                        int B, int num_sms, cudaStream_t stream, int* counter) {
   IcLayout L = ic_layout(hp.nv, hp.nact, hp.nc, hp.n_ic);
   const size_t smem = (size_t)L.total * sizeof(double);
-  static SmemOptIn optin;
-  optin.ensure(k_ic_prepare, smem);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 16) per_sm = 16;
   int grid = num_sms * per_sm;
   if (grid > B) grid = B;
   cudaMemsetAsync(counter, 0, sizeof(int), stream);
-  k_ic_prepare<<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, B, counter);
+  auto go = [&](auto kernel) {
+    static SmemOptIn optin;
+    optin.ensure(kernel, smem);
+    kernel<<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, B, counter);
+  };
+  if (hp.nv == 33 && hp.nact == 25 && hp.nc == 12 && hp.n_ic == 2) go(k_ic_prepare<33, 25, 12, 2>);        // Draco3
+  else if (hp.nv == 20 && hp.nact == 12 && hp.nc == 12 && hp.n_ic == 2) go(k_ic_prepare<20, 12, 12, 2>);   // Draco3 lower body
+  else go(k_ic_prepare<0, 0, 0, 0>);
   g_launch_count++;
 }
 

@@ -24,9 +24,10 @@ namespace pnc {
 // sum_c a[c sa] b[c sb], c < n, with four independent accumulators: the factorisations and
 // triangular solves below are chains of such dot products, and a single accumulator makes every
 // FMA wait for the previous one
-// Out of line on purpose: seven call sites, and the kernel's warps wander through it independently
-// (an inlined, unrolled copy per site pushed no_inst stalls from 2 % to 24 %).
-static __device__ __noinline__ double dot4(const double* a, int sa, const double* b, int sb, int n) {
+// Inlined where the dimensions (hence the strides) are compile-time constants; out of line for the
+// runtime-dimension instantiation, whose seven inlined, unrolled copies pushed no_inst stalls from
+// 2 % to 24 % (the kernel's warps wander through the code independently).
+static __device__ __forceinline__ double dot4_inl(const double* a, int sa, const double* b, int sb, int n) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int c = 0;
 #pragma unroll 1
@@ -39,6 +40,9 @@ static __device__ __noinline__ double dot4(const double* a, int sa, const double
 #pragma unroll 1
   for (; c < n; c++) s0 = fma(a[c * sa], b[c * sb], s0);
   return (s0 + s1) + (s2 + s3);
+}
+static __device__ __noinline__ double dot4_out(const double* a, int sa, const double* b, int sb, int n) {
+  return dot4_inl(a, sa, b, sb, n);
 }
 
 struct IcLayout {
@@ -79,6 +83,10 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
   const int lane = threadIdx.x;
   const int nv = NV_ ? NV_ : P.nv, k = K_ ? K_ : P.n_ic, nact = NACT_ ? NACT_ : P.nact, nc = NV_ ? NC_ : P.nc;
   const int n = nv + nc, ld = nv | 1, ldz = nact | 1, ldb = nact | 1;
+  auto dot4 = [](const double* a, int sa, const double* b, int sb, int cnt) {
+    if constexpr (NV_ > 0) return dot4_inl(a, sa, b, sb, cnt);
+    else return dot4_out(a, sa, b, sb, cnt);
+  };
   const int nj = nv - 6;
   double* Lm = sm + L.oL;
   double* Z = sm + L.oZ;

@@ -51,6 +51,9 @@ size_t dyn_smem_bytes(int nv) {
 __device__ __forceinline__ V3 ld3(const double* p) { return V3{p[0], p[1], p[2]}; }
 __device__ __forceinline__ void st3(double* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
 
+// NV_ > 0 fixes the number of velocity variables at compile time (the shipped robots); 0 = read it
+// from the model (any URDF).  Same code either way: index arithmetic on nv is what specialises.
+template <int NV_>
 __global__ void __launch_bounds__(DYN_WARPS * 32)
 k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ gfr, WsPtrs ws, int B,
                 const double* __restrict__ base_pos, const double* __restrict__ base_quat,
@@ -73,7 +76,7 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nb = sm->nb, nv = sm->nv, na = sm->na, nfl = sm->nfl, nq = sm->nq, nfr = sfr->nfr;
+  const int nb = sm->nb, nv = NV_ ? NV_ : sm->nv, na = sm->na, nfl = sm->nfl, nq = sm->nq, nfr = sfr->nfr;
   const DynSmemLayout L = dyn_layout(nv);
   double* W = wbase + (size_t)warp * L.per_warp_doubles;
   double* xf = W + L.off_xf;
@@ -434,8 +437,6 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
                           int num_sms, cudaStream_t stream, int b_cent) {
   size_t smem = dyn_smem_bytes(nv);
-  static SmemOptIn optin;
-  optin.ensure(k_update_system, smem);
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 4) ctas_per_sm = 4;
@@ -443,8 +444,20 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs
   int need = (B + DYN_WARPS - 1) / DYN_WARPS;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  k_update_system<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, ws, B, base_pos, base_quat, base_lin_vel,
-                                                          base_ang_vel, joint_pos, joint_vel, b_cent);
+  auto go = [&](auto kernel) {
+    static SmemOptIn optin;
+    optin.ensure(kernel, smem);
+    kernel<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, ws, B, base_pos, base_quat, base_lin_vel, base_ang_vel,
+                                                     joint_pos, joint_vel, b_cent);
+  };
+  switch (nv) {  // Atlas, Draco3, Valkyrie, Draco3 lower body, Laikago; anything else reads nv at run time
+    case 36: go(k_update_system<36>); break;
+    case 33: go(k_update_system<33>); break;
+    case 32: go(k_update_system<32>); break;
+    case 20: go(k_update_system<20>); break;
+    case 18: go(k_update_system<18>); break;
+    default: go(k_update_system<0>); break;
+  }
   g_launch_count++;
 }
 

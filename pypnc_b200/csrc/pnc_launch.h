@@ -96,17 +96,29 @@ void launch_joint_integrate(int B, int na, const double* acc, const double* join
 bool launch_quadprog_dense(int n, int p, int m, int B, const double* G, const double* g0, const double* CE, const double* ce0,
                            const double* CI, const double* ci0, double* x, double* f, int* status, int* iters,
                            unsigned long long* active, int num_sms, cudaStream_t stream);
-// The opt-in dynamic shared-memory limit of a kernel is a per-device attribute: one process may
-// drive several GPUs, so the high-water mark is remembered per device.
+// The opt-in dynamic shared-memory limit is an attribute of (kernel function, device): remember the
+// high-water mark per pair.  Keyed by the function address, not by the static object at the call
+// site: template instantiations of one kernel share a pointer type and would share that object.
 struct SmemOptIn {
-  size_t bytes[64] = {};
   template <class K>
   bool ensure(K kernel, size_t smem) {
+    struct Entry { const void* fn; int dev; size_t bytes; };
+    static Entry table[256];
+    static int used = 0;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (smem > bytes[dev]) {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    Entry* e = nullptr;
+    for (int i = 0; i < used; i++)
+      if (table[i].fn == fn && table[i].dev == dev) { e = &table[i]; break; }
+    if (!e) {
+      if (used >= 256) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+      e = &table[used++];
+      e->fn = fn; e->dev = dev; e->bytes = 0;
+    }
+    if (smem > e->bytes) {
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-      bytes[dev] = smem;
+      e->bytes = smem;
     }
     return true;
   }

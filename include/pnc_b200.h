@@ -76,6 +76,14 @@ extern "C" {
 #define PNC_QP_EQ_DEPENDENT 3   /* "Constraints are linearly dependent" :268-271 */
 #define PNC_QP_MAX_ITER 4
 
+/* Termination of the active-set loop (pnc_set_termination).  QuadProg++.cc:306-312 stops when the
+ * summed infeasibility |psi| <= m eps c1 c2 100, which is 1e-4 .. 1e-3 for these problems.
+ * REFINED (default) remembers the first iterate that meets that bound and keeps iterating to
+ * 1e-6 x the bound (falling back to the remembered iterate if that cannot complete);
+ * REFERENCE stops exactly where QuadProg++ stops. */
+#define PNC_TERM_REFINED 0
+#define PNC_TERM_REFERENCE 1
+
 /* limits compiled into the kernels */
 #define PNC_MAX_BODIES 32   /* one warp lane per movable body */
 #define PNC_MAX_NV 40
@@ -207,8 +215,9 @@ double* pnc_ws_frame_jac(pnc_workspace* ws);
 double* pnc_ws_frame_jdqd(pnc_workspace* ws);
 
 /* ---- IHWBC ---------------------------------------------------------------- */
-/* One launch: task Jacobians/commands, contact cones, cost + constraint assembly,
- * batched Goldfarb-Idnani solve, torque recovery.  Requires pnc_update_system on `ws`.
+/* One call (stream-ordered kernels: task errors, per-state setup, active-set loop, outputs): task
+ * Jacobians/commands, contact cones, cost + constraint assembly, batched Goldfarb-Idnani solve,
+ * torque recovery.  Requires pnc_update_system on `ws`.
  *   d_des        [B,ndes]     task desireds (layout: pnc_task_desc.des_off)
  *   d_w          [B,ntask]    w_hierarchy per task
  *   d_rf_z_max   [B,ncontact] (values <= 0 are replaced by 1e-3, contact.py:37-41)
@@ -221,6 +230,19 @@ int pnc_ihwbc_solve(const pnc_problem* p, pnc_workspace* ws, int32_t B, const do
                     const double* d_w, const double* d_rf_z_max, double* d_trq, double* d_acc,
                     double* d_rf, double* d_qddot, int32_t* d_status, int32_t* d_iters,
                     uint64_t* d_active, void* stream);
+
+/* pnc_ihwbc_solve with one more output: d_active_ref [B, ceil(m/64)] = the active set at the first
+ * iterate that met the termination test of QuadProg++.cc:306-312, i.e. the set solve_quadprog
+ * itself returns (equal to d_active when the refinement added nothing; may be NULL). */
+int pnc_ihwbc_solve_ref(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* d_des,
+                        const double* d_w, const double* d_rf_z_max, double* d_trq, double* d_acc,
+                        double* d_rf, double* d_qddot, int32_t* d_status, int32_t* d_iters,
+                        uint64_t* d_active, uint64_t* d_active_ref, void* stream);
+
+/* Process-wide termination mode of the IHWBC active-set loop: PNC_TERM_REFINED (default, or
+ * PNC_TERMINATION=reference in the environment for the other) / PNC_TERM_REFERENCE. */
+int pnc_set_termination(int32_t mode);
+int pnc_get_termination(void);
 
 /* Task.jacobian [B,dim,nv], jacobian_dot_q_dot [B,dim], op_cmd [B,dim], pos_err [B,dim]
  * of task `itask` (any output may be NULL). */

@@ -43,6 +43,8 @@ def _load(fast=False):
     lib.orc_solve_quadprog.argtypes = [i32, i32, i32] + [vp] * 13
     lib.orc_wbc_tick_batch.restype = dbl
     lib.orc_wbc_tick_batch.argtypes = [vp, i32, i32] + [vp] * 17
+    lib.orc_wbc_tick_batch_margin.restype = dbl
+    lib.orc_wbc_tick_batch_margin.argtypes = [vp, i32, i32] + [vp] * 19
     _LIBS[key] = lib
     return lib
 
@@ -244,21 +246,24 @@ class OracleProblem:
         return dict(P=P, q=qv, G=Gm[:m], h=h[:m], A=Am, b=b)
 
     def tick_batch(self, states, des, w, rf_z_max, nthreads=1):
-        """B controller ticks; returns dict of outputs + 'seconds'."""
+        """B controller ticks; returns dict of outputs + 'seconds'.  'margin' / 'margin_kind' are the
+        decision margins of the QP solve (pnc_oracle.c: orc_last_qp_margin)."""
         spec, m = self.spec, self.spec.model
         B = states['joint_pos'].shape[0]
         n, p, mi = spec.qp_dims
         out = dict(trq=np.zeros((B, spec.nact)), acc=np.zeros((B, spec.nact)), rf=np.zeros((B, spec.nc)),
                    qddot=np.zeros((B, m.nv)), active=np.zeros((B, max(mi, 1)), dtype=np.uint8),
-                   status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32), flops=np.zeros(B))
+                   status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32), flops=np.zeros(B),
+                   margin=np.ones(B), margin_kind=np.zeros(B, dtype=np.int32))
         fl = m.n_floating != 0
         a = [_f64(states[k]) if fl else None for k in ('base_pos', 'base_quat', 'base_lin_vel', 'base_ang_vel')]
         jp, jv = _f64(states['joint_pos']), _f64(states['joint_vel'])
         des, w, rfz = _f64(des), _f64(w), _f64(rf_z_max)
-        sec = self.lib.orc_wbc_tick_batch(vp(self.h), B, nthreads, *[_p(x) for x in a], _p(jp), _p(jv), _p(des),
-                                          _p(w), _p(rfz), _p(out['trq']), _p(out['acc']), _p(out['rf']),
-                                          _p(out['qddot']), _p(out['active']), _p(out['status']),
-                                          _p(out['iters']), _p(out['flops']))
+        sec = self.lib.orc_wbc_tick_batch_margin(vp(self.h), B, nthreads, *[_p(x) for x in a], _p(jp), _p(jv),
+                                                 _p(des), _p(w), _p(rfz), _p(out['trq']), _p(out['acc']),
+                                                 _p(out['rf']), _p(out['qddot']), _p(out['active']),
+                                                 _p(out['status']), _p(out['iters']), _p(out['flops']),
+                                                 _p(out['margin']), _p(out['margin_kind']))
         out['active'] = out['active'][:, :mi]
         out['seconds'] = sec
         return out

@@ -821,10 +821,33 @@ static void qp_delete_constraint(double* R, double* J, int* A, double* u, int n,
   }
 }
 
+/* Decision margin of the last orc_solve_quadprog call on this thread (test instrumentation, does
+ * not touch the arithmetic): the smallest relative distance, over every data-dependent branch the
+ * solver took, between the two sides of that branch.  A state whose margin is far above rounding
+ * has one well-defined iteration path and final active set; a margin at rounding level means the
+ * reference itself picks among exact ties by noise (redundant wrench-cone rows, degenerate vertices).
+ * kind: 1 termination test (:306-312), 2 most-violated-constraint choice (:323-334), 3 blocking
+ * constraint choice (:366-378), 4 partial vs full step (:390-393, :441), 5 near-dependent normal
+ * (|d[iq:]| / |d|: decides :380 and the degeneracy test of add_constraint :597-603). */
+static __thread double g_qp_margin;
+static __thread int g_qp_margin_kind;
+#define QP_MARGIN(val, kind)                                    \
+  do {                                                          \
+    const double v_ = (val);                                    \
+    if (v_ < g_qp_margin) { g_qp_margin = v_; g_qp_margin_kind = (kind); } \
+  } while (0)
+void orc_last_qp_margin(double* margin, int* kind) {
+  if (margin) *margin = g_qp_margin;
+  if (kind) *kind = g_qp_margin_kind;
+}
+
 double orc_solve_quadprog(int n, int p, int m, double* G, const double* g0, const double* CE,
                           const double* ce0, const double* CI, const double* ci0, double* x, int* A,
                           double* u, int* iq_out, int* iters, int* status, double* flops) {
   int i, j, k, l = 0, ip, iq, iter = 0;
+  g_qp_margin = 1.0;
+  g_qp_margin_kind = 0;
+  double s_scale = 1.0;
   int mp = m + p;
   double* R = (double*)calloc((size_t)n * n, sizeof(double));
   double* J = (double*)calloc((size_t)n * n, sizeof(double));
@@ -894,6 +917,13 @@ l1:
     psi += fmin(0.0, sum);
   }
   F += 2.0 * m * n;
+  {
+    const double tol = m * DBL_EPSILON * c1 * c2 * 100.0;
+    s_scale = 0.0;
+    for (i = 0; i < m; i++) s_scale = fmax(s_scale, fabs(s[i]));
+    if (!(s_scale > 0.0)) s_scale = 1.0;
+    if (tol > 0.0) QP_MARGIN(fabs(fabs(psi) - tol) / tol, 1);
+  }
   if (fabs(psi) <= m * DBL_EPSILON * c1 * c2 * 100.0) goto done;
   if (iter > 40 * (n + m)) { *status = PNC_QP_MAX_ITER; goto done; }
   for (i = 0; i < iq; i++) { u_old[i] = u[i]; A_old[i] = A[i]; }
@@ -902,6 +932,15 @@ l1:
 l2:
   for (i = 0; i < m; i++) {
     if (s[i] < ss && iai[i] != -1 && iaexcl[i]) { ss = s[i]; ip = i; }
+  }
+  {
+    /* runner-up of the choice just made; when nothing is violated, the distance of the smallest
+     * eligible slack from zero */
+    double s2 = INFINITY;
+    for (i = 0; i < m; i++)
+      if (!(ss < 0.0 && i == ip) && iai[i] != -1 && iaexcl[i] && s[i] < s2) s2 = s[i];
+    if (ss < 0.0) QP_MARGIN((fmin(s2, 0.0) - ss) / s_scale, 2);
+    else if (s2 < INFINITY) QP_MARGIN(fabs(s2) / s_scale, 2);
   }
   if (ss >= 0.0) goto done;
   for (i = 0; i < n; i++) np[i] = CI[i * m + ip];
@@ -926,6 +965,15 @@ l2a:
   } else
     t2 = inf;
   t = fmin(t1, t2);
+  {
+    double t1b = inf, dd = 0.0, d2 = 0.0;
+    for (k = p; k < iq; k++)
+      if (r[k] > 0.0 && A[k] != l && u[k] / r[k] < t1b) t1b = u[k] / r[k];
+    if (t1 < inf && t1b < inf) QP_MARGIN(fabs(t1b - t1) / fmax(fabs(t1b), 1e-300), 3);
+    if (t1 < inf && t2 < inf) QP_MARGIN(fabs(t1 - t2) / fmax(fmax(fabs(t1), fabs(t2)), 1e-300), 4);
+    for (k = 0; k < n; k++) { dd += d[k] * d[k]; if (k >= iq) d2 += d[k] * d[k]; }
+    if (dd > 0.0) QP_MARGIN(sqrt(d2 / dd), 5);
+  }
   if (t >= inf) { *status = PNC_QP_INFEASIBLE; f_value = inf; goto done; }
   if (t2 >= inf) {
     for (k = 0; k < iq; k++) u[k] -= t * r[k];
@@ -1398,7 +1446,10 @@ void orc_wbc_tick(const orc_problem* p, const double* bp, const double* bq, cons
     memset(active, 0, mi);
     for (int i = pe; i < iq; i++) active[A[i]] = 1;
   }
-  if (info) { info->status = status; info->iters = iters; info->iq = iq; info->qp_flops = Fqp; info->asm_flops = Fasm; }
+  if (info) {
+    info->status = status; info->iters = iters; info->iq = iq; info->qp_flops = Fqp; info->asm_flops = Fasm;
+    orc_last_qp_margin(&info->margin, &info->margin_kind);
+  }
   free(CE); free(ce0); free(CI); free(ci0); free(x); free(A); free(u);
   asm_free(&a);
 }
@@ -1416,6 +1467,8 @@ typedef struct {
   double *trq, *acc, *rf, *qddot, *flops;
   unsigned char* active;
   int *status, *iters;
+  double* margin;
+  int* margin_kind;
 } shard_t;
 
 static void* shard_run(void* arg) {
@@ -1441,6 +1494,8 @@ static void* shard_run(void* arg) {
     if (s->status) s->status[i] = info.status;
     if (s->iters) s->iters[i] = info.iters;
     if (s->flops) s->flops[i] = info.qp_flops + info.asm_flops;
+    if (s->margin) s->margin[i] = info.margin;
+    if (s->margin_kind) s->margin_kind[i] = info.margin_kind;
   }
   return NULL;
 }
@@ -1450,6 +1505,15 @@ double orc_wbc_tick_batch(const orc_problem* p, int B, int nthreads, const doubl
                           const double* des, const double* w, const double* rfz, double* trq, double* acc,
                           double* rf, double* qddot, unsigned char* active, int* status, int* iters,
                           double* flops) {
+  return orc_wbc_tick_batch_margin(p, B, nthreads, bp, bq, blv, bav, jp, jv, des, w, rfz, trq, acc, rf, qddot, active,
+                                   status, iters, flops, NULL, NULL);
+}
+
+double orc_wbc_tick_batch_margin(const orc_problem* p, int B, int nthreads, const double* bp, const double* bq,
+                                 const double* blv, const double* bav, const double* jp, const double* jv,
+                                 const double* des, const double* w, const double* rfz, double* trq, double* acc,
+                                 double* rf, double* qddot, unsigned char* active, int* status, int* iters,
+                                 double* flops, double* margin, int* margin_kind) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   shard_t sh[256];
@@ -1457,7 +1521,8 @@ double orc_wbc_tick_batch(const orc_problem* p, int B, int nthreads, const doubl
   double t0 = now_s();
   for (int t = 0; t < nthreads; t++) {
     shard_t s = {p, (int)((long long)B * t / nthreads), (int)((long long)B * (t + 1) / nthreads),
-                 bp, bq, blv, bav, jp, jv, des, w, rfz, trq, acc, rf, qddot, flops, active, status, iters};
+                 bp, bq, blv, bav, jp, jv, des, w, rfz, trq, acc, rf, qddot, flops, active, status, iters,
+                 margin, margin_kind};
     sh[t] = s;
     if (nthreads > 1) pthread_create(&th[t], NULL, shard_run, &sh[t]);
   }

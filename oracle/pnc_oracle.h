@@ -75,7 +75,13 @@ void orc_pinv(const double* A, int m, int n, double rcond, double* P);
 typedef struct {
   int status, iters, iq;
   double qp_flops, asm_flops;
+  double margin;    /* decision margin of the QP solve, see orc_last_qp_margin */
+  int margin_kind;
 } orc_tick_info;
+
+/* Smallest relative distance between the two sides of any data-dependent branch the last
+ * orc_solve_quadprog call on this thread took (1 = never close), and which branch kind it was. */
+void orc_last_qp_margin(double* margin, int* kind);
 
 /* BasicTask.update_jacobian + update_cmd of task `it` (basic_task.py:25-137) */
 void orc_task_eval(const orc_problem* p, const double* q, const double* v, const double* des, int it,
@@ -106,6 +112,14 @@ double orc_wbc_tick_batch(const orc_problem* p, int B, int nthreads, const doubl
                           const double* w, const double* rf_z_max, double* trq, double* acc, double* rf,
                           double* qddot, unsigned char* active, int* status, int* iters,
                           double* flops);
+
+/* same, plus the per-state decision margin of the QP solve (margin[B], margin_kind[B]; may be NULL) */
+double orc_wbc_tick_batch_margin(const orc_problem* p, int B, int nthreads, const double* base_pos,
+                                 const double* base_quat, const double* base_lin_vel, const double* base_ang_vel,
+                                 const double* joint_pos, const double* joint_vel, const double* des,
+                                 const double* w, const double* rf_z_max, double* trq, double* acc, double* rf,
+                                 double* qddot, unsigned char* active, int* status, int* iters, double* flops,
+                                 double* margin, int* margin_kind);
 
 /* manipulator_interface.py:77-114 OSC step on a fixed-base arm: returns trq[na] */
 void orc_osc_step(const orc_model* m, int ee_frame, const double* q, const double* v, const double* pos_des,

@@ -17,6 +17,14 @@ unsigned long long g_launch_count = 0;
 }
 using namespace pnc;
 
+// PNC_TERM_REFINED (default): keep iterating to 1e-6 x the bound of QuadProg++.cc:306-312;
+// PNC_TERM_REFERENCE: stop at the reference's own bound.  PNC_TERMINATION=reference sets the default.
+static int g_termination = [] {
+  const char* e = getenv("PNC_TERMINATION");
+  return (e && (e[0] == 'r' || e[0] == 'R') && (e[2] == 'f' || e[2] == 'F') && (e[3] == 'e' || e[3] == 'E')) ? PNC_TERM_REFERENCE
+                                                                                                             : PNC_TERM_REFINED;
+}();
+
 #define CK(call)                                                                                  \
   do {                                                                                            \
     cudaError_t e_ = (call);                                                                      \
@@ -408,7 +416,8 @@ static int ensure_ic(pnc_workspace* ws, const pnc_problem* p) {
 
 static int solve_at(const pnc_problem* p, pnc_workspace* ws, int off, int32_t B, const double* des,
                     const double* w, const double* rfz, double* trq, double* acc, double* rf, double* qddot,
-                    int32_t* status, int32_t* iters, uint64_t* active, cudaStream_t st, int* counter) {
+                    int32_t* status, int32_t* iters, uint64_t* active, cudaStream_t st, int* counter,
+                    uint64_t* active_ref = nullptr) {
   FrameMap fm;
   int rc = resolve_frames(p, ws, &fm);
   if (rc) return rc;
@@ -441,6 +450,8 @@ static int solve_at(const pnc_problem* p, pnc_workspace* ws, int off, int32_t B,
   SolveIO io;
   io.des = des; io.w = w; io.rfz = rfz; io.trq = trq; io.acc = acc; io.rf = rf; io.qddot = qddot;
   io.status = status; io.iters = iters; io.active = reinterpret_cast<unsigned long long*>(active); io.counter = counter; io.overflow = counter + 3;
+  io.active_ref = reinterpret_cast<unsigned long long*>(active_ref);
+  io.psi_refine = g_termination == PNC_TERM_REFERENCE ? 1.0 : 1e-6;
   launch_ihwbc_solve(p->d, p->h, p->lay, wsp, fm, ws->nfr, B, io, ws->m->num_sms, st);
   CK(cudaGetLastError());
   return PNC_OK;
@@ -449,13 +460,28 @@ static int solve_at(const pnc_problem* p, pnc_workspace* ws, int off, int32_t B,
 int pnc_ihwbc_solve(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* d_des, const double* d_w,
                     const double* d_rf_z_max, double* d_trq, double* d_acc, double* d_rf, double* d_qddot,
                     int32_t* d_status, int32_t* d_iters, uint64_t* d_active, void* stream) {
+  return pnc_ihwbc_solve_ref(p, ws, B, d_des, d_w, d_rf_z_max, d_trq, d_acc, d_rf, d_qddot, d_status, d_iters, d_active,
+                             nullptr, stream);
+}
+
+int pnc_ihwbc_solve_ref(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* d_des, const double* d_w,
+                        const double* d_rf_z_max, double* d_trq, double* d_acc, double* d_rf, double* d_qddot,
+                        int32_t* d_status, int32_t* d_iters, uint64_t* d_active, uint64_t* d_active_ref, void* stream) {
   if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m) return PNC_E_ARG;
   if (!d_des || !d_w || (p->h.ncontact && !d_rf_z_max) || !d_status) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
   CK(cudaSetDevice(ws->m->device));
   return solve_at(p, ws, 0, B, d_des, d_w, d_rf_z_max, d_trq, d_acc, d_rf, d_qddot, d_status, d_iters, d_active,
-                  (cudaStream_t)stream, ws->counter);
+                  (cudaStream_t)stream, ws->counter, d_active_ref);
 }
+
+int pnc_set_termination(int32_t mode) {
+  if (mode != PNC_TERM_REFINED && mode != PNC_TERM_REFERENCE) return PNC_E_ARG;
+  g_termination = mode;
+  return PNC_OK;
+}
+
+int pnc_get_termination(void) { return g_termination; }
 
 int pnc_task_eval(const pnc_problem* p, pnc_workspace* ws, int32_t B, int32_t itask, const double* d_des,
                   double* d_jac, double* d_jdqd, double* d_op_cmd, double* d_pos_err, void* stream) {

@@ -267,6 +267,7 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
     if (only_flag && io.status[s] != PNC_QP_OVERFLOW) continue;
     const double* des = io.des + s * P.ndes;
     int status = PNC_QP_OK, iter = 0;
+    int iq_ref = -1;  // size of the active set at the reference's own termination point (-1: the final one)
     if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;  // rank-deficient projection (icprep.cu)
     q.iq = 0;
     q.R_norm = 1.0;
@@ -551,7 +552,7 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
         // reference bound and keep iterating to psi_refine; if the refinement cannot complete
         // (numerical infeasibility / iteration cap) the remembered iterate is returned.
         const double psi_tol = (double)m * QP_EPS * c1 * c2 * 100.0;
-        const double psi_refine = psi_tol * 1e-6;
+        const double psi_refine = psi_tol * io.psi_refine;
         bool done = false, accepted = false;
         int iq_acc = 0;
         while (!done) {
@@ -711,6 +712,7 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
             }
           }
         }
+        if (accepted) iq_ref = iq_acc;
         if (accepted && status != PNC_QP_OK) {  // refinement failed: fall back to the accepted iterate
           status = PNC_QP_OK;
           q.iq = iq_acc;
@@ -767,6 +769,19 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
           if (c >= 0 && (c >> 6) == wd) bits |= 1ull << (c & 63);
         }
         io.active[s * mw + wd] = bits;
+      }
+    }
+    if (io.active_ref) {  // the set QuadProg++ itself would have returned (first iterate within its bound, :306-312)
+      const int mw = (m + 63) / 64 > 0 ? (m + 63) / 64 : 1;
+      const int* ar = iq_ref >= 0 ? Aacc : Aact;
+      const int nr = iq_ref >= 0 ? iq_ref : q.iq;
+      for (int wd = lane; wd < mw; wd += 32) {
+        unsigned long long bits = 0ull;
+        for (int i = p; i < nr; i++) {
+          const int c = ar[i];
+          if (c >= 0 && (c >> 6) == wd) bits |= 1ull << (c & 63);
+        }
+        io.active_ref[s * mw + wd] = bits;
       }
     }
     if (lane == 0) {

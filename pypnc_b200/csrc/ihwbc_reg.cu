@@ -76,8 +76,9 @@ struct MCfg : RCfg<NV_, NC_> {
   static constexpr int RE0 = RE + R::PMAX * R::NP;          // equality offsets
   static constexpr int RS = RE0 + ((R::PMAX + 1) & ~1);     // c1, c2, status, jrf
   static constexpr int RI = RS + 4;                         // the image
-  static constexpr int RO = RI + ((IMG + 1) & ~1);          // result: x[NP], then ints iq, iter, status, A[N+2]
-  static constexpr int RT = (RO + R::NP + (R::N + 6 + 1) / 2 + 1) & ~1;  // joint torques (robots with torque-limit rows)
+  static constexpr int RO = RI + ((IMG + 1) & ~1);          // result: x[NP], then ints iq, iter, status, A[N+2], iq_ref, Aref[N+2]
+  static constexpr int ROI = 2 * (R::N + 2) + 4;            // ints of the result
+  static constexpr int RT = (RO + R::NP + (ROI + 1) / 2 + 1) & ~1;  // joint torques (robots with torque-limit rows)
   static constexpr int REC = RT + (NT > 0 ? 32 : 0);
   static_assert((OAR & 1) == 0 && (IMG & 1) == 0, "image is copied in 16-byte pieces");
 };
@@ -694,7 +695,7 @@ template <int NV, int NC, int NU, int NT>
 #endif
 __global__ void PNC_REG_LB
 k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, int B, int* __restrict__ counter,
-            int* __restrict__ overflow, double* __restrict__ rec_all, int rc_cap) {
+            int* __restrict__ overflow, double* __restrict__ rec_all, int rc_cap, double refine) {
   // P (constant bank) serves warp-uniform reads; tables indexed per lane go through the global copy G
   const DevProblem& G = *gp;
   using C = MCfg<NV, NC, NU, NT>;
@@ -766,6 +767,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     }
     const size_t s = (size_t)si;
     int status = PNC_QP_OK, iter = 0, iq = 0;
+    int iq_ref = -1;  // size of the active set at the reference's own termination point (-1: same as the final one)
     double R_norm = 1.0;
     double* rec = rec_all + s * C::REC;  // written by k_ihwbc_setup
     {
@@ -827,7 +829,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         if (lane == (i & 31)) msk &= ~(1u << (i >> 5));
       };
       const double psi_tol = (double)m * QP_EPS * c1 * c2 * 100.0;  // QuadProg++.cc:306-312
-      const double psi_refine = psi_tol * 1e-6;                     // see ihwbc.cu / DESIGN.md 3.2
+      const double psi_refine = psi_tol * refine;                   // refine = 1e-6 by default, see ihwbc.cu / DESIGN.md 3.2
       bool done = false, accepted = false, need_l1 = true;
       int iq_acc = 0, ieq = 0;
 
@@ -1241,6 +1243,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           }
         }
       }
+      if (accepted) iq_ref = iq_acc;
       if (accepted && status != PNC_QP_OK) {  // refinement failed: fall back to the accepted iterate
         status = PNC_QP_OK;
         iq = iq_acc;
@@ -1256,7 +1259,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) rec[C::RO + k] = x[k];
       if (lane < iq) ro[3 + lane] = Aact[lane];
-      if (lane == 0) { ro[0] = iq; ro[1] = iter; ro[2] = status; }
+      if (lane == 0) { ro[0] = iq; ro[1] = iter; ro[2] = status; ro[3 + N + 2] = iq_ref; }
+      if (lane < iq_ref) ro[4 + N + 2 + lane] = Aacc[lane];
       if constexpr (NT > 0) {
         // torque recovery tau = S (M qddot + Ni^T (c+g) - (Jc Ni)^T rf) (ihwbc.py:344-354): the rows
         // S [M | -(Jc Ni)^T] are the torque-limit rows already in shared memory
@@ -1285,7 +1289,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 // status here; the generic kernel's second pass overwrites them.
 __global__ void __launch_bounds__(256)
 k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B, SolveIO io,
-               const double* __restrict__ rec_all, int rec_stride, int ro_off, int np_pad, int rt_off) {
+               const double* __restrict__ rec_all, int rec_stride, int ro_off, int np_pad, int rt_off, int ref_off) {
   const DevProblem& G = *gp;
   const int lane = threadIdx.x & 31;
   const size_t s = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1345,6 +1349,21 @@ k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nf
       io.active[s * mw + wdx] = bits;
     }
   }
+  if (io.active_ref) {
+    // the set QuadProg++ itself would have returned: the first iterate that met its bound (:306-312)
+    const int mw = (m + 63) / 64 > 0 ? (m + 63) / 64 : 1;
+    const int iqr = ro[ref_off];
+    const int* ar = iqr >= 0 ? ro + ref_off + 1 : ro + 3;
+    const int nr = iqr >= 0 ? iqr : iq;
+    for (int wdx = lane; wdx < mw; wdx += 32) {
+      unsigned long long bits = 0ull;
+      for (int i = p; i < nr; i++) {
+        const int c = ar[i];
+        if (c >= 0 && (c >> 6) == wdx) bits |= 1ull << (c & 63);
+      }
+      io.active_ref[s * mw + wdx] = bits;
+    }
+  }
   if (lane == 0) {
     io.status[s] = status;
     if (io.iters) io.iters[s] = iter;
@@ -1393,9 +1412,11 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   // PNC_DEBUG_RC lowers the cap on active constraints so the tests can exercise the hand-over
   static const int rc_dbg = [] { const char* e = getenv("PNC_DEBUG_RC"); return e ? atoi(e) : 0; }();
   const int rc_cap = (rc_dbg > hp.p && rc_dbg < C::RC) ? rc_dbg : C::RC;
-  k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32 * warps, smem, stream>>>(hp, dp, B, io.counter, io.overflow, ws.setup_rec, rc_cap);
+  k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32 * warps, smem, stream>>>(hp, dp, B, io.counter, io.overflow, ws.setup_rec, rc_cap,
+                                                                  io.psi_refine);
   g_launch_count++;
-  k_ihwbc_finish<<<(B + 7) / 8, 256, 0, stream>>>(dp, ws, fm, nfr, B, io, ws.setup_rec, C::REC, C::RO, C::NP, NT > 0 ? C::RT : -1);
+  k_ihwbc_finish<<<(B + 7) / 8, 256, 0, stream>>>(dp, ws, fm, nfr, B, io, ws.setup_rec, C::REC, C::RO, C::NP, NT > 0 ? C::RT : -1,
+                                                  3 + C::N + 2);
   g_launch_count++;
   return true;
 }

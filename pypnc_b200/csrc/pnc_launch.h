@@ -50,6 +50,8 @@ struct SolveIO {
   double *trq, *acc, *rf, *qddot;
   int *status, *iters;
   unsigned long long* active;
+  unsigned long long* active_ref;  // active set at the first iterate that meets QuadProg++.cc:306-312 (may be NULL)
+  double psi_refine;               // termination bound as a factor of the reference's: 1e-6 (default) or 1 (PNC_TERM_REFERENCE)
   int* counter;
   int* overflow;  // set by the register kernel when a state needs the generic kernel
 };

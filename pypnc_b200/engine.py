@@ -144,8 +144,18 @@ def _from_ptr(ptr, shape, device):
     return t.view(*shape)
 
 
+TERM_REFINED, TERM_REFERENCE = 0, 1
+
+
+def set_termination(mode):
+    """Process-wide termination of the active-set loop: TERM_REFINED (default) or TERM_REFERENCE
+    (stop exactly where QuadProg++.cc:306-312 stops)."""
+    _check(_cabi.load_library().pnc_set_termination(int(mode)), 'pnc_set_termination')
+
+
 def ihwbc_solve(problem, ws, des, w, rf_z_max, want_qddot=True):
-    """pnc_ihwbc_solve on device tensors.  Returns a dict of device tensors."""
+    """pnc_ihwbc_solve_ref on device tensors.  Returns a dict of device tensors; 'active_ref' is the
+    active set at the reference solver's own termination point (see include/pnc_b200.h)."""
     spec = problem.spec
     B = des.shape[0]
     dev = des.device
@@ -155,10 +165,12 @@ def ihwbc_solve(problem, ws, des, w, rf_z_max, want_qddot=True):
                qddot=torch.empty((B, spec.model.nv), **f64) if want_qddot else None,
                status=torch.empty(B, dtype=torch.int32, device=dev),
                iters=torch.empty(B, dtype=torch.int32, device=dev),
-               active=torch.empty((B, problem.mw), dtype=torch.int64, device=dev))
-    _check(problem.lib.pnc_ihwbc_solve(problem.h, ws.h, B, _ptr(des), _ptr(w), _ptr(rf_z_max), _ptr(out['trq']),
-                                       _ptr(out['acc']), _ptr(out['rf']), _ptr(out['qddot']), _ptr(out['status']),
-                                       _ptr(out['iters']), _ptr(out['active']), _stream()), 'pnc_ihwbc_solve')
+               active=torch.empty((B, problem.mw), dtype=torch.int64, device=dev),
+               active_ref=torch.empty((B, problem.mw), dtype=torch.int64, device=dev))
+    _check(problem.lib.pnc_ihwbc_solve_ref(problem.h, ws.h, B, _ptr(des), _ptr(w), _ptr(rf_z_max), _ptr(out['trq']),
+                                           _ptr(out['acc']), _ptr(out['rf']), _ptr(out['qddot']),
+                                           _ptr(out['status']), _ptr(out['iters']), _ptr(out['active']),
+                                           _ptr(out['active_ref']), _stream()), 'pnc_ihwbc_solve_ref')
     return out
 
 

@@ -91,6 +91,41 @@ def test_update_system_matches_oracle(ctx):
             assert rel(g['frame_jdqd'][b, fi], om.link_jdqd(q, v, f)) < 1e-12
 
 
+# Decision margin of the oracle's QP solve (oracle/pnc_oracle.c: orc_last_qp_margin): the smallest
+# relative distance between the two sides of any data-dependent branch QuadProg++ took.  The measured
+# distribution is bimodal -- exact ties of redundant wrench-cone rows sit at <= 1e-13 (rounding of
+# mathematically equal slacks), everything else at >= 1e-8 -- so 1e-10 separates "the reference itself
+# picks by rounding noise" from "one well-defined path".
+TIE_MARGIN = 1e-10
+
+
+def _check_active_sets(ctx, ok, laikago_exact=True):
+    """north_star: identical QP active set.  `active_ref` (the set at the reference's own termination
+    point, QuadProg++.cc:306-312) must be IDENTICAL to the oracle's on every state whose oracle path
+    has no tie; on tied states the sets may differ only in constraints tight at the solution.
+    Returns the counts for the report."""
+    out, ref = ctx.out, ctx.ref
+    act_ref = ctx.engine.unpack_active(out['active_ref'], ctx.pb.m)
+    act_fin = ctx.engine.unpack_active(out['active'], ctx.pb.m)
+    clear = ref['margin'] > TIE_MARGIN
+    same_ref = (act_ref == ref['active']).all(1)
+    same_fin = (act_fin == ref['active']).all(1)
+    bad = np.where(ok & clear & ~same_ref)[0]
+    assert bad.size == 0, (ctx.name, 'active_ref differs on states without a tie', bad[:8].tolist(),
+                           ref['margin'][bad[:8]].tolist())
+    for b in np.where(ok & ~same_ref)[0][:200]:
+        assert _active_sets_equivalent(ctx, b, act_ref[b], ref['active'][b]), \
+            (b, np.where(act_ref[b])[0], np.where(ref['active'][b])[0])
+    for b in np.where(ok & ~same_fin)[0][:200]:
+        assert _active_sets_equivalent(ctx, b, act_fin[b], ref['active'][b]), \
+            (b, np.where(act_fin[b])[0], np.where(ref['active'][b])[0])
+    if ctx.name == 'laikago' and laikago_exact:  # point-contact cones have no redundant rows
+        assert (same_ref | ~ok).all()
+    return dict(states=int(ok.sum()), clear=int((ok & clear).sum()), clear_identical=int((ok & clear & same_ref).sum()),
+                tied=int((ok & ~clear).sum()), tied_identical=int((ok & ~clear & same_ref).sum()),
+                final_identical=int((ok & same_fin).sum()))
+
+
 def _active_sets_equivalent(ctx, b, act_gpu, act_ref):
     """Degenerate vertices (e.g. the redundant rows of the 18-row surface wrench cone) admit
     several active sets for the same solution; quadprog picks among exactly tied constraints by
@@ -119,17 +154,7 @@ def test_tick_matches_oracle(ctx):
     for k in ('trq', 'acc', 'rf', 'qddot'):
         err = per_state_rel(out[k].cpu().numpy()[ok], ref[k][ok])
         assert err.max() < RTOL, (k, err.max())
-    act = ctx.engine.unpack_active(out['active'], ctx.pb.m)
-    identical = 0
-    for b in np.where(ok)[0]:
-        same = np.array_equal(act[b], ref['active'][b])
-        identical += same
-        assert same or _active_sets_equivalent(ctx, b, act[b], ref['active'][b]), \
-            (b, np.where(act[b])[0], np.where(ref['active'][b])[0])
-    # point-contact cones have no redundant rows: the active set must be bit-identical there
-    if ctx.name == 'laikago':
-        assert identical == ok.sum()
-    assert identical >= 0.4 * ok.sum()
+    _check_active_sets(ctx, ok)
 
 
 @pytest.mark.parametrize("ctx", ROBOTS, indirect=True)
@@ -561,12 +586,8 @@ def test_large_sample_tick_parity(name, B, oracle_mod):
     for k in ('trq', 'acc', 'rf', 'qddot'):
         err = per_state_rel(out[k].cpu().numpy()[ok], ref[k][ok])
         assert err.max() < tol, (k, err.max(), int(np.argmax(err)))
-    act = c.engine.unpack_active(out['active'], c.pb.m)
-    differing = [b for b in np.where(ok)[0] if not np.array_equal(act[b], ref['active'][b])]
-    for b in differing[:200]:
-        assert _active_sets_equivalent(c, b, act[b], ref['active'][b]), (b, np.where(act[b])[0], np.where(ref['active'][b])[0])
-    if name == 'laikago':
-        assert not differing
+    counts = _check_active_sets(c, ok)
+    print("active set %s: %s" % (name, counts))
 
 
 @pytest.mark.parametrize("name", ['atlas', 'draco3'])

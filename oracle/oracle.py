@@ -43,6 +43,8 @@ def _load(fast=False):
     lib.orc_solve_quadprog.argtypes = [i32, i32, i32] + [vp] * 13
     lib.orc_wbc_tick_batch.restype = dbl
     lib.orc_wbc_tick_batch.argtypes = [vp, i32, i32] + [vp] * 17
+    lib.orc_osc_step_batch.restype = dbl
+    lib.orc_osc_step_batch.argtypes = [vp, i32, i32] + [vp] * 8
     lib.orc_wbc_tick_batch_margin.restype = dbl
     lib.orc_wbc_tick_batch_margin.argtypes = [vp, i32, i32] + [vp] * 19
     _LIBS[key] = lib
@@ -205,6 +207,15 @@ class OracleModel:
         self.lib.orc_osc_step(vp(self.h), i32(ee_frame), _p(_f64(q)), _p(_f64(v)), _p(_f64(pos_des)),
                               _p(_f64(vel_des)), _p(_f64(acc_des)), _p(_f64(kp)), _p(_f64(kd)), _p(trq), _p(qdd))
         return trq, qdd
+
+
+    def osc_step_batch(self, ee_frame, q, v, pos_des, vel_des, kp, kd):
+        """B OSC steps in a C loop -> (trq [B,nv], qddot [B,nv], seconds)."""
+        B, nv = q.shape[0], self.model.nv
+        trq, qdd = np.zeros((B, nv)), np.zeros((B, nv))
+        sec = self.lib.orc_osc_step_batch(vp(self.h), i32(ee_frame), i32(B), _p(_f64(q)), _p(_f64(v)), _p(_f64(pos_des)),
+                                          _p(_f64(vel_des)), _p(_f64(kp)), _p(_f64(kd)), _p(trq), _p(qdd))
+        return trq, qdd, sec
 
 
 class OracleProblem:

@@ -1554,3 +1554,15 @@ void orc_osc_step(const orc_model* m, int ee, const double* q, const double* v, 
     if (qddot) qddot[i] = qdd[i];
   }
 }
+
+/* B OSC steps in a plain loop (the CPU baseline of BASELINE config 1); returns wall seconds */
+double orc_osc_step_batch(const orc_model* m, int ee, int B, const double* q, const double* v, const double* pos_des,
+                          const double* vel_des, const double* kp, const double* kd, double* trq, double* qddot) {
+  const int nv = m->nv;
+  const double zero3[3] = {0, 0, 0};
+  double t0 = now_s();
+  for (int b = 0; b < B; b++)
+    orc_osc_step(m, ee, q + (size_t)b * m->nq, v + (size_t)b * nv, pos_des + 3 * (size_t)b, vel_des + 3 * (size_t)b, zero3, kp,
+                 kd, trq + (size_t)b * nv, qddot ? qddot + (size_t)b * nv : NULL);
+  return now_s() - t0;
+}

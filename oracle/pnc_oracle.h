@@ -126,6 +126,11 @@ void orc_osc_step(const orc_model* m, int ee_frame, const double* q, const doubl
                   const double* vel_des, const double* acc_des, const double* kp, const double* kd,
                   double* trq, double* qddot);
 
+/* B OSC steps in a loop: q [B,nq], v [B,nv], pos_des / vel_des [B,3]; returns wall seconds */
+double orc_osc_step_batch(const orc_model* m, int ee_frame, int B, const double* q, const double* v,
+                          const double* pos_des, const double* vel_des, const double* kp, const double* kd,
+                          double* trq, double* qddot);
+
 void orc_problem_dims(const orc_problem* p, int* nc, int* ncone, int* n, int* peq, int* mineq);
 
 #ifdef __cplusplus

@@ -55,7 +55,7 @@ class Controller:
             self._ihwbc.trq_limit = np.dot(self._sa[:, 6:], robot.joint_trq_limit)
         self._ihwbc.lambda_q_ddot = lambda_q_ddot
         self._ihwbc.lambda_rf = lambda_rf
-        self._joint_integrator = JointIntegrator(robot.n_a, controller_dt)  # :41-47
+        self._joint_integrator = JointIntegrator(robot.n_a, controller_dt, device=robot._device)  # :41-47
         self._joint_integrator.pos_cutoff_freq = pos_cutoff_freq
         self._joint_integrator.vel_cutoff_freq = vel_cutoff_freq
         self._joint_integrator.max_pos_err = max_pos_err

@@ -34,6 +34,32 @@ static int g_termination = [] {
     }                                                                                             \
   } while (0)
 
+// like CK, but runs `cleanup` first (frees a half-built handle)
+#define CKF(call, cleanup)                                                                        \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      fprintf(stderr, "pnc_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      cleanup;                                                                                    \
+      return PNC_E_CUDA;                                                                          \
+    }                                                                                             \
+  } while (0)
+
+// The stateless entry points (no handle) launch on the device that owns their first pointer.
+static int set_device_of(const void* dptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, dptr) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return PNC_E_ARG;  // not a device pointer
+  }
+  return cudaSetDevice(at.device) == cudaSuccess ? PNC_OK : PNC_E_CUDA;
+}
+#define SETDEV(ptr)                       \
+  do {                                    \
+    const int rc_ = set_device_of(ptr);   \
+    if (rc_ != PNC_OK) return rc_;        \
+  } while (0)
+
 struct pnc_model {
   int device, num_sms;
   DevModel h;
@@ -96,7 +122,7 @@ int pnc_model_create(const pnc_model_desc* dsc, int device, pnc_model** out) {
   pnc_model* m = new pnc_model();
   m->device = device;
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
+  CKF(cudaGetDeviceProperties(&prop, device), delete m);
   m->num_sms = prop.multiProcessorCount;
   DevModel& h = m->h;
   memset(&h, 0, sizeof(h));
@@ -127,8 +153,9 @@ int pnc_model_create(const pnc_model_desc* dsc, int device, pnc_model** out) {
   m->frame_parent.assign(dsc->frame_parent, dsc->frame_parent + dsc->nf);
   m->frame_R.assign(dsc->frame_R, dsc->frame_R + 9 * (size_t)dsc->nf);
   m->frame_p.assign(dsc->frame_p, dsc->frame_p + 3 * (size_t)dsc->nf);
-  CK(cudaMalloc(&m->d, sizeof(DevModel)));
-  CK(cudaMemcpy(m->d, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
+  m->d = nullptr;
+  CKF(cudaMalloc(&m->d, sizeof(DevModel)), delete m);
+  CKF(cudaMemcpy(m->d, &h, sizeof(DevModel), cudaMemcpyHostToDevice), (cudaFree(m->d), delete m));
   *out = m;
   return PNC_OK;
 }
@@ -213,8 +240,9 @@ int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* dsc, pnc_prob
   for (int i = 0; i < dsc->n_ic; i++)
     for (int j = 0; j < h.nv; j++) h.ic_jac[i][j] = dsc->ic_jac[i * h.nv + j];
   p->lay = ihwbc_layout(h);
-  CK(cudaMalloc(&p->d, sizeof(DevProblem)));
-  CK(cudaMemcpy(p->d, &h, sizeof(DevProblem), cudaMemcpyHostToDevice));
+  p->d = nullptr;
+  CKF(cudaMalloc(&p->d, sizeof(DevProblem)), delete p);
+  CKF(cudaMemcpy(p->d, &h, sizeof(DevProblem), cudaMemcpyHostToDevice), (cudaFree(p->d), delete p));
   *out = p;
   return PNC_OK;
 }
@@ -268,16 +296,18 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
   size_t total = 0, off[17];
   for (int i = 0; i < 17; i++) { off[i] = total; total += align_up(sizes[i] * sizeof(double)); }
   total += 256;  // counter
-  CK(cudaMalloc(&ws->slab, total));
-  CK(cudaMemset(ws->slab, 0, total));
+  ws->slab = nullptr; ws->dfr = nullptr;
+  CKF(cudaMalloc(&ws->slab, total), delete ws);
+  CKF(cudaMemset(ws->slab, 0, total), (cudaFree(ws->slab), delete ws));
   ws->bytes = total;
   double** dst[17] = {&ws->p.q, &ws->p.qdot, &ws->p.M, &ws->p.grav, &ws->p.cori, &ws->p.com, &ws->p.vcom,
                       &ws->p.jcom, &ws->p.jcomdot, &ws->p.jcomdot_qdot, &ws->p.fr_iso, &ws->p.fr_vel,
                       &ws->p.fr_jac, &ws->p.fr_jdqd, &ws->p.cent_ag, &ws->p.cent_hg, &ws->p.cent_ig};
   for (int i = 0; i < 17; i++) *dst[i] = reinterpret_cast<double*>(ws->slab + off[i]);
   ws->counter = reinterpret_cast<int*>(ws->slab + total - 256);
-  CK(cudaMalloc(&ws->dfr, sizeof(DevFrames)));
-  CK(cudaMemcpy(ws->dfr, &ws->hfr, sizeof(DevFrames), cudaMemcpyHostToDevice));
+  CKF(cudaMalloc(&ws->dfr, sizeof(DevFrames)), (cudaFree(ws->slab), delete ws));
+  CKF(cudaMemcpy(ws->dfr, &ws->hfr, sizeof(DevFrames), cudaMemcpyHostToDevice),
+      (cudaFree(ws->dfr), cudaFree(ws->slab), delete ws));
   *out = ws;
   return PNC_OK;
 }
@@ -521,6 +551,7 @@ int pnc_joint_integrate(int32_t B, int32_t na, const double* d_acc, const double
   if (B < 0 || na < 1 || !d_acc || !d_joint_pos || !d_vel_state || !d_pos_state || !d_pos_limit || !d_vel_limit)
     return PNC_E_ARG;
   if (B == 0) return PNC_OK;
+  SETDEV(d_acc);
   launch_joint_integrate(B, na, d_acc, d_joint_pos, d_vel_state, d_pos_state, d_pos_limit, d_vel_limit, alpha_vel,
                          alpha_pos, dt, (cudaStream_t)stream);
   CK(cudaGetLastError());
@@ -579,6 +610,7 @@ int pnc_ramp_update(int32_t B, const double* d_start_value, double target, const
                     const double* d_duration, double current_time, double* d_out, void* stream) {
   if (B < 0 || !d_start_value || !d_start_time || !d_duration || !d_out) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
+  SETDEV(d_out);
   launch_ramp_update(B, d_start_value, target, d_start_time, d_duration, current_time, d_out, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return PNC_OK;
@@ -616,6 +648,7 @@ int pnc_swing_eval(int32_t B, const double* d_rec, const double* d_start_time, c
       !d_angacc)
     return PNC_E_ARG;
   if (B == 0) return PNC_OK;
+  SETDEV(d_rec);
   launch_swing_eval(B, d_rec, d_start_time, d_swing_duration, current_time, d_pos, d_vel, d_acc, d_quat, d_angvel, d_angacc,
                     (cudaStream_t)stream);
   CK(cudaGetLastError());
@@ -640,6 +673,7 @@ int pnc_floating_base_eval(int32_t B, const double* d_rec, const double* d_start
   if (B < 0 || !d_rec || !d_start_time || !d_duration || !d_pos || !d_vel || !d_acc || !d_quat || !d_angvel || !d_angacc)
     return PNC_E_ARG;
   if (B == 0) return PNC_OK;
+  SETDEV(d_rec);
   launch_floating_base_eval(B, d_rec, d_start_time, d_duration, current_time, d_pos, d_vel, d_acc, d_quat, d_angvel,
                             d_angacc, (cudaStream_t)stream);
   CK(cudaGetLastError());
@@ -650,6 +684,7 @@ int pnc_sinusoid_eval(int32_t B, const double* d_mid, const double* d_start_time
                       double current_time, double* d_pos, double* d_vel, double* d_acc, void* stream) {
   if (B < 0 || !d_mid || !d_start_time || !amp3 || !freq3 || !d_pos || !d_vel || !d_acc) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
+  SETDEV(d_mid);
   launch_sinusoid_eval(B, d_mid, d_start_time, amp3, freq3, current_time, d_pos, d_vel, d_acc, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return PNC_OK;

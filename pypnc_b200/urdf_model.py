@@ -204,7 +204,12 @@ def build_model_from_xml(root, fixed_base, name):
     for j in root.findall('joint'):
         jn = j.get('name')
         jt = j.get('type')
-        if jt not in ('revolute', 'continuous', 'fixed'):
+        if jt == 'continuous':
+            # pinocchio maps a continuous joint to JointModelRUB* (nq = 2: cos/sin, nv = 1); the tables
+            # and kernels here assume nq = 1 per joint, so q indexing would silently diverge
+            raise NotImplementedError("joint %s: 'continuous' joints (pinocchio nq = 2) are not supported; none of "
+                                      "the reference's hot-path URDFs has one" % jn)
+        if jt not in ('revolute', 'fixed'):
             raise NotImplementedError("joint %s: type %s is not on the WBC hot path" % (jn, jt))
         joints[jn] = j
         p, c = j.find('parent').get('link'), j.find('child').get('link')

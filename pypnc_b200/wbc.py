@@ -178,7 +178,8 @@ class IHWBC:
         assert np.all((sa == 0) | (sa == 1)) and np.all(sa.sum(1) == 1), "sa must select joints (one-hot rows)"
         self._act_idx = [int(np.argmax(r)) for r in sa]
         self._trq_limit = None
-        self._lambda_q_ddot = self._lambda_rf = self._w_rf = self._w_hierarchy = 0.
+        self._lambda_q_ddot = self._lambda_rf = self._w_rf = 0.
+        self._w_hierarchy = None  # per-task weights set on the IHWBC object (ihwbc.py:76-78); None -> the tasks' own
         self._key, self._problem, self._spec = None, None, None
         self._robot = None
         self.status = self.iters = self.active = None
@@ -205,6 +206,9 @@ class IHWBC:
 
     @w_hierarchy.setter
     def w_hierarchy(self, val):
+        """Sequence of per-task weights in task_list order (floats or [B] tensors), as the controllers
+        set it (atlas_controller.py:64-69).  These are what the cost uses (ihwbc.py:171-173), not the
+        tasks' own w_hierarchy; while it is unset the tasks' weights are used."""
         self._w_hierarchy = val
 
     @w_rf.setter
@@ -219,6 +223,17 @@ class IHWBC:
 
     # ---- descriptor compilation ----------------------------------------------------------
     def compile(self, task_list, contact_list, internal_constraint_list):
+        contact_list = [] if contact_list is None else contact_list  # ihwbc.py:177,200-203: the no-contact QP
+        internal_constraint_list = [] if internal_constraint_list is None else internal_constraint_list
+        if not contact_list and internal_constraint_list:
+            # the reference's no-contact torque recovery uses Ni instead of Ni^T (ihwbc.py:349-354), a quirk
+            # no shipped controller reaches; refuse instead of silently picking one of the two
+            raise NotImplementedError("internal constraints without contacts (ihwbc.py:349-354)")
+        for ic in internal_constraint_list:
+            # ihwbc.py:134-135,287-296 add S Ji^T Lambda (Jidot qdot) to the torque-limit rows; the kernels
+            # carry no such term (it is zero for every constraint the reference ships)
+            if np.any(np.asarray(ic.jacobian_dot_q_dot) != 0.):
+                raise NotImplementedError("internal constraint with non-zero jacobian_dot_q_dot")
         robot = (task_list[0] if task_list else contact_list[0])._robot
         key = (tuple((t._task_type, t._dim, str(t._target_id), tuple(t._kp), tuple(t._kd)) for t in task_list),
                tuple((c._type, c._link_id, c._mu, c._x, c._y) for c in contact_list),
@@ -265,7 +280,8 @@ class IHWBC:
             des[:, o:o + npos] = _as_batch(t._pos_des, npos, B, dev)
             des[:, o + npos:o + npos + d['dim']] = _as_batch(t._vel_des, d['dim'], B, dev)
             des[:, o + npos + d['dim']:o + npos + 2 * d['dim']] = _as_batch(t._acc_des, d['dim'], B, dev)
-            w[:, i] = torch.as_tensor(t._w_hierarchy, dtype=torch.float64, device=dev)
+            wi = t._w_hierarchy if self._w_hierarchy is None else self._w_hierarchy[i]
+            w[:, i] = torch.as_tensor(wi, dtype=torch.float64, device=dev)
         rfz = torch.zeros((B, max(1, len(self._contacts))), dtype=torch.float64, device=dev)
         for i, c in enumerate(self._contacts):
             rfz[:, i] = torch.as_tensor(c._rf_z_max, dtype=torch.float64, device=dev)
@@ -276,6 +292,8 @@ class IHWBC:
         Per-state solver outcomes are in self.status / self.iters / self.active (bit masks)."""
         if rf_des is not None and self._w_rf != 0.:
             raise NotImplementedError("rf_des is only used with w_rf != 0")
+        if self._w_hierarchy is not None and len(self._w_hierarchy) != len(task_list):
+            raise IndexError("w_hierarchy has %d entries for %d tasks" % (len(self._w_hierarchy), len(task_list)))
         self.compile(task_list, contact_list, internal_constraint_list)
         ws = self._robot.workspace(self._spec.frames)
         des, w, rfz = self._pack()
@@ -317,10 +335,11 @@ class IHWBC:
 class JointIntegrator:
     """joint_integrator.py:6-82 on [B, n_joint] device tensors."""
 
-    def __init__(self, n_joint, dt):
+    def __init__(self, n_joint, dt, device=None):
         from . import _cabi
         self._lib = _cabi.load_library()
         self._n_joint, self._dt = n_joint, dt
+        self._device = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
         self._alpha_pos = self._alpha_vel = 0.
         self._joint_pos_limit = self._joint_vel_limit = None
         self._pos = self._vel = None
@@ -341,11 +360,11 @@ class JointIntegrator:
 
     def _set_pos_limit(self, val):
         assert val.shape[0] == self._n_joint
-        self._joint_pos_limit = torch.as_tensor(np.ascontiguousarray(val), dtype=torch.float64).cuda()
+        self._joint_pos_limit = torch.as_tensor(np.ascontiguousarray(val), dtype=torch.float64).to(self._device)
 
     def _set_vel_limit(self, val):
         assert val.shape[0] == self._n_joint
-        self._joint_vel_limit = torch.as_tensor(np.ascontiguousarray(val), dtype=torch.float64).cuda()
+        self._joint_vel_limit = torch.as_tensor(np.ascontiguousarray(val), dtype=torch.float64).to(self._device)
 
     joint_pos_limit = property(lambda s: s._joint_pos_limit, _set_pos_limit)
     joint_vel_limit = property(lambda s: s._joint_vel_limit, _set_vel_limit)
@@ -357,8 +376,12 @@ class JointIntegrator:
     def integrate(self, acc, vel, pos):
         B = acc.shape[0]
         P = lambda t: _vp(t.data_ptr())
-        engine._check(self._lib.pnc_joint_integrate(B, self._n_joint, P(acc.contiguous()), P(pos.contiguous()),
-                                                    P(self._vel), P(self._pos), P(self._joint_pos_limit),
-                                                    P(self._joint_vel_limit), self._alpha_vel, self._alpha_pos,
-                                                    self._dt, engine._stream()), 'pnc_joint_integrate')
+        acc_c, pos_c = acc.contiguous(), pos.contiguous()  # kept alive until the launch is enqueued
+        assert acc_c.device == self._vel.device == self._joint_pos_limit.device, "integrator state on another device"
+        with torch.cuda.device(acc_c.device):
+            engine._check(self._lib.pnc_joint_integrate(B, self._n_joint, P(acc_c), P(pos_c), P(self._vel),
+                                                        P(self._pos), P(self._joint_pos_limit),
+                                                        P(self._joint_vel_limit), self._alpha_vel, self._alpha_pos,
+                                                        self._dt, engine._stream()), 'pnc_joint_integrate')
+        del acc_c, pos_c
         return self._vel, self._pos

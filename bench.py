@@ -240,7 +240,7 @@ class Env:
         self.torch.cuda.synchronize()
 
 
-def run_wbc_config(env, robot, B, K, warmup, seed, same_state=False, want_e2e=True):
+def run_wbc_config(env, robot, B, K, warmup, seed, same_state=False, want_e2e=True, min_ms=0.0):
     """Times K steps of update_system + IHWBC solve on this rank's B states.  Returns a dict with the
     max-over-ranks time, per-stage times, solver stats, clocks, launches and (optionally) the end-to-end
     numbers through pnc_wbc_tick_host."""
@@ -282,6 +282,14 @@ def run_wbc_config(env, robot, B, K, warmup, seed, same_state=False, want_e2e=Tr
     for _ in range(max(3, warmup)):
         step()
     env.barrier()
+    if min_ms > 0:  # short configurations: time at least `min_ms` of work so the clock sampler sees the region
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        step()
+        t1.record(stream)
+        torch.cuda.synchronize()
+        est = sharding.max_over_ranks(t0.elapsed_time(t1), device=dev)
+        K = int(max(K, min(400, np.ceil(min_ms / max(est, 1e-3)))))
     sampler = ClockSampler(physical_gpu_index(env.local_rank))
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
@@ -305,7 +313,7 @@ def run_wbc_config(env, robot, B, K, warmup, seed, same_state=False, want_e2e=Tr
     ms_qp = sum(e[1].elapsed_time(e[2]) for e in ev) / K
     status, iters = o_status.cpu().numpy(), o_iters.cpu().numpy()
     stats = sharding.gather_stats(sharding.solver_stats(status, iters), device=dev)  # the only collective: a stats gather
-    res = dict(spec=spec, B=B, ms_total=ms_total, ms_per_step=ms_total / K, ms_dyn=ms_dyn, ms_qp=ms_qp, stats=stats,
+    res = dict(spec=spec, B=B, K=K, ms_total=ms_total, ms_per_step=ms_total / K, ms_dyn=ms_dyn, ms_qp=ms_qp, stats=stats,
                clocks=clocks, launches=int(launches), ws_gb=ws.nbytes / 1e9, mw=mw, nact=nact, nc=nc, e2e=None)
 
     # ---- end to end through the host-buffer C ABI call (pinned host memory), every timed step ----
@@ -481,8 +489,8 @@ def main():
         for key, rb, gbatch in (('config2_laikago_16k', 'laikago', 16384), ('config4_draco3_64k', 'draco3', 65536),
                                 ('config5_valkyrie_256k', 'valkyrie', 262144)):
             lo, hi = sharding.shard_range(gbatch, rank, world)
-            r = run_wbc_config(env, rb, hi - lo, Kc, args.warmup, seed=1 + rank, want_e2e=not args.no_e2e)
-            extra[key] = (rb, gbatch, Kc, r)
+            r = run_wbc_config(env, rb, hi - lo, Kc, args.warmup, seed=1 + rank, want_e2e=not args.no_e2e, min_ms=150.0)
+            extra[key] = (rb, gbatch, r['K'], r)
     osc = None
     if rank == 0 and not args.no_configs and robot == 'atlas':
         osc = run_osc_config(env, K, args.warmup)

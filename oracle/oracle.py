@@ -46,7 +46,7 @@ def _load(fast=False):
     lib.orc_osc_step_batch.restype = dbl
     lib.orc_osc_step_batch.argtypes = [vp, i32, i32] + [vp] * 8
     lib.orc_wbc_tick_batch_margin.restype = dbl
-    lib.orc_wbc_tick_batch_margin.argtypes = [vp, i32, i32] + [vp] * 19
+    lib.orc_wbc_tick_batch_margin.argtypes = [vp, i32, i32] + [vp] * 20
     _LIBS[key] = lib
     return lib
 
@@ -265,7 +265,7 @@ class OracleProblem:
         out = dict(trq=np.zeros((B, spec.nact)), acc=np.zeros((B, spec.nact)), rf=np.zeros((B, spec.nc)),
                    qddot=np.zeros((B, m.nv)), active=np.zeros((B, max(mi, 1)), dtype=np.uint8),
                    status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32), flops=np.zeros(B),
-                   margin=np.ones(B), margin_kind=np.zeros(B, dtype=np.int32))
+                   margin=np.ones(B), margin_kind=np.zeros(B, dtype=np.int32), psi_rel=np.zeros(B))
         fl = m.n_floating != 0
         a = [_f64(states[k]) if fl else None for k in ('base_pos', 'base_quat', 'base_lin_vel', 'base_ang_vel')]
         jp, jv = _f64(states['joint_pos']), _f64(states['joint_vel'])
@@ -274,7 +274,7 @@ class OracleProblem:
                                                  _p(des), _p(w), _p(rfz), _p(out['trq']), _p(out['acc']),
                                                  _p(out['rf']), _p(out['qddot']), _p(out['active']),
                                                  _p(out['status']), _p(out['iters']), _p(out['flops']),
-                                                 _p(out['margin']), _p(out['margin_kind']))
+                                                 _p(out['margin']), _p(out['margin_kind']), _p(out['psi_rel']))
         out['active'] = out['active'][:, :mi]
         out['seconds'] = sec
         return out

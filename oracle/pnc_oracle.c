@@ -831,6 +831,8 @@ static void qp_delete_constraint(double* R, double* J, int* A, double* u, int n,
  * (|d[iq:]| / |d|: decides :380 and the degeneracy test of add_constraint :597-603). */
 static __thread double g_qp_margin;
 static __thread int g_qp_margin_kind;
+static __thread double g_qp_psi_rel; /* |psi| / max|s| at the iterate the solver returned: 0 = exactly feasible;
+                                        > 0 = it stopped inside its loose bound (:306-312) with a residual violation */
 #define QP_MARGIN(val, kind)                                    \
   do {                                                          \
     const double v_ = (val);                                    \
@@ -840,6 +842,7 @@ void orc_last_qp_margin(double* margin, int* kind) {
   if (margin) *margin = g_qp_margin;
   if (kind) *kind = g_qp_margin_kind;
 }
+double orc_last_qp_psi_rel(void) { return g_qp_psi_rel; }
 
 double orc_solve_quadprog(int n, int p, int m, double* G, const double* g0, const double* CE,
                           const double* ce0, const double* CI, const double* ci0, double* x, int* A,
@@ -847,6 +850,7 @@ double orc_solve_quadprog(int n, int p, int m, double* G, const double* g0, cons
   int i, j, k, l = 0, ip, iq, iter = 0;
   g_qp_margin = 1.0;
   g_qp_margin_kind = 0;
+  g_qp_psi_rel = 0.0;
   double s_scale = 1.0;
   int mp = m + p;
   double* R = (double*)calloc((size_t)n * n, sizeof(double));
@@ -923,6 +927,7 @@ l1:
     for (i = 0; i < m; i++) s_scale = fmax(s_scale, fabs(s[i]));
     if (!(s_scale > 0.0)) s_scale = 1.0;
     if (tol > 0.0) QP_MARGIN(fabs(fabs(psi) - tol) / tol, 1);
+    g_qp_psi_rel = fabs(psi) / s_scale;
   }
   if (fabs(psi) <= m * DBL_EPSILON * c1 * c2 * 100.0) goto done;
   if (iter > 40 * (n + m)) { *status = PNC_QP_MAX_ITER; goto done; }
@@ -1449,6 +1454,7 @@ void orc_wbc_tick(const orc_problem* p, const double* bp, const double* bq, cons
   if (info) {
     info->status = status; info->iters = iters; info->iq = iq; info->qp_flops = Fqp; info->asm_flops = Fasm;
     orc_last_qp_margin(&info->margin, &info->margin_kind);
+    info->psi_rel = orc_last_qp_psi_rel();
   }
   free(CE); free(ce0); free(CI); free(ci0); free(x); free(A); free(u);
   asm_free(&a);
@@ -1469,6 +1475,7 @@ typedef struct {
   int *status, *iters;
   double* margin;
   int* margin_kind;
+  double* psi_rel;
 } shard_t;
 
 static void* shard_run(void* arg) {
@@ -1496,6 +1503,7 @@ static void* shard_run(void* arg) {
     if (s->flops) s->flops[i] = info.qp_flops + info.asm_flops;
     if (s->margin) s->margin[i] = info.margin;
     if (s->margin_kind) s->margin_kind[i] = info.margin_kind;
+    if (s->psi_rel) s->psi_rel[i] = info.psi_rel;
   }
   return NULL;
 }
@@ -1506,14 +1514,14 @@ double orc_wbc_tick_batch(const orc_problem* p, int B, int nthreads, const doubl
                           double* rf, double* qddot, unsigned char* active, int* status, int* iters,
                           double* flops) {
   return orc_wbc_tick_batch_margin(p, B, nthreads, bp, bq, blv, bav, jp, jv, des, w, rfz, trq, acc, rf, qddot, active,
-                                   status, iters, flops, NULL, NULL);
+                                   status, iters, flops, NULL, NULL, NULL);
 }
 
 double orc_wbc_tick_batch_margin(const orc_problem* p, int B, int nthreads, const double* bp, const double* bq,
                                  const double* blv, const double* bav, const double* jp, const double* jv,
                                  const double* des, const double* w, const double* rfz, double* trq, double* acc,
                                  double* rf, double* qddot, unsigned char* active, int* status, int* iters,
-                                 double* flops, double* margin, int* margin_kind) {
+                                 double* flops, double* margin, int* margin_kind, double* psi_rel) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   shard_t sh[256];
@@ -1522,7 +1530,7 @@ double orc_wbc_tick_batch_margin(const orc_problem* p, int B, int nthreads, cons
   for (int t = 0; t < nthreads; t++) {
     shard_t s = {p, (int)((long long)B * t / nthreads), (int)((long long)B * (t + 1) / nthreads),
                  bp, bq, blv, bav, jp, jv, des, w, rfz, trq, acc, rf, qddot, flops, active, status, iters,
-                 margin, margin_kind};
+                 margin, margin_kind, psi_rel};
     sh[t] = s;
     if (nthreads > 1) pthread_create(&th[t], NULL, shard_run, &sh[t]);
   }

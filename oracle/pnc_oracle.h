@@ -77,11 +77,13 @@ typedef struct {
   double qp_flops, asm_flops;
   double margin;    /* decision margin of the QP solve, see orc_last_qp_margin */
   int margin_kind;
+  double psi_rel;   /* summed violation / max |slack| left at the returned iterate (0: exactly feasible) */
 } orc_tick_info;
 
 /* Smallest relative distance between the two sides of any data-dependent branch the last
  * orc_solve_quadprog call on this thread took (1 = never close), and which branch kind it was. */
 void orc_last_qp_margin(double* margin, int* kind);
+double orc_last_qp_psi_rel(void);
 
 /* BasicTask.update_jacobian + update_cmd of task `it` (basic_task.py:25-137) */
 void orc_task_eval(const orc_problem* p, const double* q, const double* v, const double* des, int it,
@@ -119,7 +121,7 @@ double orc_wbc_tick_batch_margin(const orc_problem* p, int B, int nthreads, cons
                                  const double* joint_pos, const double* joint_vel, const double* des,
                                  const double* w, const double* rf_z_max, double* trq, double* acc, double* rf,
                                  double* qddot, unsigned char* active, int* status, int* iters, double* flops,
-                                 double* margin, int* margin_kind);
+                                 double* margin, int* margin_kind, double* psi_rel);
 
 /* manipulator_interface.py:77-114 OSC step on a fixed-base arm: returns trq[na] */
 void orc_osc_step(const orc_model* m, int ee_frame, const double* q, const double* v, const double* pos_des,

@@ -687,11 +687,17 @@ FULL = [('atlas', 65536, 1), ('laikago', 16384, 1), ('draco3', 65536, 1), ('valk
 @pytest.mark.parametrize("name,B,seed", FULL)
 def test_full_batch_oracle_parity(name, B, seed, oracle_mod):
     """Every state of the BASELINE.json batches (config 2: Laikago 16 K, 3: Atlas 64 K, 4: Draco3 64 K,
-    5: Valkyrie 256 K; bench seed) against the oracle run on all host threads: same status, and
-    trq / acc / rf within 1e-9 relative on every state whose oracle path has no exact tie.  On tied
-    states (redundant wrench-cone rows, see TIE_MARGIN) the reference itself picks among equal slacks
-    by rounding noise and then stops at its loose bound (QuadProg++.cc:306-312, |psi| <= 1e-4..1e-3), so
-    its own answer is only defined to ~1e-6 there: those are held to 1e-5 and counted."""
+    5: Valkyrie 256 K; bench seed) against the oracle run on all host threads: same status, identical
+    active set and trq / acc / rf within 1e-9 relative on every state whose oracle path is well defined.
+
+    Two things make the REFERENCE's own answer ill-defined at the 1e-9 level, and both are measured by the
+    oracle rather than assumed: (a) exact ties between redundant wrench-cone rows (decision margin <=
+    TIE_MARGIN: the reference picks by rounding noise, so its path is not reproducible), (b) a residual
+    violation at the returned iterate (psi_rel > 0: QuadProg++.cc:306-312 stops once the summed violation
+    is below 1e-4..1e-3, i.e. up to ~1e-6 short of the optimum).  With PNC_TERM_REFERENCE the kernels stop
+    where QuadProg++ stops, so (b) cancels and only tied states may differ; with the default refined
+    termination the kernels return the optimum, so states of kind (b) differ by that residual instead.
+    Those states are held to 1e-5 and counted; every other state to 1e-9."""
     import torch
     from pypnc_b200 import engine
     spec = robots.PROBLEMS[name]()
@@ -703,28 +709,35 @@ def test_full_batch_oracle_parity(name, B, seed, oracle_mod):
     ws.update_system(*d_st)
     des, w, rfz = robots.synth_desireds(name, spec, st, engine.task_actuals_from_workspace(spec, ws), seed=seed)
     d_in = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (des, w, rfz)]
-    out = engine.ihwbc_solve(pb, ws, *d_in)
-    torch.cuda.synchronize()
     op = oracle_mod.OracleProblem(spec, fast=False)
     ref = op.tick_batch(st, des, w, rfz, nthreads=os.cpu_count() or 1)
-    status = out['status'].cpu().numpy()
-    assert np.array_equal(status, ref['status'])
-    ok = status == 0
-    assert ok.mean() > 0.999
     clear = ref['margin'] > TIE_MARGIN
-    worst_clear = worst_tied = 0.0
-    n_tied_over = 0
-    for k in ('trq', 'acc', 'rf'):
-        err = per_state_rel(out[k].cpu().numpy(), ref[k])
-        err[~ok] = 0.0
-        worst_clear = max(worst_clear, float(err[clear].max()))
-        worst_tied = max(worst_tied, float(err[~clear].max()) if (~clear).any() else 0.0)
-        n_tied_over = max(n_tied_over, int((err[~clear] > RTOL).sum()))
-    a_ref = engine.unpack_active(out['active_ref'], pb.m)
-    same = (a_ref == ref['active']).all(1)
-    print("full batch %s B=%d: clear %d (worst %.2e, identical active set %d), tied %d (worst %.2e, %d over 1e-9, "
-          "identical %d)" % (name, B, int((ok & clear).sum()), worst_clear, int((ok & clear & same).sum()),
-                             int((ok & ~clear).sum()), worst_tied, n_tied_over, int((ok & ~clear & same).sum())))
-    assert worst_clear < (5e-9 if spec.n_ic else RTOL), worst_clear
-    assert worst_tied < 1e-5, worst_tied
-    assert (same | ~clear | ~ok).all(), "active_ref differs on a state without a tie"
+    exact = ref['psi_rel'] <= 1e-11  # the oracle's returned iterate is feasible to rounding
+    tol = 5e-9 if spec.n_ic else RTOL
+    try:
+        for mode, label in ((engine.TERM_REFINED, 'refined'), (engine.TERM_REFERENCE, 'reference')):
+            engine.set_termination(mode)
+            out = engine.ihwbc_solve(pb, ws, *d_in)
+            torch.cuda.synchronize()
+            status = out['status'].cpu().numpy()
+            assert np.array_equal(status, ref['status'])
+            ok = status == 0
+            assert ok.mean() > 0.999
+            err = np.zeros(B)
+            for k in ('trq', 'acc', 'rf'):
+                err = np.maximum(err, per_state_rel(out[k].cpu().numpy(), ref[k]))
+            err[~ok] = 0.0
+            strict = clear & (exact if mode == engine.TERM_REFINED else True)
+            a_ref = engine.unpack_active(out['active_ref'], pb.m)
+            same = (a_ref == ref['active']).all(1)
+            print("FULLBATCH %s B=%d %s: strict %d worst %.2e | other %d worst %.2e, %d over 1e-9 | tied %d, loose-stop %d | "
+                  "active_ref identical: clear %d/%d tied %d/%d" %
+                  (name, B, label, int((ok & strict).sum()), float(err[strict].max()), int((ok & ~strict).sum()),
+                   float(err[~strict].max()) if (~strict).any() else 0.0, int((err[~strict] > RTOL).sum()),
+                   int((ok & ~clear).sum()), int((ok & ~exact).sum()), int((ok & clear & same).sum()), int((ok & clear).sum()),
+                   int((ok & ~clear & same).sum()), int((ok & ~clear).sum())))
+            assert float(err[strict].max()) < tol, (label, float(err[strict].max()), int(np.argmax(np.where(strict, err, 0))))
+            assert not (~strict).any() or float(err[~strict].max()) < 1e-5, (label, float(err[~strict].max()))
+            assert (same | ~clear | ~ok).all(), "active_ref differs on a state without a tie"
+    finally:
+        engine.set_termination(engine.TERM_REFINED)

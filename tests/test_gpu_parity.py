@@ -96,6 +96,24 @@ def test_update_system_matches_oracle(ctx):
             assert rel(g['frame_jdqd'][b, fi], om.link_jdqd(q, v, f)) < 1e-12
 
 
+def referee_settles(op, spec, st, des, w, rfz, ref, out_np, idxs, bar=RTOL):
+    """For the states `idxs` where the CUDA path and the fp64 oracle differ by more than the bar: solve the
+    state in 50-digit arithmetic (tests/hp_referee.py) and require the CUDA result to be within the bar of
+    THAT, or at least as close to it as the oracle is.  Returns [(state, gpu_vs_exact, oracle_vs_exact)]."""
+    from tests import hp_referee
+    res = []
+    for b in idxs:
+        hp = hp_referee.solve_state(op, spec, {k: st[k][b] for k in KEYS}, des[b], w[b], rfz[b], ref['active'][b])
+        eg = eo = 0.0
+        for k in ('trq', 'acc', 'rf'):
+            den = max(float(np.abs(hp[k]).max()), 1e-6 * float(np.abs(ref[k]).max()), 1e-300)
+            eg = max(eg, float(np.abs(out_np[k][b] - hp[k]).max()) / den)
+            eo = max(eo, float(np.abs(ref[k][b] - hp[k]).max()) / den)
+        res.append((int(b), eg, eo))
+        assert eg < bar or eg <= eo, "state %d: CUDA %.2e from the exact solution, oracle %.2e" % (b, eg, eo)
+    return res
+
+
 # Decision margin of the oracle's QP solve (oracle/pnc_oracle.c: orc_last_qp_margin): the smallest
 # relative distance between the two sides of any data-dependent branch QuadProg++ took.  The measured
 # distribution is bimodal -- exact ties of redundant wrench-cone rows sit at <= 1e-13 (rounding of
@@ -583,14 +601,21 @@ def test_large_sample_tick_parity(name, B, oracle_mod):
     assert np.array_equal(status, ref['status'])
     ok = status == 0
     assert ok.sum() >= 0.9 * B
-    # Robots with an internal constraint go through two pseudo-inverses (ihwbc.py:130-138) that the
-    # kernel applies as Cholesky solves and the oracle as the reference's explicit pinv products:
-    # both carry cond(M) * eps of rounding, and over a thousand states the worst pair differs by
-    # 1.2e-9 (measured; 5e-10 on the 96-state set, which keeps the 1e-9 bar).  5e-9 here.
-    tol = 5e-9 if c.spec.n_ic else RTOL
+    # Both sides carry cond(G) * eps of rounding (and, with an internal constraint, that of the two
+    # pseudo-inverses of ihwbc.py:130-138, which the kernel applies as Cholesky solves and the oracle as the
+    # reference's explicit pinv products).  Where the pair differs by more than 1e-9 the 50-digit referee
+    # decides: the CUDA result must be within 1e-9 of the exact solution or closer to it than the oracle.
+    out_np = {k: out[k].cpu().numpy() for k in ('trq', 'acc', 'rf', 'qddot')}
+    err = np.zeros(B)
     for k in ('trq', 'acc', 'rf', 'qddot'):
-        err = per_state_rel(out[k].cpu().numpy()[ok], ref[k][ok])
-        assert err.max() < tol, (k, err.max(), int(np.argmax(err)))
+        err = np.maximum(err, per_state_rel(out_np[k], ref[k]))
+    err[~ok] = 0.0
+    loose = ref['psi_rel'] > 1e-11  # the oracle stopped short of the optimum (QuadProg++.cc:306-312)
+    assert err[~loose].max() < 1e-8 and err.max() < 1e-5, (err.max(), int(np.argmax(err)))
+    over = np.where((err > RTOL) & ~loose)[0]
+    assert over.size <= max(4, B // 200), over.size
+    settled = referee_settles(c.op, c.spec, c.st, c.des, c.w, c.rfz, ref, out_np, over[:12])
+    print("large sample %s: worst %.2e, %d over 1e-9, referee %s" % (name, err.max(), over.size, settled))
     counts = _check_active_sets(c, ok)
     print("active set %s: %s" % (name, counts))
 
@@ -637,8 +662,7 @@ def test_controller_get_command(name, oracle_mod):
     trq = torch.stack([cmd['joint_trq'][k] for k in names], dim=1).cpu().numpy()
     ok = ctx.ref['status'] == 0
     act = np.array(spec.act_idx) - 6
-    tol = 5e-9 if spec.n_ic else RTOL
-    assert per_state_rel(trq[ok][:, act], ctx.ref['trq'][ok]).max() < tol
+    assert per_state_rel(trq[ok][:, act], ctx.ref['trq'][ok]).max() < RTOL
     passive_cols = [i for i in range(robot.n_a) if i not in set(act.tolist())]
     assert len(passive_cols) == len(passive) and np.all(trq[:, passive_cols] == 0.0)
     # first tick of the integrator (joint_integrator.py:73-82): vel = alpha_v-filtered 0 + acc dt, clipped
@@ -713,7 +737,6 @@ def test_full_batch_oracle_parity(name, B, seed, oracle_mod):
     ref = op.tick_batch(st, des, w, rfz, nthreads=os.cpu_count() or 1)
     clear = ref['margin'] > TIE_MARGIN
     exact = ref['psi_rel'] <= 1e-11  # the oracle's returned iterate is feasible to rounding
-    tol = 5e-9 if spec.n_ic else RTOL
     try:
         for mode, label in ((engine.TERM_REFINED, 'refined'), (engine.TERM_REFERENCE, 'reference')):
             engine.set_termination(mode)
@@ -736,7 +759,15 @@ def test_full_batch_oracle_parity(name, B, seed, oracle_mod):
                    float(err[~strict].max()) if (~strict).any() else 0.0, int((err[~strict] > RTOL).sum()),
                    int((ok & ~clear).sum()), int((ok & ~exact).sum()), int((ok & clear & same).sum()), int((ok & clear).sum()),
                    int((ok & ~clear & same).sum()), int((ok & ~clear).sum())))
-            assert float(err[strict].max()) < tol, (label, float(err[strict].max()), int(np.argmax(np.where(strict, err, 0))))
+            # strict states: 1e-9, or -- for the handful where fp64 conditioning puts the pair further apart --
+            # the 50-digit referee must find the CUDA result at least as close to the exact solution
+            assert float(err[strict].max()) < 1e-8, (label, float(err[strict].max()), int(np.argmax(np.where(strict, err, 0))))
+            over = np.where(strict & (err > RTOL))[0]
+            assert over.size <= max(4, B // 2000), (label, over.size)
+            if over.size:
+                out_np = {k: out[k].cpu().numpy() for k in ('trq', 'acc', 'rf')}
+                print("FULLBATCH %s %s referee (state, cuda vs exact, oracle vs exact): %s" %
+                      (name, label, referee_settles(op, spec, st, des, w, rfz, ref, out_np, over[:8])))
             assert not (~strict).any() or float(err[~strict].max()) < 1e-5, (label, float(err[~strict].max()))
             assert (same | ~clear | ~ok).all(), "active_ref differs on a state without a tie"
     finally:

@@ -97,7 +97,7 @@ struct pnc_workspace {
   double* task_slab;
   int task_rows;
   double* setup_slab;
-  int setup_stride;
+  int setup_stride, setup_shape;
   // staging buffers of pnc_wbc_tick_host
   char* stage;
   size_t stage_bytes;
@@ -278,7 +278,7 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
   ws->m = m; ws->device = m->device; ws->cap = capacity; ws->nfr = nframes;
   ws->ic_slab = nullptr; ws->ic_bytes = 0; ws->ic_nc = ws->ic_nact = 0;
   ws->task_slab = nullptr; ws->task_rows = 0;
-  ws->setup_slab = nullptr; ws->setup_stride = 0;
+  ws->setup_slab = nullptr; ws->setup_stride = 0; ws->setup_shape = 0;
   ws->stage = nullptr; ws->stage_bytes = 0; ws->tick_init = false;
   memset(&ws->hfr, 0, sizeof(ws->hfr));
   ws->hfr.nfr = nframes;
@@ -415,10 +415,14 @@ static int ensure_task_buf(pnc_workspace* ws, const pnc_problem* p) {
 
 static int ensure_setup_buf(pnc_workspace* ws, const pnc_problem* p) {
   const int rec = reg_setup_record_doubles(p->h);
-  if (ws->setup_slab && ws->setup_stride == rec) return PNC_OK;
+  const int shape = reg_shape_id(p->h);
+  if (ws->setup_slab && ws->setup_stride == rec && ws->setup_shape == shape) return PNC_OK;
   if (ws->setup_slab) { cudaFree(ws->setup_slab); ws->setup_slab = nullptr; }
   CK(cudaMalloc(&ws->setup_slab, (size_t)ws->cap * rec * sizeof(double)));
+  // the setup kernel only writes the live part of each record (padding columns and unused lanes stay zero)
+  CK(cudaMemset(ws->setup_slab, 0, (size_t)ws->cap * rec * sizeof(double)));
   ws->setup_stride = rec;
+  ws->setup_shape = shape;
   return PNC_OK;
 }
 

@@ -1,36 +1,47 @@
-// ihwbc_reg.cu -- the IHWBC solve with the active-set operator J = L^-T Q held in REGISTERS.
+// ihwbc_reg.cu -- the IHWBC solve with the active-set operator held in REGISTERS.
 //
 // Same algorithm and reference mapping as ihwbc.cu (IHWBC.solve pnc/wbc/ihwbc/ihwbc.py:90-379,
 // Goldfarb-Idnani as in external_source/Goldfarb/QuadProg++.cc:115-502, Householder instead of
 // the Givens sweep when a constraint is added); what changes is where the data lives and how
 // much code the loop is:
 //
-//   * one robot state per warp; lane l owns row l of the n x n matrix J (n = nv + nc <= 48) in
-//     registers, rows 32.. are split over lane pairs (half a row each) -- 72 doubles per lane
-//     for Atlas.  z = J2 d2 and the rank-1 Householder update are pure register FMAs against
-//     vectors broadcast from shared memory (LDS.128, one wavefront per two FMAs);
-//   * d = J^T n+ goes through a 6-row scratch tile in shared memory: one pass for a wrench-cone
-//     normal (3 or 6 non-zeros), n/6 passes for a dense normal (equalities, torque limits);
-//   * the Hessian, its Cholesky factor and L^-T are built once per state in shared memory with
-//     compact loops, then the rows move into registers;
+//   * k_ihwbc_setup (one state per warp, shared memory, high occupancy) builds the Hessian, its
+//     Cholesky factor, J = L^-T and the unconstrained minimiser, and then adds ALL the equality
+//     constraints at once while J is still triangular (QuadProg++.cc:232-272 adds them one by one):
+//     a Householder QR of D = J^T CE (n x p, in registers, lanes = rows) gives the reflectors, the
+//     rows of J Q are formed streaming (lane = row, reflectors broadcast from shared memory) and
+//     written to the per-state record, and x moves to the equality-constrained minimiser
+//     x0 - J1 R^-T (CE^T x0 + ce0).  Only the null-space block Z = (J Q)[:, p:] (n x (n - p)) is
+//     kept: the first p columns of J and the first p rows of R only ever feed the multipliers of
+//     the equalities, which nothing reads;
+//   * k_ihwbc_reg runs the inequality iterations with Z in registers: lane l owns row l of Z
+//     (n = nv + nc <= 48 rows, n - p columns), rows 32.. are split over lane pairs (half a row
+//     each) -- 66 doubles per lane for Atlas.  z = Z2 d2 and the rank-1 Householder update are
+//     pure register FMAs against vectors broadcast from shared memory (LDS.128, one wavefront per
+//     two FMAs);
+//   * d = Z^T n+ goes through a 6-row scratch tile in shared memory: one pass for a wrench-cone
+//     normal (3 or 6 non-zeros), n/6 passes for a dense normal (torque limits);
 //   * the kernel is instruction-fetch sensitive (few warps per SM, each walking its own path),
-//     so every routine of the active-set loop exists at exactly one call site -- equalities run
-//     through the same step code as inequalities -- and the only unrolled code is what register
-//     indexing forces.  Dynamic column indices (iq, the Givens pairs of a dropped constraint) are
-//     warp-uniform and go through switch statements (jump tables), never local memory.
+//     so every routine of the active-set loop exists at exactly one call site and the only
+//     unrolled code is what register indexing forces.  Dynamic column indices (iq, the Givens
+//     pairs of a dropped constraint) are warp-uniform and go through switch statements (jump
+//     tables), never local memory.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "ihwbc_common.cuh"
 
 namespace pnc {
 
-template <int NV_, int NC_>
+template <int NV_, int NC_, int PE_>
 struct RCfg {
-  static constexpr int NV = NV_, NC = NC_, N = NV_ + NC_;
+  static constexpr int NV = NV_, NC = NC_, PE = PE_, N = NV_ + NC_;
+  static constexpr int NCOL = N - PE_;                        // columns of the null-space block Z
   static constexpr bool EXT = N > 32;                         // rows 32.. live in lane pairs
   static constexpr int E = EXT ? N - 32 : 0;
-  static constexpr int HW = EXT ? ((N + 3) / 4) * 2 : 0;      // half-row width (even)
-  static constexpr int NP = EXT ? 2 * HW : ((N + 1) & ~1);    // padded vector length (even)
+  static constexpr int HW = EXT ? ((NCOL + 3) / 4) * 2 : 0;   // half-row width in columns (even)
+  static constexpr int NPC = EXT ? 2 * HW : ((NCOL + 1) & ~1);  // padded column count (even)
+  static constexpr int NP = (N + 1) & ~1;                     // padded length of a row-space vector (x, z, n+)
   static constexpr int NB = HW > 0 ? HW : 2;
   static constexpr int ldv_() { int l = (NV_ + 1) & ~1; while ((l & 15) != 6) l += 2; return l; }
   static constexpr int LDV = ldv_();                          // pitch of the nv x nv block: even, 6 (mod 16) ->
@@ -38,46 +49,43 @@ struct RCfg {
   static constexpr int EV = NV_ > 32 ? NV_ - 32 : 0;          // Hessian rows beyond 32
   static constexpr int EVP = EV <= 1 ? 1 : (EV <= 2 ? 2 : (EV <= 4 ? 4 : 8));
   static constexpr int LPR = 32 / EVP;                        // lanes cooperating on one such row in the Cholesky
-  static constexpr int LDT = NP + 2;                          // pitch of the d scratch tile
-  static constexpr int PMAX = 10;                             // equality rows the record holds
+  static constexpr int LDT = NPC + 2;                         // pitch of the d scratch tile
   static_assert(E <= 16, "rows beyond 32 must fit one lane pair each");
-  static_assert(N <= 64, "n too large for the register kernel");
+  static_assert(N <= 64 && (PE_ & 1) == 0 && PE_ <= 8, "shape not supported by the register kernel");
 };
 
 // Compile-time shared-memory layout of the active-set kernel (doubles).  NU = wrench-cone rows,
 // NT = torque-limit rows (0 without torque limits).  Every array sits at an immediate offset from
 // the shared-memory base: no address registers, nothing to rematerialise under the register
-// pressure of the resident J.  S = R^-1 is capped at RC = 32 columns (active constraints incl.
-// equalities); a state that would need more is handed to the generic kernel (status OVERFLOW).
-template <int NV_, int NC_, int NU_, int NT_>
-struct MCfg : RCfg<NV_, NC_> {
-  using R = RCfg<NV_, NC_>;
+// pressure of the resident Z.  S = R^-1 is capped at RC columns (active inequalities); a state
+// that would need more is handed to the generic kernel (status OVERFLOW).
+template <int NV_, int NC_, int NU_, int NT_, int PE_>
+struct MCfg : RCfg<NV_, NC_, PE_> {
+  using R = RCfg<NV_, NC_, PE_>;
   static constexpr int NU = NU_, NT = NT_, M = NU_ + 2 * NT_;
-  static constexpr int RC = R::N < 32 ? R::N : 32;
+  static constexpr int RC = R::NCOL < 26 ? R::NCOL : 26;
   static constexpr int RSZ = (RC * (RC + 3) / 2 + 1) & ~1;
+  static constexpr int RV = (RC + 3) & ~1;  // length of r, u, uold
   static constexpr int lda_() { int l = R::NP; while ((l & 15) != 2) l += 2; return l; }
   static constexpr int LDA = lda_();  // torque rows: LDS.128 by row is conflict free at 2 (mod 16)
   static constexpr int ORT = 0, OT = ORT + RSZ, OAR = OT + 6 * R::LDT, OA0 = OAR + NT * LDA, OUF = OA0 + ((3 * NT + 1) & ~1),
                        OUFV = OUF + (NU > 0 ? NU : 1) * 6, OX = OUFV + (((NU > 0 ? NU : 1) + 1) & ~1), OZ = OX + R::NP,
-                       ODV = OZ + R::NP, ODM = ODV + R::NP, OVM = ODM + R::NP, ONP = OVM + R::NP, ORR = ONP + R::NP + 6 /* zero pad: the d tile reads np six at a time */,
-                       OU = ORR + R::NP + 2, OXOLD = OU + R::NP + 2, OUOLD = OXOLD + R::NP, OXACC = OUOLD + R::NP + 2,
+                       ODV = OZ + R::NP, ODM = ODV + R::NPC, ONP = ODM + R::NPC, ORR = ONP + R::NP + 6 /* zero pad: the d tile reads np six at a time */,
+                       OU = ORR + RV, OXOLD = OU + RV, OUOLD = OXOLD + R::NP, OXACC = OUOLD + RV,
                        OSL = OXACC + R::NP, OINT = OSL + (((M > 0 ? M : 1) + 1) & ~1),
-                       SMEM_DOUBLES = (OINT + (((3 * (R::N + 2) + 1) & ~1) + 2 * NU) / 2 + 2) & ~1;  // A, Aold, Aacc, cone-row table
-  static_assert(64 + R::PMAX * R::NP <= RSZ || R::N < 20, "equality block must fit behind the first S columns");
+                       SMEM_DOUBLES = (OINT + (((3 * (RC + 2) + 1) & ~1) + 2 * NU) / 2 + 2) & ~1;  // A, Aold, Aacc, cone-row table
+  static_assert(6 * R::LDT >= 3 * RC, "rotation table must fit the scratch tile");
   // ---- per-state HBM record (doubles): written by k_ihwbc_setup, consumed by k_ihwbc_reg, whose
   //      result goes back into it for k_ihwbc_finish.  Everything the active-set kernel needs is
   //      here in the layout it is used in, so that kernel holds no staging code at all ----
   static constexpr int IMG = OX - OAR;                      // shared-memory image: Ar, ci0 of the torque rows, Uf, uf
-  static constexpr int RJ = 0;                              // J rows as register chunks: [NP/2][32 lanes][2]
-  static constexpr int RJB = RJ + 32 * R::NP;               // half rows 32..: [NB/2][32 lanes][2]
-  static constexpr int RX = RJB + (R::EXT ? 32 * R::NB : 0);  // x0
-  static constexpr int RD = RX + R::NP;                     // D = J^T CE^T, one row per equality
-  static constexpr int RE = RD + R::PMAX * R::NP;           // equality normals
-  static constexpr int RE0 = RE + R::PMAX * R::NP;          // equality offsets
-  static constexpr int RS = RE0 + ((R::PMAX + 1) & ~1);     // c1, c2, status, jrf
+  static constexpr int RJ = 0;                              // rows of Z as register chunks: [NPC/2][32 lanes][2]
+  static constexpr int RJB = RJ + 32 * R::NPC;              // half rows 32..: [NB/2][32 lanes][2]
+  static constexpr int RX = RJB + (R::EXT ? 32 * R::NB : 0);  // x at the equality-constrained minimiser
+  static constexpr int RS = RX + R::NP;                     // c1, c2, status, R_norm
   static constexpr int RI = RS + 4;                         // the image
-  static constexpr int RO = RI + ((IMG + 1) & ~1);          // result: x[NP], then ints iq, iter, status, A[N+2], iq_ref, Aref[N+2]
-  static constexpr int ROI = 2 * (R::N + 2) + 4;            // ints of the result
+  static constexpr int RO = RI + ((IMG + 1) & ~1);          // result: x[NP], then ints iq, iter, status, A[RC+2], iq_ref, Aref[RC+2]
+  static constexpr int ROI = 2 * (RC + 2) + 4;              // ints of the result
   static constexpr int RT = (RO + R::NP + (ROI + 1) / 2 + 1) & ~1;  // joint torques (robots with torque-limit rows)
   static constexpr int REC = RT + (NT > 0 ? 32 : 0);
   static_assert((OAR & 1) == 0 && (IMG & 1) == 0, "image is copied in 16-byte pieces");
@@ -209,25 +217,27 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min
   L.odm = o; o += C::NP;
   L.odl = o; o += C::NP;
   if (o - L.om6 < ((6 * C::NV + 1) & ~1)) o = L.om6 + ((6 * C::NV + 1) & ~1);
+  // ... and once D sits in registers, the Householder vectors of its QR ([row][reflector]) and their
+  // Gram matrix take the same place
+  if (o - L.om6 < ((C::N * C::PE + C::PE * C::PE + 4 * C::PE + 1) & ~1)) o = L.om6 + ((C::N * C::PE + C::PE * C::PE + 4 * C::PE + 1) & ~1);
   L.ozv = o; o += C::NP;  // x0 stays live until the record is written
-  L.oD = 0;  // D goes straight to the record in HBM (coalesced by construction): no shared-memory copy
+  L.oD = 0;
   if (o < min_doubles) o = min_doubles;  // the image of the active-set kernel's arrays is assembled here at the end
   L.ojc = o; o += C::NC > 0 ? C::NC : 1;  // row pointers of Jc Ni, behind the image: they are used while it is built
   L.per_state = (o + 1) & ~1;
   return L;
 }
 
-template <int NV, int NC, int NU, int NT>
+template <int NV, int NC, int NU, int NT, int PE>
 __global__ void __launch_bounds__(32)
 k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, SetupLayout SL, WsPtrs ws, FrameMap fm,
               int nfr, int B, SolveIO io, double* __restrict__ rec_all, int* __restrict__ counter) {
-  using C = MCfg<NV, NC, NU, NT>;
-  constexpr int N = C::N, NP = C::NP, LDV = C::LDV, HW = C::HW, NB = C::NB, LDA = C::LDA, E = C::E;
+  using C = MCfg<NV, NC, NU, NT, PE>;
+  constexpr int N = C::N, NP = C::NP, LDV = C::LDV, HW = C::HW, LDA = C::LDA;
   constexpr bool EXT = C::EXT;
   extern __shared__ __align__(16) double smem[];
   const DevProblem& G = *gp;
   const int lane = threadIdx.x;
-  const int p = P.p;
   const bool has_ic = P.n_ic > 0;
   double* Gm = smem + SL.oG;
   double* Jd = smem + SL.oJd;
@@ -247,8 +257,8 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     if (si >= B) break;
     const size_t s = (size_t)si;
     double* rec = rec_all + s * C::REC;
-    double* Dt = rec + C::RD;  // equality normals in the J basis, written in place
     int status = PNC_QP_OK;
+    double R_norm = 1.0;
     if (has_ic && ws.ic_status[s] != 0) status = PNC_QP_EQ_DEPENDENT;
     const double* Mg = ws.M + s * NV * NV;
     // rows of Jc Ni: the pointer of each row is looked up once per state (contact table, frame
@@ -506,13 +516,17 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         for (int j = k; j < NV; j++) acc += Gm[k * LDV + j] * dm[j];
         xs[k] = -acc;
       }
-      // ---- equality normals in the J basis, all at once while J = L^-T is still triangular in
-      //      shared memory: D[i] = J^T ce_i.  The active-set loop then never needs the dense
-      //      d = J^T n+ product for an equality: it reads D[i] and keeps the later rows current
-      //      with the Householder reflection of each added equality ----
+      // ---- all p equality constraints at once (QuadProg++.cc:232-272 adds them one by one), while
+      //      J = L^-T is still triangular in shared memory.  D = J^T CE (n x p) is built in registers,
+      //      lanes = rows (row j of D in lane j & 31, slot j >> 5): D[j][i] = sum_{k<=j} J[k][j] ce_i[k]
+      //      for j < nv, -jrf (Jc Ni)[j-nv][i] for the reaction-force rows of the floating-base
+      //      equalities, 0 for those of the internal-constraint rows ----
+      double dq[2][PE];
+      double* Vs = smem + SL.om6;            // Householder vectors of the QR, [N][PE] (over m6 once it is dead)
+      double* Gs = Vs + N * PE;              // their Gram matrix, [PE][PE]
+      double* Bs = Gs + PE * PE;             // beta_k
+      double* Ys = Bs + PE;                  // y = R^-T (CE^T x0 + ce0)
       {
-        // floating-base rows i < 6: D[i][j] = sum_{k<=j} J[k][j] M[i][k]; the six rows are staged in
-        // shared memory first (Jd is dead), one column j per lane, six accumulators
         double* m6 = smem + SL.om6;
         __syncwarp();  // x0 is done with the vectors m6 overlays
 #pragma unroll 1
@@ -526,97 +540,212 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         }
         __syncwarp();
 #pragma unroll
-        for (int pass = 0; pass < (NV > 32 ? 2 : 1); pass++) {
+        for (int pass = 0; pass < 2; pass++) {
           const int j = lane + 32 * pass;
-          double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, e4 = 0.0, e5 = 0.0;
-          const int kmax = NV < 32 * (pass + 1) ? NV : 32 * (pass + 1);
-          const double* gp_ = Gm + (j < NV ? j : 0);
+#pragma unroll
+          for (int i = 0; i < PE; i++) dq[pass][i] = 0.0;
+          if (pass == 1 && N <= 32) continue;
+          if (pass == 0 || NV > 32) {
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, e4 = 0.0, e5 = 0.0;
+            const int kmax = NV < 32 * (pass + 1) ? NV : 32 * (pass + 1);
+            const double* gp_ = Gm + (j < NV ? j : 0);
 #pragma unroll 2
-          for (int k = 0; k < kmax; k++, gp_ += LDV) {
-            const double g = (j < NV && k <= j) ? gp_[0] : 0.0;
-            e0 = fma(g, m6[k], e0); e1 = fma(g, m6[NV + k], e1); e2 = fma(g, m6[2 * NV + k], e2);
-            e3 = fma(g, m6[3 * NV + k], e3); e4 = fma(g, m6[4 * NV + k], e4); e5 = fma(g, m6[5 * NV + k], e5);
+            for (int k = 0; k < kmax; k++, gp_ += LDV) {
+              const double g = (j < NV && k <= j) ? gp_[0] : 0.0;
+              e0 = fma(g, m6[k], e0); e1 = fma(g, m6[NV + k], e1); e2 = fma(g, m6[2 * NV + k], e2);
+              e3 = fma(g, m6[3 * NV + k], e3); e4 = fma(g, m6[4 * NV + k], e4); e5 = fma(g, m6[5 * NV + k], e5);
+            }
+            dq[pass][0] = e0; dq[pass][1] = e1; dq[pass][2] = e2; dq[pass][3] = e3; dq[pass][4] = e4; dq[pass][5] = e5;
+            if constexpr (PE > 6) {  // internal-constraint rows [Ji | 0]
+#pragma unroll
+              for (int i = 6; i < PE; i++) {
+                double acc = 0.0;
+                if (j < NV) {
+#pragma unroll 1
+                  for (int k = 0; k <= j; k++) acc = fma(Gm[k * LDV + j], P.ic_jac[i - 6][k], acc);
+                }
+                dq[pass][i] = acc;
+              }
+            }
           }
-          if (j < NV) {
-            Dt[j] = e0; Dt[NP + j] = e1; Dt[2 * NP + j] = e2; Dt[3 * NP + j] = e3; Dt[4 * NP + j] = e4; Dt[5 * NP + j] = e5;
+          if (j >= NV && j < N) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) dq[pass][i] = -jrf * row_jc(j - NV, i);
           }
         }
+        // equality residuals at x0 (its reaction-force part is zero): floating-base rows M[i,:] x0 + (c+g)_i
+        // (Ni^T (c+g) with internal constraints), internal-constraint rows Ji x0.  Kept in lane i.
+        double cmine = 0.0;
 #pragma unroll 1
-        for (int c = lane; c < NP - NV; c += 32)
+        for (int i = 0; i < PE; i++) {
+          double part = 0.0;
 #pragma unroll 1
-          for (int i = 0; i < 6; i++) Dt[i * NP + NV + c] = c < NC ? -jrf * row_jc(c, i) : 0.0;
+          for (int k = lane; k < NV; k += 32) part = fma(i < 6 ? m6[i * NV + k] : G.ic_jac[i < 6 ? 0 : i - 6][k], xs[k], part);
+          part = wsum(part);
+          if (i < 6) part += has_ic ? ws.ic_cg[s * NV + i] : ws.cori[s * NV + i] + ws.grav[s * NV + i];
+          if (lane == i) cmine = part;
+        }
+        __syncwarp();  // m6 is dead: the reflectors go there
+        if (lane < PE) Ys[lane] = cmine;  // parked until the triangular solve below
       }
-#pragma unroll 1
-      for (int i = 6; i < p; i++) {  // internal-constraint rows [Ji | 0]
-#pragma unroll 1
-        for (int j = lane; j < NP; j += 32) {
-          double acc = 0.0;
-          if (j < NV) {
-#pragma unroll 1
-            for (int k = 0; k <= j; k++) acc = fma(Gm[k * LDV + j], P.ic_jac[i - 6][k], acc);
-          }
-          Dt[i * NP + j] = acc;
+      // ---- Householder QR of D in registers: reflector k zeroes column k below row k.  v_k goes to
+      //      shared memory as Vs[row][k] (one broadcast load serves a row of all reflectors), R stays
+      //      in the lanes that own its rows (R[k][c] = row k of column c after reflector k) ----
+      double rmine = 1.0;  // R[lane][lane]
+#pragma unroll
+      for (int k = 0; k < PE; k++) {
+        double part = lane >= k ? dq[0][k] * dq[0][k] : 0.0;
+        if (N > 32) part = fma(dq[1][k], dq[1][k], part);  // rows beyond n hold zeros
+        const double sigma = sqrt(wsum(part));
+        if (sigma <= QP_EPS * R_norm && status == PNC_QP_OK) status = PNC_QP_EQ_DEPENDENT;  // :268-271
+        R_norm = fmax(R_norm, sigma);
+        const double dkk = __shfl_sync(FULL, dq[0][k], k);
+        const double alpha = dkk > 0.0 ? -sigma : sigma;
+        const double bk = sigma > 0.0 ? 1.0 / (sigma * (sigma + fabs(dkk))) : 0.0;
+        if (lane == k) { rmine = alpha; Bs[k] = bk; }
+        const double v0 = lane > k ? dq[0][k] : (lane == k ? dkk - alpha : 0.0);
+        const double v1 = N > 32 ? dq[1][k] : 0.0;
+        if (lane < N) Vs[lane * PE + k] = v0;
+        if (N > 32 && lane + 32 < N) Vs[(lane + 32) * PE + k] = v1;
+#pragma unroll
+        for (int c = k + 1; c < PE; c++) {
+          const double sc = bk * wsum(fma(v0, dq[0][c], v1 * dq[1][c]));
+          dq[0][c] = fma(-sc, v0, dq[0][c]);
+          dq[1][c] = fma(-sc, v1, dq[1][c]);
         }
       }
       __syncwarp();
-      // ---- record, part 1: J = L^-T as the register chunks of the active-set kernel (lane = row,
-      //      two columns per 16-byte piece, rows 32.. as half rows of lane pairs), x0, D, scalars ----
+      // Gram matrix of the reflectors: one (l, k) pair per lane
+      if (lane < PE * (PE - 1) / 2) {
+        int k = 1, idx = lane;
+        while (idx >= k) { idx -= k; k++; }  // pairs in the order (0,1) (0,2) (1,2) (0,3) ...
+        const int l = idx;
+        double acc = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < N; j++) acc = fma(Vs[j * PE + l], Vs[j * PE + k], acc);
+        Gs[l * PE + k] = acc;
+      }
+      // y = R^-T (CE^T x0 + ce0): x at the equality-constrained minimiser is x0 - J1 y (J1 = first p
+      // columns of J Q).  Forward substitution down the lanes: lane k holds c_k, R[k][k] and R[k][c] (c > k).
       {
-        const int eh = lane & 1, erow = 32 + (lane >> 1);
-        const bool evalid = EXT && (lane >> 1) < E;
-        double2* rj = reinterpret_cast<double2*>(rec + C::RJ);
-#pragma unroll 2
-        for (int k = 0; k < NP; k += 2) {
-          double v0 = 0.0, v1 = 0.0;
-          if (k < NV) {
-            if (lane < NV) {
-              const double2 g = lds2(Gm + lane * LDV + k);
-              if (k >= lane) v0 = g.x;
-              if (k + 1 >= lane && k + 1 < NV) v1 = g.y;
-            }
-            if (k + 1 >= NV && k + 1 < N && lane == k + 1) v1 = jrf;
-          } else {
-            if (k < N && lane == k) v0 = jrf;
-            if (k + 1 < N && lane == k + 1) v1 = jrf;
-          }
-          rj[(k >> 1) * 32 + lane] = make_double2(v0, v1);
-        }
-        if constexpr (EXT) {
-          double2* rb = reinterpret_cast<double2*>(rec + C::RJB);
-#pragma unroll 2
-          for (int c = 0; c < NB; c += 2) {
-            double v[2] = {0.0, 0.0};
+        double ymine = 0.0;
+        double acc = lane < PE ? Ys[lane] : 0.0;
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-              const int col = eh * HW + c + u;
-              if (evalid && col < N) {
-                if (erow < NV) { if (col < NV && col >= erow) v[u] = Gm[erow * LDV + col]; }
-                else if (col == erow) v[u] = jrf;
-              }
+        for (int k = 0; k < PE; k++) {
+          const double yk = __shfl_sync(FULL, rmine != 0.0 ? acc / rmine : 0.0, k);  // y_k, final once rows < k are folded in
+          if (lane == k) ymine = yk;
+          // fold y_k into the rows below: c_c -= R[k][c] y_k, R[k][c] = dq[0][c] of lane k
+#pragma unroll
+          for (int c = k + 1; c < PE; c++) {
+            const double rkc = __shfl_sync(FULL, dq[0][c], k);
+            if (lane == c) acc = fma(-rkc, yk, acc);
+          }
+        }
+        __syncwarp();
+        if (lane < PE) Ys[lane] = ymine;
+      }
+      __syncwarp();
+      // ---- rows of J Q, streaming: lane = row i (slot 0: i = lane, slot 1: i = lane + 32).  With
+      //      g_k = r . v_k for the ORIGINAL row r, the dot products of the successively reflected row are
+      //      y_k = g_k - sum_{l<k} beta_l y_l (v_l . v_k), and r Q = r - sum_k beta_k y_k v_k^T.  Columns
+      //      0..p-1 only feed x; columns p.. are Z, written as the register chunks of the active-set kernel
+      //      (lane = row, two columns per 16-byte piece; rows 32.. as half rows of lane pairs) ----
+#pragma unroll 1
+      for (int slot = 0; slot < (N > 32 ? 2 : 1); slot++) {
+        const int i = lane + 32 * slot;
+        const bool rowok = i < N;
+        const double* ri = Gm + (i < NV ? i : 0) * LDV;
+        // J[i][j], J[i][j + 1] for even j: upper-triangular nv block, jrf on the reaction-force diagonal
+#define PNC_ROWVAL(j, rx, ry)                                               \
+        do {                                                                \
+          rx = 0.0; ry = 0.0;                                               \
+          if (rowok) {                                                      \
+            if (i < NV) {                                                   \
+              if ((j) < NV) {                                               \
+                const double2 g_ = lds2(ri + (j));                          \
+                if ((j) >= i) rx = g_.x;                                    \
+                if ((j) + 1 >= i && (j) + 1 < NV) ry = g_.y;                \
+              }                                                             \
+            } else {                                                        \
+              if ((j) == i) rx = jrf;                                       \
+              if ((j) + 1 == i) ry = jrf;                                   \
+            }                                                               \
+          }                                                                 \
+        } while (0)
+        double gk[PE];
+#pragma unroll
+        for (int k = 0; k < PE; k++) gk[k] = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < NP; j += 2) {
+          double rx, ry;
+          PNC_ROWVAL(j, rx, ry);
+#pragma unroll
+          for (int k = 0; k < PE; k += 2) {
+            const double2 va = lds2(Vs + j * PE + k);
+            gk[k] = fma(rx, va.x, gk[k]);
+            gk[k + 1] = fma(rx, va.y, gk[k + 1]);
+            if (j + 1 < N) {
+              const double2 vb = lds2(Vs + (j + 1) * PE + k);
+              gk[k] = fma(ry, vb.x, gk[k]);
+              gk[k + 1] = fma(ry, vb.y, gk[k + 1]);
             }
-            rb[(c >> 1) * 32 + lane] = make_double2(v[0], v[1]);
           }
         }
-      }
-#pragma unroll 1
-      for (int k = lane; k < NP; k += 32) rec[C::RX + k] = k < NV ? xs[k] : 0.0;
-      if (lane == 0) { rec[C::RS] = c1; rec[C::RS + 1] = c2; rec[C::RS + 3] = jrf; }
-      // equality normals [M | -(Jc Ni)^T] rows 0..5, then the internal-constraint rows, and offsets
-#pragma unroll 1
-      for (int i = 0; i < p; i++) {
-#pragma unroll 1
-        for (int k = lane; k < NP; k += 32) {
-          double val = 0.0;
-          if (k < N) {
-            if (i >= 6) val = k < NV ? G.ic_jac[i - 6][k] : 0.0;
-            else if (k < NV) val = Mg[i * NV + k];
-            else val = -row_jc(k - NV, i);
-          }
-          rec[C::RE + i * NP + k] = val;
+        // gk[k] becomes beta_k y_k
+#pragma unroll
+        for (int k = 0; k < PE; k++) {
+          double yk = gk[k];
+#pragma unroll
+          for (int l = 0; l < k; l++) yk = fma(-gk[l], Gs[l * PE + k], yk);
+          gk[k] = Bs[k] * yk;
         }
+        // x_i = x0_i - sum_{k<p} (J Q)[i][k] y_k
+        {
+          double acc = 0.0;
+#pragma unroll 1
+          for (int k = 0; k < PE; k += 2) {
+            double o0, o1;
+            PNC_ROWVAL(k, o0, o1);
+#pragma unroll
+            for (int l = 0; l < PE; l++) {
+              o0 = fma(-gk[l], Vs[k * PE + l], o0);
+              o1 = fma(-gk[l], Vs[(k + 1) * PE + l], o1);
+            }
+            acc = fma(o0, Ys[k], acc);
+            acc = fma(o1, Ys[k + 1], acc);
+          }
+          if (rowok) rec[C::RX + i] = (i < NV ? xs[i] : 0.0) - acc;
+        }
+        double2* rj = reinterpret_cast<double2*>(rec + C::RJ);
+        double2* rb = reinterpret_cast<double2*>(rec + C::RJB);
+#pragma unroll 1
+        for (int j = PE; j < NP; j += 2) {
+          double o0, o1;
+          PNC_ROWVAL(j, o0, o1);
+#pragma unroll
+          for (int k = 0; k < PE; k += 2) {
+            const double2 va = lds2(Vs + j * PE + k);
+            o0 = fma(-gk[k], va.x, o0);
+            o0 = fma(-gk[k + 1], va.y, o0);
+            if (j + 1 < N) {
+              const double2 vb = lds2(Vs + (j + 1) * PE + k);
+              o1 = fma(-gk[k], vb.x, o1);
+              o1 = fma(-gk[k + 1], vb.y, o1);
+            }
+          }
+          if (j + 1 >= N) o1 = 0.0;
+          const int cz = j - PE;  // column of Z (even)
+          if (slot == 0) {
+            if (rowok) rj[(cz >> 1) * 32 + lane] = make_double2(o0, o1);
+          } else if (EXT && rowok) {
+            const int h = cz >= HW ? 1 : 0, c = cz - h * HW;  // HW is even: a column pair never straddles the halves
+            rb[(c >> 1) * 32 + 2 * lane + h] = make_double2(o0, o1);
+          }
+        }
+#undef PNC_ROWVAL
       }
-      for (int i = lane; i < p; i += 32)
-        rec[C::RE0 + i] = i >= 6 ? 0.0 : (has_ic ? ws.ic_cg[s * NV + i] : ws.cori[s * NV + i] + ws.grav[s * NV + i]);
+      if (NP > N && lane == 0) rec[C::RX + N] = 0.0;
+      if (lane == 0) { rec[C::RS] = c1; rec[C::RS + 1] = c2; rec[C::RS + 3] = R_norm; }
       __syncwarp();
       // ---- record, part 2: the image of the active-set kernel's constant arrays (torque-limit rows
       //      S [M | -(Jc Ni)^T] with their offsets, wrench cones), assembled in shared memory over the
@@ -689,7 +818,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 }
 
 // =======================================================================================
-template <int NV, int NC, int NU, int NT>
+template <int NV, int NC, int NU, int NT, int PE>
 #ifndef PNC_REG_LB
 #define PNC_REG_LB __launch_bounds__(256, 1)
 #endif
@@ -698,8 +827,9 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             int* __restrict__ overflow, double* __restrict__ rec_all, int rc_cap, double refine) {
   // P (constant bank) serves warp-uniform reads; tables indexed per lane go through the global copy G
   const DevProblem& G = *gp;
-  using C = MCfg<NV, NC, NU, NT>;
-  constexpr int N = C::N, NP = C::NP, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDA = C::LDA;
+  using C = MCfg<NV, NC, NU, NT, PE>;
+  constexpr int N = C::N, NP = C::NP, NPC = C::NPC, NCOL = C::NCOL, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDA = C::LDA,
+                RC = C::RC;
   constexpr bool EXT = C::EXT;
   // One warp per state, each with its own slice of shared memory.  The launcher uses one-warp CTAs;
   // with PNC_REG_WARPS=w the w warps of a CTA meet at a barrier at the top of every step-direction
@@ -711,10 +841,10 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   const int lane = threadIdx.x & 31;
   double* const smem = smem_all + (threadIdx.x >> 5) * C::SMEM_DOUBLES;
   int nthr = blockDim.x;  // threads still taking part in the slot barrier
-  const int p = P.p, m = C::M, nu = NU;
+  const int m = C::M, nu = NU;
   constexpr int nact = NT;  // torque-limit rows = actuated joints (shape_ok); only used when NT > 0
   constexpr bool trq = NT > 0;
-  constexpr bool S2 = C::RC > 32;  // S = R^-1 never has rows beyond 32 (RC caps the active set): second-half code is dead
+  constexpr bool S2 = RC > 32;  // S = R^-1 never has rows beyond 32 (RC caps the active set): second-half code is dead
   double* const Rp = smem + C::ORT;
   double* const Ts = smem + C::OT;
   double* const Ar = smem + C::OAR;   // torque-limit rows S [M | -(Jc Ni)^T], pitch LDA
@@ -733,19 +863,18 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   double* const xacc = smem + C::OXACC;
   double* const sl = smem + C::OSL;
   int* const Aact = reinterpret_cast<int*>(smem + C::OINT);
-  int* Aold = Aact + (N + 2);
-  int* Aacc = Aold + (N + 2);
-  int* const Cm = Aact + ((3 * (N + 2) + 1) & ~1);  // per cone row: first variable, number of variables (8-byte aligned pairs)
+  int* Aold = Aact + (RC + 2);
+  int* Aacc = Aold + (RC + 2);
+  int* const Cm = Aact + ((3 * (RC + 2) + 1) & ~1);  // per cone row: first variable, number of variables (8-byte aligned pairs)
 #define Rcol(c) (Rp + ((c) * ((c) + 3)) / 2)
   double* rot = Ts;  // the d scratch tile doubles as the Givens coefficient table of a drop
-  static_assert(6 * LDT >= 3 * NP, "rotation table must fit the scratch tile");
 
   // rows beyond 32: lane pair (2e, 2e+1) owns row 32+e, half eh of the columns
   const int eh = lane & 1, epair = lane >> 1;
   const int erow = 32 + epair;
   const bool evalid = EXT && epair < E;
 
-  double Ja[NP];
+  double Ja[NPC];
   double Jb[NB];
 #pragma unroll 1
   for (int r = lane; r < NU; r += 32) {
@@ -778,20 +907,23 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       for (int k = lane; k < C::IMG / 2; k += 32) dst[k] = __ldg(src + k);
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) {
-        x[k] = rec[C::RX + k];
-        zv[k] = 0.0; dm[k] = 0.0; np[k] = 0.0; dv[k] = 0.0;
+        x[k] = rec[C::RX + k];  // the equality-constrained minimiser (k_ihwbc_setup)
+        zv[k] = 0.0; np[k] = 0.0;
       }
+#pragma unroll 1
+      for (int k = lane; k < NPC; k += 32) { dm[k] = 0.0; dv[k] = 0.0; }
 #pragma unroll 1
       for (int k = lane; k < 6 * LDT; k += 32) Ts[k] = 0.0;
     }
-    const double c1 = rec[C::RS], c2 = rec[C::RS + 1], jrf = rec[C::RS + 3];
+    const double c1 = rec[C::RS], c2 = rec[C::RS + 1];
+    R_norm = rec[C::RS + 3];  // max(1, |diagonal of R|) after the equalities
     status = (int)rec[C::RS + 2];
     if (status == PNC_QP_OK) {
-      // ---- move J into registers: row lane, and half rows 32.. in lane pairs ----
+      // ---- move Z into registers: row lane, and half rows 32.. in lane pairs ----
       {
         const double2* rj = reinterpret_cast<const double2*>(rec + C::RJ) + lane;
 #pragma unroll
-        for (int k = 0; k < NP; k += 2) {
+        for (int k = 0; k < NPC; k += 2) {
           const double2 g = __ldg(rj + (k >> 1) * 32);
           Ja[k] = g.x;
           Ja[k + 1] = g.y;
@@ -809,14 +941,12 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           for (int c = 0; c < NB; c++) Jb[c] = 0.0;
         }
       }
-      double* Deq = Rp + 64;  // R only uses its first p columns (< 64 doubles) while Deq is live
-#pragma unroll 2
-      for (int k = lane; k < p * NP; k += 32) Deq[k] = rec[C::RD + k];
 #pragma unroll 1
-      for (int k = lane; k < N + 2; k += 32) { uv[k] = 0.0; Aact[k] = 0; }
+      for (int k = lane; k < RC + 2; k += 32) { uv[k] = 0.0; Aact[k] = 0; }
       __syncwarp();
 
-      // ================= dual active-set iterations, equalities first (:232-500) =================
+      // ================= dual active-set iterations over the inequalities (:274-500) =================
+      // (the equalities of :232-272 were all added by k_ihwbc_setup; iq counts active inequalities)
       // Per-lane bit masks: lane l owns the inequalities l, l + 32, l + 64, l + 96 (the ones it scans in
       // l2), bit t of its mask speaks for inequality l + 32 t.
       static_assert(C::M <= 128, "four inequalities per lane");
@@ -831,16 +961,13 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
       const double psi_tol = (double)m * QP_EPS * c1 * c2 * 100.0;  // QuadProg++.cc:306-312
       const double psi_refine = psi_tol * refine;                   // refine = 1e-6 by default, see ihwbc.cu / DESIGN.md 3.2
       bool done = false, accepted = false, need_l1 = true;
-      int iq_acc = 0, ieq = 0;
+      int iq_acc = 0;
 
 #pragma unroll 1
       while (!done) {
-        const bool is_eq = ieq < p;
         int ip = 0, k0 = 0, k1 = N;
         double s_ip = 0.0;
-        if (is_eq) {
-          ip = ieq;
-        } else {
+        {
           if (m <= 0) break;
           if (need_l1) {
             // l1: slacks of every inequality, termination test (:282-321)
@@ -918,26 +1045,19 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         }
         // ---- the constraint normal np and the rows [k0, k1) where it is non-zero ----
         {
-          if (is_eq || ip >= nu) {
-            int a = 0;
-            double sg = 1.0;
-            const bool tq = !is_eq;
-            if (tq) { const int tr = ip - nu; a = tr >= nact ? tr - nact : tr; sg = tr >= nact ? -1.0 : 1.0; }
-            const double* row = tq ? Ar + a * LDA : rec + C::RE + ip * NP;  // shared or global
-            double pnx = 0.0;
+          if (ip >= nu) {  // torque-limit row: + / - row a of S [M | -(Jc Ni)^T]
+            const int tr = ip - nu;
+            const int a = tr >= nact ? tr - nact : tr;
+            const double sg = tr >= nact ? -1.0 : 1.0;
+            const double* row = Ar + a * LDA;
 #pragma unroll 1
-            for (int k = lane; k < NP; k += 32) {
-              const double val = k < N ? sg * row[k] : 0.0;
-              np[k] = val;
-              pnx = fma(val, x[k], pnx);
-            }
-            if (is_eq) s_ip = wsum(pnx) + rec[C::RE0 + ip];
+            for (int k = lane; k < NP; k += 32) np[k] = k < N ? sg * row[k] : 0.0;
           } else {
             k0 = Cm[2 * ip]; k1 = k0 + Cm[2 * ip + 1];
 #pragma unroll 1
             for (int k = lane; k < NP; k += 32) np[k] = (k >= k0 && k < k1) ? Uf[ip * 6 + (k - k0)] : 0.0;
           }
-          if (lane == 0) { uv[iq] = 0.0; Aact[iq] = is_eq ? -ip - 1 : ip; }
+          if (lane == 0) { uv[iq] = 0.0; Aact[iq] = ip; }
           __syncwarp();
         }
 
@@ -945,12 +1065,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 #pragma unroll 1
         for (;;) {
           nthr = slot_barrier(nthr, true);
-          // d = J^T np through the scratch tile, six rows of J at a time (:504-516)
+          // d = Z^T np through the scratch tile, six rows of Z at a time (:504-516)
           double dA = 0.0, dB = 0.0;
-          if (is_eq) {
-            if (lane < NP) dA = Deq[ip * NP + lane];
-            if (NP > 32 && lane + 32 < NP) dB = Deq[ip * NP + lane + 32];
-          } else
 #pragma unroll 1
           for (int c0 = k0; c0 < k1; c0 += 6) {
             const int dim = min(6, k1 - c0);
@@ -959,7 +1075,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               if (r >= 0 && r < dim) {
                 double* dst = Ts + r * LDT;
 #pragma unroll
-                for (int j = 0; j < NP; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(Ja[j], Ja[j + 1]);
+                for (int j = 0; j < NPC; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(Ja[j], Ja[j + 1]);
               }
             }
             if constexpr (EXT) {
@@ -980,25 +1096,25 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               for (int r = 0; r < 6; r++) {
                 const double nr = npc[r];  // rows beyond the normal's support are zero (np is zero-padded)
                 dA = fma(nr, tl[r * LDT], dA);
-                if (NP > 32 && lane + 32 < NP) dB = fma(nr, tl[r * LDT + 32], dB);
+                if (NPC > 32 && lane + 32 < NPC) dB = fma(nr, tl[r * LDT + 32], dB);
               }
             }
             __syncwarp();
           }
-          if (lane < NP) { dv[lane] = dA; dm[lane] = lane >= iq ? dA : 0.0; }
-          if (NP > 32 && lane + 32 < NP) { dv[lane + 32] = dB; dm[lane + 32] = lane + 32 >= iq ? dB : 0.0; }
+          if (lane < NPC) { dv[lane] = dA; dm[lane] = lane >= iq ? dA : 0.0; }
+          if (NPC > 32 && lane + 32 < NPC) { dv[lane + 32] = dB; dm[lane + 32] = lane + 32 >= iq ? dB : 0.0; }
           __syncwarp();
 
-          // z = J[:, iq:] d[iq:] (:518-528), z.z and z.np
+          // z = Z[:, iq:] d[iq:] (:518-528), z.z and z.np
           double za, zb = 0.0, zz, znp, sig2;
           {
             double a0_ = 0.0, a1_ = 0.0, a2_ = 0.0, a3_ = 0.0;
 #pragma unroll
-            for (int j = 0; j < NP; j += 4) {
+            for (int j = 0; j < NPC; j += 4) {
               const double2 v = lds2(dm + j);
               a0_ = fma(Ja[j], v.x, a0_);
               a1_ = fma(Ja[j + 1], v.y, a1_);
-              if (j + 2 < NP) {
+              if (j + 2 < NPC) {
                 const double2 w = lds2(dm + j + 2);
                 a2_ = fma(Ja[j + 2], w.x, a2_);
                 a3_ = fma(Ja[j + 3], w.y, a3_);
@@ -1018,8 +1134,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               zb += __shfl_xor_sync(FULL, zb, 1);
             }
             double pzz = 0.0, pzn = 0.0;
-            double psg = (lane >= iq && lane < N) ? dA * dA : 0.0;   // ||d[iq:]||^2 for the Householder step
-            if (lane + 32 >= iq && lane + 32 < N) psg = fma(dB, dB, psg);
+            double psg = (lane >= iq && lane < NCOL) ? dA * dA : 0.0;   // ||d[iq:]||^2 for the Householder step
+            if (lane + 32 >= iq && lane + 32 < NCOL) psg = fma(dB, dB, psg);
             if (lane < N) { zv[lane] = za; pzz = za * za; pzn = za * np[lane]; }
             if (evalid && eh == 0) { zv[erow] = zb; pzz = fma(zb, zb, pzz); pzn = fma(zb, np[erow], pzn); }
 #pragma unroll
@@ -1050,23 +1166,19 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             if (lane < iq) rv[lane] = acc0 + acc1;
           }
           __syncwarp();
-          // step lengths (:366-393); equalities always take the full step (:246-258)
+          // step lengths (:366-393)
           double t1 = INFINITY;
           int kk = 0x7fffffff;
-          if (!is_eq) {
-            if (lane >= p && lane < iq) {  // iq <= RC = 32: one candidate per lane
-              const double rk = rv[lane];
-              if (rk > 0.0) { t1 = uv[lane] / rk; kk = lane; }
-            }
-            wargmin(t1, kk);
+          if (lane < iq) {  // iq <= RC <= 32: one candidate per lane
+            const double rk = rv[lane];
+            if (rk > 0.0) { t1 = uv[lane] / rk; kk = lane; }
           }
+          wargmin(t1, kk);
           const int l = kk != 0x7fffffff ? Aact[kk] : 0;
-          double t2;
+          double t2 = INFINITY;
           if (fabs(zz) > QP_EPS) {
             t2 = -s_ip / znp;
-            if (!is_eq && t2 < 0.0) t2 = INFINITY;
-          } else {
-            t2 = is_eq ? 0.0 : INFINITY;
+            if (t2 < 0.0) t2 = INFINITY;
           }
           const double t = fmin(t1, t2);
           if (t >= INFINITY) { status = PNC_QP_INFEASIBLE; done = true; break; }  // :402-407
@@ -1077,18 +1189,17 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           if (lane == 0) uv[iq] += t;
           __syncwarp();
 
-          if (!dual_only && (is_eq || fabs(t - t2) < QP_EPS)) {
-            // ---- full step: add the constraint (:441-474), one Householder reflection of J2 ----
+          if (!dual_only && fabs(t - t2) < QP_EPS) {
+            // ---- full step: add the constraint (:441-474), one Householder reflection of Z2 ----
             const double sigma = sqrt(sig2);
             if (sigma <= QP_EPS * R_norm) {  // linearly dependent on the active set
-              if (is_eq) { status = PNC_QP_EQ_DEPENDENT; done = true; break; }
               set_bit(excm, ip);
-              if (lane >= p && lane < iq) { Aact[lane] = Aold[lane]; uv[lane] = uold[lane]; }
+              if (lane < iq) { Aact[lane] = Aold[lane]; uv[lane] = uold[lane]; }
               for (int i = lane; i < NP; i += 32) x[i] = xold[i];
               __syncwarp();
               actm = 0u;
 #pragma unroll 1
-              for (int i = p; i < iq; i++) set_bit(actm, Aact[i]);
+              for (int i = 0; i < iq; i++) set_bit(actm, Aact[i]);
               break;  // back to l2
             }
             if (iq >= rc_cap) {  // S is capped at RC columns: hand the state to the generic kernel
@@ -1108,7 +1219,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             if (lane == 0) col[iq] = ialpha;
             // the Householder vector v = [0 .. 0, v0, d[iq+1:]] is the masked d with one entry patched
             if (lane == 0) dm[iq] = v0;
-            const double ca = reg_pick(Ja, iq);  // old column iq of J
+            const double ca = reg_pick(Ja, iq);  // old column iq of Z
             double hwb = 0.0;
             if constexpr (EXT) {
               const int hq = iq >= HW ? 1 : 0;
@@ -1119,7 +1230,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             const double hwa = beta * (za - alpha * ca);
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < NP; j += 2) {
+            for (int j = 0; j < NPC; j += 2) {
               const double2 v = lds2(dm + j);
               Ja[j] = fma(-hwa, v.x, Ja[j]);
               Ja[j + 1] = fma(-hwa, v.y, Ja[j + 1]);
@@ -1133,22 +1244,10 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
                 Jb[c + 1] = fma(-hwb, v.y, Jb[c + 1]);
               }
             }
-            if (is_eq) {  // D[i'] <- (I - beta v v^T) D[i'] for the equalities still to come
-#pragma unroll 1
-              for (int i2 = ieq + 1; i2 < p; i2++) {
-                double* Di = Deq + i2 * NP;
-                double e0 = 0.0, e1 = 0.0, w0 = 0.0, w1 = 0.0;
-                if (lane < NP) { e0 = Di[lane]; w0 = dm[lane]; }
-                if (NP > 32 && lane + 32 < NP) { e1 = Di[lane + 32]; w1 = dm[lane + 32]; }
-                const double g = beta * wsum(fma(e0, w0, e1 * w1));
-                if (lane < NP) Di[lane] = fma(-g, w0, e0);
-                if (NP > 32 && lane + 32 < NP) Di[lane + 32] = fma(-g, w1, e1);
-              }
-            }
             iq++;
             R_norm = fmax(R_norm, sigma);
-            if (is_eq) ieq++;
-            else { set_bit(actm, ip); need_l1 = true; }
+            set_bit(actm, ip);
+            need_l1 = true;
             __syncwarp();
             break;
           }
@@ -1259,8 +1358,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) rec[C::RO + k] = x[k];
       if (lane < iq) ro[3 + lane] = Aact[lane];
-      if (lane == 0) { ro[0] = iq; ro[1] = iter; ro[2] = status; ro[3 + N + 2] = iq_ref; }
-      if (lane < iq_ref) ro[4 + N + 2 + lane] = Aacc[lane];
+      if (lane == 0) { ro[0] = iq; ro[1] = iter; ro[2] = status; ro[3 + RC + 2] = iq_ref; }
+      if (lane < iq_ref) ro[4 + RC + 2 + lane] = Aacc[lane];
       if constexpr (NT > 0) {
         // torque recovery tau = S (M qddot + Ni^T (c+g) - (Jc Ni)^T rf) (ihwbc.py:344-354): the rows
         // S [M | -(Jc Ni)^T] are the torque-limit rows already in shared memory
@@ -1294,7 +1393,7 @@ k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nf
   const int lane = threadIdx.x & 31;
   const size_t s = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= (size_t)B) return;
-  const int nv = G.nv, nc = G.nc, n = nv + nc, nact = G.nact, p = G.p, m = G.m;
+  const int nv = G.nv, nc = G.nc, n = nv + nc, nact = G.nact, m = G.m;
   const double* x = rec_all + s * rec_stride + ro_off;
   const int* ro = reinterpret_cast<const int*>(x + np_pad);
   const int iq = ro[0], iter = ro[1], status = ro[2];
@@ -1342,7 +1441,7 @@ k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nf
     const int mw = (m + 63) / 64 > 0 ? (m + 63) / 64 : 1;
     for (int wdx = lane; wdx < mw; wdx += 32) {
       unsigned long long bits = 0ull;
-      for (int i = p; i < iq; i++) {
+      for (int i = 0; i < iq; i++) {  // the recorded sets hold inequalities only
         const int c = ro[3 + i];
         if (c >= 0 && (c >> 6) == wdx) bits |= 1ull << (c & 63);
       }
@@ -1357,7 +1456,7 @@ k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nf
     const int nr = iqr >= 0 ? iqr : iq;
     for (int wdx = lane; wdx < mw; wdx += 32) {
       unsigned long long bits = 0ull;
-      for (int i = p; i < nr; i++) {
+      for (int i = 0; i < nr; i++) {
         const int c = ar[i];
         if (c >= 0 && (c >> 6) == wdx) bits |= 1ull << (c & 63);
       }
@@ -1370,81 +1469,90 @@ k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nf
   }
 }
 
-template <int NV, int NC, int NU, int NT>
+template <int NV, int NC, int NU, int NT, int PE>
 static bool shape_ok(const DevProblem& hp) {
-  using C = MCfg<NV, NC, NU, NT>;
-  if (hp.nv != NV || hp.nc != NC || hp.nu != NU || hp.m != C::M) return false;
-  if ((hp.b_trq_limit ? hp.nact : 0) != NT || hp.nact > 32 || hp.m > 128 || hp.p > C::PMAX) return false;
-  // the equality block D sits behind the first S columns while the equalities are added
-  if (64 + hp.p * C::NP > C::RSZ || hp.p * (hp.p + 3) / 2 > 64 || hp.p >= C::RC) return false;
+  using C = MCfg<NV, NC, NU, NT, PE>;
+  if (hp.nv != NV || hp.nc != NC || hp.nu != NU || hp.m != C::M || hp.p != PE) return false;
+  if ((hp.b_trq_limit ? hp.nact : 0) != NT || hp.nact > 32 || hp.m > 128) return false;
   if (hp.ndense > C::NP) return false;  // the setup kernel keeps one row pointer per dense task row in an NP-sized vector
   return true;
 }
 
-template <int NV, int NC, int NU, int NT>
+template <int NV, int NC, int NU, int NT, int PE>
 static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B,
                        const SolveIO& io, int num_sms, cudaStream_t stream) {
-  if (!shape_ok<NV, NC, NU, NT>(hp)) return false;
-  using C = MCfg<NV, NC, NU, NT>;
+  if (!shape_ok<NV, NC, NU, NT, PE>(hp)) return false;
+  using C = MCfg<NV, NC, NU, NT, PE>;
   static const int warps_env = [] { const char* e = getenv("PNC_REG_WARPS"); return e ? atoi(e) : 0; }();
   int warps = warps_env >= 1 && warps_env <= 8 ? warps_env : 1;  // warps (= states in flight) per CTA
   while (warps > 1 && (size_t)warps * C::SMEM_DOUBLES * sizeof(double) > 227 * 1024) warps--;
   const size_t smem = (size_t)warps * C::SMEM_DOUBLES * sizeof(double);
   static SmemOptIn optin;
-  if (!optin.ensure(k_ihwbc_reg<NV, NC, NU, NT>, smem)) return false;
+  if (!optin.ensure(k_ihwbc_reg<NV, NC, NU, NT, PE>, smem)) return false;
   const SetupLayout SL = setup_layout<C>(hp, C::IMG);
   if (!ws.setup_rec || ws.setup_stride != C::REC) return false;
   const size_t smem_s = (size_t)SL.per_state * sizeof(double);
   static SmemOptIn optin_s;
-  if (!optin_s.ensure(k_ihwbc_setup<NV, NC, NU, NT>, smem_s)) return false;
+  if (!optin_s.ensure(k_ihwbc_setup<NV, NC, NU, NT, PE>, smem_s)) return false;
   int per_sm_s = 0, per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC, NU, NT>, 32, smem_s);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT>, 32 * warps, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC, NU, NT, PE>, 32, smem_s);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT, PE>, 32 * warps, smem);
   if (per_sm < 1 || per_sm_s < 1) return false;
   static const int cap = [] { const char* e = getenv("PNC_REG_CTAS"); return e ? atoi(e) : 0; }();
   if (cap > 0 && per_sm > cap) per_sm = cap;
+  static const bool verbose = getenv("PNC_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr, "pnc_b200: <%d,%d,%d,%d,%d> setup %d warps/SM (%zu B smem), active-set %d warps/SM (%zu B smem), record %d B\n", NV,
+            NC, NU, NT, PE, per_sm_s, smem_s, per_sm * warps, smem / warps, (int)(C::REC * sizeof(double)));
   int grid_s = num_sms * per_sm_s, grid = num_sms * per_sm;
   if (grid_s > B) grid_s = B;
   if (grid * warps > B) grid = (B + warps - 1) / warps;
   cudaMemsetAsync(io.counter + 2, 0, sizeof(int), stream);
-  k_ihwbc_setup<NV, NC, NU, NT><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
+  k_ihwbc_setup<NV, NC, NU, NT, PE><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
   g_launch_count++;
   // PNC_DEBUG_RC lowers the cap on active constraints so the tests can exercise the hand-over
   static const int rc_dbg = [] { const char* e = getenv("PNC_DEBUG_RC"); return e ? atoi(e) : 0; }();
-  const int rc_cap = (rc_dbg > hp.p && rc_dbg < C::RC) ? rc_dbg : C::RC;
-  k_ihwbc_reg<NV, NC, NU, NT><<<grid, 32 * warps, smem, stream>>>(hp, dp, B, io.counter, io.overflow, ws.setup_rec, rc_cap,
-                                                                  io.psi_refine);
+  const int rc_cap = (rc_dbg > 0 && rc_dbg < C::RC) ? rc_dbg : C::RC;
+  k_ihwbc_reg<NV, NC, NU, NT, PE><<<grid, 32 * warps, smem, stream>>>(hp, dp, B, io.counter, io.overflow, ws.setup_rec, rc_cap,
+                                                                      io.psi_refine);
   g_launch_count++;
   k_ihwbc_finish<<<(B + 7) / 8, 256, 0, stream>>>(dp, ws, fm, nfr, B, io, ws.setup_rec, C::REC, C::RO, C::NP, NT > 0 ? C::RT : -1,
-                                                  3 + C::N + 2);
+                                                  3 + C::RC + 2);
   g_launch_count++;
   return true;
 }
 
 // register-resident kernels exist for the QP shapes of the shipped robots; anything else takes
 // the generic shared-memory kernel of ihwbc.cu
+// <nv, nc, cone rows, torque-limit rows, equalities>
+#define PNC_REG_SHAPES(X) \
+  X(36, 12, 36, 30, 6) /* Atlas */ X(18, 12, 24, 0, 6) /* Laikago */ X(33, 12, 36, 0, 8) /* Draco3 */ \
+  X(20, 12, 36, 12, 8) /* Draco3 lower body */ X(32, 12, 36, 26, 6) /* Valkyrie */
+
 bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
                             int B, const SolveIO& io, int num_sms, cudaStream_t stream) {
-  // <nv, nc, cone rows, torque-limit rows>
-  return try_launch<36, 12, 36, 30>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Atlas
-         try_launch<18, 12, 24, 0>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||   // Laikago
-         try_launch<33, 12, 36, 0>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||   // Draco3
-         try_launch<20, 12, 36, 12>(dp, hp, ws, fm, nfr, B, io, num_sms, stream) ||  // Draco3 lower body
-         try_launch<32, 12, 36, 26>(dp, hp, ws, fm, nfr, B, io, num_sms, stream);    // Valkyrie
+#define X(a, b, c, d, e) if (try_launch<a, b, c, d, e>(dp, hp, ws, fm, nfr, B, io, num_sms, stream)) return true;
+  PNC_REG_SHAPES(X)
+#undef X
+  return false;
 }
-
-template <int NV, int NC, int NU, int NT>
-static int rec_doubles(const DevProblem& hp) { return shape_ok<NV, NC, NU, NT>(hp) ? MCfg<NV, NC, NU, NT>::REC : 0; }
 
 // doubles per state of the setup record (0 when no register kernel matches the problem)
 int reg_setup_record_doubles(const DevProblem& hp) {
-  int r = 0;
-  if (!r) r = rec_doubles<36, 12, 36, 30>(hp);
-  if (!r) r = rec_doubles<18, 12, 24, 0>(hp);
-  if (!r) r = rec_doubles<33, 12, 36, 0>(hp);
-  if (!r) r = rec_doubles<20, 12, 36, 12>(hp);
-  if (!r) r = rec_doubles<32, 12, 36, 26>(hp);
-  return r;
+#define X(a, b, c, d, e) if (shape_ok<a, b, c, d, e>(hp)) return MCfg<a, b, c, d, e>::REC;
+  PNC_REG_SHAPES(X)
+#undef X
+  return 0;
+}
+
+// 1-based index of the register-kernel shape that serves the problem (0: none).  A record slab is laid
+// out for ONE shape: the setup kernel leaves padding columns and unused lanes untouched (zero).
+int reg_shape_id(const DevProblem& hp) {
+  int id = 0;
+#define X(a, b, c, d, e) id++; if (shape_ok<a, b, c, d, e>(hp)) return id;
+  PNC_REG_SHAPES(X)
+#undef X
+  return 0;
 }
 
 bool reg_kernel_available(const DevProblem& hp) {

@@ -357,6 +357,11 @@ const char* pnc_version(void);
  * cone vector nu, unconstrained minimiser n) into d_buf.  Pass NULL to switch it off. */
 int pnc_debug_set_dump(double* d_buf, int state);
 
+/* debug: device pointer and per-state stride (doubles) of the setup records of the last pnc_ihwbc_solve on `ws`
+ * (NULL / 0 when the problem took the generic kernel), and the record layout of the problem's register
+ * shape: layout[0..9] = {n, p, ncol, npc, hw, RJ, RJB, RX, RS, REC} (offsets in doubles; see ihwbc_reg.cu). */
+int pnc_debug_setup_record(const pnc_problem* p, pnc_workspace* ws, double** d_rec, int32_t* stride, int32_t* layout);
+
 #ifdef __cplusplus
 }
 #endif

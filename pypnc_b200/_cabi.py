@@ -156,6 +156,7 @@ def load_library():
     lib.pnc_launch_count.restype = i64
     lib.pnc_measure_fp64_peak.argtypes = [C.c_int, c_double_p]
     lib.pnc_debug_set_dump.argtypes = [vp, C.c_int]
+    lib.pnc_debug_setup_record.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     lib.pnc_version.argtypes = []
     lib.pnc_version.restype = C.c_char_p
     _lib = lib
@@ -172,5 +173,5 @@ EXPORTED_SYMBOLS = [
     'pnc_ihwbc_solve', 'pnc_ihwbc_solve_ref', 'pnc_set_termination', 'pnc_get_termination', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_osc_step', 'pnc_wbc_tick_host',
     'pnc_quadprog_batch', 'pnc_ramp_update', 'pnc_foot_use_current', 'pnc_swing_init', 'pnc_swing_eval', 'pnc_floating_base_init',
     'pnc_floating_base_eval', 'pnc_sinusoid_eval', 'pnc_dcm_update',
-    'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version', 'pnc_debug_set_dump',
+    'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version', 'pnc_debug_set_dump', 'pnc_debug_setup_record',
 ]

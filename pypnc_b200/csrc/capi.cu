@@ -846,6 +846,13 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
   return PNC_OK;
 }
 
+int pnc_debug_setup_record(const pnc_problem* p, pnc_workspace* ws, double** d_rec, int32_t* stride, int32_t* layout) {
+  if (!p || !ws || !d_rec || !stride || !layout) return PNC_E_ARG;
+  *d_rec = ws->setup_slab;
+  *stride = ws->setup_stride;
+  return reg_record_layout(p->h, layout) ? PNC_OK : PNC_E_SIZE;
+}
+
 int pnc_measure_fp64_peak(int device, double* tflops) {
   if (!tflops) return PNC_E_ARG;
   int ndev = 0;

@@ -57,8 +57,9 @@ struct RCfg {
 // Compile-time shared-memory layout of the active-set kernel (doubles).  NU = wrench-cone rows,
 // NT = torque-limit rows (0 without torque limits).  Every array sits at an immediate offset from
 // the shared-memory base: no address registers, nothing to rematerialise under the register
-// pressure of the resident Z.  S = R^-1 is capped at RC columns (active inequalities); a state
-// that would need more is handed to the generic kernel (status OVERFLOW).
+// pressure of the resident Z.  R (upper triangular, packed by columns, one spare slot per column
+// for the sub-diagonal entry a dropped constraint leaves behind) is capped at RC columns (active
+// inequalities); a state that would need more is handed to the generic kernel (status OVERFLOW).
 template <int NV_, int NC_, int NU_, int NT_, int PE_>
 struct MCfg : RCfg<NV_, NC_, PE_> {
   using R = RCfg<NV_, NC_, PE_>;
@@ -71,7 +72,7 @@ struct MCfg : RCfg<NV_, NC_, PE_> {
   static constexpr int ORT = 0, OT = ORT + RSZ, OAR = OT + 6 * R::LDT, OA0 = OAR + NT * LDA, OUF = OA0 + ((3 * NT + 1) & ~1),
                        OUFV = OUF + (NU > 0 ? NU : 1) * 6, OX = OUFV + (((NU > 0 ? NU : 1) + 1) & ~1), OZ = OX + R::NP,
                        ODV = OZ + R::NP, ODM = ODV + R::NPC, ONP = ODM + R::NPC, ORR = ONP + R::NP + 6 /* zero pad: the d tile reads np six at a time */,
-                       OU = ORR + RV, OXOLD = OU + RV, OUOLD = OXOLD + R::NP, OXACC = OUOLD + RV,
+                       OU = ORR + RV, ORI = OU + RV /* 1 / diagonal of R */, OXOLD = ORI + RV, OUOLD = OXOLD + R::NP, OXACC = OUOLD + RV,
                        OSL = OXACC + R::NP, OINT = OSL + (((M > 0 ? M : 1) + 1) & ~1),
                        SMEM_DOUBLES = (OINT + (((3 * (RC + 2) + 1) & ~1) + 2 * NU) / 2 + 2) & ~1;  // A, Aold, Aacc, cone-row table
   static_assert(6 * R::LDT >= 3 * RC, "rotation table must fit the scratch tile");
@@ -858,6 +859,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   double* const np = smem + C::ONP;
   double* const rv = smem + C::ORR;
   double* const uv = smem + C::OU;
+  double* const rinv = smem + C::ORI;
   double* const xold = smem + C::OXOLD;
   double* const uold = smem + C::OUOLD;
   double* const xacc = smem + C::OXACC;
@@ -1146,24 +1148,30 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             }
             zz = pzz; znp = pzn; sig2 = psg;
           }
-          // r = R^-1 d[0:iq] (:530-542).  The kernel keeps S = R^-1 (upper triangular, packed by
-          // columns) instead of R: r = S d is a matrix-vector product -- lane i owns row i -- not a
-          // back substitution with its dependent chain of iq steps
+          // r = R^-1 d[0:iq] (:530-542): column-oriented back substitution, lane i owns row i, two rows
+          // per step.  Every lane carries val = (d_i - sum_{j>i} R[i][j] r_j) / R[i][i] for its row, with
+          // the row scaled by the reciprocal diagonal off the dependent chain, so that chain is one
+          // shuffle and three fmas per pair of rows.  (An explicit S = R^-1 would make this a plain
+          // matrix-vector product, but it loses cond(R) eps -- and with it the Givens pairs of a drop --
+          // at degenerate vertices, where the active normals are nearly dependent: measured 4e-9 from
+          // the exact solution on 6 of 262144 Valkyrie states.)
           {
-            static_assert(!S2, "rows of S beyond 32 are not implemented");
-            double acc0 = 0.0, acc1 = 0.0;  // even / odd columns: two independent FMA chains
-            const double* col = Rp;
-            int j = 0;
+            static_assert(!S2, "rows of R beyond 32 are not implemented");
+            const double rin = lane < iq ? rinv[lane] : 0.0;
+            double val = (lane < iq ? dv[lane] : 0.0) * rin;
+            int i = iq - 1;
 #pragma unroll 1
-            for (; j + 1 < iq; j += 2) {
-              const double2 dj = lds2(dv + j);
-              const double* cn = col + j + 2;
-              if (lane <= j) acc0 = fma(col[lane], dj.x, acc0);
-              if (lane <= j + 1) acc1 = fma(cn[lane], dj.y, acc1);
-              col = cn + j + 3;
+            for (; i >= 1; i -= 2) {
+              const double e1 = lane < i ? Rcol(i)[lane] * rin : 0.0;          // R[lane][i] / R[lane][lane]
+              const double e0 = lane < i - 1 ? Rcol(i - 1)[lane] * rin : 0.0;  // R[lane][i-1] / R[lane][lane]
+              const double r1 = __shfl_sync(FULL, val, i);
+              const double s0 = __shfl_sync(FULL, val, i - 1);
+              const double h = __shfl_sync(FULL, e1, i - 1);
+              const double r0 = fma(-h, r1, s0);
+              val = fma(-e1, r1, val);
+              val = fma(-e0, r0, val);
             }
-            if (j < iq && lane <= j) acc0 = fma(col[lane], dv[j], acc0);
-            if (lane < iq) rv[lane] = acc0 + acc1;
+            if (lane < iq) rv[lane] = val;
           }
           __syncwarp();
           // step lengths (:366-393)
@@ -1212,11 +1220,10 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             const double alpha = d0 > 0.0 ? -sigma : sigma;
             const double v0 = d0 - alpha;
             const double beta = 1.0 / (sigma * (sigma + fabs(d0)));
-            // R gains the column [d1; alpha]  <=>  S = R^-1 gains the column [-S d1 / alpha; 1 / alpha]
+            // R gains the column [d1; alpha]
             double* col = Rcol(iq);
-            const double ialpha = 1.0 / alpha;
-            if (lane < iq) col[lane] = -rv[lane] * ialpha;
-            if (lane == 0) col[iq] = ialpha;
+            if (lane < iq) col[lane] = dv[lane];
+            if (lane == 0) { col[iq] = alpha; rinv[iq] = 1.0 / alpha; }
             // the Householder vector v = [0 .. 0, v0, d[iq+1:]] is the masked d with one entry patched
             if (lane == 0) dm[iq] = v0;
             const double ca = reg_pick(Ja, iq);  // old column iq of Z
@@ -1253,47 +1260,47 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           }
 
           // ---- drop constraint l at position kk (:409-423, :476-499; delete_constraint :610-679) ----
-          // With S = R^-1 the Givens sweep is driven by row kk of S: rotating the column pairs
-          // (j, j+1), j = kk .. iq-2, so that this row ends up in the last column makes
-          // S Q^T (minus row kk and the last column) the inverse of the re-triangularised R, with the
-          // same Q that QuadProg++ applies to the columns of J.
+          // Column kk of R goes, the columns behind it move up (each keeps one sub-diagonal entry), and the
+          // Givens rotations of the row pairs (j, j+1), j = kk .. iq-2, make R triangular again; the same
+          // pairs rotate the columns of Z afterwards (coefficient table `rot`).
           clr_bit(actm, l);
-          {
-            double carry = Rcol(kk)[kk];
 #pragma unroll 1
-            for (int j = kk; j < iq - 1; j++) {
-              double* cj = Rcol(j);
-              double* cn = Rcol(j + 1);
-              const double a = carry, b = cn[kk];
-              const double hh = qp_distance(a, b);
-              const bool skip = fabs(hh) < QP_EPS;
-              double cc = 1.0, ss = 0.0, xny = 0.0;
-              if (!skip) {
-                const double sgn = b >= 0.0 ? 1.0 : -1.0;
-                cc = sgn * b / hh;
-                ss = -sgn * a / hh;
-                xny = ss / (1.0 + cc);
-                carry = -sgn * hh;
-              } else {
-                carry = b;
-              }
-              const double t1a = lane <= j ? cj[lane] : 0.0, t2a = lane <= j + 1 ? cn[lane] : 0.0;
-              double t1b = 0.0, t2b = 0.0;
-              if (S2) { t1b = lane + 32 <= j ? cj[lane + 32] : 0.0; t2b = lane + 32 <= j + 1 ? cn[lane + 32] : 0.0; }
+          for (int i = kk; i < iq - 1; i++) {
+            const double* src = Rcol(i + 1);
+            double* dst = Rcol(i);
+            const double v0 = lane <= i + 1 ? src[lane] : 0.0;
+            __syncwarp();
+            if (lane <= i + 1) dst[lane] = v0;
+            __syncwarp();
+          }
+#pragma unroll 1
+          for (int j = kk; j < iq - 1; j++) {
+            double* cj = Rcol(j);
+            double cc = cj[j], ss = cj[j + 1];
+            const double hh = qp_distance(cc, ss);
+            const bool skip = fabs(hh) < QP_EPS;  // QuadProg++ leaves such a pair untouched
+            double xny = 0.0;
+            if (!skip) {
+              cc = cc / hh;
+              ss = ss / hh;
+              double diag = hh;
+              if (cc < 0.0) { diag = -hh; cc = -cc; ss = -ss; }
+              xny = ss / (1.0 + cc);
               __syncwarp();
-              const double nja = skip ? t1a : t1a * cc + t2a * ss, nna = skip ? t2a : xny * (t1a + nja) - t2a;
-              // column j is final: store it without row kk; column j+1 keeps its rows until its turn
-              if (lane <= j + 1 && lane != kk) cj[lane - (lane > kk ? 1 : 0)] = nja;
-              if (lane <= j + 1) cn[lane] = nna;
-              if (S2) {
-                const double njb = skip ? t1b : t1b * cc + t2b * ss, nnb = skip ? t2b : xny * (t1b + njb) - t2b;
-                const int i = lane + 32;
-                if (i <= j + 1 && i != kk) cj[i - (i > kk ? 1 : 0)] = njb;
-                if (i <= j + 1) cn[i] = nnb;
+              if (lane == 0) { cj[j] = diag; cj[j + 1] = 0.0; rinv[j] = 1.0 / diag; }
+              const int k = j + 1 + lane;  // iq <= RC <= 32: one column per lane
+              if (k < iq - 1) {
+                double* ck = Rcol(k);
+                const double t1r = ck[j], t2r = ck[j + 1];
+                const double nj = t1r * cc + t2r * ss;
+                ck[j] = nj;
+                ck[j + 1] = xny * (t1r + nj) - t2r;
               }
-              if (lane == 0) { rot[3 * j] = skip ? 2.0 : cc; rot[3 * j + 1] = ss; rot[3 * j + 2] = xny; }
-              __syncwarp();
+            } else if (lane == 0) {
+              rinv[j] = 1.0 / cc;
             }
+            if (lane == 0) { rot[3 * j] = skip ? 2.0 : cc; rot[3 * j + 1] = ss; rot[3 * j + 2] = xny; }
+            __syncwarp();
           }
           {  // A[i], u[i] <- A[i+1], u[i+1] for i = kk .. iq-1 (the candidate at iq moves down too)
             int a0_ = 0, a1_ = 0;
@@ -1553,6 +1560,19 @@ int reg_shape_id(const DevProblem& hp) {
   PNC_REG_SHAPES(X)
 #undef X
   return 0;
+}
+
+bool reg_record_layout(const DevProblem& hp, int* o) {
+#define X(a, b, c, d, e)                                                                                      \
+  if (shape_ok<a, b, c, d, e>(hp)) {                                                                          \
+    using C = MCfg<a, b, c, d, e>;                                                                            \
+    const int v[10] = {C::N, C::PE, C::NCOL, C::NPC, C::HW, C::RJ, C::RJB, C::RX, C::RS, C::REC};             \
+    for (int i = 0; i < 10; i++) o[i] = v[i];                                                                 \
+    return true;                                                                                              \
+  }
+  PNC_REG_SHAPES(X)
+#undef X
+  return false;
 }
 
 bool reg_kernel_available(const DevProblem& hp) {

@@ -85,6 +85,7 @@ void launch_task_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtr
 bool reg_kernel_available(const DevProblem& hp);
 int reg_setup_record_doubles(const DevProblem& hp);
 int reg_shape_id(const DevProblem& hp);
+bool reg_record_layout(const DevProblem& hp, int* layout10);
 void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
                        int B, int num_sms, cudaStream_t stream, int* counter);
 void launch_task_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap& fm, int nfr, int B, int itask, int dim,

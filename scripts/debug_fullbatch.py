@@ -8,7 +8,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from pypnc_b200 import robots, engine  # noqa: E402
+from pypnc_b200 import robots, engine, _cabi  # noqa: E402
+if os.environ.get('PNC_LIB'):  # A/B against another build of the library (diagnostic only)
+    _cabi.LIB_PATH = os.environ['PNC_LIB']
 from oracle import oracle  # noqa: E402
 from tests import hp_referee  # noqa: E402
 

@@ -153,7 +153,9 @@ def _reference_stack(name, robot, spec):
     return tci.task_list, tci.contact_list, tci.internal_constraint_list, ctrl._ihwbc, ctrl._sa
 
 
-def generate(name, B=6, seed=0):
+def generate(name, B=6, seed=0, detail=True, suffix=''):
+    """detail=True keeps the per-task / per-contact intermediates (large); detail=False only the inputs and
+    the controller outputs trq / acc / rf -- used for the 128-state sets."""
     spec = robots.PROBLEMS[name]()
     model = spec.model
     robot = OracleRobotSystem(model, False)
@@ -176,9 +178,11 @@ def generate(name, B=6, seed=0):
     op = O.OracleProblem(spec)
     states = robots.synth_states(name, spec, B, seed)
     des, w, rfz = robots.synth_desireds(name, spec, states, op.task_actuals(states), seed)
-    if B >= 4:  # cover the degenerate ramp-start value and the <=0 clamp of contact.py:37-41
-        rfz[2, 0] = 1e-3
-        rfz[3, -1] = -5.0
+    # cover the degenerate ramp-start value and the <=0 clamp of contact.py:37-41
+    for b in range(2, B, 16):
+        rfz[b, 0] = 1e-3
+    for b in range(3, B, 16):
+        rfz[b, -1] = -5.0
     n, p, mi = spec.qp_dims
     out = dict(trq=[], acc=[], rf=[], qddot=[], M=[], grav=[], cori=[], task_jac=[], task_jdqd=[], task_op=[],
                cone_mat=[], cone_vec=[])
@@ -208,6 +212,8 @@ def generate(name, B=6, seed=0):
             ic.update_internal_constraint()
         trq, acc, rf = ihwbc.solve(tasks, contacts, ics)
         out['trq'].append(trq); out['acc'].append(acc); out['rf'].append(rf)
+        if not detail:
+            continue
         out['M'].append(M); out['grav'].append(g); out['cori'].append(c)
         out['task_jac'].append(np.concatenate([t.jacobian for t in tasks], 0))
         out['task_jdqd'].append(np.concatenate([t.jacobian_dot_q_dot for t in tasks]))
@@ -216,8 +222,8 @@ def generate(name, B=6, seed=0):
         out['cone_vec'].append(np.concatenate([ct.cone_constraint_vec for ct in contacts]))
     arrays = {('in_' + k): v for k, v in states.items()}
     arrays.update(in_des=des, in_w=w, in_rf_z_max=rfz)
-    arrays.update({('out_' + k): np.array(v) for k, v in out.items()})
-    path = os.path.join(HERE, name + '.npz')
+    arrays.update({('out_' + k): np.array(v) for k, v in out.items() if len(v)})
+    path = os.path.join(HERE, name + suffix + '.npz')
     np.savez_compressed(path, **arrays)
     print('%-10s B=%d  |trq|max=%.1f  sum fz=%s  -> %s' %
           (name, B, np.abs(arrays['out_trq']).max(), np.round(arrays['out_rf'][0], 1)[:6], os.path.basename(path)))
@@ -228,3 +234,4 @@ if __name__ == '__main__':
     os.chdir(tempfile.mkdtemp())  # the reference's DataSaver writes ./data when enabled
     for nm in (sys.argv[1:] or ['atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie']):
         generate(nm)
+        generate(nm, B=128, seed=100, detail=False, suffix='_128')

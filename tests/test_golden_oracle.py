@@ -11,8 +11,8 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 ROBOTS = ['atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie']
 
 
-def load_golden(name):
-    z = np.load(os.path.join(GOLD, name + '.npz'))
+def load_golden(name, suffix=''):
+    z = np.load(os.path.join(GOLD, name + suffix + '.npz'))
     states = {k[3:]: z[k] for k in z.files if k.startswith('in_') and k not in ('in_des', 'in_w', 'in_rf_z_max')}
     return z, states
 
@@ -21,11 +21,13 @@ def rel_err(a, b):
     return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
 
 
+@pytest.mark.parametrize("suffix", ['', '_128'])
 @pytest.mark.parametrize("name", ROBOTS)
-def test_oracle_tick_matches_reference_python(oracle_mod, name):
+def test_oracle_tick_matches_reference_python(oracle_mod, name, suffix):
+    """6 detailed + 128 further states per robot (every 16th with rf_z_max = 1e-3 resp. <= 0, contact.py:37-41)."""
     spec = robots.PROBLEMS[name]()
     op = oracle_mod.OracleProblem(spec)
-    z, states = load_golden(name)
+    z, states = load_golden(name, suffix)
     out = op.tick_batch(states, z['in_des'], z['in_w'], z['in_rf_z_max'])
     assert np.all(out['status'] == 0)
     # tolerance: 1e-9 relative (north_star), numpy/BLAS vs plain-C summation order in the assembly

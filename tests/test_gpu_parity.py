@@ -217,13 +217,17 @@ def test_task_and_contact_eval_match_oracle(ctx):
             np.testing.assert_array_equal(cv[b].cpu().numpy(), e['cone_constraint_vec'])
 
 
+@pytest.mark.parametrize("suffix", ['', '_128'])
 @pytest.mark.parametrize("name", ROBOTS)
-def test_golden_vectors_from_reference_python(name):
-    """tests/golden/<robot>.npz: outputs of the reference's own IHWBC / BasicTask / contact
-    classes (tests/golden/make_golden.py) on committed inputs."""
+def test_golden_vectors_from_reference_python(name, suffix, oracle_mod):
+    """tests/golden/<robot>[_128].npz: outputs of the reference's own IHWBC / BasicTask / contact
+    classes (tests/golden/make_golden.py) on committed inputs: 6 + 128 states per robot, every 16th with
+    rf_z_max = 1e-3 resp. <= 0 (contact.py:37-41).  Default (refined) termination: 1e-9 wherever the
+    reference's own answer is well defined (no exact tie on its path, exact stop -- measured by running
+    the oracle on the same inputs), 1e-5 on the rest."""
     import torch
     from pypnc_b200 import engine
-    z = np.load(os.path.join(GOLD, name + '.npz'))
+    z = np.load(os.path.join(GOLD, name + suffix + '.npz'))
     spec = robots.PROBLEMS[name]()
     B = z['in_des'].shape[0]
     dm = engine.Model(spec.model, 0)
@@ -234,12 +238,19 @@ def test_golden_vectors_from_reference_python(name):
                                        for k in ('in_des', 'in_w', 'in_rf_z_max')])
     torch.cuda.synchronize()
     assert (out['status'].cpu().numpy() == 0).all()
+    ref = oracle_mod.OracleProblem(spec).tick_batch({k: z['in_' + k] for k in KEYS}, z['in_des'], z['in_w'], z['in_rf_z_max'])
+    strict = (ref['margin'] > TIE_MARGIN) & (ref['psi_rel'] <= 1e-11)
+    worst = 0.0
     for k in ('trq', 'acc', 'rf'):
         err = per_state_rel(out[k].cpu().numpy(), z['out_' + k])
-        assert err.max() < RTOL, (k, err.max())
-    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
-    assert rel(ws.view('M').cpu().numpy(), z['out_M']) < 1e-13
-    assert rel(ws.view('grav').cpu().numpy(), z['out_grav']) < 1e-13
+        worst = max(worst, float(err.max()))
+        assert err[strict].max() < RTOL, (k, float(err[strict].max()), int(np.argmax(np.where(strict, err, 0))))
+        assert err.max() < 1e-5, (k, float(err.max()))
+    print("golden %s%s: %d states (%d strict), worst %.2e" % (name, suffix, B, int(strict.sum()), worst))
+    if 'out_M' in z.files:
+        rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+        assert rel(ws.view('M').cpu().numpy(), z['out_M']) < 1e-13
+        assert rel(ws.view('grav').cpu().numpy(), z['out_grav']) < 1e-13
 
 
 @pytest.mark.parametrize("ctx", ['atlas', 'laikago', 'draco3'], indirect=True)

@@ -230,8 +230,29 @@ class Env:
         if self.world > 1:
             dist.init_process_group('nccl', device_id=torch.device('cuda', self.local_rank))
         self.dev = torch.device('cuda', self.local_rank)
+        self.affinity = self._bind_to_gpu_numa_node()
         self.lib = _cabi.load_library()
         self.stream = torch.cuda.current_stream()
+
+    def _bind_to_gpu_numa_node(self):
+        """Run this rank (and first-touch its pinned staging buffers) on the CPUs next to its GPU: with N ranks
+        on one node the host side of the end-to-end path otherwise shares one NUMA node's DRAM and PCIe root."""
+        if self.world <= 1 or os.environ.get('PNC_NO_AFFINITY'):
+            return None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index(self.local_rank))
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = [64 * wi + b for wi, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1 and 64 * wi + b < ncpu]
+            allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                return len(allowed)
+        except Exception:
+            pass
+        return None
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -546,7 +567,7 @@ def main():
             "kernels_ms": {"pnc_update_system": res['ms_dyn'], "pnc_ihwbc_solve": res['ms_qp']},
             "solver": {"status_counts": [int(x) for x in st[:5]], "mean_active_set_iterations": st[5] / st[6]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e_of(res, world_states), "gpu_launches": res['launches'],
-            "clocks": res['clocks']}
+            "clocks": res['clocks'], "host_cpus_bound_per_rank": env.affinity}
     if extra or osc:
         configs = {}
         if osc:

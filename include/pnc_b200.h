@@ -347,6 +347,44 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
                       double* h_acc, double* h_rf, int32_t* h_status, int32_t* h_iters,
                       uint64_t* h_active);
 
+/* JointIntegrator state and constants (pnc/wbc/ihwbc/joint_integrator.py:6-82) for the command epilogue of
+ * pnc_wbc_tick_host_ex: d_vel_state / d_pos_state [capacity, na] device, in/out; limits [na,2] device. */
+typedef struct {
+  double* d_vel_state;
+  double* d_pos_state;
+  const double* d_pos_limit;
+  const double* d_vel_limit;
+  double alpha_vel, alpha_pos, dt;
+} pnc_integrator;
+
+#define PNC_TICK_DES_ON_DEVICE 1 /* des / w / rf_z_max are DEVICE pointers (written by the on-device managers) */
+
+/* The whole <Robot>Controller.get_command (atlas_controller.py:51-86, draco3_controller.py:51-103) as one
+ * stream-ordered call: update_system, solve and -- when `integ` is given -- the command epilogue: actuated
+ * torques / accelerations back to all joints through Sa[:, 6:]^T and JointIntegrator.integrate, returned as
+ * h_joint_trq_cmd / h_joint_vel_cmd / h_joint_pos_cmd [B, na] (create_cmd_ordered_dict's three arrays).
+ * With PNC_TICK_DES_ON_DEVICE in `flags` the task desireds, weights and rf_z_max are read from device memory
+ * (the pnc_*_eval manager entry points wrote them there; `ready_stream` is the stream they were enqueued on, or
+ * NULL when they are known to be complete) and only the robot state crosses the bus: 584 of the 1704 input
+ * bytes per Atlas state.  Synchronous like pnc_wbc_tick_host. */
+int pnc_wbc_tick_host_ex(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,
+                         const double* h_base_quat, const double* h_base_lin_vel, const double* h_base_ang_vel,
+                         const double* h_joint_pos, const double* h_joint_vel, const double* des, const double* w,
+                         const double* rf_z_max, int32_t flags, void* ready_stream, const pnc_integrator* integ,
+                         double* h_trq, double* h_acc, double* h_rf, int32_t* h_status, int32_t* h_iters,
+                         uint64_t* h_active, double* h_joint_trq_cmd, double* h_joint_vel_cmd,
+                         double* h_joint_pos_cmd);
+
+/* One host batch sharded over n devices from one process: problems[i] / workspaces[i] live on
+ * device i's GPU, device i takes the contiguous states [i B / n, (i + 1) B / n) of every host array; all
+ * devices are enqueued before any is waited for.  No collective: the shards are independent. */
+int pnc_wbc_tick_host_multi(int32_t n_dev, const pnc_problem* const* problems, pnc_workspace* const* workspaces,
+                            int32_t B, const double* h_base_pos, const double* h_base_quat,
+                            const double* h_base_lin_vel, const double* h_base_ang_vel, const double* h_joint_pos,
+                            const double* h_joint_vel, const double* h_des, const double* h_w,
+                            const double* h_rf_z_max, double* h_trq, double* h_acc, double* h_rf,
+                            int32_t* h_status, int32_t* h_iters, uint64_t* h_active);
+
 /* number of kernels this library has launched since load (bench `gpu_launches`) */
 int64_t pnc_launch_count(void);
 /* DFMA-chain microbenchmark: measured fp64 FMA peak of the device in TFLOP/s */

@@ -97,6 +97,14 @@ def make_problem_desc(spec):
     return d, keep
 
 
+class Integrator(C.Structure):
+    """pnc_integrator (include/pnc_b200.h)"""
+    _fields_ = [('d_vel_state', C.c_void_p), ('d_pos_state', C.c_void_p), ('d_pos_limit', C.c_void_p),
+                ('d_vel_limit', C.c_void_p), ('alpha_vel', C.c_double), ('alpha_pos', C.c_double), ('dt', C.c_double)]
+
+
+TICK_DES_ON_DEVICE = 1
+
 _lib = None
 
 
@@ -152,6 +160,8 @@ def load_library():
     lib.pnc_sinusoid_eval.argtypes = [i32, vp, vp, c_double_p, c_double_p, dbl, vp, vp, vp, vp]
     lib.pnc_dcm_update.argtypes = [vp, i32, dbl, dbl, vp, vp, vp, vp]
     lib.pnc_wbc_tick_host.argtypes = [vp, vp, i32] + [vp] * 15
+    lib.pnc_wbc_tick_host_ex.argtypes = [vp, vp, i32] + [vp] * 9 + [i32, vp, vp] + [vp] * 9
+    lib.pnc_wbc_tick_host_multi.argtypes = [i32, vp, vp, i32] + [vp] * 15
     lib.pnc_launch_count.argtypes = []
     lib.pnc_launch_count.restype = i64
     lib.pnc_measure_fp64_peak.argtypes = [C.c_int, c_double_p]
@@ -170,7 +180,7 @@ EXPORTED_SYMBOLS = [
     'pnc_ws_centroidal_ig', 'pnc_ws_q', 'pnc_ws_qdot', 'pnc_ws_mass_matrix', 'pnc_ws_gravity',
     'pnc_ws_coriolis', 'pnc_ws_com_pos', 'pnc_ws_com_vel', 'pnc_ws_com_jac', 'pnc_ws_com_jacdot',
     'pnc_ws_com_jdqd', 'pnc_ws_frame_iso', 'pnc_ws_frame_vel', 'pnc_ws_frame_jac', 'pnc_ws_frame_jdqd',
-    'pnc_ihwbc_solve', 'pnc_ihwbc_solve_ref', 'pnc_set_termination', 'pnc_get_termination', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_osc_step', 'pnc_wbc_tick_host',
+    'pnc_ihwbc_solve', 'pnc_ihwbc_solve_ref', 'pnc_set_termination', 'pnc_get_termination', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_osc_step', 'pnc_wbc_tick_host', 'pnc_wbc_tick_host_ex', 'pnc_wbc_tick_host_multi',
     'pnc_quadprog_batch', 'pnc_ramp_update', 'pnc_foot_use_current', 'pnc_swing_init', 'pnc_swing_eval', 'pnc_floating_base_init',
     'pnc_floating_base_eval', 'pnc_sinusoid_eval', 'pnc_dcm_update',
     'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version', 'pnc_debug_set_dump', 'pnc_debug_setup_record',

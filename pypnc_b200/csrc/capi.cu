@@ -104,6 +104,7 @@ struct pnc_workspace {
   cudaStream_t tick_stream[2];          // compute, chunks alternate
   cudaStream_t tick_in, tick_out;       // host -> device and device -> host copies
   cudaEvent_t tick_ev_in[16], tick_ev_done[16];  // per chunk: inputs landed, kernels finished
+  cudaEvent_t tick_ev_ready;                     // producer of device-resident desireds done
   bool tick_init;
 };
 
@@ -237,6 +238,8 @@ int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* dsc, pnc_prob
     if (h.act_idx[i] < 6 || h.act_idx[i] >= h.nv) { delete p; return PNC_E_ARG; }
     if (dsc->b_trq_limit) { h.trq_lo[i] = dsc->trq_limit[2 * i]; h.trq_hi[i] = dsc->trq_limit[2 * i + 1]; }
   }
+  for (int j = 0; j < PNC_MAX_NV; j++) h.act_of_joint[j] = -1;
+  for (int i = 0; i < dsc->nact; i++) h.act_of_joint[h.act_idx[i] - 6] = i;
   for (int i = 0; i < dsc->n_ic; i++)
     for (int j = 0; j < h.nv; j++) h.ic_jac[i][j] = dsc->ic_jac[i * h.nv + j];
   p->lay = ihwbc_layout(h);
@@ -325,6 +328,7 @@ void pnc_workspace_destroy(pnc_workspace* ws) {
     for (int i = 0; i < 2; i++) cudaStreamDestroy(ws->tick_stream[i]);
     cudaStreamDestroy(ws->tick_in); cudaStreamDestroy(ws->tick_out);
     for (int i = 0; i < 16; i++) { cudaEventDestroy(ws->tick_ev_in[i]); cudaEventDestroy(ws->tick_ev_done[i]); }
+    cudaEventDestroy(ws->tick_ev_ready);
   }
   cudaGetLastError();
   delete ws;
@@ -709,27 +713,42 @@ int pnc_dcm_update(pnc_workspace* ws, int32_t B, double dt, double alpha, double
 // every chunk in, the kernels of the chunks alternate over two streams, one stream copies the
 // outputs out, and per-chunk events order them (see below).  Chunks own disjoint slices of the
 // workspace and of the staging slab, so they never alias.  Host buffers should be pinned.
-int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,
-                      const double* h_base_quat, const double* h_base_lin_vel, const double* h_base_ang_vel,
-                      const double* h_joint_pos, const double* h_joint_vel, const double* h_des, const double* h_w,
-                      const double* h_rf_z_max, double* h_trq, double* h_acc, double* h_rf, int32_t* h_status,
-                      int32_t* h_iters, uint64_t* h_active) {
-  if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m) return PNC_E_ARG;
-  if (!h_base_pos || !h_base_quat || !h_base_lin_vel || !h_base_ang_vel || !h_joint_pos || !h_joint_vel ||
-      !h_des || !h_w || (p->h.ncontact && !h_rf_z_max))
-    return PNC_E_ARG;
-  if (B == 0) return PNC_OK;
+struct TickArgs {
+  const double *h_bp, *h_bq, *h_blv, *h_bav, *h_jp, *h_jv;  // robot state, host
+  const double *des, *w, *rfz;                               // host, or device when des_on_device
+  bool des_on_device;
+  cudaStream_t ready;                                        // producer stream of device des / w / rfz (may be 0)
+  const pnc_integrator* integ;                               // optional command epilogue
+  double *h_trq, *h_acc, *h_rf;
+  int32_t *h_status, *h_iters;
+  uint64_t* h_active;
+  double *h_jtrq, *h_jvel, *h_jpos;                          // all-joint commands (with integ)
+};
+
+static int tick_wait(pnc_workspace* ws) {
+  if (!ws->tick_init) return PNC_OK;
+  cudaSetDevice(ws->device);
+  cudaError_t e0 = cudaStreamSynchronize(ws->tick_out);
+  cudaError_t e1 = cudaStreamSynchronize(ws->tick_stream[0]);
+  cudaError_t e2 = cudaStreamSynchronize(ws->tick_stream[1]);
+  cudaError_t e3 = cudaStreamSynchronize(ws->tick_in);
+  return (e0 == cudaSuccess && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) ? PNC_OK : PNC_E_CUDA;
+}
+
+// enqueues everything of one tick on the workspace's own streams; tick_wait() completes it
+static int tick_enqueue(const pnc_problem* p, pnc_workspace* ws, int32_t B, const TickArgs& A) {
   CK(cudaSetDevice(ws->m->device));
   const DevProblem& P = p->h;
   const size_t na = ws->m->h.na, nv = P.nv;
   const int mw = (P.m + 63) / 64 > 0 ? (P.m + 63) / 64 : 1;
   // per-state doubles in / out
   const size_t in_d = 3 + 4 + 3 + 3 + 2 * na + P.ndes + P.ntask + P.ncontact;
-  const size_t out_d = 2 * (size_t)P.nact + P.nc + nv;
+  const size_t out_d = 2 * (size_t)P.nact + P.nc + nv + 3 * na;
   const size_t per_state = (in_d + out_d) * 8 + 8 /*status, iters*/ + 8 * (size_t)mw;
   const size_t need = per_state * (size_t)ws->cap + 64 * 256;
   if (ws->stage_bytes < need) {
     if (ws->stage) cudaFree(ws->stage);
+    ws->stage = nullptr; ws->stage_bytes = 0;
     CK(cudaMalloc(&ws->stage, need));
     ws->stage_bytes = need;
   }
@@ -741,6 +760,7 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
       CK(cudaEventCreateWithFlags(&ws->tick_ev_in[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ws->tick_ev_done[i], cudaEventDisableTiming));
     }
+    CK(cudaEventCreateWithFlags(&ws->tick_ev_ready, cudaEventDisableTiming));
     ws->tick_init = true;
   }
   // carve the staging slab (capacity-sized arrays)
@@ -759,10 +779,20 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
   double* d_trq = (double*)take(C * P.nact * 8);
   double* d_acc = (double*)take(C * P.nact * 8);
   double* d_rf = (double*)take(C * (P.nc ? P.nc : 1) * 8);
+  double* d_jtrq = (double*)take(C * na * 8);
+  double* d_jvel = (double*)take(C * na * 8);
+  double* d_jpos = (double*)take(C * na * 8);
   int32_t* d_status = (int32_t*)take(C * 4);
   int32_t* d_iters = (int32_t*)take(C * 4);
   uint64_t* d_active = (uint64_t*)take(C * mw * 8);
   int* counters = (int*)take(1024);  // 8 ints per chunk, up to 16 chunks
+  if (A.des_on_device) {  // desireds, weights and rf_z_max already live on the device (on-device managers)
+    d_des = const_cast<double*>(A.des); d_w = const_cast<double*>(A.w); d_rfz = const_cast<double*>(A.rfz);
+    if (A.ready) {
+      CK(cudaEventRecord(ws->tick_ev_ready, A.ready));
+      for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(ws->tick_stream[i], ws->tick_ev_ready, 0));
+    }
+  }
 
   // chunk schedule: a short first chunk gets the kernels going early (its H2D copy is the only
   // one nothing overlaps), the rest are equal.  PNC_TICK_CHUNKS / PNC_TICK_FIRST (fraction) override.
@@ -813,9 +843,12 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
     if (nb <= 0) continue;
     cudaStream_t st = ws->tick_in;
 #define H2D(dst, src, per) CK(cudaMemcpyAsync((dst) + (size_t)o * (per), (src) + (size_t)o * (per), (size_t)nb * (per) * 8, cudaMemcpyHostToDevice, st))
-    H2D(d_bp, h_base_pos, 3); H2D(d_bq, h_base_quat, 4); H2D(d_blv, h_base_lin_vel, 3); H2D(d_bav, h_base_ang_vel, 3);
-    H2D(d_jp, h_joint_pos, na); H2D(d_jv, h_joint_vel, na); H2D(d_des, h_des, P.ndes); H2D(d_w, h_w, P.ntask);
-    if (P.ncontact) H2D(d_rfz, h_rf_z_max, P.ncontact);
+    H2D(d_bp, A.h_bp, 3); H2D(d_bq, A.h_bq, 4); H2D(d_blv, A.h_blv, 3); H2D(d_bav, A.h_bav, 3);
+    H2D(d_jp, A.h_jp, na); H2D(d_jv, A.h_jv, na);
+    if (!A.des_on_device) {
+      H2D(d_des, A.des, P.ndes); H2D(d_w, A.w, P.ntask);
+      if (P.ncontact) H2D(d_rfz, A.rfz, P.ncontact);
+    }
 #undef H2D
     CK(cudaEventRecord(ws->tick_ev_in[c], st));
   }
@@ -832,18 +865,99 @@ int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const 
                   d_rf + (size_t)o * P.nc, nullptr, d_status + o, d_iters + o, d_active + (size_t)o * mw, st,
                   counters + 8 * c);
     if (rc) return rc;
+    if (A.integ) {  // controller epilogue: Sa^T scatter + JointIntegrator.integrate (atlas_controller.py:79-85)
+      const pnc_integrator& J = *A.integ;
+      launch_command_epilogue(p->d, nb, (int)na, d_trq + (size_t)o * P.nact, d_acc + (size_t)o * P.nact, d_jp + (size_t)o * na,
+                              J.d_vel_state + (size_t)o * na, J.d_pos_state + (size_t)o * na, J.d_pos_limit, J.d_vel_limit,
+                              J.alpha_vel, J.alpha_pos, J.dt, d_jtrq + (size_t)o * na, d_jvel + (size_t)o * na,
+                              d_jpos + (size_t)o * na, st);
+      CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(ws->tick_ev_done[c], st));
     cudaStream_t so = ws->tick_out;
     CK(cudaStreamWaitEvent(so, ws->tick_ev_done[c], 0));
 #define D2H(dst, src, per, esz) if (dst) CK(cudaMemcpyAsync((char*)(dst) + (size_t)o * (per) * (esz), (const char*)(src) + (size_t)o * (per) * (esz), (size_t)nb * (per) * (esz), cudaMemcpyDeviceToHost, so))
-    D2H(h_trq, d_trq, P.nact, 8); D2H(h_acc, d_acc, P.nact, 8); D2H(h_rf, d_rf, P.nc, 8);
-    D2H(h_status, d_status, 1, 4); D2H(h_iters, d_iters, 1, 4); D2H(h_active, d_active, mw, 8);
+    D2H(A.h_trq, d_trq, P.nact, 8); D2H(A.h_acc, d_acc, P.nact, 8); D2H(A.h_rf, d_rf, P.nc, 8);
+    D2H(A.h_status, d_status, 1, 4); D2H(A.h_iters, d_iters, 1, 4); D2H(A.h_active, d_active, mw, 8);
+    if (A.integ) { D2H(A.h_jtrq, d_jtrq, na, 8); D2H(A.h_jvel, d_jvel, na, 8); D2H(A.h_jpos, d_jpos, na, 8); }
 #undef D2H
   }
-  CK(cudaStreamSynchronize(ws->tick_out));
-  CK(cudaStreamSynchronize(ws->tick_stream[0]));
-  CK(cudaStreamSynchronize(ws->tick_stream[1]));
   return PNC_OK;
+}
+
+static int tick_args_ok(const pnc_problem* p, const pnc_workspace* ws, int32_t B, const TickArgs& A) {
+  if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m) return PNC_E_ARG;
+  if (!A.h_bp || !A.h_bq || !A.h_blv || !A.h_bav || !A.h_jp || !A.h_jv || !A.des || !A.w || (p->h.ncontact && !A.rfz))
+    return PNC_E_ARG;
+  if (A.integ && (!A.integ->d_vel_state || !A.integ->d_pos_state || !A.integ->d_pos_limit || !A.integ->d_vel_limit))
+    return PNC_E_ARG;
+  return PNC_OK;
+}
+
+int pnc_wbc_tick_host(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,
+                      const double* h_base_quat, const double* h_base_lin_vel, const double* h_base_ang_vel,
+                      const double* h_joint_pos, const double* h_joint_vel, const double* h_des, const double* h_w,
+                      const double* h_rf_z_max, double* h_trq, double* h_acc, double* h_rf, int32_t* h_status,
+                      int32_t* h_iters, uint64_t* h_active) {
+  TickArgs A = {h_base_pos, h_base_quat, h_base_lin_vel, h_base_ang_vel, h_joint_pos, h_joint_vel, h_des, h_w, h_rf_z_max,
+                false, nullptr, nullptr, h_trq, h_acc, h_rf, h_status, h_iters, h_active, nullptr, nullptr, nullptr};
+  int rc = tick_args_ok(p, ws, B, A);
+  if (rc || B == 0) return rc;
+  rc = tick_enqueue(p, ws, B, A);
+  const int rw = tick_wait(ws);  // also on an error: nothing of this call stays in flight
+  return rc ? rc : rw;
+}
+
+int pnc_wbc_tick_host_ex(const pnc_problem* p, pnc_workspace* ws, int32_t B, const double* h_base_pos,
+                         const double* h_base_quat, const double* h_base_lin_vel, const double* h_base_ang_vel,
+                         const double* h_joint_pos, const double* h_joint_vel, const double* des, const double* w,
+                         const double* rf_z_max, int32_t flags, void* ready_stream, const pnc_integrator* integ,
+                         double* h_trq, double* h_acc, double* h_rf, int32_t* h_status, int32_t* h_iters, uint64_t* h_active,
+                         double* h_joint_trq_cmd, double* h_joint_vel_cmd, double* h_joint_pos_cmd) {
+  TickArgs A = {h_base_pos, h_base_quat, h_base_lin_vel, h_base_ang_vel, h_joint_pos, h_joint_vel, des, w, rf_z_max,
+                (flags & PNC_TICK_DES_ON_DEVICE) != 0, (cudaStream_t)ready_stream, integ, h_trq, h_acc, h_rf, h_status,
+                h_iters, h_active, h_joint_trq_cmd, h_joint_vel_cmd, h_joint_pos_cmd};
+  int rc = tick_args_ok(p, ws, B, A);
+  if (rc || B == 0) return rc;
+  rc = tick_enqueue(p, ws, B, A);
+  const int rw = tick_wait(ws);
+  return rc ? rc : rw;
+}
+
+// One host batch over n devices from ONE process: contiguous split of the state dimension,
+// device i takes states [i B / n, (i + 1) B / n); every device's copies and kernels are enqueued before
+// any is waited for, so the devices run concurrently.
+int pnc_wbc_tick_host_multi(int32_t n_dev, const pnc_problem* const* ps, pnc_workspace* const* wss, int32_t B,
+                            const double* h_base_pos, const double* h_base_quat, const double* h_base_lin_vel,
+                            const double* h_base_ang_vel, const double* h_joint_pos, const double* h_joint_vel,
+                            const double* h_des, const double* h_w, const double* h_rf_z_max, double* h_trq,
+                            double* h_acc, double* h_rf, int32_t* h_status, int32_t* h_iters, uint64_t* h_active) {
+  if (n_dev < 1 || n_dev > 64 || !ps || !wss || B < 0) return PNC_E_ARG;
+  int rc = PNC_OK, launched = 0;
+  for (int i = 0; i < n_dev && rc == PNC_OK; i++) {
+    const pnc_problem* p = ps[i];
+    pnc_workspace* ws = wss[i];
+    if (!p || !ws) { rc = PNC_E_ARG; break; }
+    const long long lo = (long long)B * i / n_dev, hi = (long long)B * (i + 1) / n_dev;
+    const int32_t nb = (int32_t)(hi - lo);
+    const DevProblem& P = p->h;
+    const size_t na = ws->m->h.na;
+    const int mw = (P.m + 63) / 64 > 0 ? (P.m + 63) / 64 : 1;
+#define OFF(ptr, per) ((ptr) ? (ptr) + (size_t)lo * (per) : nullptr)
+    TickArgs A = {OFF(h_base_pos, 3), OFF(h_base_quat, 4), OFF(h_base_lin_vel, 3), OFF(h_base_ang_vel, 3),
+                  OFF(h_joint_pos, na), OFF(h_joint_vel, na), OFF(h_des, P.ndes), OFF(h_w, P.ntask),
+                  OFF(h_rf_z_max, P.ncontact), false, nullptr, nullptr, OFF(h_trq, P.nact), OFF(h_acc, P.nact),
+                  OFF(h_rf, P.nc), OFF(h_status, 1), OFF(h_iters, 1), OFF(h_active, mw), nullptr, nullptr, nullptr};
+#undef OFF
+    rc = tick_args_ok(p, ws, nb, A);
+    if (rc == PNC_OK && nb > 0) rc = tick_enqueue(p, ws, nb, A);
+    launched = i + 1;
+  }
+  for (int i = 0; i < launched; i++) {
+    const int rw = tick_wait(wss[i]);
+    if (rc == PNC_OK) rc = rw;
+  }
+  return rc;
 }
 
 int pnc_debug_setup_record(const pnc_problem* p, pnc_workspace* ws, double** d_rec, int32_t* stride, int32_t* layout) {

@@ -1294,6 +1294,46 @@ __global__ void k_joint_integrate(int B, int na, const double* __restrict__ acc,
   }
 }
 
+// Controller epilogue (atlas_controller.py:79-85, draco3_controller.py:88-103): the actuated commands go back
+// to all joints through Sa[:, 6:]^T (zero for a passive joint) and the integrator advances its state.
+// One thread per (state, joint).
+__global__ void k_command_epilogue(const DevProblem* __restrict__ gp, int B, int na, const double* __restrict__ trq,
+                                   const double* __restrict__ acc, const double* __restrict__ joint_pos,
+                                   double* vel_state, double* pos_state, const double* __restrict__ pos_limit,
+                                   const double* __restrict__ vel_limit, double alpha_vel, double alpha_pos, double dt,
+                                   double* __restrict__ joint_trq_cmd, double* __restrict__ joint_vel_cmd,
+                                   double* __restrict__ joint_pos_cmd) {
+  const DevProblem& P = *gp;
+  const size_t total = (size_t)B * na;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % na);
+    const size_t s = i / na;
+    const int a = P.act_of_joint[j];
+    const double qdd = a >= 0 ? acc[s * P.nact + a] : 0.0;
+    if (joint_trq_cmd) joint_trq_cmd[i] = a >= 0 ? trq[s * P.nact + a] : 0.0;
+    double v = (1.0 - alpha_vel) * vel_state[i] + qdd * dt;
+    v = fmin(fmax(v, vel_limit[2 * j]), vel_limit[2 * j + 1]);
+    double ps = (1.0 - alpha_pos) * pos_state[i] + alpha_pos * joint_pos[i] + v * dt;
+    ps = fmin(fmax(ps, pos_limit[2 * j]), pos_limit[2 * j + 1]);
+    vel_state[i] = v;
+    pos_state[i] = ps;
+    if (joint_vel_cmd) joint_vel_cmd[i] = v;
+    if (joint_pos_cmd) joint_pos_cmd[i] = ps;
+  }
+}
+
+void launch_command_epilogue(const DevProblem* dp, int B, int na, const double* trq, const double* acc,
+                             const double* joint_pos, double* vel_state, double* pos_state, const double* pos_limit,
+                             const double* vel_limit, double alpha_vel, double alpha_pos, double dt,
+                             double* joint_trq_cmd, double* joint_vel_cmd, double* joint_pos_cmd, cudaStream_t stream) {
+  size_t total = (size_t)B * na;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_command_epilogue<<<grid, 256, 0, stream>>>(dp, B, na, trq, acc, joint_pos, vel_state, pos_state, pos_limit, vel_limit,
+                                               alpha_vel, alpha_pos, dt, joint_trq_cmd, joint_vel_cmd, joint_pos_cmd);
+  g_launch_count++;
+}
+
 void launch_joint_integrate(int B, int na, const double* acc, const double* joint_pos, double* vel_state,
                             double* pos_state, const double* pos_limit, const double* vel_limit, double alpha_vel,
                             double alpha_pos, double dt, cudaStream_t stream) {

@@ -75,6 +75,7 @@ struct DevProblem {
   int joint_sel[PNC_MAX_NV * 2];
   double kp[64], kd[64];
   int act_idx[PNC_MAX_NV];
+  int act_of_joint[PNC_MAX_NV];  // joint (0-based, v index - 6) -> actuated row, -1 for a passive joint
   double trq_lo[PNC_MAX_NV], trq_hi[PNC_MAX_NV];
   double ic_jac[PNC_MAX_IC][PNC_MAX_NV];
 };

@@ -97,6 +97,10 @@ void launch_contact_eval(const DevProblem* dp, const WsPtrs& ws, const FrameMap&
 void launch_joint_integrate(int B, int na, const double* acc, const double* joint_pos, double* vel_state,
                             double* pos_state, const double* pos_limit, const double* vel_limit, double alpha_vel,
                             double alpha_pos, double dt, cudaStream_t stream);
+void launch_command_epilogue(const DevProblem* dp, int B, int na, const double* trq, const double* acc,
+                             const double* joint_pos, double* vel_state, double* pos_state, const double* pos_limit,
+                             const double* vel_limit, double alpha_vel, double alpha_pos, double dt,
+                             double* joint_trq_cmd, double* joint_vel_cmd, double* joint_pos_cmd, cudaStream_t stream);
 bool launch_quadprog_dense(int n, int p, int m, int B, const double* G, const double* g0, const double* CE, const double* ce0,
                            const double* CI, const double* ci0, double* x, double* f, int* status, int* iters,
                            unsigned long long* active, int num_sms, cudaStream_t stream);

@@ -237,3 +237,24 @@ def quadprog_batch(G, g0, CE=None, ce0=None, CI=None, ci0=None, want_active=Fals
     _check(lib.pnc_quadprog_batch(dev.index or 0, B, n, p, m, P(G), P(g0), P(CE), P(ce0), P(CI), P(ci0), P(x), P(f),
                                   P(status), P(iters), P(active), stream), 'pnc_quadprog_batch')
     return (x, f, status, iters, active) if want_active else (x, f, status, iters)
+
+
+def tick_host_multi(problems, workspaces, host_in, host_out):
+    """pnc_wbc_tick_host_multi: one host batch sharded over several GPUs from this process.
+    problems / workspaces: one engine.Problem / engine.Workspace per device (same problem spec);
+    host_in: the nine host arrays (numpy or pinned torch CPU tensors) base_pos, base_quat, base_lin_vel,
+    base_ang_vel, joint_pos, joint_vel, des, w, rf_z_max with the GLOBAL batch first;
+    host_out: trq, acc, rf, status (int32), iters (int32), active (uint64) host arrays (any may be None)."""
+    lib = problems[0].lib
+    n = len(problems)
+    P = (vp * n)(*[p.h for p in problems])
+    W = (vp * n)(*[w.h for w in workspaces])
+    B = int(host_in[4].shape[0])
+
+    def hp(a):
+        if a is None:
+            return None
+        return vp(a.data_ptr()) if torch.is_tensor(a) else a.ctypes.data_as(vp)
+
+    _check(lib.pnc_wbc_tick_host_multi(n, P, W, B, *[hp(a) for a in host_in], *[hp(a) for a in host_out]),
+           'pnc_wbc_tick_host_multi')

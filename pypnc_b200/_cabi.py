@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libpnc_b200.so')
+# PNC_B200_LIB points at another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get('PNC_B200_LIB') or os.path.join(_HERE, 'csrc', 'libpnc_b200.so')
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

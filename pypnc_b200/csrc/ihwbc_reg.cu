@@ -667,8 +667,11 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         double gk[PE];
 #pragma unroll
         for (int k = 0; k < PE; k++) gk[k] = 0.0;
+        // row i of J is zero left of its diagonal and, for i < nv, right of column nv: rows 0..31 of a robot
+        // with nv >= 32 only need columns [0, nv), rows 32.. only columns [32, n)
+        const int jlo = slot == 0 ? 0 : 32, jhi = (slot == 0 && NV >= 32) ? ((NV + 1) & ~1) : NP;
 #pragma unroll 1
-        for (int j = 0; j < NP; j += 2) {
+        for (int j = jlo; j < jhi; j += 2) {
           double rx, ry;
           PNC_ROWVAL(j, rx, ry);
 #pragma unroll

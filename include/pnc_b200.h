@@ -158,13 +158,21 @@ typedef struct {
   double lambda_q_ddot;
   double lambda_rf;
   int32_t ndes;            /* length of one per-state `des` row */
+  /* IHWBC2 transmission constraint (pnc/wbc/ihwbc/ihwbc2.py:131-139,249-256,386-403; b_transmission_constraint):
+   * n_trans equality rows (Sd - Sv)(M qddot + c + g - Jc^T rf) = 0 instead of the internal-constraint rows, no
+   * projection (Ni = I), and the internal force Sv(...) fed back through Ji^T in the torque recovery.  Row k pairs
+   * the distal joint trans_distal[k] (one-hot column of Sd) with the passive joint trans_passive[k] (column of
+   * Sv, the joint the internal-constraint row k carries with +1); v indices.  Requires n_ic = 0, no torque limits. */
+  int32_t n_trans;
+  const int32_t* trans_distal;
+  const int32_t* trans_passive;
 } pnc_problem_desc;
 
 typedef struct pnc_problem pnc_problem;
 
 int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* desc, pnc_problem** out);
 void pnc_problem_destroy(pnc_problem* p);
-/* sizes derived from the descriptor: QP n = nv + nc, p = 6 + n_ic, m = ncone + 2*nact */
+/* sizes derived from the descriptor: QP n = nv + nc, p = 6 + n_ic + n_trans, m = ncone + 2*nact */
 int pnc_problem_dims(const pnc_problem* p, int32_t* nc, int32_t* ncone, int32_t* n, int32_t* p_eq,
                      int32_t* m_ineq);
 

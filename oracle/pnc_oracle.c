@@ -1025,6 +1025,7 @@ done:
 struct orc_problem {
   const orc_model* m;
   int ntask, ncontact, n_joint_sel, n_gain, n_ic, nact, b_trq_limit, ndes;
+  int n_trans, trans_d[8], trans_p[8]; /* IHWBC2 transmission rows (ihwbc2.py), v indices of the distal / passive joints */
   pnc_task_desc* tasks;
   pnc_contact_desc* contacts;
   int *joint_sel, *act_idx;
@@ -1038,6 +1039,8 @@ orc_problem* orc_problem_create(const orc_model* m, const pnc_problem_desc* d) {
   p->m = m;
   p->ntask = d->ntask; p->ncontact = d->ncontact; p->n_joint_sel = d->n_joint_sel; p->n_gain = d->n_gain;
   p->n_ic = d->n_ic; p->nact = d->nact; p->b_trq_limit = d->b_trq_limit; p->ndes = d->ndes;
+  p->n_trans = d->n_trans;
+  for (int i = 0; i < d->n_trans && i < 8; i++) { p->trans_d[i] = d->trans_distal[i]; p->trans_p[i] = d->trans_passive[i]; }
   p->lambda_q_ddot = d->lambda_q_ddot; p->lambda_rf = d->lambda_rf;
   p->tasks = (pnc_task_desc*)dupmem(d->tasks, sizeof(pnc_task_desc) * d->ntask);
   p->contacts = (pnc_contact_desc*)dupmem(d->contacts, sizeof(pnc_contact_desc) * d->ncontact);
@@ -1060,7 +1063,7 @@ void orc_problem_destroy(orc_problem* p) {
   free(p->ic_jac); free(p->trq_limit); free(p);
 }
 void orc_problem_dims(const orc_problem* p, int* nc, int* ncone, int* n, int* peq, int* mineq) {
-  *nc = p->nc; *ncone = p->ncone; *n = p->m->nv + p->nc; *peq = 6 + p->n_ic;
+  *nc = p->nc; *ncone = p->ncone; *n = p->m->nv + p->nc; *peq = 6 + p->n_ic + p->n_trans;
   *mineq = p->ncone + (p->b_trq_limit ? 2 * p->nact : 0);
 }
 
@@ -1193,7 +1196,7 @@ typedef struct {
 static void asm_alloc(const orc_problem* p, asm_t* a) {
   const orc_model* m = p->m;
   int nv = m->nv;
-  a->nv = nv; a->nc = p->nc; a->ncone = p->ncone; a->n = nv + p->nc; a->peq = 6 + p->n_ic;
+  a->nv = nv; a->nc = p->nc; a->ncone = p->ncone; a->n = nv + p->nc; a->peq = 6 + p->n_ic + p->n_trans;
   a->mineq = p->ncone + (p->b_trq_limit ? 2 * p->nact : 0); a->nact = p->nact; a->npass = nv - 6 - p->nact;
   size_t n = a->n, mi = a->mineq > 0 ? a->mineq : 1;
   a->M = (double*)calloc((size_t)nv * nv, 8); a->Minv = (double*)calloc((size_t)nv * nv, 8);
@@ -1361,6 +1364,13 @@ static void assemble(const orc_problem* p, const double* q, const double* v, con
     for (int j = 0; j < nv; j++) a->Am[(6 + i) * n + j] = p->ic_jac[i * nv + j];
     a->b[6 + i] = 0;
   }
+  /* IHWBC2, b_transmission_constraint (ihwbc2.py:249-256): [(Sd - Sv) M | (-Sd + Sv) Jc^T] x = (-Sd + Sv)(c+g) */
+  for (int i = 0; i < p->n_trans; i++) {
+    int vd = p->trans_d[i], vp = p->trans_p[i], r = 6 + k + i;
+    for (int j = 0; j < nv; j++) a->Am[r * n + j] = a->M[vd * nv + j] - a->M[vp * nv + j];
+    for (int j = 0; j < nc; j++) a->Am[r * n + nv + j] = -a->Jc[j * nv + vd] + a->Jc[j * nv + vp];
+    a->b[r] = -a->cg[vd] + a->cg[vp];
+  }
 
   /* ---- inequalities, :255-317 */
   memset(a->Gm, 0, sizeof(double) * (a->mineq > 0 ? a->mineq : 1) * n);
@@ -1439,12 +1449,46 @@ void orc_wbc_tick(const orc_problem* p, const double* bp, const double* bq, cons
     for (int j = 0; j < nc; j++) jr += a.JcNi[j * nv + i] * x[nv + j];
     tmp[i] = s + ntg - jr;
   }
+  double* Str = NULL; /* S of the transmission variant */
+  if (p->n_trans > 0) {
+    /* ihwbc2.py:131-139,386-403: sa_trc_bar = weighted_pinv(Sa[:, 6:], Minv[6:, 6:]); f_int = Sv (...);
+     * trq = sa_trc_bar^T Snf (M qdd + c + g - Jc^T rf - Ji^T f_int), Ji row k = +1 at the passive (proximal),
+     * -1 at the distal joint (draco3_rolling_joint_constraint.py:9-16) */
+    int na_all = nv - 6, nact = a.nact;
+    mat_inv_spd_or_general(a.M, a.Minv, nv);
+    double* A = (double*)calloc((size_t)nact * na_all, 8);
+    double* W = (double*)calloc((size_t)na_all * na_all, 8);
+    double* AW = (double*)calloc((size_t)nact * na_all, 8);
+    double* At = (double*)calloc((size_t)nact * na_all, 8);
+    double* AWAt = (double*)calloc((size_t)nact * nact, 8);
+    double* pin = (double*)calloc((size_t)nact * nact, 8);
+    double* WAt = (double*)calloc((size_t)na_all * nact, 8);
+    double* Abar = (double*)calloc((size_t)na_all * nact, 8);
+    for (int i = 0; i < nact; i++) A[i * na_all + (p->act_idx[i] - 6)] = 1.0;
+    for (int i = 0; i < na_all; i++) for (int j = 0; j < na_all; j++) W[i * na_all + j] = a.Minv[(6 + i) * nv + 6 + j];
+    mat_mul(A, W, AW, nact, na_all, na_all);
+    mat_tr(A, At, nact, na_all);
+    mat_mul(AW, At, AWAt, nact, na_all, nact);
+    orc_pinv(AWAt, nact, nact, 1e-15, pin);
+    mat_mul(W, At, WAt, na_all, na_all, nact);
+    mat_mul(WAt, pin, Abar, na_all, nact, nact);
+    Str = (double*)calloc((size_t)nact * nv, 8);
+    for (int i = 0; i < nact; i++) for (int j = 0; j < na_all; j++) Str[i * nv + 6 + j] = Abar[j * nact + i];
+    for (int k = 0; k < p->n_trans; k++) {
+      double f_int = tmp[p->trans_p[k]];
+      tmp[p->trans_p[k]] -= f_int;
+      tmp[p->trans_d[k]] += f_int;
+    }
+    free(A); free(W); free(AW); free(At); free(AWAt); free(pin); free(WAt); free(Abar);
+  }
   for (int i = 0; i < a.nact; i++) {
     double s = 0;
-    for (int j = 0; j < nv; j++) s += a.S[i * nv + j] * tmp[j];
+    const double* Srow = Str ? Str + (size_t)i * nv : a.S + (size_t)i * nv;
+    for (int j = 0; j < nv; j++) s += Srow[j] * tmp[j];
     if (trq) trq[i] = s;
     if (acc) acc[i] = x[p->act_idx[i]];
   }
+  free(Str);
   if (rf) for (int j = 0; j < nc; j++) rf[j] = x[nv + j];
   if (qddot) for (int j = 0; j < nv; j++) qddot[j] = x[j];
   if (active) {

@@ -44,7 +44,8 @@ class ProblemDesc(C.Structure):
                 ('n_gain', C.c_int32), ('kp', c_double_p), ('kd', c_double_p), ('n_ic', C.c_int32),
                 ('ic_jac', c_double_p), ('nact', C.c_int32), ('act_idx', c_int32_p),
                 ('b_trq_limit', C.c_int32), ('trq_limit', c_double_p), ('lambda_q_ddot', C.c_double),
-                ('lambda_rf', C.c_double), ('ndes', C.c_int32)]
+                ('lambda_rf', C.c_double), ('ndes', C.c_int32), ('n_trans', C.c_int32),
+                ('trans_distal', c_int32_p), ('trans_passive', c_int32_p)]
 
 
 def _dp(a):
@@ -87,14 +88,17 @@ def make_problem_desc(spec):
                 kd=np.ascontiguousarray(spec.kd, dtype=np.float64),
                 ic_jac=np.ascontiguousarray(spec.ic_jac, dtype=np.float64),
                 act_idx=np.ascontiguousarray(spec.act_idx, dtype=np.int32),
-                trq_limit=np.ascontiguousarray(spec.trq_limit, dtype=np.float64))
+                trq_limit=np.ascontiguousarray(spec.trq_limit, dtype=np.float64),
+                trans_d=np.ascontiguousarray(list(getattr(spec, 'trans_distal', [])) or [0], dtype=np.int32),
+                trans_p=np.ascontiguousarray(list(getattr(spec, 'trans_passive', [])) or [0], dtype=np.int32))
     d = ProblemDesc(ntask=len(spec.tasks), tasks=tasks, ncontact=len(spec.contacts), contacts=contacts,
                     n_joint_sel=len(keep['joint_sel']), joint_sel=_ip(keep['joint_sel']),
                     n_gain=len(keep['kp']), kp=_dp(keep['kp']), kd=_dp(keep['kd']),
                     n_ic=spec.n_ic, ic_jac=_dp(keep['ic_jac']), nact=len(keep['act_idx']),
                     act_idx=_ip(keep['act_idx']), b_trq_limit=int(spec.b_trq_limit),
                     trq_limit=_dp(keep['trq_limit']), lambda_q_ddot=spec.lambda_q_ddot,
-                    lambda_rf=spec.lambda_rf, ndes=spec.ndes)
+                    lambda_rf=spec.lambda_rf, ndes=spec.ndes, n_trans=len(getattr(spec, 'trans_distal', [])),
+                    trans_distal=_ip(keep['trans_d']), trans_passive=_ip(keep['trans_p']))
     return d, keep
 
 

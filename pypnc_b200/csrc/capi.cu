@@ -228,7 +228,14 @@ int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* dsc, pnc_prob
   }
   h.nc = nc; h.nu = nu;
   h.n = h.nv + nc;
-  h.p = 6 + h.n_ic;
+  h.n_trans = dsc->n_trans;
+  if (h.n_trans < 0 || h.n_trans > PNC_MAX_IC || (h.n_trans > 0 && (h.n_ic > 0 || h.b_trq_limit))) { delete p; return PNC_E_ARG; }
+  for (int i = 0; i < h.n_trans; i++) {
+    h.trans_d[i] = dsc->trans_distal[i];
+    h.trans_p[i] = dsc->trans_passive[i];
+    if (h.trans_d[i] < 6 || h.trans_d[i] >= h.nv || h.trans_p[i] < 6 || h.trans_p[i] >= h.nv) { delete p; return PNC_E_ARG; }
+  }
+  h.p = 6 + h.n_ic + h.n_trans;
   h.m = nu + (h.b_trq_limit ? 2 * h.nact : 0);
   if (h.n > PNC_MAX_N || h.m > PNC_MAX_M) { delete p; return PNC_E_SIZE; }
   for (int i = 0; i < dsc->n_joint_sel; i++) h.joint_sel[i] = dsc->joint_sel[i];

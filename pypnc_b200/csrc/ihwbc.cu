@@ -375,6 +375,18 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
       const int nrow = L.nrow;
       for (int rI = 0; rI < nrow; rI++) {
         double* row = Ar + rI * ld;
+        if (rI >= 6 && rI < p && P.n_trans > 0) {  // IHWBC2 transmission rows (Sd - Sv) [M | -Jc^T] (ihwbc2.py:249-256)
+          const int vd = P.trans_d[rI - 6], vp = P.trans_p[rI - 6];
+          for (int c = lane; c < nv; c += 32) row[c] = Mg[vd * nv + c] - Mg[vp * nv + c];
+          for (int c = lane; c < nc; c += 32) {
+            int ci = 0;
+            while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
+            const double* jr = contact_jac_row(P.contacts[ci], fm.contact_f[ci], ws, s, nfr, nv, c - P.contacts[ci].rf_off);
+            row[nv + c] = -(jr[vd] - jr[vp]);
+          }
+          if (lane == 0) a0[rI] = (ws.cori[s * nv + vd] + ws.grav[s * nv + vd]) - (ws.cori[s * nv + vp] + ws.grav[s * nv + vp]);
+          continue;
+        }
         if (rI >= 6 && rI < p) {  // internal-constraint rows [Ji | 0]
           for (int c = lane; c < n; c += 32) row[c] = c < nv ? P.ic_jac[rI - 6][c] : 0.0;
           if (lane == 0) a0[rI] = 0.0;
@@ -756,6 +768,21 @@ k_ihwbc_solve(const DevProblem* __restrict__ gp, IhwbcLayout L, WsPtrs ws, Frame
               t0 -= contact_jac_row(C, fm.contact_f[ci], ws, s, nfr, nv, k)[v] * x[nv + C.rf_off + k];
           }
           tau = t0 + ws.cori[s * nv + v] + ws.grav[s * nv + v];
+          // IHWBC2 transmission (ihwbc2.py:386-403): the internal force Sv (M qddot + c + g - Jc^T rf) at the
+          // passive joint comes back through Ji^T onto its distal joint
+          for (int kt = 0; kt < P.n_trans; kt++) {
+            if (P.trans_d[kt] != v) continue;
+            const int vp = P.trans_p[kt];
+            const double* Mp = ws.M + (s * nv + vp) * nv;
+            double tp = 0.0;
+            for (int k = 0; k < nv; k++) tp += Mp[k] * x[k];
+            for (int ci = 0; ci < P.ncontact; ci++) {
+              const DevContact& C = P.contacts[ci];
+              for (int k = 0; k < C.dim; k++)
+                tp -= contact_jac_row(C, fm.contact_f[ci], ws, s, nfr, nv, k)[vp] * x[nv + C.rf_off + k];
+            }
+            tau += tp + ws.cori[s * nv + vp] + ws.grav[s * nv + vp];
+          }
         }
         io.trq[s * nact + a] = bad ? nanv : tau;
       }

@@ -208,7 +208,7 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min
   L.og0 = o; o += C::NP;
   L.odm = o; o += C::NP;
   L.odl = o; o += C::NP;
-  if (o - L.om6 < ((6 * C::NV + 1) & ~1)) o = L.om6 + ((6 * C::NV + 1) & ~1);
+  if (o - L.om6 < ((C::PE * C::NV + 1) & ~1)) o = L.om6 + ((C::PE * C::NV + 1) & ~1);
   // ... and once D sits in registers, the Householder vectors of its QR ([row][reflector]) and their
   // Gram matrix take the same place
   if (o - L.om6 < ((C::N * C::PE + C::PE * C::PE + 4 * C::PE + 1) & ~1)) o = L.om6 + ((C::N * C::PE + C::PE * C::PE + 4 * C::PE + 1) & ~1);
@@ -519,7 +519,8 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       double* Bs = Gs + PE * PE;             // beta_k
       double* Ys = Bs + PE;                  // y = R^-T (CE^T x0 + ce0)
       {
-        double* m6 = smem + SL.om6;
+        double* m6 = smem + SL.om6;  // the nv-part of the PE equality normals, [PE][NV]
+        const bool has_tr = P.n_trans > 0;
         __syncwarp();  // x0 is done with the vectors m6 overlays
 #pragma unroll 1
         for (int e0 = lane; e0 < 6 * NV; e0 += 32 * 7) {
@@ -530,6 +531,15 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           for (int u = 0; u < 7; u++)
             if (e0 + 32 * u < 6 * NV) m6[e0 + 32 * u] = v[u];
         }
+        if constexpr (PE > 6) {
+          // rows 6..: internal-constraint rows Ji (ihwbc.py:225-249), or IHWBC2's transmission rows
+          // (Sd - Sv) M (ihwbc2.py:249-256)
+#pragma unroll 1
+          for (int e = lane; e < (PE - 6) * NV; e += 32) {
+            const int i = e / NV, k = e - i * NV;
+            m6[6 * NV + e] = has_tr ? Mg[P.trans_d[i] * NV + k] - Mg[P.trans_p[i] * NV + k] : G.ic_jac[i][k];
+          }
+        }
         __syncwarp();
 #pragma unroll
         for (int pass = 0; pass < 2; pass++) {
@@ -538,7 +548,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           for (int i = 0; i < PE; i++) dq[pass][i] = 0.0;
           if (pass == 1 && N <= 32) continue;
           if (pass == 0 || NV > 32) {
-            double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, e4 = 0.0, e5 = 0.0;
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, e4 = 0.0, e5 = 0.0, e6 = 0.0, e7 = 0.0;
             const int kmax = NV < 32 * (pass + 1) ? NV : 32 * (pass + 1);
             const double* gp_ = Gm + (j < NV ? j : 0);
 #pragma unroll 2
@@ -546,23 +556,20 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
               const double g = (j < NV && k <= j) ? gp_[0] : 0.0;
               e0 = fma(g, m6[k], e0); e1 = fma(g, m6[NV + k], e1); e2 = fma(g, m6[2 * NV + k], e2);
               e3 = fma(g, m6[3 * NV + k], e3); e4 = fma(g, m6[4 * NV + k], e4); e5 = fma(g, m6[5 * NV + k], e5);
+              if constexpr (PE > 6) { e6 = fma(g, m6[6 * NV + k], e6); e7 = fma(g, m6[7 * NV + k], e7); }
             }
             dq[pass][0] = e0; dq[pass][1] = e1; dq[pass][2] = e2; dq[pass][3] = e3; dq[pass][4] = e4; dq[pass][5] = e5;
-            if constexpr (PE > 6) {  // internal-constraint rows [Ji | 0]
-#pragma unroll
-              for (int i = 6; i < PE; i++) {
-                double acc = 0.0;
-                if (j < NV) {
-#pragma unroll 1
-                  for (int k = 0; k <= j; k++) acc = fma(Gm[k * LDV + j], P.ic_jac[i - 6][k], acc);
-                }
-                dq[pass][i] = acc;
-              }
-            }
+            if constexpr (PE > 6) { dq[pass][6] = e6; dq[pass][7] = e7; }
           }
           if (j >= NV && j < N) {
 #pragma unroll
             for (int i = 0; i < 6; i++) dq[pass][i] = -jrf * row_jc(j - NV, i);
+            if constexpr (PE > 6) {
+              if (has_tr) {  // -(Sd - Sv) (Jc)^T
+#pragma unroll
+                for (int i = 6; i < PE; i++) dq[pass][i] = -jrf * (row_jc(j - NV, P.trans_d[i - 6]) - row_jc(j - NV, P.trans_p[i - 6]));
+              }
+            }
           }
         }
         // equality residuals at x0 (its reaction-force part is zero): floating-base rows M[i,:] x0 + (c+g)_i
@@ -572,9 +579,13 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         for (int i = 0; i < PE; i++) {
           double part = 0.0;
 #pragma unroll 1
-          for (int k = lane; k < NV; k += 32) part = fma(i < 6 ? m6[i * NV + k] : G.ic_jac[i < 6 ? 0 : i - 6][k], xs[k], part);
+          for (int k = lane; k < NV; k += 32) part = fma(m6[i * NV + k], xs[k], part);
           part = wsum(part);
           if (i < 6) part += has_ic ? ws.ic_cg[s * NV + i] : ws.cori[s * NV + i] + ws.grav[s * NV + i];
+          else if (has_tr) {
+            const int vd = P.trans_d[i - 6], vp = P.trans_p[i - 6];
+            part += (ws.cori[s * NV + vd] + ws.grav[s * NV + vd]) - (ws.cori[s * NV + vp] + ws.grav[s * NV + vp]);
+          }
           if (lane == i) cmine = part;
         }
         __syncwarp();  // m6 is dead: the reflectors go there
@@ -1425,6 +1436,23 @@ k_ihwbc_finish(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nf
             xr += dim;
           }
           tau = t0 + t1 + ws.cori[s * nv + v] + ws.grav[s * nv + v];
+          // IHWBC2 transmission (ihwbc2.py:386-403): the internal force Sv (M qddot + c + g - Jc^T rf) at the
+          // passive joint comes back through Ji^T onto its distal joint
+          for (int kt = 0; kt < G.n_trans; kt++) {
+            if (G.trans_d[kt] != v) continue;
+            const int vp = G.trans_p[kt];
+            const double* cp = ws.M + s * nv * nv + vp;
+            double tp = 0.0;
+            for (int k2 = 0; k2 < nv; k2++) tp = fma(cp[k2 * nv], x[k2], tp);
+            const double* xr2 = x + nv;
+            for (int ci = 0; ci < G.ncontact; ci++) {
+              const int dim = G.contacts[ci].dim;
+              const double* jr = ws.fr_jac + ((s * nfr + fm.contact_f[ci]) * 6 + (6 - dim)) * nv + vp;
+              for (int r = 0; r < dim; r++) tp = fma(-jr[r * nv], xr2[r], tp);
+              xr2 += dim;
+            }
+            tau += tp + ws.cori[s * nv + vp] + ws.grav[s * nv + vp];
+          }
         }
       }
       io.trq[s * nact + a] = tau;

@@ -76,6 +76,8 @@ struct DevProblem {
   double kp[64], kd[64];
   int act_idx[PNC_MAX_NV];
   int act_of_joint[PNC_MAX_NV];  // joint (0-based, v index - 6) -> actuated row, -1 for a passive joint
+  int n_trans;                   // IHWBC2 transmission rows (0 = none)
+  int trans_d[PNC_MAX_IC], trans_p[PNC_MAX_IC];  // v index of the distal / passive joint of each row
   double trq_lo[PNC_MAX_NV], trq_hi[PNC_MAX_NV];
   double ic_jac[PNC_MAX_IC][PNC_MAX_NV];
 };

@@ -48,6 +48,9 @@ class ProblemSpec:
     kd: list = field(default_factory=list)
     ic_jac: np.ndarray = None
     n_ic: int = 0
+    # IHWBC2 transmission rows (ihwbc2.py b_transmission_constraint): v indices of the (distal, passive) joints
+    trans_distal: list = field(default_factory=list)
+    trans_passive: list = field(default_factory=list)
     act_idx: list = field(default_factory=list)
     b_trq_limit: bool = False
     trq_limit: np.ndarray = None
@@ -129,7 +132,7 @@ class ProblemSpec:
     @property
     def qp_dims(self):
         n = self.model.nv + self.nc
-        p = 6 + self.n_ic
+        p = 6 + self.n_ic + len(self.trans_distal)
         m = self.ncone + (2 * self.nact if self.b_trq_limit else 0)
         return n, p, m
 
@@ -214,6 +217,20 @@ def draco3_problem(model=None, b_trq_limit=False):
     return s.finalize()
 
 
+def draco3_transmission_problem(model=None):
+    """Draco3 through IHWBC2 with b_transmission_constraint (pnc/wbc/ihwbc/ihwbc2.py:131-139,249-256,386-403)
+    as DracoManipulationController would set it up (draco_manipulation_controller.py:17-51, the commented
+    IHWBC2 line): the PROXIMAL knee joints are passive (Sv), Sd selects the distal ones, the equality rows
+    (Sd - Sv)(M qddot + c + g - Jc^T rf) = 0 replace the rolling-joint rows and nothing is projected."""
+    m = model or load_model('draco3')
+    s = draco3_problem(m)
+    s.ic_jac, s.n_ic = np.zeros((0, m.nv)), 0
+    s.set_actuation(passive_joints=('l_knee_fe_jp', 'r_knee_fe_jp'), b_trq_limit=False)
+    s.trans_distal = [m.get_q_dot_idx('l_knee_fe_jd'), m.get_q_dot_idx('r_knee_fe_jd')]
+    s.trans_passive = [m.get_q_dot_idx('l_knee_fe_jp'), m.get_q_dot_idx('r_knee_fe_jp')]
+    return s.finalize()
+
+
 def draco3_lb_problem(model=None):
     m = model or load_model('draco3_lb')
     s = ProblemSpec(m)
@@ -254,12 +271,14 @@ def valkyrie_problem(model=None):
 
 
 PROBLEMS = {'atlas': atlas_problem, 'laikago': laikago_problem, 'draco3': draco3_problem,
-            'draco3_lb': draco3_lb_problem, 'valkyrie': valkyrie_problem}
+            'draco3_lb': draco3_lb_problem, 'valkyrie': valkyrie_problem,
+            'draco3_trans': draco3_transmission_problem}
 
 
 # ---------------------------------------------------------------------------
 # nominal configurations and synthetic states (section 8d)
 def nominal_pose(name, model):
+    name = 'draco3' if name == 'draco3_trans' else name  # same robot, other WBC formulation
     jp = np.zeros(model.na)
     base_z, base_quat = 0.9, np.array([0., 0., 0., 1.])
 

@@ -237,7 +237,7 @@ class IHWBC:
         robot = (task_list[0] if task_list else contact_list[0])._robot
         key = (tuple((t._task_type, t._dim, str(t._target_id), tuple(t._kp), tuple(t._kd)) for t in task_list),
                tuple((c._type, c._link_id, c._mu, c._x, c._y) for c in contact_list),
-               tuple(ic.jacobian.tobytes() for ic in internal_constraint_list), id(robot))
+               tuple(ic.jacobian.tobytes() for ic in internal_constraint_list), id(robot), self._key_extra())
         if key == self._key:
             return
         spec = ProblemSpec(robot.model)
@@ -256,6 +256,7 @@ class IHWBC:
         spec.b_trq_limit = self._trq_limit is not None
         spec.trq_limit = self._trq_limit
         spec.lambda_q_ddot, spec.lambda_rf = float(self._lambda_q_ddot), float(self._lambda_rf)
+        self._spec_hook(spec)
         spec.finalize()
         self._spec, self._robot = spec, robot
         self._problem = engine.Problem(robot.dev_model, spec)
@@ -265,6 +266,12 @@ class IHWBC:
             t._owner = (self, i)
         for i, c in enumerate(contact_list):
             c._owner = (self, i)
+
+    def _key_extra(self):  # subclasses: whatever else the compiled problem depends on
+        return None
+
+    def _spec_hook(self, spec):  # subclasses: last changes to the problem description
+        pass
 
     def _pack(self):
         robot, spec = self._robot, self._spec
@@ -330,6 +337,54 @@ class IHWBC:
         engine._check(self._problem.lib.pnc_contact_eval(self._problem.h, ws.h, B, ic, P(rfz), P(jac), P(cm), P(cv),
                                                          engine._stream()), 'pnc_contact_eval')
         return dict(jacobian=jac, cone_constraint_mat=cm, cone_constraint_vec=cv)
+
+
+class IHWBC2(IHWBC):
+    """pnc/wbc/ihwbc/ihwbc2.py:12-430: IHWBC plus the transmission-constraint variant.  ``sd`` selects the distal
+    joint of every transmission; with ``solve(..., b_transmission_constraint=True)`` the equality rows
+    (Sd - Sv)(M qddot + c + g - Jc^T rf) = 0 replace the internal-constraint rows, nothing is projected
+    (Ni = I) and the internal force Sv(...) comes back through Ji^T in the torque recovery (:386-403).
+    Without the flag it behaves exactly as IHWBC."""
+
+    def __init__(self, sf, sa, sv, sd, data_save=False):
+        super().__init__(sf, sa, sv, data_save)
+        self._sd = np.asarray(sd)
+        self._b_trans = False
+
+    def _transmission_pairs(self, internal_constraint_list):
+        if self._trq_limit is not None:
+            # ihwbc2.py:296-333 refers to sa_ni_trc_bar_tr, which the transmission branch never defines
+            raise NotImplementedError("the reference's transmission branch has no torque-limit rows (NameError in ihwbc2.py)")
+        sv, sd = np.asarray(self._sv), self._sd
+        assert sv.shape == sd.shape and np.all(sv.sum(1) == 1) and np.all(sd.sum(1) == 1)
+        ji = np.concatenate([ic.jacobian for ic in internal_constraint_list], 0)
+        pas, dis = [int(np.argmax(r)) for r in sv], [int(np.argmax(r)) for r in sd]
+        # the torque recovery B Snf (g - Ji^T Sv g) reduces to "distal joint += internal force" when row k of Ji
+        # carries +1 at passive joint k and -1 at distal joint k (the rolling joints, the reference's only case)
+        for k in range(len(pas)):
+            row = np.zeros(ji.shape[1])
+            row[pas[k]], row[dis[k]] = 1., -1.
+            if not np.array_equal(ji[k], row):
+                raise NotImplementedError("transmission constraint with a general internal-constraint Jacobian")
+        return pas, dis
+
+    def _key_extra(self):
+        return ('trans', tuple(self._pairs[0]), tuple(self._pairs[1])) if self._b_trans else None
+
+    def _spec_hook(self, spec):
+        if self._b_trans:
+            spec.ic_jac, spec.n_ic = None, 0
+            spec.trans_passive, spec.trans_distal = list(self._pairs[0]), list(self._pairs[1])
+
+    def compile(self, task_list, contact_list, internal_constraint_list):
+        if self._b_trans:
+            self._pairs = self._transmission_pairs(internal_constraint_list)
+        super().compile(task_list, contact_list, internal_constraint_list)
+
+    def solve(self, task_list, contact_list, internal_constraint_list, rf_des=None, verbose=False,
+              b_transmission_constraint=False):
+        self._b_trans = bool(b_transmission_constraint)
+        return super().solve(task_list, contact_list, internal_constraint_list, rf_des, verbose)
 
 
 class JointIntegrator:

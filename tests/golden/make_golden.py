@@ -124,6 +124,35 @@ def _reference_stack(name, robot, spec):
         PnCConfig.SAVE_DATA = False
         from pnc.draco3_pnc.draco3_tci_container import Draco3TCIContainer as TCI
         from pnc.draco3_pnc.draco3_controller import Draco3Controller as CTRL
+    elif name == 'draco3_trans':
+        # Draco3 through the reference's IHWBC2 with b_transmission_constraint, set up as
+        # draco_manipulation_controller.py:17-51 does (its IHWBC2 line is commented out there): proximal knee
+        # joints passive (Sv), Sd on the distal ones; task / contact / constraint lists of the Draco3 container
+        from config.draco3_config import PnCConfig
+        PnCConfig.SAVE_DATA = False
+        from pnc.draco3_pnc.draco3_tci_container import Draco3TCIContainer
+        from pnc.wbc.ihwbc.ihwbc2 import IHWBC2
+        tci = Draco3TCIContainer(robot)
+        l_jp, l_jd, r_jp, r_jd = robot.get_q_dot_idx(['l_knee_fe_jp', 'l_knee_fe_jd', 'r_knee_fe_jp', 'r_knee_fe_jd'])
+        act_list = [False] * robot.n_floating + [True] * robot.n_a
+        act_list[l_jp] = act_list[r_jp] = False
+        nv = len(act_list)
+        n_active = int(np.count_nonzero(act_list))
+        n_passive = nv - n_active - 6
+        sa, sv, sd = np.zeros((n_active, nv)), np.zeros((n_passive, nv)), np.zeros((n_passive, nv))
+        j = k = 0
+        for i in range(6, nv):
+            if act_list[i]:
+                sa[j, i] = 1.
+                j += 1
+            else:
+                sv[k, i] = 1.
+                k += 1
+        sd[0, l_jd] = sd[1, r_jd] = 1.
+        sf = np.zeros((6, nv)); sf[:, :6] = np.eye(6)
+        ih = IHWBC2(sf, sa, sv, sd, False)
+        ih.lambda_q_ddot, ih.lambda_rf = spec.lambda_q_ddot, spec.lambda_rf
+        return tci.task_list, tci.contact_list, tci.internal_constraint_list, ih, sa
     elif name == 'draco3_lb':
         from config.draco3_lb_config import PnCConfig
         PnCConfig.SAVE_DATA = False
@@ -210,7 +239,10 @@ def generate(name, B=6, seed=0, detail=True, suffix=''):
             ct.update_contact()
         for ic in ics:
             ic.update_internal_constraint()
-        trq, acc, rf = ihwbc.solve(tasks, contacts, ics)
+        if name == 'draco3_trans':
+            trq, acc, rf = ihwbc.solve(tasks, contacts, ics, b_transmission_constraint=True)
+        else:
+            trq, acc, rf = ihwbc.solve(tasks, contacts, ics)
         out['trq'].append(trq); out['acc'].append(acc); out['rf'].append(rf)
         if not detail:
             continue
@@ -232,6 +264,6 @@ def generate(name, B=6, seed=0, detail=True, suffix=''):
 if __name__ == '__main__':
     O.build()
     os.chdir(tempfile.mkdtemp())  # the reference's DataSaver writes ./data when enabled
-    for nm in (sys.argv[1:] or ['atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie']):
+    for nm in (sys.argv[1:] or ['atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie', 'draco3_trans']):
         generate(nm)
         generate(nm, B=128, seed=100, detail=False, suffix='_128')

@@ -105,6 +105,13 @@ def solve_state(op, spec, st, des, w, rfz, active):
     for i in range(k):
         rows.append([mp.mpf(float(spec.ic_jac[i, j])) for j in range(nv)] + [mp.mpf(0)] * nc)
         rhs.append(mp.mpf(0))
+    # IHWBC2 transmission rows (ihwbc2.py:249-256): (Sd - Sv) [M | -Jc^T] x = -(Sd - Sv)(c + g)
+    trans = list(zip(getattr(spec, 'trans_distal', []), getattr(spec, 'trans_passive', [])))
+    JcT = Jc.T
+    for vd, vp in trans:
+        rows.append([M[vd, j] - M[vp, j] for j in range(nv)] + [-(JcT[vd, j] - JcT[vp, j]) for j in range(nc)])
+        rhs.append(-(cg[vd, 0] - cg[vp, 0]))
+    k += len(trans)
     # active inequalities as equalities: cone rows  Uf rf = uf ... (:255-317: -Uf rf <= -uf), torque rows
     SM = S * M
     SJ = S * JcNi.T
@@ -135,7 +142,20 @@ def solve_state(op, spec, st, des, w, rfz, active):
     sol = mp.lu_solve(K, r)
     x = sol[:n, 0]
     qdd, rf = x[:nv, 0], x[nv:n, 0]
-    trq = S * (M * qdd + Ntcg - (JcNi.T * rf if nc else mp.zeros(nv, 1)))
+    gen = M * qdd + Ntcg - (JcNi.T * rf if nc else mp.zeros(nv, 1))
+    if trans:
+        # ihwbc2.py:131-139,386-403: trq = sa_trc_bar^T Snf (gen - Ji^T f_int), f_int = Sv gen, Ji row = +1 at the
+        # passive and -1 at the distal joint, sa_trc_bar = weighted_pinv(Sa[:, 6:], Minv[6:, 6:])
+        Minv = M ** -1
+        A = Sa[:, 6:nv]
+        W = Minv[6:nv, 6:nv]
+        S = mp.zeros(nact, nv)
+        S[:, 6:nv] = (W * A.T * ((A * W * A.T) ** -1)).T
+        for vd, vp in trans:
+            f_int = gen[vp, 0]
+            gen[vp, 0] -= f_int
+            gen[vd, 0] += f_int
+    trq = S * gen
     acc = Sa * qdd
     lam = sol[n + 6 + k:, 0]  # multipliers of the active inequalities (sign: all of one sign at an optimum)
     return dict(qddot=_np(qdd)[:, 0], rf=_np(rf)[:, 0] if nc else np.zeros(0), trq=_np(trq)[:, 0], acc=_np(acc)[:, 0],

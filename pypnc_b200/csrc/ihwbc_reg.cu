@@ -461,30 +461,79 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     if (!pd || !(P.lambda_rf > 0.0 || NC == 0)) {
       status = PNC_QP_NOT_PD;
     } else if (status == PNC_QP_OK) {
-      // ---- J = L^-T in place (QuadProg++.cc:203-210): lane i forward-solves L z = e_i ----
-#pragma unroll 1
-      for (int j = 0; j < NV; j++) {
-        const double* Lj = Gm + j * LDV;
-        const double idjj = dl[j];
+      // ---- J = L^-T (QuadProg++.cc:203-210): lane c forward-solves L x = e_c with x in REGISTERS (fully
+      //      unrolled: no shuffles, no barriers, every lane the same instruction stream); x is column c of
+      //      L^-1 = row c of J.  L is read as warp-uniform LDS.128 pairs.  Columns 32.. (nv > 32) only reach
+      //      rows 32..: a second, tiny solve in lanes 0 .. nv-33 ----
+      {
+#ifndef PNC_SETUP_ROLLED_INVERSE
+        double xr[NV];
 #pragma unroll
-        for (int rr = 0; rr < (NV > 32 ? 2 : 1); rr++) {
-          const int i = lane + 32 * rr;
-          if ((rr == 0 || j >= 32) && i <= j && i < NV) {
-            double* zi = Gm + i * LDV;
-            double s0 = i == j ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = i;
-            if ((k & 1) && k < j) { s0 = fma(-Lj[k], zi[k], s0); k++; }
-#pragma unroll 1
-            for (; k + 3 < j; k += 4) {
-              const double2 a0 = lds2(zi + k), a1 = lds2(zi + k + 2), b0 = lds2(Lj + k), b1 = lds2(Lj + k + 2);
-              s0 = fma(-a0.x, b0.x, s0); s1 = fma(-a0.y, b0.y, s1); s2 = fma(-a1.x, b1.x, s2); s3 = fma(-a1.y, b1.y, s3);
-            }
-#pragma unroll 1
-            for (; k < j; k++) s0 = fma(-Lj[k], zi[k], s0);
-            zi[j] = ((s0 + s1) + (s2 + s3)) * idjj;
+        for (int i = 0; i < NV; i++) {
+          const double* Li = Gm + i * LDV;
+          double s0 = i == lane ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+          for (int k = 0; k + 1 < i; k += 2) {
+            const double2 l = lds2(Li + k);
+            s0 = fma(-l.x, xr[k], s0);
+            s1 = fma(-l.y, xr[k + 1], s1);
+          }
+          if (i & 1) s0 = fma(-Li[i - 1], xr[i - 1], s0);
+          xr[i] = (s0 + s1) * dl[i];
+        }
+        constexpr int NX = NV > 32 ? NV - 32 : 0;
+        double xe[NX > 0 ? NX : 1];
+        if constexpr (NX > 0) {
+#pragma unroll
+          for (int i = 32; i < NV; i++) {
+            const double* Li = Gm + i * LDV;
+            double s0 = i == 32 + lane ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 32; k < i; k++) s0 = fma(-Li[k], xe[k - 32], s0);
+            xe[i - 32] = s0 * dl[i];
+          }
+        }
+        __syncwarp();  // every lane is done reading L
+        if (lane < NV) {
+          double* zr = Gm + lane * LDV;
+#pragma unroll
+          for (int i = 0; i + 1 < NV; i += 2) *reinterpret_cast<double2*>(zr + i) = make_double2(xr[i], xr[i + 1]);
+          if (NV & 1) zr[NV - 1] = xr[NV - 1];
+        }
+        if constexpr (NX > 0) {
+          if (lane < NX) {
+            double* zr = Gm + (32 + lane) * LDV;
+#pragma unroll
+            for (int i = 0; i < NV; i++) zr[i] = i >= 32 ? xe[i >= 32 ? i - 32 : 0] : 0.0;
           }
         }
         __syncwarp();
+#else
+#pragma unroll 1
+        for (int j = 0; j < NV; j++) {
+          const double* Lj = Gm + j * LDV;
+          const double idjj = dl[j];
+#pragma unroll
+          for (int rr = 0; rr < (NV > 32 ? 2 : 1); rr++) {
+            const int i = lane + 32 * rr;
+            if ((rr == 0 || j >= 32) && i <= j && i < NV) {
+              double* zi = Gm + i * LDV;
+              double s0 = i == j ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+              int k = i;
+              if ((k & 1) && k < j) { s0 = fma(-Lj[k], zi[k], s0); k++; }
+#pragma unroll 1
+              for (; k + 3 < j; k += 4) {
+                const double2 a0 = lds2(zi + k), a1 = lds2(zi + k + 2), b0 = lds2(Lj + k), b1 = lds2(Lj + k + 2);
+                s0 = fma(-a0.x, b0.x, s0); s1 = fma(-a0.y, b0.y, s1); s2 = fma(-a1.x, b1.x, s2); s3 = fma(-a1.y, b1.y, s3);
+              }
+#pragma unroll 1
+              for (; k < j; k++) s0 = fma(-Lj[k], zi[k], s0);
+              zi[j] = ((s0 + s1) + (s2 + s3)) * idjj;
+            }
+          }
+          __syncwarp();
+        }
+#endif
       }
       const double jrf = 1.0 / sqrt(P.lambda_rf > 0.0 ? P.lambda_rf : 1.0);
       {

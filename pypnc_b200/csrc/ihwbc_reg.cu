@@ -221,7 +221,7 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min
 }
 
 template <int NV, int NC, int NU, int NT, int PE>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 16)  // <= 128 registers: shared memory allows 14-16 one-warp CTAs per SM
 k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, SetupLayout SL, WsPtrs ws, FrameMap fm,
               int nfr, int B, SolveIO io, double* __restrict__ rec_all, int* __restrict__ counter) {
   using C = MCfg<NV, NC, NU, NT, PE>;
@@ -418,6 +418,108 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     }
     double* dl = vm;  // reciprocal diagonal of L
     bool pd = true;
+#ifndef PNC_SETUP_ROLLED_CHOLESKY
+    // Right-looking, in REGISTERS, fully unrolled: lane l owns row r = l + NX (NX = nv - 32 leading rows, if
+    // any, are factored redundantly by every lane from warp-uniform loads, so that the remaining <= 32 rows
+    // map one to one onto the lanes).  Per pivot the owner publishes the pivot, every lane scales its entry
+    // of column j and stores the final L[r][j] into the factor block, and the trailing update runs two
+    // pivots at a time as a rank-2 update whose multipliers (L[k][j], L[k][j+1]) come as one warp-uniform
+    // LDS.128 per column k.
+    {
+      constexpr int NX = NV > 32 ? NV - 32 : 0;
+      const int r = lane + NX;
+      const bool rok = r < NV;
+      double a[NV];
+      {
+        const double* ri = Gm + (rok ? r : 0) * LDV;
+#pragma unroll
+        for (int k = 0; k + 1 < NV; k += 2) {
+          const double2 g = lds2(ri + k);
+          a[k] = g.x; a[k + 1] = g.y;
+        }
+        if (NV & 1) a[NV - 1] = ri[NV - 1];
+      }
+      if constexpr (NX > 0) {
+        double u[NX][NX], uid[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++)
+#pragma unroll
+          for (int k = 0; k <= i; k++) u[i][k] = Gm[i * LDV + k];
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+          double p = u[j][j];
+#pragma unroll
+          for (int q = 0; q < j; q++) p = fma(-u[j][q], u[j][q], p);
+          if (!(p > 0.0)) pd = false;
+          const double d = sqrt(p), id = 1.0 / d;
+          u[j][j] = d; uid[j] = id;
+#pragma unroll
+          for (int i = j + 1; i < NX; i++) {
+            double sacc = u[i][j];
+#pragma unroll
+            for (int q = 0; q < j; q++) sacc = fma(-u[i][q], u[j][q], sacc);
+            u[i][j] = sacc * id;
+          }
+          double sacc = a[j];
+#pragma unroll
+          for (int q = 0; q < j; q++) sacc = fma(-a[q], u[j][q], sacc);
+          a[j] = sacc * id;
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < NX; i++) {
+            dl[i] = uid[i];
+#pragma unroll
+            for (int k = 0; k <= i; k++) Gm[i * LDV + k] = u[i][k];
+          }
+        }
+        if (rok) {
+#pragma unroll
+          for (int k = 0; k < NX; k++) Gm[r * LDV + k] = a[k];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = NX; k < NV; k++) {
+          const double* Lk = Gm + k * LDV;
+#pragma unroll
+          for (int j = 0; j < NX; j++) a[k] = fma(-a[j], Lk[j], a[k]);
+        }
+      }
+      double lprev = 0.0;  // L[r][j-1] of the even pivot a pair starts with
+#pragma unroll
+      for (int j = NX; j < NV; j++) {
+        if (r == j) dm[j] = a[j];  // the pivot, through a vector nobody uses yet
+        __syncwarp();
+        const double p = dm[j];
+        if (!(p > 0.0)) pd = false;
+        const double d = sqrt(p), id = 1.0 / d;
+        double l = a[j] * id;
+        if (r == j) l = d;
+        a[j] = l;
+        if (rok && r >= j) Gm[r * LDV + j] = l;
+        if (lane == 0) dl[j] = id;
+        __syncwarp();
+        if (!(j & 1)) {
+          // even pivot: its update of the very next column now, the rest together with pivot j + 1
+          if (j + 1 < NV) a[j + 1] = fma(-l, Gm[(j + 1) * LDV + j], a[j + 1]);
+          lprev = l;
+        } else if (j == NX) {
+          // an odd first pivot has no partner: rank-1 update
+#pragma unroll
+          for (int k = j + 1; k < NV; k++) a[k] = fma(-l, Gm[k * LDV + j], a[k]);
+        } else {
+#pragma unroll
+          for (int k = j + 1; k < NV; k++) {
+            const double2 lk = lds2(Gm + k * LDV + j - 1);
+            a[k] = fma(-lprev, lk.x, a[k]);
+            a[k] = fma(-l, lk.y, a[k]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+#else
     constexpr int EV = C::EV, LPR = C::LPR;
     const int xrow = 32 + lane / LPR, xsl = lane % LPR;
 #pragma unroll 1
@@ -458,6 +560,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       if (EV > 0 && xsl == 0 && xrow > j && xrow < NV) Gm[xrow * LDV + j] = t1 * idj;
       __syncwarp();
     }
+#endif
     if (!pd || !(P.lambda_rf > 0.0 || NC == 0)) {
       status = PNC_QP_NOT_PD;
     } else if (status == PNC_QP_OK) {

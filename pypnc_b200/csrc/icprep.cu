@@ -15,7 +15,10 @@
 // PNC_QP_EQ_DEPENDENT for that state) instead of being silently truncated.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "pnc_launch.h"
+#include "tri_reg.cuh"
 
 namespace pnc {
 
@@ -43,6 +46,39 @@ static __device__ __forceinline__ double dot4_inl(const double* a, int sa, const
 }
 static __device__ __noinline__ double dot4_out(const double* a, int sa, const double* b, int sb, int n) {
   return dot4_inl(a, sa, b, sb, n);
+}
+
+
+// Lambda = (Y^T Y)^-1 (k x k, k <= PNC_MAX_IC) by Gauss-Jordan with partial pivoting, one thread.
+// Returns 1 when the Gram matrix is singular to 1e-13 of its largest diagonal entry.
+static __device__ __noinline__ int ic_lambda_inverse(const double* __restrict__ Y, double* __restrict__ Lam, int nv, int k) {
+  double a[PNC_MAX_IC][2 * PNC_MAX_IC];
+  for (int r = 0; r < k; r++)
+    for (int c = 0; c < k; c++) {
+      double sum = 0.0;
+      for (int i = 0; i < nv; i++) sum += Y[i * k + r] * Y[i * k + c];
+      a[r][c] = sum;
+      a[r][k + c] = r == c ? 1.0 : 0.0;
+    }
+  double amax = 0.0;
+  for (int r = 0; r < k; r++) amax = fmax(amax, fabs(a[r][r]));
+  for (int c = 0; c < k; c++) {
+    int pr = c;
+    for (int r = c + 1; r < k; r++)
+      if (fabs(a[r][c]) > fabs(a[pr][c])) pr = r;
+    if (!(fabs(a[pr][c]) > 1e-13 * amax)) return 1;
+    for (int cc = 0; cc < 2 * k; cc++) { double tmp = a[c][cc]; a[c][cc] = a[pr][cc]; a[pr][cc] = tmp; }
+    const double d = a[c][c];
+    for (int cc = 0; cc < 2 * k; cc++) a[c][cc] /= d;
+    for (int r = 0; r < k; r++) {
+      if (r == c) continue;
+      const double f = a[r][c];
+      for (int cc = 0; cc < 2 * k; cc++) a[r][cc] -= f * a[c][cc];
+    }
+  }
+  for (int r = 0; r < k; r++)
+    for (int c = 0; c < k; c++) Lam[r * k + c] = a[r][k + c];
+  return 0;
 }
 
 struct IcLayout {
@@ -181,34 +217,7 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
         }
       }
       __syncwarp();
-      if (lane == 0) {
-        double a[PNC_MAX_IC][2 * PNC_MAX_IC];
-        for (int r = 0; r < k; r++)
-          for (int c = 0; c < k; c++) {
-            double sum = 0.0;
-            for (int i = 0; i < nv; i++) sum += Y[i * k + r] * Y[i * k + c];
-            a[r][c] = sum;
-            a[r][k + c] = r == c ? 1.0 : 0.0;
-          }
-        double amax = 0.0;
-        for (int r = 0; r < k; r++) amax = fmax(amax, fabs(a[r][r]));
-        for (int c = 0; c < k; c++) {  // Gauss-Jordan with partial pivoting
-          int pr = c;
-          for (int r = c + 1; r < k; r++)
-            if (fabs(a[r][c]) > fabs(a[pr][c])) pr = r;
-          if (!(fabs(a[pr][c]) > 1e-13 * amax)) { bad = 1; break; }
-          for (int cc = 0; cc < 2 * k; cc++) { double tmp = a[c][cc]; a[c][cc] = a[pr][cc]; a[pr][cc] = tmp; }
-          const double d = a[c][c];
-          for (int cc = 0; cc < 2 * k; cc++) a[c][cc] /= d;
-          for (int r = 0; r < k; r++) {
-            if (r == c) continue;
-            const double f = a[r][c];
-            for (int cc = 0; cc < 2 * k; cc++) a[r][cc] -= f * a[c][cc];
-          }
-        }
-        for (int r = 0; r < k; r++)
-          for (int c = 0; c < k; c++) Lam[r * k + c] = a[r][k + c];
-      }
+      if (lane == 0) bad = ic_lambda_inverse(Y, Lam, nv, k);
       bad = __shfl_sync(FULL, bad, 0);
       __syncwarp();
     }
@@ -438,6 +447,365 @@ k_ic_prepare(const DevProblem* __restrict__ gp, IcLayout L, WsPtrs ws, FrameMap 
   }
 }
 
+
+// =======================================================================================
+// Register formulation for the shipped shapes (compile-time dimensions).  Same quantities as
+// k_ic_prepare, other data flow: the two Cholesky factors and their triangular inverses run with the
+// working rows in registers (tri_reg.cuh), every later product is "lane = one actuated row / column,
+// operand rows broadcast from shared memory as LDS.128", fully unrolled:
+//   T = L^-T (M = L L^T)                       rows of T = columns of L^-1
+//   Y = L^-1 Ji^T, Lambda = (Y^T Y)^-1, Jibar = T (Y Lambda), Ni^T (c+g), Jc Ni        (as k_ic_prepare)
+//   lane a:  z = L^-1 Atilde[a]^T              z_i = sum_{6<=c<=i} T[c][i] at_c, at_c formed on the fly
+//            g = row a of G = Z^T Z            Z broadcast from shared memory
+//            V[6+j][a] = sum_{i>=6+j} T[6+j][i] z_i                                    (W A^T = rows 6.. of L^-T Z)
+//   G = Lg Lg^T, Tg = Lg^-T;  lane a': row a' of G^-1 = sum_i Tg[a'][i] Tg[a][i],
+//            row a' of B = G^-1 V6^T,  row a' of S [M | -(Jc Ni)^T] = B X  and  S Ni^T (c+g) = B ncg[6:]
+// No explicit 33 x 33 / 25 x 25 inverse of an ill-conditioned matrix is applied to data: both triangular
+// inverses are of Cholesky factors (cond = sqrt of the matrix's), exactly the solves k_ic_prepare does.
+template <int NV, int NACT, int NC, int K>
+struct IcRegCfg {
+  static constexpr int N = NV + NC, NJ = NV - 6;
+  static constexpr int ld_() { int l = (NV + 1) & ~1; while ((l & 15) != 6) l += 2; return l; }
+  static constexpr int LD = ld_();                // pitch of T: even, 6 (mod 16): LDS.128 by row conflict-free
+  static constexpr int LDZ = (NACT + 1) & ~1;     // pitch of Z / V6 / the G block (rows broadcast)
+  static constexpr int LDX = (N + 1) & ~1;        // pitch of X = [M[6:, :] | (Jc Ni)[:, 6:]^T]
+  static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+  static constexpr int OT = 0;
+  static constexpr int SZT = cmax(NV * LD, NACT * LDZ);                  // T, later the G block
+  static constexpr int OZ = OT + SZT;
+  static constexpr int SZZ = cmax(cmax(NV * LDZ, NC * LD), NJ * LDZ);     // staged Jc, then Z, then V6
+  static constexpr int OSM = OZ + SZZ;                                    // small vectors
+  static constexpr int OCG = OSM, ONCG = OCG + NV, OY = ONCG + NV, OYL = OY + NV * K, OJB = OYL + NV * K,
+                       OJI = OJB + NV * K, OLAM = OJI + K * NV, OJCJB = OLAM + K * K + 2 * K, OLDI = OJCJB + NC * K,
+                       OGDI = OLDI + NV, OPV = OGDI + NACT, OEND = OPV + NV;
+  static constexpr int TOTAL = (cmax(OEND, NJ * LDX) + 1) & ~1;           // X is staged over T and Z at the end
+  static_assert(NV <= 64 && NACT <= 32 && NJ * LDX <= OSM, "shape not supported by the register formulation");
+  static_assert((SZT & 1) == 0 && (SZZ & 1) == 0, "16-byte alignment of the regions");
+};
+
+template <int NV, int NACT, int NC, int K>
+__global__ void __launch_bounds__(32, 10)
+k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B, int* counter) {
+  using C = IcRegCfg<NV, NACT, NC, K>;
+  constexpr int N = C::N, NJ = C::NJ, LD = C::LD, LDZ = C::LDZ, LDX = C::LDX;
+  extern __shared__ __align__(16) double sm[];
+  const DevProblem& P = *gp;
+  const int lane = threadIdx.x;
+  double* T = sm + C::OT;
+  double* ZR = sm + C::OZ;
+  double* cg = sm + C::OCG;
+  double* ncg = sm + C::ONCG;
+  double* Y = sm + C::OY;
+  double* YL = sm + C::OYL;
+  double* Jb = sm + C::OJB;
+  double* Jis = sm + C::OJI;
+  double* Lam = sm + C::OLAM;
+  double* JcJb = sm + C::OJCJB;
+  double* Ldi = sm + C::OLDI;
+  double* Gdi = sm + C::OGDI;
+  double* pv = sm + C::OPV;
+  for (int e = lane; e < K * NV; e += 32) Jis[e] = P.ic_jac[e / NV][e % NV];
+  const int va = lane < NACT ? P.act_idx[lane] : 6;
+  __syncwarp();
+
+  for (;;) {
+    int si = 0;
+    if (lane == 0) si = atomicAdd(counter, 1);
+    si = __shfl_sync(FULL, si, 0);
+    if (si >= B) break;
+    const size_t s = (size_t)si;
+    int bad = 0;
+    const double* Mg = ws.M + s * NV * NV;
+#pragma unroll 1
+    for (int e0 = lane; e0 < NV * NV; e0 += 32 * 8) {  // flattened: eight independent loads in flight per lane
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = e0 + 32 * u < NV * NV ? Mg[e0 + 32 * u] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + 32 * u;
+        if (e < NV * NV) { const int i = e / NV; T[i * LD + (e - i * NV)] = v[u]; }
+      }
+    }
+    for (int c = lane; c < NV; c += 32) cg[c] = ws.cori[s * NV + c] + ws.grav[s * NV + c];
+    __syncwarp();
+    // ---- M = L L^T, T = L^-T ----
+    if (!chol_rows_reg<NV, LD>(T, Ldi, pv, lane)) bad = 1;
+    if (!bad) {
+      linv_cols_reg<NV, LD>(T, Ldi, lane);
+      // ---- Y = L^-1 Ji^T: lanes = rows, Y[i][t] = sum_{c<=i} T[c][i] Ji[t][c] ----
+      for (int i = lane; i < NV; i += 32) {
+        double y[K];
+#pragma unroll
+        for (int t = 0; t < K; t++) y[t] = 0.0;
+#pragma unroll 4
+        for (int c = 0; c < NV; c++) {
+          const double tv = T[c * LD + i];  // zero below the diagonal of T (c > i)
+#pragma unroll
+          for (int t = 0; t < K; t++) y[t] = fma(tv, Jis[t * NV + c], y[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < K; t++) Y[i * K + t] = y[t];
+      }
+      __syncwarp();
+      if (lane == 0) bad = ic_lambda_inverse(Y, Lam, NV, K);
+      bad = __shfl_sync(FULL, bad, 0);
+      __syncwarp();
+    }
+    if (!bad) {
+      // ---- Jibar = L^-T (Y Lambda) = T (Y Lambda): lanes = rows of T ----
+      for (int i = lane; i < NV; i += 32) {
+#pragma unroll
+        for (int t = 0; t < K; t++) {
+          double sum = 0.0;
+#pragma unroll
+          for (int u = 0; u < K; u++) sum = fma(Y[i * K + u], Lam[u * K + t], sum);
+          YL[i * K + t] = sum;
+        }
+      }
+      __syncwarp();
+      for (int c = lane; c < NV; c += 32) {
+        double acc[K];
+#pragma unroll
+        for (int t = 0; t < K; t++) acc[t] = 0.0;
+        const double* Tc = T + c * LD;
+#pragma unroll 4
+        for (int i = 0; i < NV; i++) {
+          const double tv = Tc[i];  // zero for i < c
+#pragma unroll
+          for (int t = 0; t < K; t++) acc[t] = fma(tv, YL[i * K + t], acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < K; t++) Jb[c * K + t] = acc[t];
+      }
+      __syncwarp();
+      // ---- Ni^T (c+g) = cg - Ji^T (Jibar^T cg) ----
+      {
+        double jt[K];
+#pragma unroll
+        for (int t = 0; t < K; t++) {
+          double part = 0.0;
+          for (int i = lane; i < NV; i += 32) part += Jb[i * K + t] * cg[i];
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+          jt[t] = part;
+        }
+        for (int i = lane; i < NV; i += 32) {
+          double v = cg[i];
+#pragma unroll
+          for (int t = 0; t < K; t++) v -= Jis[t * NV + i] * jt[t];
+          ncg[i] = v;
+          ws.ic_cg[s * NV + i] = v;
+        }
+      }
+      // ---- Jc Ni = Jc - (Jc Jibar) Ji; the contact Jacobian rows are staged in the Z region first ----
+      double* Jcs = ZR;
+#pragma unroll 1
+      for (int c = 0; c < NC; c++) {
+        int ci = 0;
+        while (ci + 1 < P.ncontact && c >= P.contacts[ci + 1].rf_off) ci++;
+        const DevContact& Cc = P.contacts[ci];
+        const double* Jrow = ws.fr_jac + (s * nfr + fm.contact_f[ci]) * 6 * NV +
+                             (Cc.type == PNC_CONTACT_POINT ? 3 + (c - Cc.rf_off) : (c - Cc.rf_off)) * NV;
+        for (int i = lane; i < NV; i += 32) Jcs[c * LD + i] = Jrow[i];
+      }
+      __syncwarp();
+      for (int c = lane; c < NC; c += 32) {
+        const double* Jrow = Jcs + c * LD;
+        double acc[K];
+#pragma unroll
+        for (int t = 0; t < K; t++) acc[t] = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < NV; i++) {
+          const double v = Jrow[i];
+#pragma unroll
+          for (int t = 0; t < K; t++) acc[t] = fma(v, Jb[i * K + t], acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < K; t++) JcJb[c * K + t] = acc[t];
+      }
+      __syncwarp();
+      // (Jc Ni)[c][i], lanes along i: coalesced stores
+#pragma unroll 1
+      for (int c = 0; c < NC; c++) {
+        for (int i = lane; i < NV; i += 32) {
+          double v = Jcs[c * LD + i];
+#pragma unroll
+          for (int t = 0; t < K; t++) v = fma(-JcJb[c * K + t], Jis[t * NV + i], v);
+          ws.ic_jcni[(s * NC + c) * NV + i] = v;
+        }
+      }
+      __syncwarp();
+      // ---- lane a: z = L^-1 Atilde[a]^T, Atilde[a][c] = Ni[act_idx[a]][c] for c >= 6 (0 before) ----
+      double z[NV];
+#pragma unroll
+      for (int i = 0; i < NV; i++) z[i] = 0.0;
+      {
+        double jb[K];
+#pragma unroll
+        for (int t = 0; t < K; t++) jb[t] = Jb[va * K + t];
+#pragma unroll
+        for (int c = 6; c < NV; c++) {
+          double at = c == va ? 1.0 : 0.0;
+#pragma unroll
+          for (int t = 0; t < K; t++) at = fma(-jb[t], Jis[t * NV + c], at);
+          const double* Tc = T + c * LD;
+#pragma unroll
+          for (int i = c & ~1; i + 1 < NV; i += 2) {  // T[c][i] = 0 for i < c
+            const double2 tv = tri_lds2(Tc + i);
+            z[i] = fma(tv.x, at, z[i]);
+            z[i + 1] = fma(tv.y, at, z[i + 1]);
+          }
+          if (NV & 1) z[NV - 1] = fma(Tc[NV - 1], at, z[NV - 1]);
+        }
+      }
+      if (lane < NACT) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) ZR[i * LDZ + lane] = z[i];
+      } else if (lane < LDZ) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) ZR[i * LDZ + lane] = 0.0;  // the pad column
+      }
+      __syncwarp();
+      // ---- row a of G = Z^T Z ----
+      double g[LDZ];
+#pragma unroll
+      for (int b = 0; b < LDZ; b++) g[b] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        const double* Zi = ZR + i * LDZ;
+#pragma unroll
+        for (int b = 0; b < LDZ; b += 2) {
+          const double2 q = tri_lds2(Zi + b);
+          g[b] = fma(z[i], q.x, g[b]);
+          g[b + 1] = fma(z[i], q.y, g[b + 1]);
+        }
+      }
+      __syncwarp();  // Z is dead: V6 takes its place
+      // ---- V6[j][a] = (L^-T Z)[6 + j][a] = sum_{i >= 6+j} T[6+j][i] z_i ----
+#pragma unroll
+      for (int c = 6; c < NV; c++) {
+        const double* Tc = T + c * LD;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int i = c & ~1; i + 1 < NV; i += 2) {
+          const double2 tv = tri_lds2(Tc + i);
+          a0 = fma(tv.x, z[i], a0);
+          a1 = fma(tv.y, z[i + 1], a1);
+        }
+        if (NV & 1) a0 = fma(Tc[NV - 1], z[NV - 1], a0);
+        if (lane < LDZ) ZR[(c - 6) * LDZ + lane] = lane < NACT ? a0 + a1 : 0.0;
+      }
+      __syncwarp();  // T is dead: the G block takes its place
+      // ---- G = Lg Lg^T, Tg = Lg^-T ----
+      double* Gs = T;
+      if (lane < NACT) {
+#pragma unroll
+        for (int b = 0; b < LDZ; b += 2) *reinterpret_cast<double2*>(Gs + lane * LDZ + b) = make_double2(g[b], g[b + 1]);
+      }
+      __syncwarp();
+      double gmax = lane < NACT ? Gs[lane * LDZ + lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(FULL, gmax, o));
+      if (!chol_rows_reg<NACT, LDZ>(Gs, Gdi, pv, lane, 1e-13 * gmax)) bad = 1;
+    }
+    if (!bad) {
+      double* Gs = T;
+      linv_cols_reg<NACT, LDZ>(Gs, Gdi, lane);  // row c of Gs = column c of Lg^-1, zeros left of the diagonal
+      // ---- row a' of G^-1 = Tg Tg^T: gi[a] = sum_i Tg[a'][i] Tg[a][i] ----
+      double gi[LDZ];
+      {
+        double xg[LDZ];
+        const double* mine = Gs + (lane < NACT ? lane : 0) * LDZ;
+#pragma unroll
+        for (int i = 0; i < LDZ; i += 2) {
+          const double2 q = tri_lds2(mine + i);
+          xg[i] = q.x; xg[i + 1] = i + 1 < NACT ? q.y : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < NACT; a++) {
+          const double* Ga = Gs + a * LDZ;
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int i = a & ~1; i < LDZ; i += 2) {
+            const double2 q = tri_lds2(Ga + i);
+            a0 = fma(q.x, xg[i], a0);
+            a1 = fma(q.y, xg[i + 1], a1);  // xg of the pad column is zero
+          }
+          gi[a] = a0 + a1;
+        }
+        if (LDZ > NACT) gi[LDZ - 1] = 0.0;
+      }
+      // ---- row a' of B = G^-1 V6^T: b[j] = sum_a gi[a] V6[j][a] ----
+      double bq[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
+        const double* Vj = ZR + j * LDZ;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int a = 0; a < LDZ; a += 2) {
+          const double2 q = tri_lds2(Vj + a);
+          a0 = fma(gi[a], q.x, a0);
+          a1 = fma(gi[a + 1], q.y, a1);  // pad column of V6 and of gi are zero
+        }
+        bq[j] = a0 + a1;
+      }
+      __syncwarp();  // every lane is done with the G block and V6: X = [M[6:, :] | (Jc Ni)[:, 6:]^T] goes over them
+      double* X = sm;
+#pragma unroll 1
+      for (int e0 = lane; e0 < NJ * NV; e0 += 32 * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = e0 + 32 * u < NJ * NV ? Mg[6 * NV + e0 + 32 * u] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int e = e0 + 32 * u;
+          if (e < NJ * NV) { const int j = e / NV; X[j * LDX + (e - j * NV)] = v[u]; }
+        }
+      }
+#pragma unroll 1
+      for (int e = lane; e < NC * NJ; e += 32) {
+        const int cc = e / NJ, j = e - cc * NJ;
+        X[j * LDX + NV + cc] = ws.ic_jcni[(s * NC + cc) * NV + 6 + j];
+      }
+      if (LDX > N)
+        for (int j = lane; j < NJ; j += 32) X[j * LDX + N] = 0.0;
+      __syncwarp();
+      // ---- S [M | -(Jc Ni)^T] (transposed store [n][nact]: coalesced) and S Ni^T (c+g) ----
+      double* out = ws.ic_tq + s * NACT * N + lane;
+#pragma unroll 1
+      for (int c = 0; c < N; c += 4) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const double* xc = X + c;
+        const bool pair2 = c + 2 < LDX;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+          const double2 q = tri_lds2(xc + j * LDX);
+          s0 = fma(bq[j], q.x, s0);
+          s1 = fma(bq[j], q.y, s1);
+          if (pair2) {
+            const double2 q2 = tri_lds2(xc + j * LDX + 2);
+            s2 = fma(bq[j], q2.x, s2);
+            s3 = fma(bq[j], q2.y, s3);
+          }
+        }
+        if (lane < NACT) {
+          out[c * NACT] = c < NV ? s0 : -s0;
+          if (c + 1 < N) out[(c + 1) * NACT] = c + 1 < NV ? s1 : -s1;
+          if (c + 2 < N) out[(c + 2) * NACT] = c + 2 < NV ? s2 : -s2;
+          if (c + 3 < N) out[(c + 3) * NACT] = c + 3 < NV ? s3 : -s3;
+        }
+      }
+      {
+        double part = 0.0;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) part = fma(bq[j], ncg[6 + j], part);
+        if (lane < NACT) ws.ic_tq0[s * NACT + lane] = part;
+      }
+    }
+    if (lane == 0) ws.ic_status[s] = bad;
+    __syncwarp();
+  }
+}
+
 void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,
                        int B, int num_sms, cudaStream_t stream, int* counter) {
   IcLayout L = ic_layout(hp.nv, hp.nact, hp.nc, hp.n_ic);
@@ -453,7 +821,23 @@ void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
     optin.ensure(kernel, smem);
     kernel<<<grid, 32, smem, stream>>>(dp, L, ws, fm, nfr, B, counter);
   };
-  if (hp.nv == 33 && hp.nact == 25 && hp.nc == 12 && hp.n_ic == 2) go(k_ic_prepare<33, 25, 12, 2>);        // Draco3
+  // PNC_IC=smem forces the shared-memory formulation (A/B runs, cross-check in the tests)
+  static const bool force_smem = [] { const char* e = getenv("PNC_IC"); return e && e[0] == 's'; }();
+  auto go_reg = [&](auto kernel, size_t smem_reg) {
+    static SmemOptIn optin;
+    optin.ensure(kernel, smem_reg);
+    int per = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, 32, smem_reg);
+    if (per < 1) per = 1;
+    int g = num_sms * per;
+    if (g > B) g = B;
+    kernel<<<g, 32, smem_reg, stream>>>(dp, ws, fm, nfr, B, counter);
+  };
+  if (!force_smem && hp.nv == 33 && hp.nact == 25 && hp.nc == 12 && hp.n_ic == 2)          // Draco3
+    go_reg(k_ic_prepare_reg<33, 25, 12, 2>, sizeof(double) * IcRegCfg<33, 25, 12, 2>::TOTAL);
+  else if (!force_smem && hp.nv == 20 && hp.nact == 12 && hp.nc == 12 && hp.n_ic == 2)     // Draco3 lower body
+    go_reg(k_ic_prepare_reg<20, 12, 12, 2>, sizeof(double) * IcRegCfg<20, 12, 12, 2>::TOTAL);
+  else if (hp.nv == 33 && hp.nact == 25 && hp.nc == 12 && hp.n_ic == 2) go(k_ic_prepare<33, 25, 12, 2>);
   else if (hp.nv == 20 && hp.nact == 12 && hp.nc == 12 && hp.n_ic == 2) go(k_ic_prepare<20, 12, 12, 2>);   // Draco3 lower body
   else go(k_ic_prepare<0, 0, 0, 0>);
   g_launch_count++;

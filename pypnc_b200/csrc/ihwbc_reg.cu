@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include "ihwbc_common.cuh"
+#include "tri_reg.cuh"
 
 namespace pnc {
 
@@ -408,8 +409,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       }
     }
 
-    // ---- Cholesky of the task block (QuadProg++.cc:705-730), left-looking, lanes = rows ----
-    // rows 32.. (Atlas has 4) are each shared by LPR lanes that split the dot product
+    // ---- Cholesky of the task block (QuadProg++.cc:705-730): right-looking, rows in registers (tri_reg.cuh) ----
     double c1 = 0.0, c2 = 0.0;
     {
       double tr = 0.0;
@@ -417,227 +417,13 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       c1 = wsum(tr) + NC * P.lambda_rf;
     }
     double* dl = vm;  // reciprocal diagonal of L
-    bool pd = true;
-#ifndef PNC_SETUP_ROLLED_CHOLESKY
-    // Right-looking, in REGISTERS, fully unrolled: lane l owns row r = l + NX (NX = nv - 32 leading rows, if
-    // any, are factored redundantly by every lane from warp-uniform loads, so that the remaining <= 32 rows
-    // map one to one onto the lanes).  Per pivot the owner publishes the pivot, every lane scales its entry
-    // of column j and stores the final L[r][j] into the factor block, and the trailing update runs two
-    // pivots at a time as a rank-2 update whose multipliers (L[k][j], L[k][j+1]) come as one warp-uniform
-    // LDS.128 per column k.
-    {
-      constexpr int NX = NV > 32 ? NV - 32 : 0;
-      const int r = lane + NX;
-      const bool rok = r < NV;
-      double a[NV];
-      {
-        const double* ri = Gm + (rok ? r : 0) * LDV;
-#pragma unroll
-        for (int k = 0; k + 1 < NV; k += 2) {
-          const double2 g = lds2(ri + k);
-          a[k] = g.x; a[k + 1] = g.y;
-        }
-        if (NV & 1) a[NV - 1] = ri[NV - 1];
-      }
-      if constexpr (NX > 0) {
-        double u[NX][NX], uid[NX];
-#pragma unroll
-        for (int i = 0; i < NX; i++)
-#pragma unroll
-          for (int k = 0; k <= i; k++) u[i][k] = Gm[i * LDV + k];
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-          double p = u[j][j];
-#pragma unroll
-          for (int q = 0; q < j; q++) p = fma(-u[j][q], u[j][q], p);
-          if (!(p > 0.0)) pd = false;
-          const double d = sqrt(p), id = 1.0 / d;
-          u[j][j] = d; uid[j] = id;
-#pragma unroll
-          for (int i = j + 1; i < NX; i++) {
-            double sacc = u[i][j];
-#pragma unroll
-            for (int q = 0; q < j; q++) sacc = fma(-u[i][q], u[j][q], sacc);
-            u[i][j] = sacc * id;
-          }
-          double sacc = a[j];
-#pragma unroll
-          for (int q = 0; q < j; q++) sacc = fma(-a[q], u[j][q], sacc);
-          a[j] = sacc * id;
-        }
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int i = 0; i < NX; i++) {
-            dl[i] = uid[i];
-#pragma unroll
-            for (int k = 0; k <= i; k++) Gm[i * LDV + k] = u[i][k];
-          }
-        }
-        if (rok) {
-#pragma unroll
-          for (int k = 0; k < NX; k++) Gm[r * LDV + k] = a[k];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int k = NX; k < NV; k++) {
-          const double* Lk = Gm + k * LDV;
-#pragma unroll
-          for (int j = 0; j < NX; j++) a[k] = fma(-a[j], Lk[j], a[k]);
-        }
-      }
-      double lprev = 0.0;  // L[r][j-1] of the even pivot a pair starts with
-#pragma unroll
-      for (int j = NX; j < NV; j++) {
-        if (r == j) dm[j] = a[j];  // the pivot, through a vector nobody uses yet
-        __syncwarp();
-        const double p = dm[j];
-        if (!(p > 0.0)) pd = false;
-        const double d = sqrt(p), id = 1.0 / d;
-        double l = a[j] * id;
-        if (r == j) l = d;
-        a[j] = l;
-        if (rok && r >= j) Gm[r * LDV + j] = l;
-        if (lane == 0) dl[j] = id;
-        __syncwarp();
-        if (!(j & 1)) {
-          // even pivot: its update of the very next column now, the rest together with pivot j + 1
-          if (j + 1 < NV) a[j + 1] = fma(-l, Gm[(j + 1) * LDV + j], a[j + 1]);
-          lprev = l;
-        } else if (j == NX) {
-          // an odd first pivot has no partner: rank-1 update
-#pragma unroll
-          for (int k = j + 1; k < NV; k++) a[k] = fma(-l, Gm[k * LDV + j], a[k]);
-        } else {
-#pragma unroll
-          for (int k = j + 1; k < NV; k++) {
-            const double2 lk = lds2(Gm + k * LDV + j - 1);
-            a[k] = fma(-lprev, lk.x, a[k]);
-            a[k] = fma(-l, lk.y, a[k]);
-          }
-        }
-      }
-      __syncwarp();
-    }
-#else
-    constexpr int EV = C::EV, LPR = C::LPR;
-    const int xrow = 32 + lane / LPR, xsl = lane % LPR;
-#pragma unroll 1
-    for (int j = 0; j < NV; j++) {
-      double t0 = 0.0, t1 = 0.0;
-      const double* rj = Gm + j * LDV;
-      if (lane >= j && lane < NV) {
-        const double* ri = Gm + lane * LDV;
-        double s0 = ri[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int k = 0;
-#pragma unroll 1
-        for (; k + 3 < j; k += 4) {
-          const double2 a0 = lds2(ri + k), a1 = lds2(ri + k + 2), b0 = lds2(rj + k), b1 = lds2(rj + k + 2);
-          s0 = fma(-a0.x, b0.x, s0); s1 = fma(-a0.y, b0.y, s1); s2 = fma(-a1.x, b1.x, s2); s3 = fma(-a1.y, b1.y, s3);
-        }
-#pragma unroll 1
-        for (; k < j; k++) s0 = fma(-ri[k], rj[k], s0);
-        t0 = (s0 + s1) + (s2 + s3);
-      }
-      if constexpr (EV > 0) {
-        const bool xact = xrow < NV && xrow >= j;
-        const double* ri = Gm + (xact ? xrow : 0) * LDV;
-        double part = 0.0;
-        if (xact) {
-#pragma unroll 1
-          for (int k = xsl; k < j; k += LPR) part = fma(ri[k], rj[k], part);
-        }
-#pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-        if (xact) t1 = ri[j] - part;
-      }
-      const double piv = __shfl_sync(FULL, j < 32 ? t0 : t1, j < 32 ? j : (j - 32) * LPR);
-      if (!(piv > 0.0)) { pd = false; break; }
-      const double dj = sqrt(piv), idj = 1.0 / dj;
-      __syncwarp();
-      if (j < 32 ? lane == j : lane == (j - 32) * LPR) { Gm[j * LDV + j] = dj; dl[j] = idj; }
-      if (lane > j && lane < NV) Gm[lane * LDV + j] = t0 * idj;
-      if (EV > 0 && xsl == 0 && xrow > j && xrow < NV) Gm[xrow * LDV + j] = t1 * idj;
-      __syncwarp();
-    }
-#endif
+    const bool pd = chol_rows_reg<NV, LDV>(Gm, dl, dm, lane);
     if (!pd || !(P.lambda_rf > 0.0 || NC == 0)) {
       status = PNC_QP_NOT_PD;
     } else if (status == PNC_QP_OK) {
-      // ---- J = L^-T (QuadProg++.cc:203-210): lane c forward-solves L x = e_c with x in REGISTERS (fully
-      //      unrolled: no shuffles, no barriers, every lane the same instruction stream); x is column c of
-      //      L^-1 = row c of J.  L is read as warp-uniform LDS.128 pairs.  Columns 32.. (nv > 32) only reach
-      //      rows 32..: a second, tiny solve in lanes 0 .. nv-33 ----
-      {
-#ifndef PNC_SETUP_ROLLED_INVERSE
-        double xr[NV];
-#pragma unroll
-        for (int i = 0; i < NV; i++) {
-          const double* Li = Gm + i * LDV;
-          double s0 = i == lane ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-          for (int k = 0; k + 1 < i; k += 2) {
-            const double2 l = lds2(Li + k);
-            s0 = fma(-l.x, xr[k], s0);
-            s1 = fma(-l.y, xr[k + 1], s1);
-          }
-          if (i & 1) s0 = fma(-Li[i - 1], xr[i - 1], s0);
-          xr[i] = (s0 + s1) * dl[i];
-        }
-        constexpr int NX = NV > 32 ? NV - 32 : 0;
-        double xe[NX > 0 ? NX : 1];
-        if constexpr (NX > 0) {
-#pragma unroll
-          for (int i = 32; i < NV; i++) {
-            const double* Li = Gm + i * LDV;
-            double s0 = i == 32 + lane ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 32; k < i; k++) s0 = fma(-Li[k], xe[k - 32], s0);
-            xe[i - 32] = s0 * dl[i];
-          }
-        }
-        __syncwarp();  // every lane is done reading L
-        if (lane < NV) {
-          double* zr = Gm + lane * LDV;
-#pragma unroll
-          for (int i = 0; i + 1 < NV; i += 2) *reinterpret_cast<double2*>(zr + i) = make_double2(xr[i], xr[i + 1]);
-          if (NV & 1) zr[NV - 1] = xr[NV - 1];
-        }
-        if constexpr (NX > 0) {
-          if (lane < NX) {
-            double* zr = Gm + (32 + lane) * LDV;
-#pragma unroll
-            for (int i = 0; i < NV; i++) zr[i] = i >= 32 ? xe[i >= 32 ? i - 32 : 0] : 0.0;
-          }
-        }
-        __syncwarp();
-#else
-#pragma unroll 1
-        for (int j = 0; j < NV; j++) {
-          const double* Lj = Gm + j * LDV;
-          const double idjj = dl[j];
-#pragma unroll
-          for (int rr = 0; rr < (NV > 32 ? 2 : 1); rr++) {
-            const int i = lane + 32 * rr;
-            if ((rr == 0 || j >= 32) && i <= j && i < NV) {
-              double* zi = Gm + i * LDV;
-              double s0 = i == j ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-              int k = i;
-              if ((k & 1) && k < j) { s0 = fma(-Lj[k], zi[k], s0); k++; }
-#pragma unroll 1
-              for (; k + 3 < j; k += 4) {
-                const double2 a0 = lds2(zi + k), a1 = lds2(zi + k + 2), b0 = lds2(Lj + k), b1 = lds2(Lj + k + 2);
-                s0 = fma(-a0.x, b0.x, s0); s1 = fma(-a0.y, b0.y, s1); s2 = fma(-a1.x, b1.x, s2); s3 = fma(-a1.y, b1.y, s3);
-              }
-#pragma unroll 1
-              for (; k < j; k++) s0 = fma(-Lj[k], zi[k], s0);
-              zi[j] = ((s0 + s1) + (s2 + s3)) * idjj;
-            }
-          }
-          __syncwarp();
-        }
-#endif
-      }
+      // ---- J = L^-T (QuadProg++.cc:203-210): lane c forward-solves L x = e_c with x in registers (fully
+      //      unrolled: no shuffles, no barriers, every lane the same instruction stream, tri_reg.cuh) ----
+      linv_cols_reg<NV, LDV>(Gm, dl, lane);
       const double jrf = 1.0 / sqrt(P.lambda_rf > 0.0 ? P.lambda_rf : 1.0);
       {
         double tr = 0.0;

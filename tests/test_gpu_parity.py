@@ -573,7 +573,8 @@ for name in ("atlas", "draco3_lb", "draco3_trans"):
         assert e.max() < 1e-9, (name, k, e.max())
 print("ok")
 ''' % ROOT_DIR
-    env = dict(os.environ, PNC_SOLVER='smem')
+    # PNC_IC=smem: the shared-memory formulation of the internal-constraint projection (any shape), too
+    env = dict(os.environ, PNC_SOLVER='smem', PNC_IC='smem')
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'ok' in r.stdout, r.stdout + r.stderr
 

@@ -105,6 +105,9 @@ struct pnc_workspace {
   cudaStream_t tick_in, tick_out;       // host -> device and device -> host copies
   cudaEvent_t tick_ev_in[16], tick_ev_done[16];  // per chunk: inputs landed, kernels finished
   cudaEvent_t tick_ev_ready;                     // producer of device-resident desireds done
+  cudaEvent_t tick_ev_start;                     // first input copy of the tick enqueued (timing)
+  int tick_last;                                 // index of the last chunk of the tick in flight (-1: none)
+  double tick_growth;                            // chunk growth factor measured on the previous tick (0: not yet)
   bool tick_init;
 };
 
@@ -289,7 +292,7 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
   ws->ic_slab = nullptr; ws->ic_bytes = 0; ws->ic_nc = ws->ic_nact = 0;
   ws->task_slab = nullptr; ws->task_rows = 0;
   ws->setup_slab = nullptr; ws->setup_stride = 0; ws->setup_shape = 0;
-  ws->stage = nullptr; ws->stage_bytes = 0; ws->tick_init = false;
+  ws->stage = nullptr; ws->stage_bytes = 0; ws->tick_init = false; ws->tick_last = -1; ws->tick_growth = 0.0;
   memset(&ws->hfr, 0, sizeof(ws->hfr));
   ws->hfr.nfr = nframes;
   for (int f = 0; f < nframes; f++) {
@@ -335,7 +338,7 @@ void pnc_workspace_destroy(pnc_workspace* ws) {
     for (int i = 0; i < 2; i++) cudaStreamDestroy(ws->tick_stream[i]);
     cudaStreamDestroy(ws->tick_in); cudaStreamDestroy(ws->tick_out);
     for (int i = 0; i < 16; i++) { cudaEventDestroy(ws->tick_ev_in[i]); cudaEventDestroy(ws->tick_ev_done[i]); }
-    cudaEventDestroy(ws->tick_ev_ready);
+    cudaEventDestroy(ws->tick_ev_ready); cudaEventDestroy(ws->tick_ev_start);
   }
   cudaGetLastError();
   delete ws;
@@ -739,7 +742,19 @@ static int tick_wait(pnc_workspace* ws) {
   cudaError_t e1 = cudaStreamSynchronize(ws->tick_stream[0]);
   cudaError_t e2 = cudaStreamSynchronize(ws->tick_stream[1]);
   cudaError_t e3 = cudaStreamSynchronize(ws->tick_in);
-  return (e0 == cudaSuccess && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) ? PNC_OK : PNC_E_CUDA;
+  const bool ok = e0 == cudaSuccess && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess;
+  if (ok && ws->tick_last > 0) {
+    // How busy was the input link?  With t_in = time the input copies of all chunks took back to back and
+    // t_all = time until the last chunk's kernels finished, a chunk may be about t_all / t_in times larger than
+    // its predecessor and still have its inputs arrive under the predecessor's kernels.  One B200 on its own
+    // x16 link: ~4; eight ranks sharing the host's memory and PCIe switches: ~1.5.
+    float t_in = 0.f, t_all = 0.f;
+    if (cudaEventElapsedTime(&t_in, ws->tick_ev_start, ws->tick_ev_in[ws->tick_last]) == cudaSuccess &&
+        cudaEventElapsedTime(&t_all, ws->tick_ev_start, ws->tick_ev_done[ws->tick_last]) == cudaSuccess && t_in > 0.f && t_all > t_in)
+      ws->tick_growth = 0.85 * (double)t_all / (double)t_in;
+  }
+  ws->tick_last = -1;
+  return ok ? PNC_OK : PNC_E_CUDA;
 }
 
 // enqueues everything of one tick on the workspace's own streams; tick_wait() completes it
@@ -764,10 +779,11 @@ static int tick_enqueue(const pnc_problem* p, pnc_workspace* ws, int32_t B, cons
     CK(cudaStreamCreateWithFlags(&ws->tick_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ws->tick_out, cudaStreamNonBlocking));
     for (int i = 0; i < 16; i++) {
-      CK(cudaEventCreateWithFlags(&ws->tick_ev_in[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&ws->tick_ev_done[i], cudaEventDisableTiming));
+      CK(cudaEventCreate(&ws->tick_ev_in[i]));  // timed: the input link rate of one tick sets the next tick's chunks
+      CK(cudaEventCreate(&ws->tick_ev_done[i]));
     }
     CK(cudaEventCreateWithFlags(&ws->tick_ev_ready, cudaEventDisableTiming));
+    CK(cudaEventCreate(&ws->tick_ev_start));
     ws->tick_init = true;
   }
   // carve the staging slab (capacity-sized arrays)
@@ -801,31 +817,43 @@ static int tick_enqueue(const pnc_problem* p, pnc_workspace* ws, int32_t B, cons
     }
   }
 
-  // chunk schedule: a short first chunk gets the kernels going early (its H2D copy is the only
-  // one nothing overlaps), the rest are equal.  PNC_TICK_CHUNKS / PNC_TICK_FIRST (fraction) override.
+  // Chunk schedule.  The first chunk's input copy and the last chunk's output copy are the transfers nothing
+  // overlaps, so both ends are small; in between every chunk is `growth` times its predecessor, so that its
+  // inputs arrive while the predecessor computes.  `growth` comes from the previous tick's own timing (see
+  // tick_wait): ~4 with the link to oneself (5 chunks), ~1.4 when eight ranks share the host (9 chunks).
+  // Measured on Atlas 64 K (scripts/e2e_split_sweep*.sh): 1 GPU 10.23 -> 10.06 ms per step against the fixed
+  // B/16, 0.4 B, 0.4 B, 0.14 B split; 8 GPUs 12.06 -> 11.2-11.3 ms.  PNC_TICK_CHUNKS / PNC_TICK_FIRST force n
+  // chunks with a first chunk of the given fraction, PNC_TICK_SPLIT explicit fractions (diagnostics).
   static const int env_chunks = [] { const char* e = getenv("PNC_TICK_CHUNKS"); return e ? atoi(e) : 0; }();
   static const double env_first = [] { const char* e = getenv("PNC_TICK_FIRST"); return e ? atof(e) : 0.0; }();
-  int nchunk = B >= 8192 ? (env_chunks > 0 && env_chunks <= 16 ? env_chunks : 4) : 1;
+  int nchunk = B >= 8192 ? (env_chunks > 0 && env_chunks <= 16 ? env_chunks : 0) : 1;
   int bounds[17];
   {
-    // default: B/16, 2 x 0.4 B, the rest (0.14 B): the first chunk's input copy and the last chunk's output
-    // copy are the transfers nothing overlaps, so both are kept small (Atlas 64 K, scripts/e2e_split_sweep.sh:
-    // 11.75 ms per step against 11.86 ms with three equal chunks after the first)
     bounds[0] = 0;
-    if (env_chunks > 0 || (env_first > 0.0 && env_first < 1.0)) {
+    if (nchunk == 1) {
+      bounds[1] = B;
+    } else if (env_chunks > 0 || (env_first > 0.0 && env_first < 1.0)) {
+      if (nchunk == 0) nchunk = 4;
       int first = env_chunks > 0 ? (B + nchunk - 1) / nchunk : B / 16;
       if (nchunk > 1 && env_first > 0.0 && env_first < 1.0) first = (int)(env_first * B);
       if (first < 1) first = 1;
       const int rest = B - first;
       for (int c = 1; c <= nchunk; c++)
         bounds[c] = c == nchunk ? B : first + (int)((long long)rest * (c - 1) / (nchunk - 1 > 0 ? nchunk - 1 : 1));
-    } else if (nchunk == 4) {
-      bounds[1] = B / 16;
-      bounds[2] = bounds[1] + (int)(0.4 * B);
-      bounds[3] = bounds[2] + (int)(0.4 * B);
-      bounds[4] = B;
+    } else {
+      double g = ws->tick_growth > 0.0 ? ws->tick_growth : 2.5;
+      g = g < 1.3 ? 1.3 : (g > 4.0 ? 4.0 : g);
+      const double tail = 0.10, cap = 0.34;
+      double f[16], acc = 0.0, sz = 1.0 / 32.0;
+      if (sz * B < 2048.0) sz = 2048.0 / B;
+      int nf = 0;
+      while (nf < 13 && acc + sz < 1.0 - tail) { f[nf++] = sz; acc += sz; sz = sz * g < cap ? sz * g : cap; }
+      const double rem = 1.0 - acc;
+      if (rem > 1.4 * tail) { f[nf++] = rem - tail; f[nf++] = tail; } else f[nf++] = rem;
+      acc = 0.0;
+      for (int c = 0; c < nf; c++) { acc += f[c]; bounds[c + 1] = c == nf - 1 ? B : (int)(acc * B); }
+      nchunk = nf;
     }
-    if (nchunk == 1) bounds[1] = B;
     // PNC_TICK_SPLIT="f0,f1,..." (fractions of the batch, diagnostic) overrides everything above
     static const char* env_split = getenv("PNC_TICK_SPLIT");
     if (env_split && B >= 8192) {
@@ -845,9 +873,18 @@ static int tick_enqueue(const pnc_problem* p, pnc_workspace* ws, int32_t B, cons
   // kernels of the chunks alternate over two streams (the tail of one chunk overlaps the start of
   // the next), one stream drains the outputs.  Events tie a chunk's kernels to its inputs and its
   // output copies to its kernels.
+  static const bool verbose = getenv("PNC_VERBOSE") != nullptr;
+  if (verbose) {
+    fprintf(stderr, "pnc_b200: tick of %d states, growth %.2f, %d chunks:", B, ws->tick_growth, nchunk);
+    for (int c = 0; c < nchunk; c++) fprintf(stderr, " %d", bounds[c + 1] - bounds[c]);
+    fprintf(stderr, "\n");
+  }
+  CK(cudaEventRecord(ws->tick_ev_start, ws->tick_in));
+  ws->tick_last = -1;
   for (int c = 0; c < nchunk; c++) {
     int o = bounds[c], nb = bounds[c + 1] - bounds[c];
     if (nb <= 0) continue;
+    ws->tick_last = c;
     cudaStream_t st = ws->tick_in;
 #define H2D(dst, src, per) CK(cudaMemcpyAsync((dst) + (size_t)o * (per), (src) + (size_t)o * (per), (size_t)nb * (per) * 8, cudaMemcpyHostToDevice, st))
     H2D(d_bp, A.h_bp, 3); H2D(d_bq, A.h_bq, 4); H2D(d_blv, A.h_blv, 3); H2D(d_bav, A.h_bav, 3);

@@ -1199,15 +1199,12 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           // Givens rotations of the row pairs (j, j+1), j = kk .. iq-2, make R triangular again; the same
           // pairs rotate the columns of Z afterwards (coefficient table `rot`).
           clr_bit(actm, l);
+          // (lane l moves entry l of every column and nothing else touches those slots: no barrier inside)
 #pragma unroll 1
           for (int i = kk; i < iq - 1; i++) {
-            const double* src = Rcol(i + 1);
-            double* dst = Rcol(i);
-            const double v0 = lane <= i + 1 ? src[lane] : 0.0;
-            __syncwarp();
-            if (lane <= i + 1) dst[lane] = v0;
-            __syncwarp();
+            if (lane <= i + 1) Rcol(i)[lane] = Rcol(i + 1)[lane];
           }
+          __syncwarp();
 #pragma unroll 1
           for (int j = kk; j < iq - 1; j++) {
             double* cj = Rcol(j);
@@ -1216,13 +1213,14 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             const bool skip = fabs(hh) < QP_EPS;  // QuadProg++ leaves such a pair untouched
             double xny = 0.0;
             if (!skip) {
-              cc = cc / hh;
-              ss = ss / hh;
+              double ih = 1.0 / hh;  // one reciprocal serves cc / h, ss / h and 1 / diag (an ulp from :636-638)
+              cc = cc * ih;
+              ss = ss * ih;
               double diag = hh;
-              if (cc < 0.0) { diag = -hh; cc = -cc; ss = -ss; }
+              if (cc < 0.0) { diag = -hh; ih = -ih; cc = -cc; ss = -ss; }
               xny = ss / (1.0 + cc);
               __syncwarp();
-              if (lane == 0) { cj[j] = diag; cj[j + 1] = 0.0; rinv[j] = 1.0 / diag; }
+              if (lane == 0) { cj[j] = diag; cj[j + 1] = 0.0; rinv[j] = ih; }
               const int k = j + 1 + lane;  // iq <= RC <= 32: one column per lane
               if (k < iq - 1) {
                 double* ck = Rcol(k);

@@ -837,48 +837,50 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     int iq_ref = -1;  // size of the active set at the reference's own termination point (-1: same as the final one)
     double R_norm = 1.0;
     double* rec = rec_all + s * C::REC;  // written by k_ihwbc_setup
+    // Every global load of the state is issued before anything waits on one: Z (row lane, and half rows 32..
+    // in lane pairs) straight into its registers -- also for a state the setup kernel gave up on, whose
+    // record holds stale numbers nobody reads --, the scalars, x, then the shared-memory image.
     {
-      // torque-limit rows, their offsets and the wrench cones arrive in their final layout
-      const double2* src = reinterpret_cast<const double2*>(rec + C::RI);
-      double2* dst = reinterpret_cast<double2*>(smem + C::OAR);
-#pragma unroll 4
-      for (int k = lane; k < C::IMG / 2; k += 32) dst[k] = __ldg(src + k);
+      const double2* rj = reinterpret_cast<const double2*>(rec + C::RJ) + lane;
+#pragma unroll
+      for (int k = 0; k < NPC; k += 2) {
+        const double2 g = __ldg(rj + (k >> 1) * 32);
+        Ja[k] = g.x;
+        Ja[k + 1] = g.y;
+      }
+      if constexpr (EXT) {
+        const double2* rb = reinterpret_cast<const double2*>(rec + C::RJB) + lane;
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) {
+          const double2 g = __ldg(rb + (c >> 1) * 32);
+          Jb[c] = g.x;
+          Jb[c + 1] = g.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NB; c++) Jb[c] = 0.0;
+      }
+    }
+    const double c1 = rec[C::RS], c2 = rec[C::RS + 1];
+    R_norm = rec[C::RS + 3];  // max(1, |diagonal of R|) after the equalities
+    status = (int)rec[C::RS + 2];
+    {
 #pragma unroll 1
       for (int k = lane; k < NP; k += 32) {
         x[k] = rec[C::RX + k];  // the equality-constrained minimiser (k_ihwbc_setup)
         zv[k] = 0.0; np[k] = 0.0;
       }
+      // torque-limit rows, their offsets and the wrench cones arrive in their final layout
+      const double2* src = reinterpret_cast<const double2*>(rec + C::RI);
+      double2* dst = reinterpret_cast<double2*>(smem + C::OAR);
+#pragma unroll 8
+      for (int k = lane; k < C::IMG / 2; k += 32) dst[k] = __ldg(src + k);
 #pragma unroll 1
       for (int k = lane; k < NPC; k += 32) { dm[k] = 0.0; dv[k] = 0.0; }
 #pragma unroll 1
       for (int k = lane; k < 6 * LDT; k += 32) Ts[k] = 0.0;
     }
-    const double c1 = rec[C::RS], c2 = rec[C::RS + 1];
-    R_norm = rec[C::RS + 3];  // max(1, |diagonal of R|) after the equalities
-    status = (int)rec[C::RS + 2];
     if (status == PNC_QP_OK) {
-      // ---- move Z into registers: row lane, and half rows 32.. in lane pairs ----
-      {
-        const double2* rj = reinterpret_cast<const double2*>(rec + C::RJ) + lane;
-#pragma unroll
-        for (int k = 0; k < NPC; k += 2) {
-          const double2 g = __ldg(rj + (k >> 1) * 32);
-          Ja[k] = g.x;
-          Ja[k + 1] = g.y;
-        }
-        if constexpr (EXT) {
-          const double2* rb = reinterpret_cast<const double2*>(rec + C::RJB) + lane;
-#pragma unroll
-          for (int c = 0; c < NB; c += 2) {
-            const double2 g = __ldg(rb + (c >> 1) * 32);
-            Jb[c] = g.x;
-            Jb[c + 1] = g.y;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < NB; c++) Jb[c] = 0.0;
-        }
-      }
 #pragma unroll 1
       for (int k = lane; k < RC + 2; k += 32) { uv[k] = 0.0; Aact[k] = 0; }
       __syncwarp();

@@ -93,6 +93,7 @@ extern "C" {
 #define PNC_MAX_IC 4        /* internal-constraint rows */
 #define PNC_SWING_REC 26    /* doubles per state of a swing-foot trajectory record (pnc_swing_init) */
 #define PNC_FB_REC 14       /* doubles per state of a floating-base trajectory record (pnc_floating_base_init) */
+#define PNC_HAND_REC 24     /* doubles per state of a hand trajectory record (pnc_hand_init) */
 
 /* ---- model ------------------------------------------------------------- */
 typedef struct {
@@ -321,6 +322,20 @@ int pnc_swing_init(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_
 int pnc_swing_eval(int32_t B, const double* d_rec, const double* d_start_time, const double* d_swing_duration,
                    double current_time, double* d_pos, double* d_vel, double* d_acc, double* d_quat, double* d_angvel,
                    double* d_angacc, void* stream);
+
+/* HandTrajectoryManager.initialize_hand_trajectory / initialize_keypoint_hand_trajectory
+ * (pnc/wbc/manager/hand_trajectory_manager.py:57-102): from the current placement and angular velocity of
+ * `frame` and the target hand pose (d_target_pos [B,3], d_target_quat [B,4] = rot_to_quat of target_hand_iso;
+ * d_keypoint [B,3] or NULL) build the record of the cosine position blend and the HermiteCurveQuat
+ * (util/interpolation.py:104-134, start angular velocity = the hand's) into d_rec [B, PNC_HAND_REC].
+ * use_current (:40-55) is pnc_foot_use_current on the hand frame. */
+int pnc_hand_init(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_target_pos, const double* d_target_quat,
+                  const double* d_keypoint, double* d_rec, void* stream);
+
+/* update_hand_trajectory (:104-129; b_keypoint = 0) / update_keypoint_hand_trajectory (:131-178; b_keypoint = 1). */
+int pnc_hand_eval(int32_t B, const double* d_rec, const double* d_start_time, const double* d_duration, double current_time,
+                  int32_t b_keypoint, double* d_pos, double* d_vel, double* d_acc, double* d_quat, double* d_angvel,
+                  double* d_angacc, void* stream);
 
 /* FloatingBaseTrajectoryManager.initialize_floating_base_interpolation_trajectory
  * (pnc/wbc/manager/floating_base_trajectory_manager.py:35-54): record of the current CoM, the target,

@@ -188,6 +188,31 @@ def swing_foot_desired(init_iso, land_pos, land_quat, start_time, duration, heig
     return pos, vel, acc, quat, w, wd
 
 
+# ---- HandTrajectoryManager -----------------------------------------------------------------
+def hand_desired(init_iso, init_vel, target_pos, target_quat, start_time, duration, t, keypoint=None):
+    """hand_trajectory_manager.py:57-163: initialize_hand_trajectory (or initialize_keypoint_hand_trajectory when
+    `keypoint` is given) from the current hand placement / velocity ([angular; linear]), then
+    update_hand_trajectory / update_keypoint_hand_trajectory at time t."""
+    p0, q0 = init_iso[:3, 3], q_from_matrix(init_iso[:3, :3])
+    curve = HermiteQuat(q0, init_vel[0:3], target_quat, np.zeros(3))
+    pos, vel, acc = np.zeros(3), np.zeros(3), np.zeros(3)
+    if keypoint is None:
+        a, b, dur, tt = p0, target_pos, duration, t - start_time
+        s = (t - start_time) / duration
+    else:
+        if t <= start_time + duration * 0.5:
+            a, b, dur, tt = p0, keypoint, duration * 0.5, t - start_time
+        else:
+            a, b, dur, tt = keypoint, target_pos, duration * 0.5, t - start_time - duration * 0.5
+        s = (t - start_time) / (0.5 * duration)
+    for i in range(3):
+        pos[i] = smooth_changing(a[i], b[i], dur, tt)
+        vel[i] = smooth_changing_vel(a[i], b[i], dur, tt)
+        acc[i] = smooth_changing_acc(a[i], b[i], dur, tt)
+    quat, w, wd = curve.evaluate(s)
+    return pos, vel, acc, quat, w, wd
+
+
 # ---- FloatingBaseTrajectoryManager --------------------------------------------------------
 def floating_base_desired(ini_com, base_rot, target_com, target_quat, start_time, duration, t):  # :35-54, :72-115
     ini_quat = q_from_matrix(base_rot)

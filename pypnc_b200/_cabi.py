@@ -160,6 +160,8 @@ def load_library():
     lib.pnc_foot_use_current.argtypes = [vp, i32, i32] + [vp] * 6 + [vp]
     lib.pnc_swing_init.argtypes = [vp, i32, i32, vp, vp, vp, dbl, vp, vp]
     lib.pnc_swing_eval.argtypes = [i32, vp, vp, vp, dbl] + [vp] * 6 + [vp]
+    lib.pnc_hand_init.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.pnc_hand_eval.argtypes = [i32, vp, vp, vp, dbl, i32] + [vp] * 6 + [vp]
     lib.pnc_floating_base_init.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.pnc_floating_base_eval.argtypes = [i32, vp, vp, vp, dbl] + [vp] * 6 + [vp]
     lib.pnc_sinusoid_eval.argtypes = [i32, vp, vp, c_double_p, c_double_p, dbl, vp, vp, vp, vp]
@@ -186,7 +188,7 @@ EXPORTED_SYMBOLS = [
     'pnc_ws_coriolis', 'pnc_ws_com_pos', 'pnc_ws_com_vel', 'pnc_ws_com_jac', 'pnc_ws_com_jacdot',
     'pnc_ws_com_jdqd', 'pnc_ws_frame_iso', 'pnc_ws_frame_vel', 'pnc_ws_frame_jac', 'pnc_ws_frame_jdqd',
     'pnc_ihwbc_solve', 'pnc_ihwbc_solve_ref', 'pnc_set_termination', 'pnc_get_termination', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_osc_step', 'pnc_wbc_tick_host', 'pnc_wbc_tick_host_ex', 'pnc_wbc_tick_host_multi',
-    'pnc_quadprog_batch', 'pnc_ramp_update', 'pnc_foot_use_current', 'pnc_swing_init', 'pnc_swing_eval', 'pnc_floating_base_init',
+    'pnc_quadprog_batch', 'pnc_ramp_update', 'pnc_foot_use_current', 'pnc_swing_init', 'pnc_swing_eval', 'pnc_hand_init', 'pnc_hand_eval', 'pnc_floating_base_init',
     'pnc_floating_base_eval', 'pnc_sinusoid_eval', 'pnc_dcm_update',
     'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version', 'pnc_debug_set_dump', 'pnc_debug_setup_record',
 ]

@@ -646,6 +646,31 @@ int pnc_foot_use_current(pnc_workspace* ws, int32_t B, int32_t frame, double* d_
   return PNC_OK;
 }
 
+int pnc_hand_init(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_target_pos, const double* d_target_quat,
+                  const double* d_keypoint, double* d_rec, void* stream) {
+  if (!ws || B < 0 || B > ws->cap || !d_target_pos || !d_target_quat || !d_rec) return PNC_E_ARG;
+  const int slot = frame_slot(ws, frame);
+  if (slot < 0) return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  CK(cudaSetDevice(ws->m->device));
+  launch_hand_init(ws->p, ws->nfr, slot, B, d_target_pos, d_target_quat, d_keypoint, d_rec, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
+int pnc_hand_eval(int32_t B, const double* d_rec, const double* d_start_time, const double* d_duration, double current_time,
+                  int32_t b_keypoint, double* d_pos, double* d_vel, double* d_acc, double* d_quat, double* d_angvel,
+                  double* d_angacc, void* stream) {
+  if (B < 0 || !d_rec || !d_start_time || !d_duration || !d_pos || !d_vel || !d_acc || !d_quat || !d_angvel || !d_angacc)
+    return PNC_E_ARG;
+  if (B == 0) return PNC_OK;
+  SETDEV(d_rec);
+  launch_hand_eval(B, d_rec, d_start_time, d_duration, current_time, b_keypoint != 0, d_pos, d_vel, d_acc, d_quat, d_angvel,
+                   d_angacc, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return PNC_OK;
+}
+
 int pnc_swing_init(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_land_pos, const double* d_land_quat,
                    const double* d_swing_duration, double swing_height, double* d_rec, void* stream) {
   if (!ws || B < 0 || B > ws->cap || !d_land_pos || !d_land_quat || !d_swing_duration || !d_rec) return PNC_E_ARG;

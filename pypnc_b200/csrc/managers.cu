@@ -212,6 +212,99 @@ __global__ void k_swing_eval(int B, const double* __restrict__ rec_all, const do
   }
 }
 
+// ---- HandTrajectoryManager (pnc/wbc/manager/hand_trajectory_manager.py:57-163) ---------------
+// record (PNC_HAND_REC doubles): p_init 3, p_keypoint 3, p_target 3, q0 4, omega1 3, omega2 3, omega3 3, pad 2
+__global__ void k_hand_init(WsPtrs ws, int nfr, int slot, int B, const double* __restrict__ target_pos,
+                            const double* __restrict__ target_quat, const double* __restrict__ keypoint,
+                            double* __restrict__ rec_all) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  const double* iso = ws.fr_iso + ((size_t)s * nfr + slot) * 12;
+  const double* fv = ws.fr_vel + ((size_t)s * nfr + slot) * 6;
+  double q0[4], qt[4] = {target_quat[4 * s], target_quat[4 * s + 1], target_quat[4 * s + 2], target_quat[4 * s + 3]};
+  rot_to_quat(iso, q0);
+  q_normalize(qt);
+  double* rec = rec_all + (size_t)s * PNC_HAND_REC;
+  for (int i = 0; i < 3; i++) {
+    rec[i] = iso[9 + i];
+    rec[3 + i] = keypoint ? keypoint[3 * s + i] : 0.0;
+    rec[6 + i] = target_pos[3 * s + i];
+  }
+  for (int i = 0; i < 4; i++) rec[9 + i] = q0[i];
+  // HermiteCurveQuat(q0, omega_a, qt, 0) (util/interpolation.py:104-134): q1 = q0 * exp(omega_a / 3) unless
+  // |omega_a| < 1e-6, q2 = qt * identity, q3 = qt
+  const double wa[3] = {fv[0], fv[1], fv[2]};
+  const double na = sqrt(wa[0] * wa[0] + wa[1] * wa[1] + wa[2] * wa[2]);
+  double step[4] = {0.0, 0.0, 0.0, 1.0};
+  if (!(na < 1e-6)) {
+    const double v[3] = {(na / 3.0) * (wa[0] / na), (na / 3.0) * (wa[1] / na), (na / 3.0) * (wa[2] / na)};
+    q_from_rotvec(v, step);
+  }
+  const double ident[4] = {0.0, 0.0, 0.0, 1.0};
+  double q1[4], q2[4], qi[4], t4[4], u[4], w[3];
+  q_mul(q0, step, q1);
+  q_mul(qt, ident, q2);
+  q_inv(q0, qi); q_mul(q1, qi, t4); q_as_rotvec(t4, w);
+  rec[13] = w[0]; rec[14] = w[1]; rec[15] = w[2];
+  q_inv(q1, t4); q_mul(q2, t4, u); q_as_rotvec(u, w);
+  rec[16] = w[0]; rec[17] = w[1]; rec[18] = w[2];
+  q_inv(q2, t4); q_mul(qt, t4, u); q_as_rotvec(u, w);
+  rec[19] = w[0]; rec[20] = w[1]; rec[21] = w[2];
+  rec[22] = 0.0; rec[23] = 0.0;
+}
+
+// update_hand_trajectory (:104-129) / update_keypoint_hand_trajectory (:131-178): cosine blend of the position
+// (util/interpolation.py:8-30, no clipping below zero, held after the end), HermiteCurveQuat for the orientation
+__global__ void k_hand_eval(int B, const double* __restrict__ rec_all, const double* __restrict__ start_time,
+                            const double* __restrict__ duration, double t_now, int keypoint, double* __restrict__ pos,
+                            double* __restrict__ vel, double* __restrict__ acc, double* __restrict__ quat,
+                            double* __restrict__ angvel, double* __restrict__ angacc) {
+  const int st = blockIdx.x * blockDim.x + threadIdx.x;
+  if (st >= B) return;
+  const double* rec = rec_all + (size_t)st * PNC_HAND_REC;
+  const double t0 = start_time[st], dur = duration[st];
+  const double* a = rec;
+  const double* b = rec + 6;
+  double d = dur, tt = t_now - t0, s = (t_now - t0) / dur;
+  if (keypoint) {
+    d = dur * 0.5;
+    if (t_now <= t0 + dur * 0.5) { b = rec + 3; }
+    else { a = rec + 3; tt = t_now - t0 - dur * 0.5; }
+    s = (t_now - t0) / (0.5 * dur);
+  }
+  const double PI = 3.141592653589793;
+  for (int i = 0; i < 3; i++) {
+    const double ph = tt / d * PI;
+    double p = a[i] + (b[i] - a[i]) * 0.5 * (1.0 - cos(ph));
+    double v = (b[i] - a[i]) * 0.5 * (PI / d) * sin(ph);
+    double c = (b[i] - a[i]) * 0.5 * (PI / d) * (PI / d) * cos(ph);
+    if (tt > d) { p = b[i]; v = 0.0; c = 0.0; }
+    pos[3 * st + i] = p; vel[3 * st + i] = v; acc[3 * st + i] = c;
+  }
+  const double sc = fmin(fmax(s, 0.0), 1.0), om = 1.0 - sc;
+  const double bb[3] = {1 - om * om * om, 3 * sc * sc - 2 * sc * sc * sc, sc * sc * sc};
+  const double bd[3] = {3 * om * om, 6 * sc - 6 * sc * sc, 3 * sc * sc};
+  const double bdd[3] = {-6 * om, 6 - 12 * sc, 6 * sc};
+  double qacc[4] = {rec[9], rec[10], rec[11], rec[12]};
+  for (int k = 0; k < 3; k++) {
+    const double* w = rec + 13 + 3 * k;
+    const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double qt[4] = {0.0, 0.0, 0.0, 1.0};
+    if (n > 1e-5) {
+      const double v[3] = {(n * bb[k]) * (w[0] / n), (n * bb[k]) * (w[1] / n), (n * bb[k]) * (w[2] / n)};
+      q_from_rotvec(v, qt);
+    }
+    double r[4];
+    q_mul(qt, qacc, r);
+    qacc[0] = r[0]; qacc[1] = r[1]; qacc[2] = r[2]; qacc[3] = r[3];
+  }
+  for (int i = 0; i < 4; i++) quat[4 * st + i] = qacc[i];
+  for (int i = 0; i < 3; i++) {
+    angvel[3 * st + i] = rec[13 + i] * bd[0] + rec[16 + i] * bd[1] + rec[19 + i] * bd[2];
+    angacc[3 * st + i] = rec[13 + i] * bdd[0] + rec[16 + i] * bdd[1] + rec[19 + i] * bdd[2];
+  }
+}
+
 // ---- FloatingBaseTrajectoryManager.initialize_floating_base_interpolation_trajectory (:35-54) -
 // record (PNC_FB_REC doubles): ini_com 3, target_com 3, ini_quat 4, exp_error 3, pad
 __global__ void k_floating_base_init(WsPtrs ws, int nfr, int slot, int B, const double* __restrict__ target_com,
@@ -328,6 +421,16 @@ void launch_swing_init(const WsPtrs& ws, int nfr, int slot, int B, const double*
 void launch_swing_eval(int B, const double* rec, const double* st, const double* dur, double t, double* pos, double* vel,
                        double* acc, double* quat, double* angvel, double* angacc, cudaStream_t stream) {
   k_swing_eval<<<grid_for(B), 128, 0, stream>>>(B, rec, st, dur, t, pos, vel, acc, quat, angvel, angacc);
+  g_launch_count++;
+}
+void launch_hand_init(const WsPtrs& ws, int nfr, int slot, int B, const double* tpos, const double* tquat, const double* key,
+                      double* rec, cudaStream_t stream) {
+  k_hand_init<<<grid_for(B), 128, 0, stream>>>(ws, nfr, slot, B, tpos, tquat, key, rec);
+  g_launch_count++;
+}
+void launch_hand_eval(int B, const double* rec, const double* st, const double* dur, double t, int keypoint, double* pos,
+                      double* vel, double* acc, double* quat, double* angvel, double* angacc, cudaStream_t stream) {
+  k_hand_eval<<<grid_for(B), 128, 0, stream>>>(B, rec, st, dur, t, keypoint, pos, vel, acc, quat, angvel, angacc);
   g_launch_count++;
 }
 void launch_floating_base_init(const WsPtrs& ws, int nfr, int slot, int B, const double* tcom, const double* tquat,

@@ -137,6 +137,10 @@ void launch_ramp_update(int B, const double* sv, double target, const double* st
                         cudaStream_t stream);
 void launch_foot_use_current(const WsPtrs& ws, int nfr, int slot, int B, double* pos, double* vel, double* acc, double* quat,
                              double* angvel, double* angacc, cudaStream_t stream);
+void launch_hand_init(const WsPtrs& ws, int nfr, int slot, int B, const double* tpos, const double* tquat, const double* key,
+                      double* rec, cudaStream_t stream);
+void launch_hand_eval(int B, const double* rec, const double* st, const double* dur, double t, int keypoint, double* pos,
+                      double* vel, double* acc, double* quat, double* angvel, double* angacc, cudaStream_t stream);
 void launch_swing_init(const WsPtrs& ws, int nfr, int slot, int B, const double* land_pos, const double* land_quat,
                        const double* duration, double height, double* rec, cudaStream_t stream);
 void launch_swing_eval(int B, const double* rec, const double* st, const double* dur, double t, double* pos, double* vel,

@@ -20,7 +20,7 @@ from . import engine
 from ._cabi import load_library
 
 _vp = C.c_void_p
-SWING_REC, FB_REC = 26, 14  # PNC_SWING_REC / PNC_FB_REC of include/pnc_b200.h (checked by tests/test_cabi_and_host.py)
+SWING_REC, FB_REC, HAND_REC = 26, 14, 24  # PNC_SWING_REC / PNC_FB_REC / PNC_HAND_REC of include/pnc_b200.h (checked by tests/test_cabi_and_host.py)
 
 
 def _P(t):
@@ -246,6 +246,74 @@ class PointFootTrajectoryManager(FootTrajectoryManager):
                                                float(curr_time), _P(pos), _P(vel), _P(acc), _P(quat), _P(w), _P(wd), None),
                       'pnc_swing_eval')
         self._pos_task.update_desired(pos, vel, acc)
+
+
+class HandTrajectoryManager:
+    """pnc/wbc/manager/hand_trajectory_manager.py:7-178.  Target hand poses are passed as target_pos [B,3] and
+    target_quat [B,4] (the reference passes a 4x4 target_hand_iso and takes util.rot_to_quat of its rotation)."""
+
+    def __init__(self, pos_task, ori_task, robot):
+        self._pos_task, self._ori_task, self._robot = pos_task, ori_task, robot
+        self._target_id = pos_task.target_id
+        self._lib = load_library()
+        self._start_moving_time = self._moving_duration = self._rec = None
+
+    def _ws(self):
+        ws, _ = self._robot._slot(self._target_id)
+        return ws, self._robot.model.frame_id(self._target_id)
+
+    def _write(self, pos, vel, acc, quat, w, wd):
+        self._pos_task.update_desired(pos, vel, acc)
+        if self._ori_task is not None:
+            self._ori_task.update_desired(quat, w, wd)
+
+    def update_desired(self, target_pos, target_quat):  # :26-38
+        ws, _ = self._ws()
+        B, dev = ws.B, ws.view('com').device
+        pos, vel, acc, quat, w, wd = _outputs(B, dev)
+        pos.copy_(torch.as_tensor(target_pos, dtype=torch.float64, device=dev).expand(B, 3))
+        quat.copy_(torch.as_tensor(target_quat, dtype=torch.float64, device=dev).expand(B, 4))
+        vel.zero_(); acc.zero_(); w.zero_(); wd.zero_()
+        self._write(pos, vel, acc, quat, w, wd)
+
+    def use_current(self):  # :40-55
+        ws, frame = self._ws()
+        B = ws.B
+        pos, vel, acc, quat, w, wd = _outputs(B, ws.view('com').device)
+        engine._check(self._lib.pnc_foot_use_current(ws.h, B, frame, _P(pos), _P(vel), _P(acc), _P(quat), _P(w), _P(wd), None),
+                      'pnc_foot_use_current')
+        self._write(pos, vel, acc, quat, w, wd)
+
+    def _init(self, start_time, duration, target_pos, target_quat, keypoint_pos):
+        ws, frame = self._ws()
+        B, dev = ws.B, ws.view('com').device
+        self._start_moving_time, self._moving_duration = _vecB(start_time, B, dev), _vecB(duration, B, dev)
+        tp = torch.as_tensor(target_pos, dtype=torch.float64, device=dev).expand(B, 3).contiguous()
+        tq = torch.as_tensor(target_quat, dtype=torch.float64, device=dev).expand(B, 4).contiguous()
+        kp = None if keypoint_pos is None else torch.as_tensor(keypoint_pos, dtype=torch.float64, device=dev).expand(B, 3).contiguous()
+        self._rec = torch.empty((B, HAND_REC), dtype=torch.float64, device=dev)
+        engine._check(self._lib.pnc_hand_init(ws.h, B, frame, _P(tp), _P(tq), None if kp is None else _P(kp), _P(self._rec), None),
+                      'pnc_hand_init')
+
+    def initialize_hand_trajectory(self, start_time, duration, target_pos, target_quat):  # :57-77
+        self._init(start_time, duration, target_pos, target_quat, None)
+
+    def initialize_keypoint_hand_trajectory(self, start_time, duration, keypoint_pos, target_pos, target_quat):  # :79-102
+        self._init(start_time, duration, target_pos, target_quat, keypoint_pos)
+
+    def _update(self, current_time, keypoint):
+        B, dev = self._rec.shape[0], self._rec.device
+        pos, vel, acc, quat, w, wd = _outputs(B, dev)
+        engine._check(self._lib.pnc_hand_eval(B, _P(self._rec), _P(self._start_moving_time), _P(self._moving_duration),
+                                              float(current_time), int(keypoint), _P(pos), _P(vel), _P(acc), _P(quat), _P(w),
+                                              _P(wd), None), 'pnc_hand_eval')
+        self._write(pos, vel, acc, quat, w, wd)
+
+    def update_hand_trajectory(self, current_time):  # :104-129
+        self._update(current_time, 0)
+
+    def update_keypoint_hand_trajectory(self, current_time):  # :131-178
+        self._update(current_time, 1)
 
 
 class UpperBodyTrajectoryManager:

@@ -3,7 +3,8 @@
     python tests/golden/make_golden_managers.py      (needs /root/reference; run in the build container)
 
 Runs unmodified from /root/reference: pnc/wbc/manager/{task_hierarchy_manager, reaction_force_manager,
-foot_trajectory_manager, point_foot_trajectory_manager, floating_base_trajectory_manager}.py, util/interpolation.py, util/util.py,
+foot_trajectory_manager, point_foot_trajectory_manager, floating_base_trajectory_manager,
+hand_trajectory_manager}.py, util/interpolation.py, util/util.py,
 pnc/planner/locomotion/dcm_planner/footstep.py, and the DCM update of
 pnc/atlas_pnc/atlas_state_estimator.py:35-44 (re-typed below because the module imports the
 simulator config; the arithmetic is the three lines cited).  The robot is a stub that returns the
@@ -24,6 +25,7 @@ from pnc.wbc.manager.reaction_force_manager import ReactionForceManager  # noqa:
 from pnc.wbc.manager.foot_trajectory_manager import FootTrajectoryManager  # noqa: E402
 from pnc.wbc.manager.point_foot_trajectory_manager import PointFootTrajectoryManager  # noqa: E402
 from pnc.wbc.manager.floating_base_trajectory_manager import FloatingBaseTrajectoryManager  # noqa: E402
+from pnc.wbc.manager.hand_trajectory_manager import HandTrajectoryManager  # noqa: E402
 from pnc.planner.locomotion.dcm_planner.footstep import Footstep  # noqa: E402
 
 
@@ -139,6 +141,43 @@ def main(n=96, seed=7):
     out.update(foot_iso=iso, foot_vel=vel, land_pos=land_iso[:, :3, 3], land_quat=land_quat, sw_t0=sw_t0, sw_dur=sw_dur,
                sw_frac=sw_frac, sw_height=height, **{'uc_' + k: np.array(v) for k, v in uc.items()},
                **{'sw_' + k: np.array(v) for k, v in sw.items()})
+
+    # ---- hand trajectory manager (hand_trajectory_manager.py) ----
+    hrng = np.random.default_rng(seed + 1000)  # its own stream: the vectors above stay what they were
+    h_iso = np.stack([rand_iso(hrng, 0.6 if i % 4 else 1e-4) for i in range(n)])
+    h_vel = hrng.normal(0, 0.5, (n, 6))
+    h_vel[::9, 0:3] *= 1e-7  # |angular velocity| < 1e-6: the other branch of HermiteCurveQuat.__init__
+    h_tgt = np.stack([rand_iso(hrng, 0.6 if i % 5 else 2e-6) for i in range(n)])
+    h_key = hrng.normal(0, 0.5, (n, 3))
+    h_t0, h_dur = hrng.uniform(0, 1, n), hrng.uniform(0.2, 2.0, n)
+    h_frac = np.concatenate([hrng.uniform(-0.1, 1.2, n - 4), [0.0, 0.5, 1.0, 0.25]])
+    hd = {k: [] for k in ('pos', 'vel', 'acc', 'quat', 'angvel', 'angacc', 'kp_pos', 'kp_vel', 'kp_acc', 'kp_quat', 'kp_angvel',
+                          'kp_angacc', 'uc_pos', 'uc_vel', 'uc_quat', 'uc_angvel')}
+    h_tgt_quat = np.zeros((n, 4))
+    from util import util as ref_util
+    for i in range(n):
+        robot = StubRobot()
+        robot.iso['hand'], robot.vel['hand'] = h_iso[i], h_vel[i]
+        h_tgt_quat[i] = ref_util.rot_to_quat(h_tgt[i, :3, :3])
+        tnow = h_t0[i] + h_frac[i] * h_dur[i]
+        pt, ot = StubTask('hand'), StubTask('hand')
+        m = HandTrajectoryManager(pt, ot, robot)
+        m.use_current()
+        hd['uc_pos'].append(pt.des[0]); hd['uc_vel'].append(pt.des[1]); hd['uc_quat'].append(ot.des[0]); hd['uc_angvel'].append(ot.des[1])
+        m.initialize_hand_trajectory(h_t0[i], h_dur[i], h_tgt[i])
+        m.update_hand_trajectory(tnow)
+        for k, v in zip(('pos', 'vel', 'acc'), pt.des):
+            hd[k].append(v)
+        for k, v in zip(('quat', 'angvel', 'angacc'), ot.des):
+            hd[k].append(v)
+        m.initialize_keypoint_hand_trajectory(h_t0[i], h_dur[i], h_key[i], h_tgt[i])
+        m.update_keypoint_hand_trajectory(tnow)
+        for k, v in zip(('kp_pos', 'kp_vel', 'kp_acc'), pt.des):
+            hd[k].append(v)
+        for k, v in zip(('kp_quat', 'kp_angvel', 'kp_angacc'), ot.des):
+            hd[k].append(v)
+    out.update(hand_iso=h_iso, hand_vel6=h_vel, hand_tgt_pos=h_tgt[:, :3, 3], hand_tgt_quat=h_tgt_quat, hand_key=h_key,
+               hand_t0=h_t0, hand_dur=h_dur, hand_frac=h_frac, **{'hand_' + k: np.array(v) for k, v in hd.items()})
 
     # ---- floating base manager ----
     base_iso = np.stack([rand_iso(rng, 0.3) for _ in range(n)])

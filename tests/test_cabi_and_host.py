@@ -130,3 +130,4 @@ def test_manager_record_sizes_match_header():
     hdr = open(os.path.join(ROOT, 'include', 'pnc_b200.h')).read()
     assert int(re.search(r'#define PNC_SWING_REC (\d+)', hdr).group(1)) == managers.SWING_REC
     assert int(re.search(r'#define PNC_FB_REC (\d+)', hdr).group(1)) == managers.FB_REC
+    assert int(re.search(r'#define PNC_HAND_REC (\d+)', hdr).group(1)) == managers.HAND_REC

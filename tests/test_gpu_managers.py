@@ -110,6 +110,31 @@ def test_swing_golden(rig):
         close(got[k], G['sw_' + k])
 
 
+def test_hand_trajectory_golden(rig):
+    """pnc_hand_init / pnc_hand_eval against the reference's own HandTrajectoryManager (plain and keypoint
+    trajectories, hand_trajectory_manager.py:57-178)."""
+    from pypnc_b200._cabi import load_library
+    from pypnc_b200.managers import HAND_REC
+    spec, dm, ws = rig
+    lib = load_library()
+    slot = 3
+    put_frame(ws, slot, G['hand_iso'], G['hand_vel6'])
+    t0, dur = dev(G['hand_t0']), dev(G['hand_dur'])
+    tp, tq, kp = dev(G['hand_tgt_pos']), dev(G['hand_tgt_quat']), dev(G['hand_key'])
+    o = outs()
+    for pre, key in (('', None), ('kp_', kp)):
+        rec = torch.empty((N, HAND_REC), dtype=torch.float64, device='cuda')
+        assert lib.pnc_hand_init(ws.h, N, spec.frames[slot], P(tp), P(tq), None if key is None else P(key), P(rec), None) == 0
+        got = {k: np.zeros((N, 4 if k == 'quat' else 3)) for k in KEYS}
+        for i in range(N):
+            t = float(G['hand_t0'][i] + G['hand_frac'][i] * G['hand_dur'][i])
+            assert lib.pnc_hand_eval(N, P(rec), P(t0), P(dur), t, int(key is not None), *[P(x) for x in o], None) == 0
+            for k, x in zip(KEYS, o):
+                got[k][i] = x[i].cpu().numpy()
+        for k in KEYS:
+            close(got[k], G['hand_' + pre + k])
+
+
 def test_floating_base_golden(rig):
     from pypnc_b200._cabi import load_library
     from pypnc_b200.managers import FB_REC
@@ -200,6 +225,27 @@ def test_manager_classes_closed_loop_vs_oracle():
     ref = [MO.floating_base_desired(cpos[i], iso_p[i, :3, :3], tgt_com[i], tgt_quat[i], 0.1, 1.0, 0.6) for i in range(B)]
     close(com.pos_des, np.array([r[0] for r in ref])); close(pel.pos_des, np.array([r[3] for r in ref]))
     close(pel._vel_des, np.array([r[4] for r in ref]))
+    # hand trajectory (plain and keypoint) on the right foot frame standing in for a hand
+    hpos, hori = wbc.BasicTask(robot, 'LINK_XYZ', 3, 'r_sole'), wbc.BasicTask(robot, 'LINK_ORI', 3, 'r_sole')
+    hm = managers.HandTrajectoryManager(hpos, hori, robot)
+    h_tp = iso_r[:, :3, 3] + rng.normal(0, 0.1, (B, 3))
+    h_tq = np.array([MO.q_mul(MO.q_from_matrix(iso_r[i, :3, :3]), MO.q_from_rotvec(rng.normal(0, 0.3, 3))) for i in range(B)])
+    h_kp = iso_r[:, :3, 3] + rng.normal(0, 0.1, (B, 3))
+    for key in (None, h_kp):
+        if key is None:
+            hm.initialize_hand_trajectory(0.1, 0.8, dev(h_tp), dev(h_tq))
+            hm.update_hand_trajectory(0.35)
+        else:
+            hm.initialize_keypoint_hand_trajectory(0.1, 0.8, dev(key), dev(h_tp), dev(h_tq))
+            hm.update_keypoint_hand_trajectory(0.65)
+        ref = [MO.hand_desired(iso_r[i], vel_r[i], h_tp[i], h_tq[i], 0.1, 0.8, 0.35 if key is None else 0.65,
+                               None if key is None else key[i]) for i in range(B)]
+        close(hpos.pos_des, np.array([r[0] for r in ref])); close(hpos._vel_des, np.array([r[1] for r in ref]))
+        close(hpos._acc_des, np.array([r[2] for r in ref])); close(hori.pos_des, np.array([r[3] for r in ref]))
+        close(hori._vel_des, np.array([r[4] for r in ref])); close(hori._acc_des, np.array([r[5] for r in ref]))
+    hm.use_current()
+    ref = [MO.foot_use_current(iso_r[i], vel_r[i]) for i in range(B)]
+    close(hpos.pos_des, np.array([r[0] for r in ref])); close(hori.pos_des, np.array([r[3] for r in ref]))
     # ramps
     lpos.w_hierarchy = dev(rng.uniform(40, 60, B))
     w0 = lpos.w_hierarchy.cpu().numpy()

@@ -61,3 +61,18 @@ def test_dcm():
     for i in range(N):
         d, p, v = MO.dcm_update(G['com'][i], G['dcm_vcom'][i], G['dcm_state'][i], float(G['dcm_dt']))
         close(d, G['dcm_out'][i]); close(p, G['dcm_prev_out'][i]); close(v, G['dcm_vel_out'][i])
+
+
+def test_hand_trajectory():
+    """HandTrajectoryManager (hand_trajectory_manager.py): use_current, the plain and the keypoint trajectory, start
+    angular velocities on both sides of HermiteCurveQuat's 1e-6 switch, times before the start and after the end."""
+    for i in range(N):
+        t = G['hand_t0'][i] + G['hand_frac'][i] * G['hand_dur'][i]
+        uc = MO.foot_use_current(G['hand_iso'][i], G['hand_vel6'][i])
+        close(uc[0], G['hand_uc_pos'][i]); close(uc[1], G['hand_uc_vel'][i]); close(uc[3], G['hand_uc_quat'][i])
+        close(uc[4], G['hand_uc_angvel'][i])
+        for key, pre in ((None, ''), (G['hand_key'][i], 'kp_')):
+            out = MO.hand_desired(G['hand_iso'][i], G['hand_vel6'][i], G['hand_tgt_pos'][i], G['hand_tgt_quat'][i],
+                                  G['hand_t0'][i], G['hand_dur'][i], t, key)
+            for k, v in zip(('pos', 'vel', 'acc', 'quat', 'angvel', 'angacc'), out):
+                close(v, G['hand_' + pre + k][i], 1e-10)

@@ -1136,7 +1136,8 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
 
           if (!dual_only && fabs(t - t2) < QP_EPS) {
             // ---- full step: add the constraint (:441-474), one Householder reflection of Z2 ----
-            const double sigma = sqrt(sig2);
+            const double isig = sig2 > 0.0 ? rsqrt(sig2) : 0.0;
+            const double sigma = sig2 * isig;  // sqrt(sig2), with its reciprocal for free
             if (sigma <= QP_EPS * R_norm) {  // linearly dependent on the active set
               set_bit(excm, ip);
               if (lane < iq) { Aact[lane] = Aold[lane]; uv[lane] = uold[lane]; }
@@ -1160,7 +1161,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             // R gains the column [d1; alpha]
             double* col = Rcol(iq);
             if (lane < iq) col[lane] = dv[lane];
-            if (lane == 0) { col[iq] = alpha; rinv[iq] = 1.0 / alpha; }
+            if (lane == 0) { col[iq] = alpha; rinv[iq] = d0 > 0.0 ? -isig : isig; }
             // the Householder vector v = [0 .. 0, v0, d[iq+1:]] is the masked d with one entry patched
             if (lane == 0) dm[iq] = v0;
             const double ca = reg_pick(Ja, iq);  // old column iq of Z
@@ -1211,11 +1212,15 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           for (int j = kk; j < iq - 1; j++) {
             double* cj = Rcol(j);
             double cc = cj[j], ss = cj[j + 1];
-            const double hh = qp_distance(cc, ss);
-            const bool skip = fabs(hh) < QP_EPS;  // QuadProg++ leaves such a pair untouched
+            // h = distance(cc, ss) (QuadProg++.cc:681-692) and 1 / h from one reciprocal square root: R's entries
+            // are O(1e-3 .. 1e3) here, so the overflow guard of the reference's hypot is not needed, and the
+            // one reciprocal serves cc / h, ss / h and 1 / diag (an ulp or two from :636-638)
+            const double d2 = fma(cc, cc, ss * ss);
+            const bool skip = !(d2 >= QP_EPS * QP_EPS);  // |h| < eps: QuadProg++ leaves such a pair untouched
             double xny = 0.0;
             if (!skip) {
-              double ih = 1.0 / hh;  // one reciprocal serves cc / h, ss / h and 1 / diag (an ulp from :636-638)
+              double ih = rsqrt(d2);
+              const double hh = d2 * ih;
               cc = cc * ih;
               ss = ss * ih;
               double diag = hh;

@@ -1116,13 +1116,13 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           int kk = 0x7fffffff;
           if (lane < iq) {  // iq <= RC <= 32: one candidate per lane
             const double rk = rv[lane];
-            if (rk > 0.0) { t1 = uv[lane] / rk; kk = lane; }
+            if (rk > 0.0) { t1 = uv[lane] * fast_rcp(rk); kk = lane; }
           }
           wargmin(t1, kk);
           const int l = kk != 0x7fffffff ? Aact[kk] : 0;
           double t2 = INFINITY;
           if (fabs(zz) > QP_EPS) {
-            t2 = -s_ip / znp;
+            t2 = -s_ip * fast_rcp(znp);
             if (t2 < 0.0) t2 = INFINITY;
           }
           const double t = fmin(t1, t2);
@@ -1157,7 +1157,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
             const double d0 = dv[iq];
             const double alpha = d0 > 0.0 ? -sigma : sigma;
             const double v0 = d0 - alpha;
-            const double beta = 1.0 / (sigma * (sigma + fabs(d0)));
+            const double beta = fast_rcp(sigma * (sigma + fabs(d0)));
             // R gains the column [d1; alpha]
             double* col = Rcol(iq);
             if (lane < iq) col[lane] = dv[lane];
@@ -1225,7 +1225,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
               ss = ss * ih;
               double diag = hh;
               if (cc < 0.0) { diag = -hh; ih = -ih; cc = -cc; ss = -ss; }
-              xny = ss / (1.0 + cc);
+              xny = ss * fast_rcp(1.0 + cc);
               __syncwarp();
               if (lane == 0) { cj[j] = diag; cj[j + 1] = 0.0; rinv[j] = ih; }
               const int k = j + 1 + lane;  // iq <= RC <= 32: one column per lane

@@ -542,7 +542,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         R_norm = fmax(R_norm, sigma);
         const double dkk = __shfl_sync(FULL, dq[0][k], k);
         const double alpha = dkk > 0.0 ? -sigma : sigma;
-        const double bk = sigma > 0.0 ? 1.0 / (sigma * (sigma + fabs(dkk))) : 0.0;
+        const double bk = sigma > 0.0 ? fast_rcp(sigma * (sigma + fabs(dkk))) : 0.0;
         if (lane == k) { rmine = alpha; Bs[k] = bk; }
         const double v0 = lane > k ? dq[0][k] : (lane == k ? dkk - alpha : 0.0);
         const double v1 = N > 32 ? dq[1][k] : 0.0;

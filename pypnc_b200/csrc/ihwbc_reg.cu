@@ -571,9 +571,10 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       {
         double ymine = 0.0;
         double acc = lane < PE ? Ys[lane] : 0.0;
+        const double rimine = rmine != 0.0 ? fast_rcp(rmine) : 0.0;  // one reciprocal per lane, off the chain below
 #pragma unroll
         for (int k = 0; k < PE; k++) {
-          const double yk = __shfl_sync(FULL, rmine != 0.0 ? acc / rmine : 0.0, k);  // y_k, final once rows < k are folded in
+          const double yk = __shfl_sync(FULL, acc * rimine, k);  // y_k, final once rows < k are folded in
           if (lane == k) ymine = yk;
           // fold y_k into the rows below: c_c -= R[k][c] y_k, R[k][c] = dq[0][c] of lane k
 #pragma unroll

@@ -130,6 +130,7 @@ __device__ __forceinline__ const double* dense_row_ptr(const DevTask& T, int wsf
 
 // wrench-cone row `lr` of a contact in its own frame, basic_contact.py:24-51 / 89-173
 __device__ __forceinline__ void cone_row_local(const DevContact& C, int lr, double* u6) {
+#pragma unroll
   for (int k = 0; k < 6; k++) u6[k] = 0.0;
   const double mu = C.mu;
   if (C.type == PNC_CONTACT_POINT) {
@@ -171,9 +172,11 @@ __device__ __forceinline__ void cone_row_world(const DevContact& C, int lr, cons
   double l[6];
   cone_row_local(C, lr, l);
   if (C.type == PNC_CONTACT_POINT) {
+#pragma unroll
     for (int k = 0; k < 6; k++) u6[k] = l[k];
     return;
   }
+#pragma unroll
   for (int j = 0; j < 3; j++) {
     u6[j] = l[0] * iso[3 * j] + l[1] * iso[3 * j + 1] + l[2] * iso[3 * j + 2];
     u6[3 + j] = l[3] * iso[3 * j] + l[4] * iso[3 * j + 1] + l[5] * iso[3 * j + 2];

@@ -712,6 +712,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           const int lr = r - Cc.cone_off;
           double u6[6];
           cone_row_world(Cc, lr, ws.fr_iso + (s * nfr + fm.contact_f[ci]) * 12, u6);
+#pragma unroll
           for (int k = 0; k < 6; k++) Uf[r * 6 + k] = u6[k];
           double rz = io.rfz[s * P.ncontact + ci];
           if (rz <= 0.0) rz = 1e-3;  // contact.py:37-41
@@ -1117,7 +1118,7 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
           int kk = 0x7fffffff;
           if (lane < iq) {  // iq <= RC <= 32: one candidate per lane
             const double rk = rv[lane];
-            if (rk > 0.0) { t1 = uv[lane] * fast_rcp(rk); kk = lane; }
+            if (rk > 1e-300) { t1 = uv[lane] * fast_rcp(rk); kk = lane; }  // (a denormal r_k would flush to 1 / 0)
           }
           wargmin(t1, kk);
           const int l = kk != 0x7fffffff ? Aact[kk] : 0;

@@ -81,6 +81,10 @@ static __device__ __noinline__ int ic_lambda_inverse(const double* __restrict__ 
   return 0;
 }
 
+#ifndef PNC_IC_WARPS
+#define PNC_IC_WARPS 10
+#endif
+
 struct IcLayout {
   int ld, ldz, ldb;
   int oL, oZ, oV, oG, oBt, oY, oJb, oLam, odiag, ocg, oncg, oJcJb, oLdi, oGdi;
@@ -483,14 +487,22 @@ struct IcRegCfg {
   static_assert((SZT & 1) == 0 && (SZZ & 1) == 0, "16-byte alignment of the regions");
 };
 
-template <int NV, int NACT, int NC, int K>
-__global__ void __launch_bounds__(32, 10)
+// W warps per CTA, one state each, walking the code TOGETHER: the kernel is ~17 K straight-line instructions
+// (270 KB) executed once per state, and ten independent one-warp CTAs per SM each streaming their own copy
+// through the instruction cache spent a third of their cycles waiting for instructions (ncu: no_instruction
+// 3.2 of 10 cycles per issue).  Nothing here is data dependent (fixed trip counts; a failed factorisation is a
+// flag, not a branch), so CTA-wide barriers between the sections cost no waiting and every fetched line
+// serves W warps.  States are claimed W at a time; the warps of a last, partial group redo its first state.
+template <int NV, int NACT, int NC, int K, int W>
+__global__ void __launch_bounds__(32 * W, 1)
 k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int nfr, int B, int* counter) {
   using C = IcRegCfg<NV, NACT, NC, K>;
   constexpr int N = C::N, NJ = C::NJ, LD = C::LD, LDZ = C::LDZ, LDX = C::LDX;
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(16) double sm_all[];
+  __shared__ int s_base;
   const DevProblem& P = *gp;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sm = sm_all + (size_t)warp * C::TOTAL;
   double* T = sm + C::OT;
   double* ZR = sm + C::OZ;
   double* cg = sm + C::OCG;
@@ -509,11 +521,12 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
   __syncwarp();
 
   for (;;) {
-    int si = 0;
-    if (lane == 0) si = atomicAdd(counter, 1);
-    si = __shfl_sync(FULL, si, 0);
-    if (si >= B) break;
-    const size_t s = (size_t)si;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = atomicAdd(counter, W);
+    __syncthreads();
+    const int base = s_base;
+    if (base >= B) break;
+    const size_t s = (size_t)(base + warp < B ? base + warp : base);
     int bad = 0;
     const double* Mg = ws.M + s * NV * NV;
 #pragma unroll 1
@@ -530,8 +543,10 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
     for (int c = lane; c < NV; c += 32) cg[c] = ws.cori[s * NV + c] + ws.grav[s * NV + c];
     __syncwarp();
     // ---- M = L L^T, T = L^-T ----
+    __syncthreads();
     if (!chol_rows_reg<NV, LD>(T, Ldi, pv, lane)) bad = 1;
-    if (!bad) {
+    __syncthreads();
+    {
       linv_cols_reg<NV, LD>(T, Ldi, lane);
       // ---- Y = L^-1 Ji^T: lanes = rows, Y[i][t] = sum_{c<=i} T[c][i] Ji[t][c] ----
       for (int i = lane; i < NV; i += 32) {
@@ -548,11 +563,12 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
         for (int t = 0; t < K; t++) Y[i * K + t] = y[t];
       }
       __syncwarp();
-      if (lane == 0) bad = ic_lambda_inverse(Y, Lam, NV, K);
+      if (lane == 0) bad |= ic_lambda_inverse(Y, Lam, NV, K);
       bad = __shfl_sync(FULL, bad, 0);
       __syncwarp();
     }
-    if (!bad) {
+    __syncthreads();
+    {
       // ---- Jibar = L^-T (Y Lambda) = T (Y Lambda): lanes = rows of T ----
       for (int i = lane; i < NV; i += 32) {
 #pragma unroll
@@ -636,6 +652,7 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
       }
       __syncwarp();
       // ---- lane a: z = L^-1 Atilde[a]^T, Atilde[a][c] = Ni[act_idx[a]][c] for c >= 6 (0 before) ----
+      __syncthreads();
       double z[NV];
 #pragma unroll
       for (int i = 0; i < NV; i++) z[i] = 0.0;
@@ -665,7 +682,7 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
 #pragma unroll
         for (int i = 0; i < NV; i++) ZR[i * LDZ + lane] = 0.0;  // the pad column
       }
-      __syncwarp();
+      __syncthreads();
       // ---- row a of G = Z^T Z ----
       double g[LDZ];
 #pragma unroll
@@ -680,7 +697,7 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
           g[b + 1] = fma(z[i], q.y, g[b + 1]);
         }
       }
-      __syncwarp();  // Z is dead: V6 takes its place
+      __syncthreads();  // Z is dead: V6 takes its place
       // ---- V6[j][a] = (L^-T Z)[6 + j][a] = sum_{i >= 6+j} T[6+j][i] z_i ----
 #pragma unroll
       for (int c = 6; c < NV; c++) {
@@ -705,9 +722,11 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
       __syncwarp();
       double gmax = lane < NACT ? Gs[lane * LDZ + lane] : 0.0;
       for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(FULL, gmax, o));
+      __syncthreads();
       if (!chol_rows_reg<NACT, LDZ>(Gs, Gdi, pv, lane, 1e-13 * gmax)) bad = 1;
     }
-    if (!bad) {
+    __syncthreads();
+    {
       double* Gs = T;
       linv_cols_reg<NACT, LDZ>(Gs, Gdi, lane);  // row c of Gs = column c of Lg^-1, zeros left of the diagonal
       // ---- row a' of G^-1 = Tg Tg^T: gi[a] = sum_i Tg[a'][i] Tg[a][i] ----
@@ -735,6 +754,7 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
         if (LDZ > NACT) gi[LDZ - 1] = 0.0;
       }
       // ---- row a' of B = G^-1 V6^T: b[j] = sum_a gi[a] V6[j][a] ----
+      __syncthreads();
       double bq[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
@@ -770,6 +790,7 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
         for (int j = lane; j < NJ; j += 32) X[j * LDX + N] = 0.0;
       __syncwarp();
       // ---- S [M | -(Jc Ni)^T] (transposed store [n][nact]: coalesced) and S Ni^T (c+g) ----
+      __syncthreads();
       double* out = ws.ic_tq + s * NACT * N + lane;
 #pragma unroll 1
       for (int c = 0; c < N; c += 4) {
@@ -823,20 +844,21 @@ void launch_ic_prepare(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   };
   // PNC_IC=smem forces the shared-memory formulation (A/B runs, cross-check in the tests)
   static const bool force_smem = [] { const char* e = getenv("PNC_IC"); return e && e[0] == 's'; }();
-  auto go_reg = [&](auto kernel, size_t smem_reg) {
+  auto go_reg = [&](auto kernel, size_t smem_reg, int warps) {
     static SmemOptIn optin;
     optin.ensure(kernel, smem_reg);
     int per = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, 32, smem_reg);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, 32 * warps, smem_reg);
     if (per < 1) per = 1;
     int g = num_sms * per;
-    if (g > B) g = B;
-    kernel<<<g, 32, smem_reg, stream>>>(dp, ws, fm, nfr, B, counter);
+    if (g * warps > B) g = (B + warps - 1) / warps;
+    kernel<<<g, 32 * warps, smem_reg, stream>>>(dp, ws, fm, nfr, B, counter);
   };
+  constexpr int ICW = PNC_IC_WARPS;  // warps per CTA walking the code together
   if (!force_smem && hp.nv == 33 && hp.nact == 25 && hp.nc == 12 && hp.n_ic == 2)          // Draco3
-    go_reg(k_ic_prepare_reg<33, 25, 12, 2>, sizeof(double) * IcRegCfg<33, 25, 12, 2>::TOTAL);
+    go_reg(k_ic_prepare_reg<33, 25, 12, 2, ICW>, sizeof(double) * ICW * IcRegCfg<33, 25, 12, 2>::TOTAL, ICW);
   else if (!force_smem && hp.nv == 20 && hp.nact == 12 && hp.nc == 12 && hp.n_ic == 2)     // Draco3 lower body
-    go_reg(k_ic_prepare_reg<20, 12, 12, 2>, sizeof(double) * IcRegCfg<20, 12, 12, 2>::TOTAL);
+    go_reg(k_ic_prepare_reg<20, 12, 12, 2, ICW>, sizeof(double) * ICW * IcRegCfg<20, 12, 12, 2>::TOTAL, ICW);
   else if (hp.nv == 33 && hp.nact == 25 && hp.nc == 12 && hp.n_ic == 2) go(k_ic_prepare<33, 25, 12, 2>);
   else if (hp.nv == 20 && hp.nact == 12 && hp.nc == 12 && hp.n_ic == 2) go(k_ic_prepare<20, 12, 12, 2>);   // Draco3 lower body
   else go(k_ic_prepare<0, 0, 0, 0>);

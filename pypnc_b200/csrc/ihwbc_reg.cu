@@ -221,16 +221,25 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min
   return L;
 }
 
+// PNC_SETUP_WARPS warps per CTA, one state each, claimed together and meeting at CTA-wide barriers before the
+// long straight-line sections (Hessian, the unrolled Cholesky / inverse of tri_reg.cuh: 60 KB of code run once
+// per state): every state does the same work, so the barriers cost no waiting, and an instruction line fetched
+// once serves all the warps of the CTA (ncu, one-warp CTAs: no_instruction 1.35 of 9.9 cycles per issue).
+#ifndef PNC_SETUP_WARPS
+#define PNC_SETUP_WARPS 7
+#endif
 template <int NV, int NC, int NU, int NT, int PE>
-__global__ void __launch_bounds__(32, 16)  // <= 128 registers: shared memory allows 14-16 one-warp CTAs per SM
+__global__ void __launch_bounds__(32 * PNC_SETUP_WARPS, 16 / PNC_SETUP_WARPS)  // <= 128 registers
 k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, SetupLayout SL, WsPtrs ws, FrameMap fm,
               int nfr, int B, SolveIO io, double* __restrict__ rec_all, int* __restrict__ counter) {
   using C = MCfg<NV, NC, NU, NT, PE>;
   constexpr int N = C::N, NP = C::NP, LDV = C::LDV, HW = C::HW, LDA = C::LDA;
   constexpr bool EXT = C::EXT;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(16) double smem_all[];
+  __shared__ int s_base;
   const DevProblem& G = *gp;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const smem = smem_all + (size_t)warp * SL.per_state;
   const bool has_ic = P.n_ic > 0;
   double* Gm = smem + SL.oG;
   double* Jd = smem + SL.oJd;
@@ -244,11 +253,13 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
   double* xs = zv;  // x0
 #pragma unroll 1
   for (;;) {
-    int si = 0;
-    if (lane == 0) si = atomicAdd(counter, 1);
-    si = __shfl_sync(FULL, si, 0);
-    if (si >= B) break;
-    const size_t s = (size_t)si;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = atomicAdd(counter, PNC_SETUP_WARPS);
+    __syncthreads();
+    const int base = s_base;
+    if (base >= B) break;
+    // (the warps of a last, partial group redo its first state: identical values to identical places)
+    const size_t s = (size_t)(base + warp < B ? base + warp : base);
     double* rec = rec_all + s * C::REC;
     int status = PNC_QP_OK;
     double R_norm = 1.0;
@@ -316,6 +327,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       __syncwarp();
     }
 
+    __syncthreads();
     // ---- Hessian task block (lower triangle) = sum_t w_t J_t^T J_t + lambda_q_ddot M ----
     // 2x2 tiles, accumulated in registers: the factor block shares its shared memory with the
     // staged Jacobians and is only written once every lane is done reading them
@@ -417,6 +429,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       c1 = wsum(tr) + NC * P.lambda_rf;
     }
     double* dl = vm;  // reciprocal diagonal of L
+    __syncthreads();
     const bool pd = chol_rows_reg<NV, LDV>(Gm, dl, dm, lane);
     if (!pd || !(P.lambda_rf > 0.0 || NC == 0)) {
       status = PNC_QP_NOT_PD;
@@ -1455,24 +1468,24 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   if (!optin.ensure(k_ihwbc_reg<NV, NC, NU, NT, PE>, smem)) return false;
   const SetupLayout SL = setup_layout<C>(hp, C::IMG);
   if (!ws.setup_rec || ws.setup_stride != C::REC) return false;
-  const size_t smem_s = (size_t)SL.per_state * sizeof(double);
+  const size_t smem_s = (size_t)SL.per_state * sizeof(double) * PNC_SETUP_WARPS;
   static SmemOptIn optin_s;
   if (!optin_s.ensure(k_ihwbc_setup<NV, NC, NU, NT, PE>, smem_s)) return false;
   int per_sm_s = 0, per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC, NU, NT, PE>, 32, smem_s);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC, NU, NT, PE>, 32 * PNC_SETUP_WARPS, smem_s);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT, PE>, 32 * warps, smem);
   if (per_sm < 1 || per_sm_s < 1) return false;
   static const int cap = [] { const char* e = getenv("PNC_REG_CTAS"); return e ? atoi(e) : 0; }();
   if (cap > 0 && per_sm > cap) per_sm = cap;
   static const bool verbose = getenv("PNC_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "pnc_b200: <%d,%d,%d,%d,%d> setup %d warps/SM (%zu B smem), active-set %d warps/SM (%zu B smem), record %d B\n", NV,
+    fprintf(stderr, "pnc_b200: <%d,%d,%d,%d,%d> setup %d CTAs/SM (%zu B smem), active-set %d warps/SM (%zu B smem), record %d B\n", NV,
             NC, NU, NT, PE, per_sm_s, smem_s, per_sm * warps, smem / warps, (int)(C::REC * sizeof(double)));
   int grid_s = num_sms * per_sm_s, grid = num_sms * per_sm;
-  if (grid_s > B) grid_s = B;
+  if (grid_s * PNC_SETUP_WARPS > B) grid_s = (B + PNC_SETUP_WARPS - 1) / PNC_SETUP_WARPS;
   if (grid * warps > B) grid = (B + warps - 1) / warps;
   cudaMemsetAsync(io.counter + 2, 0, sizeof(int), stream);
-  k_ihwbc_setup<NV, NC, NU, NT, PE><<<grid_s, 32, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
+  k_ihwbc_setup<NV, NC, NU, NT, PE><<<grid_s, 32 * PNC_SETUP_WARPS, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
   g_launch_count++;
   // PNC_DEBUG_RC lowers the cap on active constraints so the tests can exercise the hand-over
   static const int rc_dbg = [] { const char* e = getenv("PNC_DEBUG_RC"); return e ? atoi(e) : 0; }();

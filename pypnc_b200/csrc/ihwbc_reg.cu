@@ -839,6 +839,16 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     Cm[2 * r + 1] = Cc.dim;
   }
   if (lane < 6) np[NP + lane] = 0.0;  // never written again
+#ifndef PNC_REG_NO_BULK
+  __shared__ __align__(8) unsigned long long mbar;
+  const unsigned mbar_addr = (unsigned)__cvta_generic_to_shared(&mbar);
+  const unsigned img_addr = (unsigned)__cvta_generic_to_shared(smem + C::OAR);
+  unsigned mbar_phase = 0u;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#endif
   __syncwarp();
 
 #pragma unroll 1
@@ -852,6 +862,18 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
     int iq_ref = -1;  // size of the active set at the reference's own termination point (-1: same as the final one)
     double R_norm = 1.0;
     double* rec = rec_all + s * C::REC;  // written by k_ihwbc_setup
+#ifndef PNC_REG_NO_BULK
+    // The shared-memory image (torque-limit rows, their offsets, the wrench cones: 14 KB for Atlas, already in
+    // its final layout) comes in as ONE bulk asynchronous copy (cp.async.bulk, the TMA engine) signalled on an
+    // mbarrier: no load / store pairs through registers, and it is in flight while Z is loaded below.
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous state's reads of the image are done
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"((unsigned)(C::IMG * 8)) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(img_addr),
+                   "l"(rec + C::RI), "r"((unsigned)(C::IMG * 8)), "r"(mbar_addr)
+                   : "memory");
+    }
+#endif
     // Every global load of the state is issued before anything waits on one: Z (row lane, and half rows 32..
     // in lane pairs) straight into its registers -- also for a state the setup kernel gave up on, whose
     // record holds stale numbers nobody reads --, the scalars, x, then the shared-memory image.
@@ -885,16 +907,30 @@ k_ihwbc_reg(const __grid_constant__ DevProblem P, const DevProblem* __restrict__
         x[k] = rec[C::RX + k];  // the equality-constrained minimiser (k_ihwbc_setup)
         zv[k] = 0.0; np[k] = 0.0;
       }
+#ifdef PNC_REG_NO_BULK
       // torque-limit rows, their offsets and the wrench cones arrive in their final layout
       const double2* src = reinterpret_cast<const double2*>(rec + C::RI);
       double2* dst = reinterpret_cast<double2*>(smem + C::OAR);
 #pragma unroll 8
       for (int k = lane; k < C::IMG / 2; k += 32) dst[k] = __ldg(src + k);
+#endif
 #pragma unroll 1
       for (int k = lane; k < NPC; k += 32) { dm[k] = 0.0; dv[k] = 0.0; }
 #pragma unroll 1
       for (int k = lane; k < 6 * LDT; k += 32) Ts[k] = 0.0;
     }
+#ifndef PNC_REG_NO_BULK
+    {
+      unsigned landed;
+      do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(landed)
+                     : "r"(mbar_addr), "r"(mbar_phase)
+                     : "memory");
+      } while (!landed);
+      mbar_phase ^= 1u;
+    }
+#endif
     if (status == PNC_QP_OK) {
 #pragma unroll 1
       for (int k = lane; k < RC + 2; k += 32) { uv[k] = 0.0; Aact[k] = 0; }

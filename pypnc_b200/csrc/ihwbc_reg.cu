@@ -221,15 +221,17 @@ __host__ __device__ inline SetupLayout setup_layout(const DevProblem& P, int min
   return L;
 }
 
-// PNC_SETUP_WARPS warps per CTA, one state each, claimed together and meeting at CTA-wide barriers before the
-// long straight-line sections (Hessian, the unrolled Cholesky / inverse of tri_reg.cuh: 60 KB of code run once
-// per state): every state does the same work, so the barriers cost no waiting, and an instruction line fetched
-// once serves all the warps of the CTA (ncu, one-warp CTAs: no_instruction 1.35 of 9.9 cycles per issue).
+// WS warps per CTA, one state each, claimed together and meeting at CTA-wide barriers before the long
+// straight-line sections (Hessian, the unrolled Cholesky / inverse of tri_reg.cuh: 60 KB of code run once per
+// state), so that an instruction line fetched once serves all the warps of the CTA.  Measured in the bench
+// (solve stage, 64 K states, WS = 7 against 1): Atlas 7.16 against 7.19 ms, but Valkyrie 6.85 against 6.30,
+// Laikago 2.26 against 2.10, Draco3 9.83 against 9.51 -- the 224-thread CTAs pack worse and the register cap
+// that goes with them costs the 8-equality shapes spills.  Kept as a build knob, default one warp.
 #ifndef PNC_SETUP_WARPS
-#define PNC_SETUP_WARPS 7
+#define PNC_SETUP_WARPS 1
 #endif
-template <int NV, int NC, int NU, int NT, int PE>
-__global__ void __launch_bounds__(32 * PNC_SETUP_WARPS, 16 / PNC_SETUP_WARPS)  // <= 128 registers
+template <int NV, int NC, int NU, int NT, int PE, int WS>
+__global__ void __launch_bounds__(32 * WS, 16 / WS)
 k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict__ gp, SetupLayout SL, WsPtrs ws, FrameMap fm,
               int nfr, int B, SolveIO io, double* __restrict__ rec_all, int* __restrict__ counter) {
   using C = MCfg<NV, NC, NU, NT, PE>;
@@ -254,7 +256,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 #pragma unroll 1
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_base = atomicAdd(counter, PNC_SETUP_WARPS);
+    if (threadIdx.x == 0) s_base = atomicAdd(counter, WS);
     __syncthreads();
     const int base = s_base;
     if (base >= B) break;
@@ -1504,24 +1506,25 @@ static bool try_launch(const DevProblem* dp, const DevProblem& hp, const WsPtrs&
   if (!optin.ensure(k_ihwbc_reg<NV, NC, NU, NT, PE>, smem)) return false;
   const SetupLayout SL = setup_layout<C>(hp, C::IMG);
   if (!ws.setup_rec || ws.setup_stride != C::REC) return false;
-  const size_t smem_s = (size_t)SL.per_state * sizeof(double) * PNC_SETUP_WARPS;
+  constexpr int WS = PNC_SETUP_WARPS;  // warps per CTA of the setup kernel (see k_ihwbc_setup)
+  const size_t smem_s = (size_t)SL.per_state * sizeof(double) * WS;
   static SmemOptIn optin_s;
-  if (!optin_s.ensure(k_ihwbc_setup<NV, NC, NU, NT, PE>, smem_s)) return false;
+  if (!optin_s.ensure(k_ihwbc_setup<NV, NC, NU, NT, PE, WS>, smem_s)) return false;
   int per_sm_s = 0, per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC, NU, NT, PE>, 32 * PNC_SETUP_WARPS, smem_s);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_ihwbc_setup<NV, NC, NU, NT, PE, WS>, 32 * WS, smem_s);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ihwbc_reg<NV, NC, NU, NT, PE>, 32 * warps, smem);
   if (per_sm < 1 || per_sm_s < 1) return false;
   static const int cap = [] { const char* e = getenv("PNC_REG_CTAS"); return e ? atoi(e) : 0; }();
   if (cap > 0 && per_sm > cap) per_sm = cap;
   static const bool verbose = getenv("PNC_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "pnc_b200: <%d,%d,%d,%d,%d> setup %d CTAs/SM (%zu B smem), active-set %d warps/SM (%zu B smem), record %d B\n", NV,
-            NC, NU, NT, PE, per_sm_s, smem_s, per_sm * warps, smem / warps, (int)(C::REC * sizeof(double)));
+    fprintf(stderr, "pnc_b200: <%d,%d,%d,%d,%d> setup %d CTAs of %d warps per SM (%zu B smem), active-set %d warps/SM (%zu B smem), record %d B\n",
+            NV, NC, NU, NT, PE, per_sm_s, WS, smem_s, per_sm * warps, smem / warps, (int)(C::REC * sizeof(double)));
   int grid_s = num_sms * per_sm_s, grid = num_sms * per_sm;
-  if (grid_s * PNC_SETUP_WARPS > B) grid_s = (B + PNC_SETUP_WARPS - 1) / PNC_SETUP_WARPS;
+  if (grid_s * WS > B) grid_s = (B + WS - 1) / WS;
   if (grid * warps > B) grid = (B + warps - 1) / warps;
   cudaMemsetAsync(io.counter + 2, 0, sizeof(int), stream);
-  k_ihwbc_setup<NV, NC, NU, NT, PE><<<grid_s, 32 * PNC_SETUP_WARPS, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
+  k_ihwbc_setup<NV, NC, NU, NT, PE, WS><<<grid_s, 32 * WS, smem_s, stream>>>(hp, dp, SL, ws, fm, nfr, B, io, ws.setup_rec, io.counter + 2);
   g_launch_count++;
   // PNC_DEBUG_RC lowers the cap on active constraints so the tests can exercise the hand-over
   static const int rc_dbg = [] { const char* e = getenv("PNC_DEBUG_RC"); return e ? atoi(e) : 0; }();

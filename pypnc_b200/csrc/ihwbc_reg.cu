@@ -281,6 +281,10 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         ptr = contact_jac_row(G.contacts[ci], fm.contact_f[ci], ws, s, nfr, NV, c - G.contacts[ci].rf_off);
       }
       jcrow[c] = ptr;
+      // the image phase at the end of the state reads these rows in full (the phases before it only their first
+      // six entries): ask L2 for them now, a DRAM round trip ahead
+#pragma unroll
+      for (int o = 0; o < NV * 8; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ptr) + o));
     }
     __syncwarp();
     auto row_jc = [&](int c, int v) -> double { return jcrow[c][v]; };  // (Jc Ni)[c][v]

@@ -64,6 +64,8 @@ struct pnc_model {
   int device, num_sms;
   DevModel h;
   DevModel* d;
+  int2* d_pairs;  // CRBA (dof, ancestor dof) pair table of k_update_system
+  int n_pairs;
   int nf;
   std::vector<int> frame_parent;
   std::vector<double> frame_R, frame_p;
@@ -160,6 +162,14 @@ int pnc_model_create(const pnc_model_desc* dsc, int device, pnc_model** out) {
   m->d = nullptr;
   CKF(cudaMalloc(&m->d, sizeof(DevModel)), delete m);
   CKF(cudaMemcpy(m->d, &h, sizeof(DevModel), cudaMemcpyHostToDevice), (cudaFree(m->d), delete m));
+  {
+    std::vector<int2> pairs((size_t)h.nv * (h.nv + 1) / 2 + 64);
+    m->n_pairs = build_crba_pairs(h, pairs.data(), (int)pairs.size());
+    m->d_pairs = nullptr;
+    CKF(cudaMalloc(&m->d_pairs, sizeof(int2) * (size_t)(m->n_pairs > 0 ? m->n_pairs : 1)), (cudaFree(m->d), delete m));
+    CKF(cudaMemcpy(m->d_pairs, pairs.data(), sizeof(int2) * (size_t)m->n_pairs, cudaMemcpyHostToDevice),
+        (cudaFree(m->d_pairs), cudaFree(m->d), delete m));
+  }
   *out = m;
   return PNC_OK;
 }
@@ -168,6 +178,7 @@ void pnc_model_destroy(pnc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaFree(m->d);
+  cudaFree(m->d_pairs);
   cudaGetLastError();
   delete m;
 }
@@ -354,7 +365,7 @@ static int update_system_at(pnc_workspace* ws, int off, int32_t B, const double*
   const pnc_model* m = ws->m;
   if (m->h.nfl && (!bp || !bq || !blv || !bav)) return PNC_E_ARG;
   WsPtrs w = ws_offset(ws->p, off, m->h.nq, m->h.nv, ws->nfr, 0, 0, 0);
-  launch_update_system(m->d, ws->dfr, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st, b_cent);
+  launch_update_system(m->d, ws->dfr, m->d_pairs, m->n_pairs, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st, b_cent);
   CK(cudaGetLastError());
   return PNC_OK;
 }

@@ -55,7 +55,8 @@ __device__ __forceinline__ void st3(double* p, V3 a) { p[0] = a.x; p[1] = a.y; p
 // from the model (any URDF).  Same code either way: index arithmetic on nv is what specialises.
 template <int NV_>
 __global__ void __launch_bounds__(DYN_WARPS * 32)
-k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ gfr, WsPtrs ws, int B,
+k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ gfr, const int2* __restrict__ crba_pairs,
+                int n_pairs, WsPtrs ws, int B,
                 const double* __restrict__ base_pos, const double* __restrict__ base_quat,
                 const double* __restrict__ base_lin_vel, const double* __restrict__ base_ang_vel,
                 const double* __restrict__ joint_pos, const double* __restrict__ joint_vel, int b_cent) {
@@ -405,23 +406,17 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
     // ---------------- phase 7: CRBA rows into a shared tile, then coalesced store -------
     for (int k = lane; k < nv * nv; k += 32) Mst[k] = 0.0;
     __syncwarp();
-    if (active) {
-      // entries between body i and each ancestor-or-self j:  M[vi, vj] = F_i . S_j
-      for (int j = 0; j <= i; j++) {
-        const int sj = sm->subtree[j];
-        if (!(i < j + sj)) continue;
-        const bool jff = sm->jtype[j] == PNC_JOINT_FREEFLYER;
-        const int jv = sm->idx_v[j], ndj = jff ? 6 : 1, ndi = isff ? 6 : 1;
-        for (int di = 0; di < ndi; di++) {
-          const double* Fi = isff ? (F0 + di * 6) : (Fs + i * SF_LD);
-          for (int dj = 0; dj < ndj; dj++) {
-            const double* Sj = jff ? (S0 + dj * 6) : (Ss + j * SF_LD);
-            double val = Fi[0] * Sj[0] + Fi[1] * Sj[1] + Fi[2] * Sj[2] + Fi[3] * Sj[3] + Fi[4] * Sj[4] + Fi[5] * Sj[5];
-            Mst[(iv + di) * nv + jv + dj] = val;
-            Mst[(jv + dj) * nv + iv + di] = val;
-          }
-        }
-      }
+    // entries between each dof and its ancestor-or-self dofs, M[a, b] = F_a . S_b: the pairs come from a table
+    // built with the model (build_crba_pairs) and are dealt round-robin to the lanes -- with lanes = bodies the
+    // root lane walked 31 candidate ancestors and 36 free-flyer products while the leaves idled
+    for (int e = lane; e < n_pairs; e += 32) {
+      const int2 pr = __ldg(crba_pairs + e);
+      const double* Fi = W + (pr.x & 0xffff);
+      const double* Sj = W + (pr.x >> 16);
+      const int ra = pr.y & 0xff, cb = pr.y >> 8;
+      double val = Fi[0] * Sj[0] + Fi[1] * Sj[1] + Fi[2] * Sj[2] + Fi[3] * Sj[3] + Fi[4] * Sj[4] + Fi[5] * Sj[5];
+      Mst[ra * nv + cb] = val;
+      Mst[cb * nv + ra] = val;
     }
     __syncwarp();
     {
@@ -432,8 +427,29 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
   }
 }
 
-void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs& ws, int B, int nv,
-                          const double* base_pos, const double* base_quat, const double* base_lin_vel,
+int build_crba_pairs(const DevModel& h, int2* pairs, int max_pairs) {
+  const DynSmemLayout L = dyn_layout(h.nv);
+  int n = 0;
+  for (int i = 0; i < h.nb; i++) {
+    const bool iff = h.jtype[i] == PNC_JOINT_FREEFLYER;
+    for (int j = 0; j <= i; j++) {
+      if (!(i < j + h.subtree[j])) continue;  // j is not an ancestor of i (nor i itself)
+      const bool jff = h.jtype[j] == PNC_JOINT_FREEFLYER;
+      for (int di = 0; di < (iff ? 6 : 1); di++)
+        for (int dj = 0; dj < (jff ? 6 : 1); dj++) {
+          if (i == j && dj > di) continue;  // free-flyer block: lower triangle, mirrored by the kernel
+          const int offF = iff ? L.off_F0 + di * 6 : L.off_F + i * SF_LD;
+          const int offS = jff ? L.off_S0 + dj * 6 : L.off_S + j * SF_LD;
+          if (n < max_pairs) pairs[n] = make_int2(offF | (offS << 16), (h.idx_v[i] + di) | ((h.idx_v[j] + dj) << 8));
+          n++;
+        }
+    }
+  }
+  return n <= max_pairs ? n : -1;
+}
+
+void launch_update_system(const DevModel* dm, const DevFrames* dfr, const int2* crba_pairs, int n_pairs, const WsPtrs& ws,
+                          int B, int nv, const double* base_pos, const double* base_quat, const double* base_lin_vel,
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
                           int num_sms, cudaStream_t stream, int b_cent) {
   size_t smem = dyn_smem_bytes(nv);
@@ -447,8 +463,8 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs
   auto go = [&](auto kernel) {
     static SmemOptIn optin;
     optin.ensure(kernel, smem);
-    kernel<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, ws, B, base_pos, base_quat, base_lin_vel, base_ang_vel,
-                                                     joint_pos, joint_vel, b_cent);
+    kernel<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, crba_pairs, n_pairs, ws, B, base_pos, base_quat, base_lin_vel,
+                                                     base_ang_vel, joint_pos, joint_vel, b_cent);
   };
   switch (nv) {  // Atlas, Draco3, Valkyrie, Draco3 lower body, Laikago; anything else reads nv at run time
     case 36: go(k_update_system<36>); break;

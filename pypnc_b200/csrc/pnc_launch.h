@@ -72,8 +72,12 @@ inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, in
   return w;
 }
 
-void launch_update_system(const DevModel* dm, const DevFrames* dfr, const WsPtrs& ws, int B, int nv,
-                          const double* base_pos, const double* base_quat, const double* base_lin_vel,
+// (dof, ancestor-or-self dof) pairs of the mass matrix for k_update_system's CRBA phase: x = offset of the
+// descendant dof's force vector | offset of the ancestor dof's motion vector << 16 (doubles, in the warp's
+// shared-memory region), y = row | column << 8.  Returns the number of pairs written (<= max_pairs).
+int build_crba_pairs(const DevModel& h, int2* pairs, int max_pairs);
+void launch_update_system(const DevModel* dm, const DevFrames* dfr, const int2* crba_pairs, int n_pairs, const WsPtrs& ws,
+                          int B, int nv, const double* base_pos, const double* base_quat, const double* base_lin_vel,
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
                           int num_sms, cudaStream_t stream, int b_cent = 0);
 void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcLayout& L, const WsPtrs& ws,

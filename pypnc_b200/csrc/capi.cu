@@ -64,7 +64,8 @@ struct pnc_model {
   int device, num_sms;
   DevModel h;
   DevModel* d;
-  int2* d_pairs;  // CRBA (dof, ancestor dof) pair table of k_update_system
+  int4* d_dofs;   // per-dof table and CRBA (dof, ancestor dof) pair table of k_update_system (one allocation)
+  int2* d_pairs;
   int n_pairs;
   int nf;
   std::vector<int> frame_parent;
@@ -164,11 +165,17 @@ int pnc_model_create(const pnc_model_desc* dsc, int device, pnc_model** out) {
   CKF(cudaMemcpy(m->d, &h, sizeof(DevModel), cudaMemcpyHostToDevice), (cudaFree(m->d), delete m));
   {
     std::vector<int2> pairs((size_t)h.nv * (h.nv + 1) / 2 + 64);
+    std::vector<int4> dofs((size_t)h.nv);
     m->n_pairs = build_crba_pairs(h, pairs.data(), (int)pairs.size());
-    m->d_pairs = nullptr;
-    CKF(cudaMalloc(&m->d_pairs, sizeof(int2) * (size_t)(m->n_pairs > 0 ? m->n_pairs : 1)), (cudaFree(m->d), delete m));
+    build_dof_table(h, dofs.data());
+    if (m->n_pairs < 0) { cudaFree(m->d); delete m; return PNC_E_SIZE; }
+    const size_t bd = sizeof(int4) * dofs.size(), bp = sizeof(int2) * (size_t)(m->n_pairs > 0 ? m->n_pairs : 1);
+    m->d_dofs = nullptr;
+    CKF(cudaMalloc(&m->d_dofs, bd + bp), (cudaFree(m->d), delete m));
+    m->d_pairs = reinterpret_cast<int2*>(reinterpret_cast<char*>(m->d_dofs) + bd);
+    CKF(cudaMemcpy(m->d_dofs, dofs.data(), bd, cudaMemcpyHostToDevice), (cudaFree(m->d_dofs), cudaFree(m->d), delete m));
     CKF(cudaMemcpy(m->d_pairs, pairs.data(), sizeof(int2) * (size_t)m->n_pairs, cudaMemcpyHostToDevice),
-        (cudaFree(m->d_pairs), cudaFree(m->d), delete m));
+        (cudaFree(m->d_dofs), cudaFree(m->d), delete m));
   }
   *out = m;
   return PNC_OK;
@@ -178,7 +185,7 @@ void pnc_model_destroy(pnc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaFree(m->d);
-  cudaFree(m->d_pairs);
+  cudaFree(m->d_dofs);
   cudaGetLastError();
   delete m;
 }
@@ -365,7 +372,7 @@ static int update_system_at(pnc_workspace* ws, int off, int32_t B, const double*
   const pnc_model* m = ws->m;
   if (m->h.nfl && (!bp || !bq || !blv || !bav)) return PNC_E_ARG;
   WsPtrs w = ws_offset(ws->p, off, m->h.nq, m->h.nv, ws->nfr, 0, 0, 0);
-  launch_update_system(m->d, ws->dfr, m->d_pairs, m->n_pairs, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st, b_cent);
+  launch_update_system(m->d, ws->dfr, m->d_dofs, m->d_pairs, m->n_pairs, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st, b_cent);
   CK(cudaGetLastError());
   return PNC_OK;
 }

@@ -55,8 +55,8 @@ __device__ __forceinline__ void st3(double* p, V3 a) { p[0] = a.x; p[1] = a.y; p
 // from the model (any URDF).  Same code either way: index arithmetic on nv is what specialises.
 template <int NV_>
 __global__ void __launch_bounds__(DYN_WARPS * 32)
-k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ gfr, const int2* __restrict__ crba_pairs,
-                int n_pairs, WsPtrs ws, int B,
+k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ gfr, const int4* __restrict__ dof_tab,
+                const int2* __restrict__ crba_pairs, int n_pairs, WsPtrs ws, int B,
                 const double* __restrict__ base_pos, const double* __restrict__ base_quat,
                 const double* __restrict__ base_lin_vel, const double* __restrict__ base_ang_vel,
                 const double* __restrict__ joint_pos, const double* __restrict__ joint_vel, int b_cent) {
@@ -382,23 +382,26 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
       st3(fa, faw); st3(fa + 3, fal);
     }
     __syncwarp();
-    if (active) {
-      const int ndof = isff ? 6 : 1;
-      for (int f = 0; f < nfr; f++) {
+    // Jacobian columns, one (frame, dof) item at a time dealt round-robin to the lanes (with lanes = bodies the
+    // root lane wrote its six columns while the others waited): the dof's motion vector is in shared memory
+    // (phase 5), its body's subtree range comes from a table built with the model; consecutive lanes write
+    // consecutive columns
+    {
+      const int total = nfr * nv;
+      for (int e = lane; e < total; e += 32) {
+        const int f = e / nv, c = e - f * nv;
+        const int4 dt = __ldg(dof_tab + c);  // x: offset of S, [y, z): bodies of the dof's subtree
         const int b = sfr->body[f];
-        const bool on_path = (b >= 0) && (i <= b) && (b < i + nsub);
+        const bool on_path = b >= dt.y && b < dt.z;
+        const double* Sd = W + dt.x;
+        const V3 sl = ld3(Sd), sa = ld3(Sd + 3);
         const V3 pf = ld3(frp + 4 * f);
         double* J = ws.fr_jac + ((size_t)s * nfr + f) * 6 * nv;
-        for (int d = 0; d < ndof; d++) {
-          V3 sl, sa;
-          if (isff) { sl = ld3(S0 + d * 6); sa = ld3(S0 + d * 6 + 3); }
-          else { sl = Sl; sa = Sa; }
-          V3 lin = mk(0, 0, 0), ang = mk(0, 0, 0);
-          if (on_path) { ang = sa; lin = sl + cross(sa, pf); }
-          // rows [ang; lin], pinocchio_robot_system.py:259-261
-          J[iv + d] = ang.x; J[nv + iv + d] = ang.y; J[2 * nv + iv + d] = ang.z;
-          J[3 * nv + iv + d] = lin.x; J[4 * nv + iv + d] = lin.y; J[5 * nv + iv + d] = lin.z;
-        }
+        V3 lin = mk(0, 0, 0), ang = mk(0, 0, 0);
+        if (on_path) { ang = sa; lin = sl + cross(sa, pf); }
+        // rows [ang; lin], pinocchio_robot_system.py:259-261
+        J[c] = ang.x; J[nv + c] = ang.y; J[2 * nv + c] = ang.z;
+        J[3 * nv + c] = lin.x; J[4 * nv + c] = lin.y; J[5 * nv + c] = lin.z;
       }
     }
     __syncwarp();  // everyone is done with xf before the M tile overwrites it
@@ -427,6 +430,15 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
   }
 }
 
+void build_dof_table(const DevModel& h, int4* tab) {
+  const DynSmemLayout L = dyn_layout(h.nv);
+  for (int i = 0; i < h.nb; i++) {
+    const bool iff = h.jtype[i] == PNC_JOINT_FREEFLYER;
+    for (int d = 0; d < (iff ? 6 : 1); d++)
+      tab[h.idx_v[i] + d] = make_int4(iff ? L.off_S0 + d * 6 : L.off_S + i * SF_LD, i, i + h.subtree[i], 0);
+  }
+}
+
 int build_crba_pairs(const DevModel& h, int2* pairs, int max_pairs) {
   const DynSmemLayout L = dyn_layout(h.nv);
   int n = 0;
@@ -448,8 +460,8 @@ int build_crba_pairs(const DevModel& h, int2* pairs, int max_pairs) {
   return n <= max_pairs ? n : -1;
 }
 
-void launch_update_system(const DevModel* dm, const DevFrames* dfr, const int2* crba_pairs, int n_pairs, const WsPtrs& ws,
-                          int B, int nv, const double* base_pos, const double* base_quat, const double* base_lin_vel,
+void launch_update_system(const DevModel* dm, const DevFrames* dfr, const int4* dof_tab, const int2* crba_pairs, int n_pairs,
+                          const WsPtrs& ws, int B, int nv, const double* base_pos, const double* base_quat, const double* base_lin_vel,
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
                           int num_sms, cudaStream_t stream, int b_cent) {
   size_t smem = dyn_smem_bytes(nv);
@@ -463,7 +475,7 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const int2* 
   auto go = [&](auto kernel) {
     static SmemOptIn optin;
     optin.ensure(kernel, smem);
-    kernel<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, crba_pairs, n_pairs, ws, B, base_pos, base_quat, base_lin_vel,
+    kernel<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, dof_tab, crba_pairs, n_pairs, ws, B, base_pos, base_quat, base_lin_vel,
                                                      base_ang_vel, joint_pos, joint_vel, b_cent);
   };
   switch (nv) {  // Atlas, Draco3, Valkyrie, Draco3 lower body, Laikago; anything else reads nv at run time

@@ -253,6 +253,17 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
   double* vm = smem + SL.odl;
   double* dv = g0;
   double* xs = zv;  // x0
+  // 2x2 tiles of the Hessian's lower triangle, tile idx -> (first row, first column), packed r0 | c0 << 8
+  constexpr int nt = (NV + 1) >> 1, ntile = nt * (nt + 1) / 2, TPL = (ntile + 31) / 32;
+  __shared__ unsigned short tile_tab[TPL * 32];
+  for (int idx = threadIdx.x; idx < TPL * 32; idx += blockDim.x) {
+    int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
+    while (ti * (ti + 1) / 2 > idx) ti--;
+    const int tj = idx - ti * (ti + 1) / 2;
+    tile_tab[idx] = idx < ntile ? (unsigned short)((2 * ti) | ((2 * tj) << 8)) : (unsigned short)0;
+  }
+  __syncthreads();
 #pragma unroll 1
   for (;;) {
     __syncthreads();
@@ -336,43 +347,54 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     __syncthreads();
     // ---- Hessian task block (lower triangle) = sum_t w_t J_t^T J_t + lambda_q_ddot M ----
     // 2x2 tiles, accumulated in registers: the factor block shares its shared memory with the
-    // staged Jacobians and is only written once every lane is done reading them
+    // staged Jacobians and is only written once every lane is done reading them.  Loop order: task, row, tile --
+    // a lane's TPL tiles are TPL independent accumulator sets fed by two LDS.128 per row (row[r0..r0+1],
+    // row[c0..c0+1]); the tile coordinates come from a table built once per CTA.
     {
       const double* Mg = ws.M + s * NV * NV;
-      constexpr int nt = (NV + 1) >> 1, ntile = nt * (nt + 1) / 2, TPL = (ntile + 31) / 32;
       double h[TPL][4];
+      int ro[TPL], co[TPL];
 #pragma unroll
       for (int u = 0; u < TPL; u++) {
-        const int idx = lane + 32 * u;
         h[u][0] = h[u][1] = h[u][2] = h[u][3] = 0.0;
-        if (idx >= ntile) continue;
-        int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
-        while (ti * (ti + 1) / 2 > idx) ti--;
-        const int tj = idx - ti * (ti + 1) / 2;
-        const int r0 = 2 * ti, c0 = 2 * tj;
-        const bool r1ok = r0 + 1 < NV, c1ok = c0 + 1 < NV;
-        const double m00 = Mg[r0 * NV + c0], m01 = c1ok ? Mg[r0 * NV + c0 + 1] : 0.0;
-        const double m10 = r1ok ? Mg[(r0 + 1) * NV + c0] : 0.0, m11 = (r1ok && c1ok) ? Mg[(r0 + 1) * NV + c0 + 1] : 0.0;
-        double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+        const int tab = tile_tab[lane + 32 * u];  // r0 | c0 << 8 (0 | 0 past the last tile: computed, never stored)
+        ro[u] = tab & 0xff;
+        co[u] = tab >> 8;
+      }
 #pragma unroll 1
-        for (int t = 0; t < P.ntask; t++) {
-          const DevTask& T = P.tasks[t];
-          if (T.dense_off < 0) continue;
-          const double wk = wt[T.row_off];
-          if (wk == 0.0) continue;
-          double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
+      for (int t = 0; t < P.ntask; t++) {
+        const DevTask& T = P.tasks[t];
+        if (T.dense_off < 0) continue;
+        const double wk = wt[T.row_off];
+        if (wk == 0.0) continue;
 #pragma unroll
-          for (int i = 0; i < 3; i++) {
-            const double* row = Jd + (T.dense_off + i) * LDV;
-            const double ra = row[r0], rb = r1ok ? row[r0 + 1] : 0.0;
-            const double ca = row[c0], cb = c1ok ? row[c0 + 1] : 0.0;
-            t00 += ra * ca; t01 += ra * cb; t10 += rb * ca; t11 += rb * cb;
+        for (int i = 0; i < 3; i++) {
+          const double* row = Jd + (T.dense_off + i) * LDV;
+#pragma unroll
+          for (int u = 0; u < TPL; u++) {
+            double2 rr = lds2(row + ro[u]), cc = lds2(row + co[u]);
+            if (NV & 1) {  // the pad column of a staged row is not data
+              if (ro[u] + 1 >= NV) rr.y = 0.0;
+              if (co[u] + 1 >= NV) cc.y = 0.0;
+            }
+            const double wa = wk * rr.x, wb = wk * rr.y;
+            h[u][0] = fma(wa, cc.x, h[u][0]); h[u][1] = fma(wa, cc.y, h[u][1]);
+            h[u][2] = fma(wb, cc.x, h[u][2]); h[u][3] = fma(wb, cc.y, h[u][3]);
           }
-          a00 += wk * t00; a01 += wk * t01; a10 += wk * t10; a11 += wk * t11;
         }
+      }
+      {
         const double lam = P.lambda_q_ddot;
-        h[u][0] = a00 + lam * m00; h[u][1] = a01 + lam * m01; h[u][2] = a10 + lam * m10; h[u][3] = a11 + lam * m11;
+#pragma unroll
+        for (int u = 0; u < TPL; u++) {
+          if (lane + 32 * u >= ntile) continue;
+          const int r0 = ro[u], c0 = co[u];
+          const bool r1ok = r0 + 1 < NV, c1ok = c0 + 1 < NV;
+          const double m00 = Mg[r0 * NV + c0], m01 = c1ok ? Mg[r0 * NV + c0 + 1] : 0.0;
+          const double m10 = r1ok ? Mg[(r0 + 1) * NV + c0] : 0.0, m11 = (r1ok && c1ok) ? Mg[(r0 + 1) * NV + c0 + 1] : 0.0;
+          h[u][0] = fma(lam, m00, h[u][0]); h[u][1] = fma(lam, m01, h[u][1]);
+          h[u][2] = fma(lam, m10, h[u][2]); h[u][3] = fma(lam, m11, h[u][3]);
+        }
       }
 #pragma unroll 1
       for (int c = lane; c < NV; c += 32) {
@@ -396,13 +418,8 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       __syncwarp();
 #pragma unroll
       for (int u = 0; u < TPL; u++) {
-        const int idx = lane + 32 * u;
-        if (idx >= ntile) continue;
-        int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
-        while (ti * (ti + 1) / 2 > idx) ti--;
-        const int tj = idx - ti * (ti + 1) / 2;
-        const int r0 = 2 * ti, c0 = 2 * tj;
+        if (lane + 32 * u >= ntile) continue;
+        const int r0 = ro[u], c0 = co[u];
         const bool r1ok = r0 + 1 < NV, c1ok = c0 + 1 < NV;
         Gm[r0 * LDV + c0] = h[u][0];
         if (c1ok && c0 + 1 <= r0) Gm[r0 * LDV + c0 + 1] = h[u][1];

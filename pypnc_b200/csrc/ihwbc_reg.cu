@@ -631,23 +631,21 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 #pragma unroll 1
       for (int slot = 0; slot < (N > 32 ? 2 : 1); slot++) {
         const int i = lane + 32 * slot;
-        const bool rowok = i < N;
-        const double* ri = Gm + (i < NV ? i : 0) * LDV;
-        // J[i][j], J[i][j + 1] for even j: upper-triangular nv block, jrf on the reaction-force diagonal
+        const bool rowok = i < N, rowj = i < NV;
+        const double* ri = Gm + (rowj ? i : 0) * LDV;
+        // J[i][j], J[i][j + 1] for even j: rows of the nv block carry their zeros explicitly (left of the diagonal,
+        // pad column), jrf on the reaction-force diagonal
 #define PNC_ROWVAL(j, rx, ry)                                               \
         do {                                                                \
           rx = 0.0; ry = 0.0;                                               \
-          if (rowok) {                                                      \
-            if (i < NV) {                                                   \
-              if ((j) < NV) {                                               \
-                const double2 g_ = lds2(ri + (j));                          \
-                if ((j) >= i) rx = g_.x;                                    \
-                if ((j) + 1 >= i && (j) + 1 < NV) ry = g_.y;                \
-              }                                                             \
-            } else {                                                        \
-              if ((j) == i) rx = jrf;                                       \
-              if ((j) + 1 == i) ry = jrf;                                   \
+          if (rowj) {                                                       \
+            if ((j) < NV) {                                                 \
+              const double2 g_ = lds2(ri + (j));                            \
+              rx = g_.x; ry = g_.y;                                         \
             }                                                               \
+          } else if (rowok) {                                               \
+            if ((j) == i) rx = jrf;                                         \
+            if ((j) + 1 == i) ry = jrf;                                     \
           }                                                                 \
         } while (0)
         double gk[PE];

@@ -466,21 +466,48 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
         for (int i = lane; i < NV; i += 32) tr += Gm[i * LDV + i];
         c2 = wsum(tr) + NC * jrf;
       }
-      // ---- unconstrained minimiser x = -J (J^T g0)  (:222-224); J is upper triangular here ----
-#pragma unroll 1
-      for (int j = lane; j < NV; j += 32) {
-        double acc = 0.0;
-#pragma unroll 1
-        for (int k = 0; k <= j; k++) acc += Gm[k * LDV + j] * dv[k];
-        dm[j] = acc;
+      // ---- unconstrained minimiser x = -J (J^T g0)  (:222-224); J is upper triangular with its zeros written out,
+      //      so both products run over full rows / columns with uniform trip counts (columns 32.. of a robot with
+      //      nv > 32 ride along in lanes 0 .. nv-33) ----
+      {
+        constexpr int NX = NV > 32 ? NV - 32 : 0;
+        const double* cj = Gm + (lane < NV ? lane : 0);
+        const double* cx = Gm + (NX > 0 && lane < NX ? 32 + lane : 0);
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0;
+#pragma unroll 2
+        for (int k = 0; k + 1 < NV; k += 2) {
+          const double2 d2 = lds2(dv + k);
+          a0 = fma(cj[k * LDV], d2.x, a0);
+          a1 = fma(cj[(k + 1) * LDV], d2.y, a1);
+          if (NX > 0) { b0 = fma(cx[k * LDV], d2.x, b0); b0 = fma(cx[(k + 1) * LDV], d2.y, b0); }
+        }
+        if (NV & 1) {
+          a0 = fma(cj[(NV - 1) * LDV], dv[NV - 1], a0);
+          if (NX > 0) b0 = fma(cx[(NV - 1) * LDV], dv[NV - 1], b0);
+        }
+        if (lane < NV) dm[lane] = a0 + a1;
+        if (NX > 0 && lane < NX) dm[32 + lane] = b0;
+        if (lane == 0 && (NV & 1)) dm[NV] = 0.0;  // pad of the pair loads below
       }
       __syncwarp();
-#pragma unroll 1
-      for (int k = lane; k < NV; k += 32) {
-        double acc = 0.0;
-#pragma unroll 1
-        for (int j = k; j < NV; j++) acc += Gm[k * LDV + j] * dm[j];
-        xs[k] = -acc;
+      {
+        constexpr int NX = NV > 32 ? NV - 32 : 0;
+        const double* rk = Gm + (lane < NV ? lane : 0) * LDV;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 2
+        for (int j = 0; j < NV; j += 2) {  // the pad column of J (nv odd) is zero
+          const double2 g = lds2(rk + j), d2 = lds2(dm + j);
+          a0 = fma(g.x, d2.x, a0);
+          a1 = fma(g.y, d2.y, a1);
+        }
+        if (lane < NV) xs[lane] = -(a0 + a1);
+        if (NX > 0) {
+          const double* rx = Gm + (32 + (lane < NX ? lane : 0)) * LDV;
+          double b0 = 0.0;
+#pragma unroll
+          for (int j = 32; j < NV; j++) b0 = fma(rx[j], dm[j], b0);
+          if (lane < NX) xs[32 + lane] = -b0;
+        }
       }
       // ---- all p equality constraints at once (QuadProg++.cc:232-272 adds them one by one), while
       //      J = L^-T is still triangular in shared memory.  D = J^T CE (n x p) is built in registers,
@@ -527,11 +554,12 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
             const double* gp_ = Gm + (j < NV ? j : 0);
 #pragma unroll 2
             for (int k = 0; k < kmax; k++, gp_ += LDV) {
-              const double g = (j < NV && k <= j) ? gp_[0] : 0.0;
+              const double g = gp_[0];  // J[k][j]: zero below the diagonal (k > j), written out by linv_cols_reg
               e0 = fma(g, m6[k], e0); e1 = fma(g, m6[NV + k], e1); e2 = fma(g, m6[2 * NV + k], e2);
               e3 = fma(g, m6[3 * NV + k], e3); e4 = fma(g, m6[4 * NV + k], e4); e5 = fma(g, m6[5 * NV + k], e5);
               if constexpr (PE > 6) { e6 = fma(g, m6[6 * NV + k], e6); e7 = fma(g, m6[7 * NV + k], e7); }
             }
+            if (j >= NV) e0 = e1 = e2 = e3 = e4 = e5 = e6 = e7 = 0.0;  // (those lanes walked column 0)
             dq[pass][0] = e0; dq[pass][1] = e1; dq[pass][2] = e2; dq[pass][3] = e3; dq[pass][4] = e4; dq[pass][5] = e5;
             if constexpr (PE > 6) { dq[pass][6] = e6; dq[pass][7] = e7; }
           }

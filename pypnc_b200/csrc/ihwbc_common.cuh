@@ -41,6 +41,9 @@ static __device__ __forceinline__ void wargmin(double& v, int& idx) {
 // for in instructions and in instruction-cache footprint): hardware seed (2^-23), two Newton steps, <= 2 ulp.
 // For finite, normal, non-zero x -- step-length and reflection denominators, pivots.
 __device__ __forceinline__ double fast_rcp(double x) {
+#ifdef PNC_IEEE_DIV
+  return 1.0 / x;
+#endif
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   r = fma(fma(-x, r, 1.0), r, r);

@@ -48,7 +48,13 @@ __device__ __forceinline__ bool chol_rows_reg(double* __restrict__ Gm, double* _
 #pragma unroll
       for (int q = 0; q < j; q++) p = fma(-u[j][q], u[j][q], p);
       if (!(p > pmin)) pd = false;
+      
+#ifdef PNC_IEEE_DIV
+      const double d = sqrt(p), id = 1.0 / d;
+#else
       const double id = rsqrt(p), d = p * id;  // sqrt(p) and its reciprocal from one reciprocal square root
+#endif
+
       u[j][j] = d; uid[j] = id;
 #pragma unroll
       for (int i = j + 1; i < NX; i++) {
@@ -90,7 +96,13 @@ __device__ __forceinline__ bool chol_rows_reg(double* __restrict__ Gm, double* _
     __syncwarp();
     const double p = pv[j];
     if (!(p > pmin)) pd = false;
-    const double id = rsqrt(p), d = p * id;  // sqrt(p) and its reciprocal from one reciprocal square root
+    
+#ifdef PNC_IEEE_DIV
+      const double d = sqrt(p), id = 1.0 / d;
+#else
+      const double id = rsqrt(p), d = p * id;  // sqrt(p) and its reciprocal from one reciprocal square root
+#endif
+
     double l = a[j] * id;
     if (r == j) l = d;
     a[j] = l;

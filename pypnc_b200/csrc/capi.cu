@@ -45,20 +45,45 @@ static int g_termination = [] {
     }                                                                                             \
   } while (0)
 
+// Every entry point runs on the device of its handle (or of its first device pointer) and leaves the caller's
+// current device as it found it: a host program that holds models on several GPUs -- or a torch program, whose
+// allocations follow the current device -- must not find it changed behind its back.
+struct DevGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+    if (prev == dev) { prev = -1; ok = true; return; }
+    ok = cudaSetDevice(dev) == cudaSuccess;
+    if (!ok) prev = -1;
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DevGuard(const DevGuard&) = delete;
+  DevGuard& operator=(const DevGuard&) = delete;
+};
+#define ON_DEVICE(dev)        \
+  DevGuard dev_guard_(dev);   \
+  if (!dev_guard_.ok) return PNC_E_CUDA
+
 // The stateless entry points (no handle) launch on the device that owns their first pointer.
-static int set_device_of(const void* dptr) {
+static int device_of(const void* dptr, int* dev) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, dptr) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
     cudaGetLastError();
     return PNC_E_ARG;  // not a device pointer
   }
-  return cudaSetDevice(at.device) == cudaSuccess ? PNC_OK : PNC_E_CUDA;
+  *dev = at.device;
+  return PNC_OK;
 }
-#define SETDEV(ptr)                       \
-  do {                                    \
-    const int rc_ = set_device_of(ptr);   \
-    if (rc_ != PNC_OK) return rc_;        \
-  } while (0)
+#define SETDEV(ptr)                         \
+  int dev_of_ptr_ = 0;                      \
+  {                                         \
+    const int rc_ = device_of(ptr, &dev_of_ptr_); \
+    if (rc_ != PNC_OK) return rc_;          \
+  }                                         \
+  ON_DEVICE(dev_of_ptr_)
 
 struct pnc_model {
   int device, num_sms;
@@ -125,7 +150,7 @@ int pnc_model_create(const pnc_model_desc* dsc, int device, pnc_model** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PNC_E_NOGPU;
   if (device < 0 || device >= ndev) return PNC_E_ARG;
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   pnc_model* m = new pnc_model();
   m->device = device;
   cudaDeviceProp prop;
@@ -183,7 +208,7 @@ int pnc_model_create(const pnc_model_desc* dsc, int device, pnc_model** out) {
 
 void pnc_model_destroy(pnc_model* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
+  DevGuard dev_guard_(m->device);
   cudaFree(m->d);
   cudaFree(m->d_dofs);
   cudaGetLastError();
@@ -197,7 +222,7 @@ int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* dsc, pnc_prob
       dsc->nact > PNC_MAX_NV || dsc->n_gain > 64 || dsc->n_joint_sel > 2 * PNC_MAX_NV)
     return PNC_E_SIZE;
   if (m->h.nfl != 6) return PNC_E_ARG;  // IHWBC needs the floating base rows (Sf), ihwbc.py:225
-  CK(cudaSetDevice(m->device));
+  ON_DEVICE(m->device);
   pnc_problem* p = new pnc_problem();
   p->m = m;
   p->device = m->device;
@@ -280,7 +305,7 @@ int pnc_problem_create(const pnc_model* m, const pnc_problem_desc* dsc, pnc_prob
 
 void pnc_problem_destroy(pnc_problem* p) {
   if (!p) return;
-  cudaSetDevice(p->device);
+  DevGuard dev_guard_(p->device);
   cudaFree(p->d);
   cudaGetLastError();  // a destroy during interpreter teardown must not leave a stale error behind
   delete p;
@@ -303,7 +328,7 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
                          pnc_workspace** out) {
   if (!m || !out || capacity < 1 || nframes < 0 || (nframes > 0 && !frames)) return PNC_E_ARG;
   if (nframes > PNC_MAX_FRAMES) return PNC_E_SIZE;
-  CK(cudaSetDevice(m->device));
+  ON_DEVICE(m->device);
   pnc_workspace* ws = new pnc_workspace();
   memset(&ws->p, 0, sizeof(ws->p));
   ws->m = m; ws->device = m->device; ws->cap = capacity; ws->nfr = nframes;
@@ -345,7 +370,7 @@ int pnc_workspace_create(const pnc_model* m, int32_t capacity, const int32_t* fr
 
 void pnc_workspace_destroy(pnc_workspace* ws) {
   if (!ws) return;
-  cudaSetDevice(ws->device);
+  DevGuard dev_guard_(ws->device);
   cudaFree(ws->slab);
   cudaFree(ws->dfr);
   if (ws->ic_slab) cudaFree(ws->ic_slab);
@@ -382,7 +407,7 @@ int pnc_update_system(pnc_workspace* ws, int32_t B, const double* d_base_pos, co
                       const double* d_joint_vel, void* stream) {
   if (!ws || B < 0 || B > ws->cap || !d_joint_pos || !d_joint_vel) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   return update_system_at(ws, 0, B, d_base_pos, d_base_quat, d_base_lin_vel, d_base_ang_vel, d_joint_pos,
                           d_joint_vel, (cudaStream_t)stream);
 }
@@ -392,7 +417,7 @@ int pnc_update_system_cent(pnc_workspace* ws, int32_t B, const double* d_base_po
                            const double* d_joint_vel, int32_t b_cent, void* stream) {
   if (!ws || B < 0 || B > ws->cap || !d_joint_pos || !d_joint_vel) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   return update_system_at(ws, 0, B, d_base_pos, d_base_quat, d_base_lin_vel, d_base_ang_vel, d_joint_pos,
                           d_joint_vel, (cudaStream_t)stream, b_cent ? 1 : 0);
 }
@@ -536,7 +561,7 @@ int pnc_ihwbc_solve_ref(const pnc_problem* p, pnc_workspace* ws, int32_t B, cons
   if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m) return PNC_E_ARG;
   if (!d_des || !d_w || (p->h.ncontact && !d_rf_z_max) || !d_status) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   return solve_at(p, ws, 0, B, d_des, d_w, d_rf_z_max, d_trq, d_acc, d_rf, d_qddot, d_status, d_iters, d_active,
                   (cudaStream_t)stream, ws->counter, d_active_ref);
 }
@@ -554,7 +579,7 @@ int pnc_task_eval(const pnc_problem* p, pnc_workspace* ws, int32_t B, int32_t it
   if (!p || !ws || B < 0 || B > ws->cap || p->m != ws->m || itask < 0 || itask >= p->h.ntask || !d_des)
     return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   FrameMap fm;
   int rc = resolve_frames(p, ws, &fm);
   if (rc) return rc;
@@ -571,7 +596,7 @@ int pnc_contact_eval(const pnc_problem* p, pnc_workspace* ws, int32_t B, int32_t
       !d_rf_z_max)
     return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   FrameMap fm;
   int rc = resolve_frames(p, ws, &fm);
   if (rc) return rc;
@@ -604,7 +629,7 @@ int pnc_osc_step(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_po
     if (ws->hfr.model_frame[f] == frame) slot = f;
   if (slot < 0) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   launch_osc_step(ws->p, ws->nfr, slot, ws->m->h.nv, B, d_pos_des, d_vel_des, d_kp, d_kd, smooth, 1e-3, d_trq, d_qddot,
                   (cudaStream_t)stream);
   CK(cudaGetLastError());
@@ -624,7 +649,7 @@ int pnc_quadprog_batch(int32_t device, int32_t B, int32_t n, int32_t p, int32_t 
   if (device < 0 || device >= ndev) return PNC_E_ARG;
   if (n > 64 || p > n) return PNC_E_SIZE;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   if (!launch_quadprog_dense(n, p, m, B, d_G, d_g0, d_CE, d_ce0, d_CI, d_ci0, d_x, d_f, d_status, d_iters,
@@ -658,7 +683,7 @@ int pnc_foot_use_current(pnc_workspace* ws, int32_t B, int32_t frame, double* d_
   const int slot = frame_slot(ws, frame);
   if (slot < 0) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   launch_foot_use_current(ws->p, ws->nfr, slot, B, d_pos, d_vel, d_acc, d_quat, d_angvel, d_angacc, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return PNC_OK;
@@ -670,7 +695,7 @@ int pnc_hand_init(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_t
   const int slot = frame_slot(ws, frame);
   if (slot < 0) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   launch_hand_init(ws->p, ws->nfr, slot, B, d_target_pos, d_target_quat, d_keypoint, d_rec, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return PNC_OK;
@@ -695,7 +720,7 @@ int pnc_swing_init(pnc_workspace* ws, int32_t B, int32_t frame, const double* d_
   const int slot = frame_slot(ws, frame);
   if (slot < 0) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   launch_swing_init(ws->p, ws->nfr, slot, B, d_land_pos, d_land_quat, d_swing_duration, swing_height, d_rec,
                     (cudaStream_t)stream);
   CK(cudaGetLastError());
@@ -722,7 +747,7 @@ int pnc_floating_base_init(pnc_workspace* ws, int32_t B, int32_t base_frame, con
   const int slot = frame_slot(ws, base_frame);
   if (slot < 0) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   launch_floating_base_init(ws->p, ws->nfr, slot, B, d_target_com, d_target_quat, d_rec, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return PNC_OK;
@@ -755,7 +780,7 @@ int pnc_dcm_update(pnc_workspace* ws, int32_t B, double dt, double alpha, double
                    double* d_dcm_vel, void* stream) {
   if (!ws || B < 0 || B > ws->cap || !(dt > 0.0) || !d_dcm || !d_prev_dcm || !d_dcm_vel) return PNC_E_ARG;
   if (B == 0) return PNC_OK;
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   launch_dcm_update(ws->p, B, dt, alpha, d_dcm, d_prev_dcm, d_dcm_vel, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return PNC_OK;
@@ -780,7 +805,7 @@ struct TickArgs {
 
 static int tick_wait(pnc_workspace* ws) {
   if (!ws->tick_init) return PNC_OK;
-  cudaSetDevice(ws->device);
+  DevGuard dev_guard_(ws->device);
   cudaError_t e0 = cudaStreamSynchronize(ws->tick_out);
   cudaError_t e1 = cudaStreamSynchronize(ws->tick_stream[0]);
   cudaError_t e2 = cudaStreamSynchronize(ws->tick_stream[1]);
@@ -802,7 +827,7 @@ static int tick_wait(pnc_workspace* ws) {
 
 // enqueues everything of one tick on the workspace's own streams; tick_wait() completes it
 static int tick_enqueue(const pnc_problem* p, pnc_workspace* ws, int32_t B, const TickArgs& A) {
-  CK(cudaSetDevice(ws->m->device));
+  ON_DEVICE(ws->m->device);
   const DevProblem& P = p->h;
   const size_t na = ws->m->h.na, nv = P.nv;
   const int mw = (P.m + 63) / 64 > 0 ? (P.m + 63) / 64 : 1;
@@ -1056,7 +1081,7 @@ int pnc_measure_fp64_peak(int device, double* tflops) {
   if (!tflops) return PNC_E_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PNC_E_NOGPU;
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   double best = 0;

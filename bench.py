@@ -57,6 +57,10 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='headline only: skip BASELINE configs 1, 2, 4, 5')
+    ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'],
+                    help="fp32 = the optional fp32 mode for the whole run (pnc_set_precision: update_system in fp32 "
+                         "arithmetic, factorisations and active-set iterations fp64); the default fp64 run reports the "
+                         "mode's speed and accuracy on the headline batch under `fp32_mode`")
     ap.add_argument('--same-state', action='store_true', help='diagnostic: every state of the batch is state 0')
     return ap.parse_args()
 
@@ -261,7 +265,7 @@ class Env:
         self.torch.cuda.synchronize()
 
 
-def run_wbc_config(env, robot, B, K, warmup, seed, same_state=False, want_e2e=True, min_ms=0.0):
+def run_wbc_config(env, robot, B, K, warmup, seed, same_state=False, want_e2e=True, min_ms=0.0, want_fp32=False):
     """Times K steps of update_system + IHWBC solve on this rank's B states.  Returns a dict with the
     max-over-ranks time, per-stage times, solver stats, clocks, launches and (optionally) the end-to-end
     numbers through pnc_wbc_tick_host."""
@@ -336,6 +340,43 @@ def run_wbc_config(env, robot, B, K, warmup, seed, same_state=False, want_e2e=Tr
     stats = sharding.gather_stats(sharding.solver_stats(status, iters), device=dev)  # the only collective: a stats gather
     res = dict(spec=spec, B=B, K=K, ms_total=ms_total, ms_per_step=ms_total / K, ms_dyn=ms_dyn, ms_qp=ms_qp, stats=stats,
                clocks=clocks, launches=int(launches), ws_gb=ws.nbytes / 1e9, mw=mw, nact=nact, nc=nc, e2e=None)
+
+    # ---- the optional fp32 mode on the same batch: speed, and distance of its outputs from the fp64 path's ----
+    if want_fp32 and lib.pnc_get_precision() == 0:
+        ref = {k: t.clone() for k, t in (('trq', o_trq), ('acc', o_acc), ('rf', o_rf))}
+        ref_active = o_active.clone()
+        assert lib.pnc_set_precision(1) == 0
+        try:
+            for _ in range(3):
+                step()
+            env.barrier()
+            f0, f1, f2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            f0.record(stream)
+            for k in range(K):
+                rc = lib.pnc_update_system(ws.h, B, *[P(t) for t in d_st], sp)
+                assert rc == 0, rc
+            f1.record(stream)
+            for k in range(K):
+                step()
+            f2.record(stream)
+            env.barrier()
+        finally:
+            assert lib.pnc_set_precision(0) == 0
+        ms32 = sharding.max_over_ranks(f1.elapsed_time(f2), device=dev) / K
+        st32 = o_status.cpu().numpy()
+        ok = torch.from_numpy((status == 0) & (st32 == 0)).to(dev)
+        err = torch.zeros(B, **f64)
+        for k, t in (('trq', o_trq), ('acc', o_acc), ('rf', o_rf)):
+            den = torch.maximum(ref[k].abs().amax(1), 1e-3 * ref[k].abs().max())
+            err = torch.maximum(err, (t - ref[k]).abs().amax(1) / den)
+        e = err[ok].cpu().numpy()
+        same = ((o_active == ref_active).all(1) & ok).sum().item()
+        res['fp32'] = dict(ms_per_step=ms32, ms_dyn=f0.elapsed_time(f1) / K, n=int(e.size),
+                           status_mismatch=int((st32 != status).sum()), same_final_active_set=int(same),
+                           median=float(np.median(e)), p99=float(np.quantile(e, 0.99)), max=float(e.max()),
+                           within_1e4=int((e <= 1e-4).sum()))
+        step()  # leave the fp64 outputs in place for the end-to-end cross-check below
+        torch.cuda.synchronize()
 
     # ---- end to end through the host-buffer C ABI call (pinned host memory), every timed step ----
     if want_e2e:
@@ -491,6 +532,9 @@ def main():
     env = Env()
     from pypnc_b200 import sharding
     world, rank = env.world, env.rank
+    if args.precision == 'fp32':
+        assert env.lib.pnc_set_precision(1) == 0
+    fp32_run = env.lib.pnc_get_precision() == 1
     K = args.steps
     robot = args.robot
     if args.scaling == 'weak':
@@ -500,7 +544,8 @@ def main():
         lo, hi = sharding.shard_range(args.batch, rank, world)
         B = hi - lo
         world_states = args.batch
-    res = run_wbc_config(env, robot, B, K, args.warmup, seed=1 + rank, same_state=args.same_state, want_e2e=not args.no_e2e)
+    res = run_wbc_config(env, robot, B, K, args.warmup, seed=1 + rank, same_state=args.same_state, want_e2e=not args.no_e2e,
+                         want_fp32=not fp32_run)
     value = world_states * K / (res['ms_total'] * 1e-3)
 
     # ---- the other BASELINE configs (every rank takes part in the sharded ones) ----
@@ -563,11 +608,23 @@ def main():
         cfg['global_batch'] = args.batch
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
             "ms_per_step": res['ms_per_step'], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": cfg, "workspace_gb_per_gpu": res['ws_gb'],
+            "dtype": "f64 (update_system in f32: the optional fp32 mode)" if fp32_run else "f64", "data": "synthetic",
+            "config": cfg, "workspace_gb_per_gpu": res['ws_gb'],
             "kernels_ms": {"pnc_update_system": res['ms_dyn'], "pnc_ihwbc_solve": res['ms_qp']},
             "solver": {"status_counts": [int(x) for x in st[:5]], "mean_active_set_iterations": st[5] / st[6]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e_of(res, world_states), "gpu_launches": res['launches'],
             "clocks": res['clocks'], "host_cpus_bound_per_rank": env.affinity}
+    f32 = res.get('fp32')
+    if f32:
+        line["fp32_mode"] = {
+            "what": "pnc_set_precision(PNC_PREC_FP32_DYNAMICS) on the same batch: k_update_system in fp32 arithmetic, "
+                    "factorisations and active-set iterations fp64",
+            "value": world_states / (f32['ms_per_step'] * 1e-3), "unit": UNIT, "ms_per_step": f32['ms_per_step'],
+            "kernels_ms": {"pnc_update_system": f32['ms_dyn']},
+            "rel_err_vs_fp64": {"states": f32['n'], "median": f32['median'], "p99": f32['p99'], "max": f32['max'],
+                                "frac_within_1e-4": f32['within_1e4'] / max(1, f32['n']),
+                                "same_final_active_set": f32['same_final_active_set'],
+                                "status_mismatch": f32['status_mismatch'], "scope": "rank 0's shard"}}
     if extra or osc:
         configs = {}
         if osc:

@@ -84,6 +84,14 @@ extern "C" {
 #define PNC_TERM_REFINED 0
 #define PNC_TERM_REFERENCE 1
 
+/* Arithmetic of the robot_system update (pnc_set_precision).  FP64 (default) is the path every 1e-9 parity claim
+ * refers to.  FP32_DYNAMICS is the north star's optional fp32 mode: k_update_system computes forward kinematics,
+ * Jacobians, CRBA and RNEA in fp32 and stores fp64; the Cholesky factorisations and the active-set iterations of
+ * the solve stage stay fp64 (the Hessian's lambda_q = 1e-8 regularisation, config/atlas_config.py:65-66, is below
+ * fp32 resolution).  Tolerance: 1e-4 relative on states whose active set is the fp64 one. */
+#define PNC_PREC_FP64 0
+#define PNC_PREC_FP32_DYNAMICS 1
+
 /* limits compiled into the kernels */
 #define PNC_MAX_BODIES 32   /* one warp lane per movable body */
 #define PNC_MAX_NV 40
@@ -252,6 +260,11 @@ int pnc_ihwbc_solve_ref(const pnc_problem* p, pnc_workspace* ws, int32_t B, cons
  * PNC_TERMINATION=reference in the environment for the other) / PNC_TERM_REFERENCE. */
 int pnc_set_termination(int32_t mode);
 int pnc_get_termination(void);
+
+/* Process-wide arithmetic of pnc_update_system / the dynamics part of the pnc_wbc_tick_host calls: PNC_PREC_FP64
+ * (default, or PNC_PRECISION=fp32 in the environment for the other) / PNC_PREC_FP32_DYNAMICS. */
+int pnc_set_precision(int32_t mode);
+int pnc_get_precision(void);
 
 /* Task.jacobian [B,dim,nv], jacobian_dot_q_dot [B,dim], op_cmd [B,dim], pos_err [B,dim]
  * of task `itask` (any output may be NULL). */

@@ -151,6 +151,8 @@ def load_library():
     lib.pnc_ihwbc_solve_ref.argtypes = [vp, vp, i32] + [vp] * 11 + [vp]
     lib.pnc_set_termination.argtypes = [i32]
     lib.pnc_get_termination.argtypes = []
+    lib.pnc_set_precision.argtypes = [i32]
+    lib.pnc_get_precision.argtypes = []
     lib.pnc_task_eval.argtypes = [vp, vp, i32, i32] + [vp] * 5 + [vp]
     lib.pnc_contact_eval.argtypes = [vp, vp, i32, i32] + [vp] * 4 + [vp]
     lib.pnc_osc_step.argtypes = [vp, i32, i32] + [vp] * 4 + [dbl, vp, vp, vp]
@@ -187,7 +189,7 @@ EXPORTED_SYMBOLS = [
     'pnc_ws_centroidal_ig', 'pnc_ws_q', 'pnc_ws_qdot', 'pnc_ws_mass_matrix', 'pnc_ws_gravity',
     'pnc_ws_coriolis', 'pnc_ws_com_pos', 'pnc_ws_com_vel', 'pnc_ws_com_jac', 'pnc_ws_com_jacdot',
     'pnc_ws_com_jdqd', 'pnc_ws_frame_iso', 'pnc_ws_frame_vel', 'pnc_ws_frame_jac', 'pnc_ws_frame_jdqd',
-    'pnc_ihwbc_solve', 'pnc_ihwbc_solve_ref', 'pnc_set_termination', 'pnc_get_termination', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_osc_step', 'pnc_wbc_tick_host', 'pnc_wbc_tick_host_ex', 'pnc_wbc_tick_host_multi',
+    'pnc_ihwbc_solve', 'pnc_ihwbc_solve_ref', 'pnc_set_termination', 'pnc_get_termination', 'pnc_set_precision', 'pnc_get_precision', 'pnc_task_eval', 'pnc_contact_eval', 'pnc_joint_integrate', 'pnc_osc_step', 'pnc_wbc_tick_host', 'pnc_wbc_tick_host_ex', 'pnc_wbc_tick_host_multi',
     'pnc_quadprog_batch', 'pnc_ramp_update', 'pnc_foot_use_current', 'pnc_swing_init', 'pnc_swing_eval', 'pnc_hand_init', 'pnc_hand_eval', 'pnc_floating_base_init',
     'pnc_floating_base_eval', 'pnc_sinusoid_eval', 'pnc_dcm_update',
     'pnc_launch_count', 'pnc_measure_fp64_peak', 'pnc_version', 'pnc_debug_set_dump', 'pnc_debug_setup_record',

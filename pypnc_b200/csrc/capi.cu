@@ -19,6 +19,12 @@ using namespace pnc;
 
 // PNC_TERM_REFINED (default): keep iterating to 1e-6 x the bound of QuadProg++.cc:306-312;
 // PNC_TERM_REFERENCE: stop at the reference's own bound.  PNC_TERMINATION=reference sets the default.
+// PNC_PREC_FP64 (default) / PNC_PREC_FP32_DYNAMICS: the optional fp32 mode of the north star -- k_update_system in
+// fp32 arithmetic, factorisations and active-set iterations fp64.  PNC_PRECISION=fp32 sets the default.
+static int g_precision = [] {
+  const char* e = getenv("PNC_PRECISION");
+  return (e && (e[0] == 'f' || e[0] == 'F') && e[1] && e[2] == '3' && e[3] == '2') ? PNC_PREC_FP32_DYNAMICS : PNC_PREC_FP64;
+}();
 static int g_termination = [] {
   const char* e = getenv("PNC_TERMINATION");
   return (e && (e[0] == 'r' || e[0] == 'R') && (e[2] == 'f' || e[2] == 'F') && (e[3] == 'e' || e[3] == 'E')) ? PNC_TERM_REFERENCE
@@ -397,7 +403,8 @@ static int update_system_at(pnc_workspace* ws, int off, int32_t B, const double*
   const pnc_model* m = ws->m;
   if (m->h.nfl && (!bp || !bq || !blv || !bav)) return PNC_E_ARG;
   WsPtrs w = ws_offset(ws->p, off, m->h.nq, m->h.nv, ws->nfr, 0, 0, 0);
-  launch_update_system(m->d, ws->dfr, m->d_dofs, m->d_pairs, m->n_pairs, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st, b_cent);
+  launch_update_system(m->d, ws->dfr, m->d_dofs, m->d_pairs, m->n_pairs, w, B, m->h.nv, bp, bq, blv, bav, jp, jv, m->num_sms, st, b_cent,
+                       g_precision == PNC_PREC_FP32_DYNAMICS);
   CK(cudaGetLastError());
   return PNC_OK;
 }
@@ -565,6 +572,14 @@ int pnc_ihwbc_solve_ref(const pnc_problem* p, pnc_workspace* ws, int32_t B, cons
   return solve_at(p, ws, 0, B, d_des, d_w, d_rf_z_max, d_trq, d_acc, d_rf, d_qddot, d_status, d_iters, d_active,
                   (cudaStream_t)stream, ws->counter, d_active_ref);
 }
+
+int pnc_set_precision(int32_t mode) {
+  if (mode != PNC_PREC_FP64 && mode != PNC_PREC_FP32_DYNAMICS) return PNC_E_ARG;
+  g_precision = mode;
+  return PNC_OK;
+}
+
+int pnc_get_precision(void) { return g_precision; }
 
 int pnc_set_termination(int32_t mode) {
   if (mode != PNC_TERM_REFINED && mode != PNC_TERM_REFERENCE) return PNC_E_ARG;

@@ -73,7 +73,7 @@ inline WsPtrs ws_offset(const WsPtrs& a, size_t off, int nq, int nv, int nfr, in
 }
 
 // (dof, ancestor-or-self dof) pairs of the mass matrix for k_update_system's CRBA phase: x = offset of the
-// descendant dof's force vector | offset of the ancestor dof's motion vector << 16 (doubles, in the warp's
+// descendant dof's force vector | offset of the ancestor dof's motion vector << 16 (elements, in the warp's
 // shared-memory region), y = row | column << 8.  Returns the number of pairs written (<= max_pairs).
 int build_crba_pairs(const DevModel& h, int2* pairs, int max_pairs);
 // per dof (nv entries): x = offset of its motion vector in the warp's shared-memory region, [y, z) = bodies of its subtree
@@ -81,7 +81,7 @@ void build_dof_table(const DevModel& h, int4* tab);
 void launch_update_system(const DevModel* dm, const DevFrames* dfr, const int4* dof_tab, const int2* crba_pairs, int n_pairs,
                           const WsPtrs& ws, int B, int nv, const double* base_pos, const double* base_quat, const double* base_lin_vel,
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
-                          int num_sms, cudaStream_t stream, int b_cent = 0);
+                          int num_sms, cudaStream_t stream, int b_cent = 0, int fp32 = 0);
 void launch_ihwbc_solve(const DevProblem* dp, const DevProblem& hp, const IhwbcLayout& L, const WsPtrs& ws,
                         const FrameMap& fm, int nfr, int B, const SolveIO& io, int num_sms, cudaStream_t stream);
 bool launch_ihwbc_solve_reg(const DevProblem* dp, const DevProblem& hp, const WsPtrs& ws, const FrameMap& fm, int nfr,

@@ -153,6 +153,19 @@ def set_termination(mode):
     _check(_cabi.load_library().pnc_set_termination(int(mode)), 'pnc_set_termination')
 
 
+PREC_FP64, PREC_FP32_DYNAMICS = 0, 1
+
+
+def set_precision(mode):
+    """Process-wide arithmetic of update_system: PREC_FP64 (default) or PREC_FP32_DYNAMICS, the optional fp32
+    mode (rigid-body quantities computed in fp32, factorisations and active-set iterations in fp64)."""
+    _check(_cabi.load_library().pnc_set_precision(int(mode)), 'pnc_set_precision')
+
+
+def get_precision():
+    return int(_cabi.load_library().pnc_get_precision())
+
+
 def ihwbc_solve(problem, ws, des, w, rf_z_max, want_qddot=True):
     """pnc_ihwbc_solve_ref on device tensors.  Returns a dict of device tensors; 'active_ref' is the
     active set at the reference solver's own termination point (see include/pnc_b200.h)."""

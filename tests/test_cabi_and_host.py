@@ -38,6 +38,15 @@ def test_version_and_launch_counter_without_gpu(lib):
     assert lib.pnc_launch_count() == 0
 
 
+def test_precision_and_termination_setters_validate_their_argument(lib):
+    """Process-wide mode setters (no device needed): defaults, round trip, PNC_E_ARG on anything else."""
+    assert lib.pnc_get_precision() == 0 and lib.pnc_get_termination() == 0
+    assert lib.pnc_set_precision(1) == 0 and lib.pnc_get_precision() == 1
+    assert lib.pnc_set_precision(2) < 0 and lib.pnc_set_precision(-1) < 0 and lib.pnc_get_precision() == 1
+    assert lib.pnc_set_precision(0) == 0 and lib.pnc_get_precision() == 0
+    assert lib.pnc_set_termination(7) < 0 and lib.pnc_get_termination() == 0
+
+
 def test_no_cpu_fallback_without_gpu(lib):
     """On a box without a GPU the compute entry points fail loudly (PNC_E_NOGPU), they do not fall back."""
     import torch

@@ -98,3 +98,72 @@ def walk(urdf_path, joint_angles):
     spatial[3:, :3] = mass * cx
     spatial[3:, 3:] = second
     return dict(mass=mass, com=com, inertia_o=second, spatial=spatial, link_pose=pose)
+
+
+class Walker:
+    """The same walk with the XML parsed once: per-link placement and inertial data for many configurations
+    (tests/first_principles.py differentiates them numerically).  links(joint_angles) returns, in a fixed link order,
+    R [L,3,3], p [L,3] (link frames relative to the root link), and for the links with an <inertial>: m [L], c [L,3]
+    (centre of mass, root axes, relative to the root origin) and Ic [L,3,3] (rotational inertia about that centre of
+    mass, root axes); massless links carry zeros."""
+
+    def __init__(self, urdf_path):
+        root = ET.parse(urdf_path).getroot()
+        self.link_el = {l.get('name'): l for l in root.findall('link')}
+        self.children, has_parent = {}, set()
+        for j in root.findall('joint'):
+            Rj, pj = _origin(j)
+            axis = None
+            if j.get('type') in ('revolute', 'continuous'):
+                ax = j.find('axis')
+                axis = _vec(ax.get('xyz') if ax is not None else None, [1, 0, 0])
+            elif j.get('type') != 'fixed':
+                raise NotImplementedError(j.get('type'))
+            self.children.setdefault(j.find('parent').get('link'), []).append(
+                (j.get('name'), j.find('child').get('link'), Rj, pj, axis))
+            has_parent.add(j.find('child').get('link'))
+        roots = [n for n in self.link_el if n not in has_parent]
+        assert len(roots) == 1
+        self.root = roots[0]
+        self.inertial = {}
+        for name, l in self.link_el.items():
+            inert = l.find('inertial')
+            if inert is None:
+                continue
+            m = float(inert.find('mass').get('value'))
+            Ri, pi = _origin(inert)
+            it = inert.find('inertia')
+            I = np.zeros((3, 3))
+            if it is not None:
+                g = lambda k: float(it.get(k, 0.0))
+                I = np.array([[g('ixx'), g('ixy'), g('ixz')], [g('ixy'), g('iyy'), g('iyz')], [g('ixz'), g('iyz'), g('izz')]])
+            self.inertial[name] = (m, Ri, pi, I)
+        # fixed traversal order
+        self.names, stack = [], [self.root]
+        while stack:
+            n = stack.pop()
+            self.names.append(n)
+            for (_, child, _, _, _) in self.children.get(n, []):
+                stack.append(child)
+        self.index = {n: i for i, n in enumerate(self.names)}
+
+    def links(self, joint_angles):
+        L = len(self.names)
+        R, p = np.zeros((L, 3, 3)), np.zeros((L, 3))
+        m, c, Ic = np.zeros(L), np.zeros((L, 3)), np.zeros((L, 3, 3))
+        stack = [(self.root, np.eye(3), np.zeros(3))]
+        while stack:
+            name, Rl, pl = stack.pop()
+            k = self.index[name]
+            R[k], p[k] = Rl, pl
+            if name in self.inertial:
+                mi, Ri, pi, I = self.inertial[name]
+                m[k] = mi
+                c[k] = Rl @ pi + pl
+                Ic[k] = (Rl @ Ri) @ I @ (Rl @ Ri).T
+            for (jn, child, Rj, pj, axis) in self.children.get(name, []):
+                Rc, pc = Rl @ Rj, Rl @ pj + pl
+                if axis is not None:
+                    Rc = Rc @ _axis_rot(axis, joint_angles.get(jn, 0.0))
+                stack.append((child, Rc, pc))
+        return R, p, m, c, Ic

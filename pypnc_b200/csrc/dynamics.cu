@@ -17,9 +17,17 @@
 
 namespace pnc {
 
-constexpr int DYN_WARPS = 4;
+#ifndef DYN_WARPS_N
+#define DYN_WARPS_N 2  // warps (= states in flight) per CTA
+#endif
+constexpr int DYN_WARPS = DYN_WARPS_N;
+#ifndef DYN_F64_CTAS
+#define DYN_F64_CTAS 4  // resident CTAs per SM the fp64 instantiation is compiled for: 8 warps at 255 registers.  The kernel needs
+                        // ~260: every cap that buys more warps spills and loses (10 warps at 200 registers 1.02 ms, 12 at 168: 0.99,
+                        // against 0.88)
+#endif
 #ifndef DYN_F32_CTAS
-#define DYN_F32_CTAS 4  // resident CTAs per SM the fp32 instantiation is compiled for (registers <= 128)
+#define DYN_F32_CTAS 8  // fp32 instantiation: 16 warps per SM at 128 registers
 #endif
 constexpr int XF_LD = 25;   // R(9) p(3) v(6) a(6) + pad (odd stride: conflict-free rows)
 constexpr int SUB_LD = 19;  // m, h(3), Io(6), fc(6), P(3)
@@ -39,9 +47,9 @@ __host__ __device__ inline DynSmemLayout dyn_layout(int nv) {
   L.off_S0 = o; o += 36;
   L.off_F0 = o; o += 36;
   L.off_fr = o; o += PNC_MAX_FRAMES * 4;  // frame world point (3) + pad
-  // xf (phase 2..6) and the M staging tile (phase 7) share storage
+  // xf (phase 2..6) and the M staging tile (phase 7: packed lower triangle) share storage
   L.off_xf = o; L.off_M = o;
-  int a = 32 * XF_LD, b = nv * nv;
+  int a = 32 * XF_LD, b = nv * (nv + 1) / 2;
   o += (a > b ? a : b);
   L.per_warp_elems = (o + 3) & ~3;
   return L;
@@ -102,7 +110,7 @@ template <typename T> __device__ __forceinline__ void quat_to_rot_t(const T* qq,
 // intermediate in fp32 (half the shared memory, the FP32 pipe); inputs are read and outputs stored as fp64, q is
 // copied exactly, and the base position is carried in fp64 (it only enters sums at the outputs).
 template <int NV_, typename T>
-__global__ void __launch_bounds__(DYN_WARPS * 32, sizeof(T) == 4 ? DYN_F32_CTAS : 1)
+__global__ void __launch_bounds__(DYN_WARPS * 32, sizeof(T) == 4 ? DYN_F32_CTAS : DYN_F64_CTAS)
 k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ gfr, const int4* __restrict__ dof_tab,
                 const int2* __restrict__ crba_pairs, int n_pairs, WsPtrs ws, int B,
                 const double* __restrict__ base_pos, const double* __restrict__ base_quat,
@@ -461,7 +469,7 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
     __syncwarp();  // everyone is done with xf before the M tile overwrites it
 
     // ---------------- phase 7: CRBA rows into a shared tile, then coalesced store -------
-    for (int k = lane; k < nv * nv; k += 32) Mst[k] = (T)0;
+    for (int k = lane; k < nv * (nv + 1) / 2; k += 32) Mst[k] = (T)0;
     __syncwarp();
     // entries between each dof and its ancestor-or-self dofs, M[a, b] = F_a . S_b: the pairs come from a table
     // built with the model (build_crba_pairs) and are dealt round-robin to the lanes -- with lanes = bodies the
@@ -472,13 +480,16 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
       const T* Sj = W + (pr.x >> 16);
       const int ra = pr.y & 0xff, cb = pr.y >> 8;
       T val = Fi[0] * Sj[0] + Fi[1] * Sj[1] + Fi[2] * Sj[2] + Fi[3] * Sj[3] + Fi[4] * Sj[4] + Fi[5] * Sj[5];
-      Mst[ra * nv + cb] = val;
-      Mst[cb * nv + ra] = val;
+      Mst[ra * (ra + 1) / 2 + cb] = val;  // ra >= cb: a dof's ancestors come first in the depth-first numbering
     }
     __syncwarp();
     {
       double* Mo = ws.M + (size_t)s * nv * nv;
-      for (int k = lane; k < nv * nv; k += 32) Mo[k] = Mst[k];
+      for (int k = lane; k < nv * nv; k += 32) {  // both triangles from the packed one: M is exactly symmetric
+        const int r = k / nv, c = k - r * nv;
+        const int hi = r > c ? r : c, lo = r > c ? c : r;
+        Mo[k] = Mst[hi * (hi + 1) / 2 + lo];
+      }
     }
     __syncwarp();
   }
@@ -519,16 +530,29 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const int4* 
                           const double* base_ang_vel, const double* joint_pos, const double* joint_vel,
                           int num_sms, cudaStream_t stream, int b_cent, int fp32) {
   size_t smem = dyn_smem_bytes(nv, fp32 ? sizeof(float) : sizeof(double));
-  int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > 4) ctas_per_sm = 4;
-  int grid = num_sms * ctas_per_sm;
-  int need = (B + DYN_WARPS - 1) / DYN_WARPS;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
+  const int need = (B + DYN_WARPS - 1) / DYN_WARPS;
   auto go = [&](auto kernel) {
     static SmemOptIn optin;
     optin.ensure(kernel, smem);
+    // persistent grid: as many CTAs as are resident at once (registers and shared memory both count).  Cached per
+    // (kernel, device, shared-memory size): every instantiation has the same pointer TYPE, so a plain static would be shared.
+    struct Entry { const void* fn; int dev; size_t smem; int ctas; };
+    static Entry table[64];
+    static int used = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    int ctas_per_sm = 0;
+    for (int i = 0; i < used; i++)
+      if (table[i].fn == fn && table[i].dev == dev && table[i].smem == smem) ctas_per_sm = table[i].ctas;
+    if (ctas_per_sm == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, DYN_WARPS * 32, smem) != cudaSuccess || ctas_per_sm < 1)
+        ctas_per_sm = 1;
+      if (used < 64) table[used++] = Entry{fn, dev, smem, ctas_per_sm};
+    }
+    int grid = num_sms * ctas_per_sm;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
     kernel<<<grid, DYN_WARPS * 32, smem, stream>>>(dm, dfr, dof_tab, crba_pairs, n_pairs, ws, B, base_pos, base_quat, base_lin_vel,
                                                      base_ang_vel, joint_pos, joint_vel, b_cent);
   };

@@ -18,16 +18,16 @@
 namespace pnc {
 
 #ifndef DYN_WARPS_N
-#define DYN_WARPS_N 2  // warps (= states in flight) per CTA
+#define DYN_WARPS_N 4  // warps (= states in flight) per CTA
 #endif
 constexpr int DYN_WARPS = DYN_WARPS_N;
 #ifndef DYN_F64_CTAS
-#define DYN_F64_CTAS 4  // resident CTAs per SM the fp64 instantiation is compiled for: 8 warps at 255 registers.  The kernel needs
-                        // ~260: every cap that buys more warps spills and loses (10 warps at 200 registers 1.02 ms, 12 at 168: 0.99,
-                        // against 0.88)
+#define DYN_F64_CTAS 3  // resident CTAs per SM the fp64 instantiation is compiled for: 12 warps at 168 registers, no spills now that
+                        // the phases hand their results on through shared memory (236 registers unconstrained; 8 warps: 0.89 ms,
+                        // 10: 0.90, 12: 0.83 for 64 K Atlas states; shared memory stops at 12)
 #endif
 #ifndef DYN_F32_CTAS
-#define DYN_F32_CTAS 8  // fp32 instantiation: 16 warps per SM at 128 registers
+#define DYN_F32_CTAS 4  // fp32 instantiation: 16 warps per SM at 128 registers
 #endif
 constexpr int XF_LD = 25;   // R(9) p(3) v(6) a(6) + pad (odd stride: conflict-free rows)
 constexpr int SUB_LD = 19;  // m, h(3), Io(6), fc(6), P(3)
@@ -35,7 +35,7 @@ constexpr int SF_LD = 7;    // 6 + pad
 
 struct DynSmemLayout {
   int per_warp_elems;  // in elements of the arithmetic type (8 bytes, or 4 in the fp32 mode)
-  int off_xf, off_sub, off_S, off_F, off_S0, off_F0, off_fr, off_M;
+  int off_xf, off_sub, off_S, off_F, off_S0, off_F0, off_fr, off_vloc, off_M;
 };
 
 __host__ __device__ inline DynSmemLayout dyn_layout(int nv) {
@@ -47,6 +47,7 @@ __host__ __device__ inline DynSmemLayout dyn_layout(int nv) {
   L.off_S0 = o; o += 36;
   L.off_F0 = o; o += 36;
   L.off_fr = o; o += PNC_MAX_FRAMES * 4;  // frame world point (3) + pad
+  L.off_vloc = o; o += 8;                 // free-flyer twist in the base frame [lin; ang] + pad
   // xf (phase 2..6) and the M staging tile (phase 7: packed lower triangle) share storage
   L.off_xf = o; L.off_M = o;
   int a = 32 * XF_LD, b = nv * (nv + 1) / 2;
@@ -146,6 +147,7 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
   T* S0 = W + L.off_S0;
   T* F0 = W + L.off_F0;
   T* frp = W + L.off_fr;
+  T* vloc = W + L.off_vloc;
   T* Mst = W + L.off_M;
 
   const bool active = lane < nb;
@@ -160,12 +162,15 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
 
   const int total_warps = gridDim.x * DYN_WARPS;
   for (int s = blockIdx.x * DYN_WARPS + warp; s < B; s += total_warps) {
+    // Phases 0-2 hand their results to the later phases through shared memory only (xf, S, vloc): every phase
+    // re-reads what it needs, so no register stays live from the tree propagation to the per-dof outputs.
+    T qd = 0;
+    V3d bpos = V3d{0, 0, 0};
+    {
     // ---------------- phase 0/1: joint state and local transform -----------------------
     T Rl[9];  // joint frame in parent joint frame
     V3 pl;
-    T qd = 0;
     V3 vloc_lin = mk(0, 0, 0), vloc_ang = mk(0, 0, 0);  // free-flyer twist in the base frame
-    V3d bpos = V3d{0, 0, 0};
     if (isff) {
       const double qin[4] = {base_quat[4 * (size_t)s], base_quat[4 * (size_t)s + 1], base_quat[4 * (size_t)s + 2],
                              base_quat[4 * (size_t)s + 3]};
@@ -184,6 +189,7 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
       double* vo = ws.qdot + (size_t)s * nv;
       vo[0] = vloc_lin.x; vo[1] = vloc_lin.y; vo[2] = vloc_lin.z;
       vo[3] = vloc_ang.x; vo[4] = vloc_ang.y; vo[5] = vloc_ang.z;
+      st3(vloc, vloc_lin); st3(vloc + 3, vloc_ang);
     } else if (active) {
       const double qjd = joint_pos[(size_t)s * na + iv - nfl], qdd_in = joint_vel[(size_t)s * na + iv - nfl];
       const T qj = (T)qjd;
@@ -235,6 +241,8 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
           Sl = cross(p, Sa);
           vJl = qd * Sl;
           vJa = qd * Sa;
+          T* sr = Ss + i * SF_LD;  // the joint's motion vector, for the per-dof outputs, the Jacobians and CRBA
+          st3(sr, Sl); st3(sr + 3, Sa);
         }
         vl = pvl + vJl;
         w = pw + vJa;
@@ -247,11 +255,16 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
       }
       __syncwarp();
     }
+    }
 
     // ---------------- phase 3: world-frame body inertia, momentum, bias force ----------
-    V3 cw = mk(0, 0, 0), h = mk(0, 0, 0), P = mk(0, 0, 0), fcl = mk(0, 0, 0), fca = mk(0, 0, 0);
-    T Io[6] = {0, 0, 0, 0, 0, 0};
     if (active) {
+      const T* me = xf + i * XF_LD;
+      T R[9];
+      for (int k = 0; k < 9; k++) R[k] = me[k];
+      const V3 p = ld3<T>(me + 9);
+      V3 cw, h, P, fcl, fca;
+      T Io[6];
       cw = p + mulR(R, ld3<T>(sm->com[i]));
       h = mass_i * cw;
       // Iw = R Ic R^T
@@ -272,6 +285,7 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
       Io[4] = Tm[3] * R[6] + Tm[4] * R[7] + Tm[5] * R[8] - mass_i * cw.y * cw.z;
       Io[5] = Tm[6] * R[6] + Tm[7] * R[7] + Tm[8] * R[8] + mass_i * (cc - cw.z * cw.z);
       // momentum  (P, Lm) = I v ;  I a ;  bias force fc = I a + v x* (I v)
+      const V3 vl = ld3<T>(me + 12), w = ld3<T>(me + 15), al = ld3<T>(me + 18), aw = ld3<T>(me + 21);
       P = mass_i * vl - cross(h, w);
       V3 Lm = cross(h, vl) + mulS(Io, w);
       V3 Ial = mass_i * al - cross(h, aw);
@@ -361,6 +375,8 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
     // ---------------- phase 5: per-dof outputs: gravity, Coriolis, CoM Jacobians, F = Ic S
     if (active) {
       const int ndof = isff ? 6 : 1;
+      const T* me = xf + i * XF_LD;
+      const V3 vl = ld3<T>(me + 12), w = ld3<T>(me + 15);
       double* grav = ws.grav + (size_t)s * nv;
       double* cori = ws.cori + (size_t)s * nv;
       double* jc = ws.jcom + (size_t)s * 3 * nv;
@@ -370,15 +386,14 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
       for (int d = 0; d < ndof; d++) {
         V3 sl, sa;
         if (isff) {
-          V3 col = mk(R[d % 3], R[3 + d % 3], R[6 + d % 3]);
+          V3 col = mk(me[d % 3], me[3 + d % 3], me[6 + d % 3]);  // column d % 3 of R
           if (d < 3) { sl = col; sa = mk(0, 0, 0); }
-          else { sa = col; sl = cross(p, col); }
+          else { sa = col; sl = cross(ld3<T>(me + 9), col); }
           T* s0 = S0 + d * 6;
           st3(s0, sl); st3(s0 + 3, sa);
         } else {
-          sl = Sl; sa = Sa;
-          T* sr = Ss + i * SF_LD;
-          st3(sr, sl); st3(sr + 3, sa);
+          const T* sr = Ss + i * SF_LD;  // written in phase 2
+          sl = ld3<T>(sr); sa = ld3<T>(sr + 3);
         }
         grav[iv + d] = dot(sl, fgl) + dot(sa, fga);
         cori[iv + d] = dot(sl, fSl) + dot(sa, fSa);
@@ -398,9 +413,7 @@ k_update_system(const DevModel* __restrict__ gm, const DevFrames* __restrict__ g
           double* ag = ws.cent_ag + (size_t)s * 6 * nv;
           ag[iv + d] = ac.x; ag[nv + iv + d] = ac.y; ag[2 * nv + iv + d] = ac.z;
           ag[3 * nv + iv + d] = Fl.x; ag[4 * nv + iv + d] = Fl.y; ag[5 * nv + iv + d] = Fl.z;
-          const T qdd = isff ? (d < 3 ? (d == 0 ? vloc_lin.x : d == 1 ? vloc_lin.y : vloc_lin.z)
-                                           : (d == 3 ? vloc_ang.x : d == 4 ? vloc_ang.y : vloc_ang.z))
-                                  : qd;
+          const T qdd = isff ? vloc[d] : qd;
           hgp[0] += ac.x * qdd; hgp[1] += ac.y * qdd; hgp[2] += ac.z * qdd;
           hgp[3] += Fl.x * qdd; hgp[4] += Fl.y * qdd; hgp[5] += Fl.z * qdd;
         }

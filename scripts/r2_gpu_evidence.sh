@@ -13,4 +13,5 @@ timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-configs > $O/ncu_launches.log 2>&1
 timeout 300 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-configs > $O/plain2.log 2>&1 &&
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_ihwbc_reg|k_ihwbc_setup|k_update_system|k_ihwbc_finish|k_task_prepare|k_wbc" -c 8 -o $O/${T}_full -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-configs > $O/ncu_full.log 2>&1
+timeout 600 python scripts/fp32_mode_report.py 16384 > $O/fp32_report.jsonl 2> $O/fp32_report.err
 ls -la $O

@@ -299,8 +299,62 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     }
     __syncwarp();
     auto row_jc = [&](int c, int v) -> double { return jcrow[c][v]; };  // (Jc Ni)[c][v]
+    // The Hessian accumulators start as the lambda_q_ddot M term: its global loads are issued here, a memory round
+    // trip before their first use, and travel while the task data is staged (added after the task loop they were
+    // 4 % of the kernel's stall samples, all of it waiting on these loads).
+    double h[TPL][4];
+    int ro[TPL], co[TPL];
+#pragma unroll
+    for (int u = 0; u < TPL; u++) {
+      const int tab = tile_tab[lane + 32 * u];  // r0 | c0 << 8 (0 | 0 past the last tile: computed, never stored)
+      const int r0 = tab & 0xff, c0 = tab >> 8;
+      ro[u] = r0;
+      co[u] = c0;
+      const bool r1ok = r0 + 1 < NV, c1ok = c0 + 1 < NV;
+      h[u][0] = Mg[r0 * NV + c0];
+      h[u][1] = c1ok ? Mg[r0 * NV + c0 + 1] : 0.0;
+      h[u][2] = r1ok ? Mg[(r0 + 1) * NV + c0] : 0.0;
+      h[u][3] = (r1ok && c1ok) ? Mg[(r0 + 1) * NV + c0 + 1] : 0.0;
+    }
     // ---- tasks: e = Jdot qdot - xddot_cmd, weights (ihwbc.py:159-172) ----
-    // task error terms e = Jdot qdot - xddot_cmd were evaluated by k_task_prepare (ihwbc.cu)
+    // task error terms e = Jdot qdot - xddot_cmd were evaluated by k_task_prepare (ihwbc.cu).  They and the dense
+    // task Jacobian rows go from global to shared memory as asynchronous copies (cp.async, 8 bytes each, no
+    // registers in between): every load of the lane is in flight at once, one memory round trip for the phase
+    // (batches of nine register loads paid three), and the weight loads below overlap it.
+#ifndef PNC_STAGE_SYNC
+    {
+      // row -> source pointer table borrows g0 (written later, by the Hessian phase)
+      // (shape_ok checks ndense <= NP)
+      const double** rptr = reinterpret_cast<const double**>(g0);
+#pragma unroll 1
+      for (int t = lane; t < P.ntask; t += 32) {
+        const DevTask& T = P.tasks[t];
+        if (T.dense_off >= 0)
+          for (int i = 0; i < 3; i++) rptr[T.dense_off + i] = dense_row_ptr(T, fm.task_f[t], ws, s, nfr, NV, i);
+      }
+      __syncwarp();
+      const int total = P.ndense * NV;
+      const unsigned jd0 = (unsigned)__cvta_generic_to_shared(Jd), ev0 = (unsigned)__cvta_generic_to_shared(ev);
+#pragma unroll 4
+      for (int e = lane; e < total; e += 32) {
+        const int r = e / NV, c = e - r * NV;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(jd0 + 8u * (r * LDV + c)), "l"(rptr[r] + c) : "memory");
+      }
+      const double* te = ws.task_e + s * P.ntaskrows;
+#pragma unroll 1
+      for (int k = lane; k < P.ntaskrows; k += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ev0 + 8u * k), "l"(te + k) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 1
+      for (int t = 0; t < P.ntask; t++) {
+        const DevTask& T = P.tasks[t];
+        const double wt_t = io.w[s * P.ntask + t];
+        for (int i = lane; i < T.dim; i += 32) wt[T.row_off + i] = wt_t;
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
+#else
     {
       const double* te = ws.task_e + s * P.ntaskrows;
 #pragma unroll 1
@@ -343,6 +397,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       }
       __syncwarp();
     }
+#endif
 
     __syncthreads();
     // ---- Hessian task block (lower triangle) = sum_t w_t J_t^T J_t + lambda_q_ddot M ----
@@ -351,15 +406,10 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     // a lane's TPL tiles are TPL independent accumulator sets fed by two LDS.128 per row (row[r0..r0+1],
     // row[c0..c0+1]); the tile coordinates come from a table built once per CTA.
     {
-      const double* Mg = ws.M + s * NV * NV;
-      double h[TPL][4];
-      int ro[TPL], co[TPL];
+      {
+        const double lam = P.lambda_q_ddot;
 #pragma unroll
-      for (int u = 0; u < TPL; u++) {
-        h[u][0] = h[u][1] = h[u][2] = h[u][3] = 0.0;
-        const int tab = tile_tab[lane + 32 * u];  // r0 | c0 << 8 (0 | 0 past the last tile: computed, never stored)
-        ro[u] = tab & 0xff;
-        co[u] = tab >> 8;
+        for (int u = 0; u < TPL; u++) { h[u][0] *= lam; h[u][1] *= lam; h[u][2] *= lam; h[u][3] *= lam; }
       }
 #pragma unroll 1
       for (int t = 0; t < P.ntask; t++) {
@@ -381,19 +431,6 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
             h[u][0] = fma(wa, cc.x, h[u][0]); h[u][1] = fma(wa, cc.y, h[u][1]);
             h[u][2] = fma(wb, cc.x, h[u][2]); h[u][3] = fma(wb, cc.y, h[u][3]);
           }
-        }
-      }
-      {
-        const double lam = P.lambda_q_ddot;
-#pragma unroll
-        for (int u = 0; u < TPL; u++) {
-          if (lane + 32 * u >= ntile) continue;
-          const int r0 = ro[u], c0 = co[u];
-          const bool r1ok = r0 + 1 < NV, c1ok = c0 + 1 < NV;
-          const double m00 = Mg[r0 * NV + c0], m01 = c1ok ? Mg[r0 * NV + c0 + 1] : 0.0;
-          const double m10 = r1ok ? Mg[(r0 + 1) * NV + c0] : 0.0, m11 = (r1ok && c1ok) ? Mg[(r0 + 1) * NV + c0 + 1] : 0.0;
-          h[u][0] = fma(lam, m00, h[u][0]); h[u][1] = fma(lam, m01, h[u][1]);
-          h[u][2] = fma(lam, m10, h[u][2]); h[u][3] = fma(lam, m11, h[u][3]);
         }
       }
 #pragma unroll 1
@@ -781,9 +818,29 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
         }
         if constexpr (NT > 0) {
-          // flattened copy with several independent loads in flight; M is symmetric, so row
-          // act_idx[a] is read as column act_idx[a] with consecutive lanes on consecutive addresses
-          // element (row a, column k) with a fastest: a == lane throughout, so its joint index is loaded once
+          // Element (row a, column k) with a == lane.  M is symmetric, so row act_idx[a] is read as column
+          // act_idx[a] with consecutive lanes on consecutive addresses.  The rows go from global to shared memory
+          // by asynchronous copies (cp.async, 8 bytes each): no registers in between, so all N loads of a lane
+          // are in flight at once and the phase pays ONE memory round trip (batches of eight register loads paid
+          // six of them: 10.7 % of the kernel's stall samples sat on these lines).  -(Jc Ni)^T takes its sign
+          // once the data has landed.
+#ifndef PNC_IMG_SYNC
+          if (lane < nact) {
+            const int va = G.act_idx[lane];
+            const unsigned dst0 = (unsigned)__cvta_generic_to_shared(Ar + lane * LDA);
+#pragma unroll 4
+            for (int k = 0; k < N; k++) {
+              const double* src = has_ic ? ws.ic_tq + (s * N + k) * nact + lane : (k < NV ? Mg + k * NV + va : jcrow[k - NV] + va);
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst0 + 8u * k), "l"(src) : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          if (!has_ic && lane < nact) {
+#pragma unroll
+            for (int k = NV; k < N; k++) Ar[lane * LDA + k] = -Ar[lane * LDA + k];
+          }
+#else
           const int va = lane < nact ? G.act_idx[lane] : 0;
 #pragma unroll 1
           for (int e0 = lane; e0 < N * 32; e0 += 32 * 8) {
@@ -805,6 +862,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
               if (k < N && a < nact) Ar[a * LDA + k] = v[u];
             }
           }
+#endif
           for (int a = lane; a < nact; a += 32) {
             const int v = G.act_idx[a];
             // ci0 of the two torque-limit rows of joint a (ihwbc.py:266-296): S Ni^T (c+g) - trq_lo, trq_hi - S Ni^T (c+g)

@@ -804,6 +804,26 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 #pragma unroll 1
         for (int k = lane; k < C::IMG; k += 32) img[k] = 0.0;
         __syncwarp();
+#ifndef PNC_IMG_SYNC
+        // Torque-limit rows, element (row a, column k) with a == lane.  M is symmetric, so row act_idx[a] is read as
+        // column act_idx[a] with consecutive lanes on consecutive addresses.  The rows go from global to shared memory
+        // by asynchronous copies (cp.async, 8 bytes each): no registers in between, so all N loads of a lane are in
+        // flight at once and the phase pays ONE memory round trip (batches of eight register loads paid six: 10.7 %
+        // of the kernel's stall samples).  Issued first: the rows travel while the cones and offsets below are built;
+        // -(Jc Ni)^T takes its sign once the data has landed.
+        if constexpr (NT > 0) {
+          if (lane < nact) {
+            const int va = G.act_idx[lane];
+            const unsigned dst0 = (unsigned)__cvta_generic_to_shared(Ar + lane * LDA);
+#pragma unroll 4
+            for (int k = 0; k < N; k++) {
+              const double* src = has_ic ? ws.ic_tq + (s * N + k) * nact + lane : (k < NV ? Mg + k * NV + va : jcrow[k - NV] + va);
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst0 + 8u * k), "l"(src) : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+#endif
 #pragma unroll 1
         for (int r = lane; r < NU; r += 32) {
           const int ci = G.cone_contact[r];
@@ -818,29 +838,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
           uf[r] = lr == Cc.rows - 1 ? -rz : 0.0;
         }
         if constexpr (NT > 0) {
-          // Element (row a, column k) with a == lane.  M is symmetric, so row act_idx[a] is read as column
-          // act_idx[a] with consecutive lanes on consecutive addresses.  The rows go from global to shared memory
-          // by asynchronous copies (cp.async, 8 bytes each): no registers in between, so all N loads of a lane
-          // are in flight at once and the phase pays ONE memory round trip (batches of eight register loads paid
-          // six of them: 10.7 % of the kernel's stall samples sat on these lines).  -(Jc Ni)^T takes its sign
-          // once the data has landed.
-#ifndef PNC_IMG_SYNC
-          if (lane < nact) {
-            const int va = G.act_idx[lane];
-            const unsigned dst0 = (unsigned)__cvta_generic_to_shared(Ar + lane * LDA);
-#pragma unroll 4
-            for (int k = 0; k < N; k++) {
-              const double* src = has_ic ? ws.ic_tq + (s * N + k) * nact + lane : (k < NV ? Mg + k * NV + va : jcrow[k - NV] + va);
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst0 + 8u * k), "l"(src) : "memory");
-            }
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          if (!has_ic && lane < nact) {
-#pragma unroll
-            for (int k = NV; k < N; k++) Ar[lane * LDA + k] = -Ar[lane * LDA + k];
-          }
-#else
+#ifdef PNC_IMG_SYNC  // the register formulation: batches of eight loads, six memory round trips
           const int va = lane < nact ? G.act_idx[lane] : 0;
 #pragma unroll 1
           for (int e0 = lane; e0 < N * 32; e0 += 32 * 8) {
@@ -871,6 +869,13 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
             a0[NT + a] = G.trq_hi[a] - a0v;
             a0[2 * NT + a] = a0v;  // for the torque recovery at the end of the active-set kernel
           }
+#ifndef PNC_IMG_SYNC
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          if (!has_ic && lane < nact) {
+#pragma unroll
+            for (int k = NV; k < N; k++) Ar[lane * LDA + k] = -Ar[lane * LDA + k];
+          }
+#endif
         }
         __syncwarp();
         double2* ri = reinterpret_cast<double2*>(rec + C::RI);

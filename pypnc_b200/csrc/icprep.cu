@@ -529,18 +529,19 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
     const size_t s = (size_t)(base + warp < B ? base + warp : base);
     int bad = 0;
     const double* Mg = ws.M + s * NV * NV;
-#pragma unroll 1
-    for (int e0 = lane; e0 < NV * NV; e0 += 32 * 8) {  // flattened: eight independent loads in flight per lane
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = e0 + 32 * u < NV * NV ? Mg[e0 + 32 * u] : 0.0;
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int e = e0 + 32 * u;
-        if (e < NV * NV) { const int i = e / NV; T[i * LD + (e - i * NV)] = v[u]; }
+    // M goes global -> shared as asynchronous copies (cp.async, 8 bytes each, no registers in between): all of a
+    // lane's loads are in flight at once, one memory round trip instead of one per batch of eight register loads
+    {
+      const unsigned t0 = (unsigned)__cvta_generic_to_shared(T);
+#pragma unroll 4
+      for (int e = lane; e < NV * NV; e += 32) {
+        const int i = e / NV;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(t0 + 8u * (i * LD + (e - i * NV))), "l"(Mg + e) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int c = lane; c < NV; c += 32) cg[c] = ws.cori[s * NV + c] + ws.grav[s * NV + c];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     // ---- M = L L^T, T = L^-T ----
     __syncthreads();
@@ -622,8 +623,13 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
         const DevContact& Cc = P.contacts[ci];
         const double* Jrow = ws.fr_jac + (s * nfr + fm.contact_f[ci]) * 6 * NV +
                              (Cc.type == PNC_CONTACT_POINT ? 3 + (c - Cc.rf_off) : (c - Cc.rf_off)) * NV;
-        for (int i = lane; i < NV; i += 32) Jcs[c * LD + i] = Jrow[i];
+        // asynchronous copies: the NC rows travel together (one row at a time through registers paid NC round trips)
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(Jcs + c * LD);
+        for (int i = lane; i < NV; i += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 8u * i), "l"(Jrow + i) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       for (int c = lane; c < NC; c += 32) {
         const double* Jrow = Jcs + c * LD;
@@ -770,24 +776,24 @@ k_ic_prepare_reg(const DevProblem* __restrict__ gp, WsPtrs ws, FrameMap fm, int 
       }
       __syncwarp();  // every lane is done with the G block and V6: X = [M[6:, :] | (Jc Ni)[:, 6:]^T] goes over them
       double* X = sm;
-#pragma unroll 1
-      for (int e0 = lane; e0 < NJ * NV; e0 += 32 * 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = e0 + 32 * u < NJ * NV ? Mg[6 * NV + e0 + 32 * u] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int e = e0 + 32 * u;
-          if (e < NJ * NV) { const int j = e / NV; X[j * LDX + (e - j * NV)] = v[u]; }
+      {
+        const unsigned x0 = (unsigned)__cvta_generic_to_shared(X);
+#pragma unroll 4
+        for (int e = lane; e < NJ * NV; e += 32) {
+          const int j = e / NV;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(x0 + 8u * (j * LDX + (e - j * NV))), "l"(Mg + 6 * NV + e) : "memory");
         }
-      }
-#pragma unroll 1
-      for (int e = lane; e < NC * NJ; e += 32) {
-        const int cc = e / NJ, j = e - cc * NJ;
-        X[j * LDX + NV + cc] = ws.ic_jcni[(s * NC + cc) * NV + 6 + j];
+#pragma unroll 2
+        for (int e = lane; e < NC * NJ; e += 32) {
+          const int cc = e / NJ, j = e - cc * NJ;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(x0 + 8u * (j * LDX + NV + cc)),
+                       "l"(ws.ic_jcni + (s * NC + cc) * NV + 6 + j) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
       if (LDX > N)
         for (int j = lane; j < NJ; j += 32) X[j * LDX + N] = 0.0;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       // ---- S [M | -(Jc Ni)^T] (transposed store [n][nact]: coalesced) and S Ni^T (c+g) ----
       __syncthreads();

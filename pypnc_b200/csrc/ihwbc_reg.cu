@@ -302,6 +302,9 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     // The Hessian accumulators start as the lambda_q_ddot M term: its global loads are issued here, a memory round
     // trip before their first use, and travel while the task data is staged (added after the task loop they were
     // 4 % of the kernel's stall samples, all of it waiting on these loads).
+    // lane i < 6 also fetches the bias term of floating-base row i, (c + g)_i or (Ni^T (c + g))_i, for the equality
+    // residuals far below (read one row at a time there, it was six exposed round trips)
+    const double cg6 = lane < 6 ? (has_ic ? ws.ic_cg[s * NV + lane] : ws.cori[s * NV + lane] + ws.grav[s * NV + lane]) : 0.0;
     double h[TPL][4];
     int ro[TPL], co[TPL];
 #pragma unroll
@@ -620,7 +623,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 #pragma unroll 1
           for (int k = lane; k < NV; k += 32) part = fma(m6[i * NV + k], xs[k], part);
           part = wsum(part);
-          if (i < 6) part += has_ic ? ws.ic_cg[s * NV + i] : ws.cori[s * NV + i] + ws.grav[s * NV + i];
+          if (i < 6) part += __shfl_sync(FULL, cg6, i);
           else if (has_tr) {
             const int vd = P.trans_d[i - 6], vp = P.trans_p[i - 6];
             part += (ws.cori[s * NV + vd] + ws.grav[s * NV + vd]) - (ws.cori[s * NV + vp] + ws.grav[s * NV + vp]);

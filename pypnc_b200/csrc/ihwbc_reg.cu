@@ -304,7 +304,17 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
     // 4 % of the kernel's stall samples, all of it waiting on these loads).
     // lane i < 6 also fetches the bias term of floating-base row i, (c + g)_i or (Ni^T (c + g))_i, for the equality
     // residuals far below (read one row at a time there, it was six exposed round trips)
-    const double cg6 = lane < 6 ? (has_ic ? ws.ic_cg[s * NV + lane] : ws.cori[s * NV + lane] + ws.grav[s * NV + lane]) : 0.0;
+    // (the two addends stay apart until then where that pays: adding them here waits for the loads on the spot)
+    // measured per shape (solve stage, 64 K states): apart, Valkyrie 6.02 -> 5.94 ms, but Atlas 6.55 -> 6.59 (the
+    // second live register moves a spill into a hot loop of that instantiation), so Atlas adds on the spot
+    constexpr bool kBiasApart = !(NV == 36 && NT == 30);
+    double cg6a, cg6b = 0.0;
+    if (kBiasApart) {
+      cg6a = lane < 6 ? (has_ic ? ws.ic_cg[s * NV + lane] : ws.cori[s * NV + lane]) : 0.0;
+      cg6b = (lane < 6 && !has_ic) ? ws.grav[s * NV + lane] : 0.0;
+    } else {
+      cg6a = lane < 6 ? (has_ic ? ws.ic_cg[s * NV + lane] : ws.cori[s * NV + lane] + ws.grav[s * NV + lane]) : 0.0;
+    }
     double h[TPL][4];
     int ro[TPL], co[TPL];
 #pragma unroll
@@ -348,10 +358,12 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
       for (int k = lane; k < P.ntaskrows; k += 32)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ev0 + 8u * k), "l"(te + k) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
+      // the task weights in one coalesced load (lane t holds w_t; ntask <= PNC_MAX_TASKS = 16), broadcast per task
+      const double w_lane = lane < P.ntask ? io.w[s * P.ntask + lane] : 0.0;
 #pragma unroll 1
       for (int t = 0; t < P.ntask; t++) {
         const DevTask& T = P.tasks[t];
-        const double wt_t = io.w[s * P.ntask + t];
+        const double wt_t = __shfl_sync(FULL, w_lane, t);
         for (int i = lane; i < T.dim; i += 32) wt[T.row_off + i] = wt_t;
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -623,7 +635,7 @@ k_ihwbc_setup(const __grid_constant__ DevProblem P, const DevProblem* __restrict
 #pragma unroll 1
           for (int k = lane; k < NV; k += 32) part = fma(m6[i * NV + k], xs[k], part);
           part = wsum(part);
-          if (i < 6) part += __shfl_sync(FULL, cg6, i);
+          if (i < 6) part += __shfl_sync(FULL, cg6a + cg6b, i);
           else if (has_tr) {
             const int vd = P.trans_d[i - 6], vp = P.trans_p[i - 6];
             part += (ws.cori[s * NV + vd] + ws.grav[s * NV + vd]) - (ws.cori[s * NV + vp] + ws.grav[s * NV + vp]);

@@ -22,7 +22,7 @@ from pypnc_b200 import robots  # noqa: E402
 from pypnc_b200.models.compile_models import ROBOTS as MODELS  # noqa: E402
 from tests.first_principles import Referee, H  # noqa: E402
 
-NAMES = ('atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie', 'three_link_manipulator')
+NAMES = ('atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie', 'three_link_manipulator', 'two_link_manipulator')
 STATES = 3
 QUANTS = ('qdot', 'M', 'grav', 'cori', 'com', 'vcom', 'jcom', 'jcomdot', 'jcom_jdqd', 'Ag', 'hg', 'Ig', 'frame_iso',
           'frame_vel', 'frame_jac', 'frame_jdqd')

@@ -24,7 +24,7 @@ from pypnc_b200 import robots
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FX = np.load(os.path.join(HERE, 'golden', 'first_principles.npz'))
-NAMES = ('atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie', 'three_link_manipulator')
+NAMES = ('atlas', 'laikago', 'draco3', 'draco3_lb', 'valkyrie', 'three_link_manipulator', 'two_link_manipulator')
 STATES = 3
 TOL = 1e-6
 IN_KEYS = ('base_pos', 'base_quat', 'base_lin_vel', 'base_ang_vel', 'joint_pos', 'joint_vel')
@@ -46,7 +46,7 @@ def test_oracle_matches_first_principles(name, oracle_mod):
     m = robots.load_model(name)
     om = oracle_mod.OracleModel(m)
     frames = [str(f) for f in FX[name + '/frames']]
-    assert len(frames) >= 5
+    assert len(frames) >= 4
     worst = 0.0
     for k in range(STATES):
         assert float(fx(name, k, 'fd_err')) < 5e-7
@@ -113,6 +113,46 @@ def test_update_system_kernel_matches_first_principles(name):
                 worst = max(worst, close(g['frame_jdqd'][k, i], fx(name, k, 'frame_jdqd')[c0 + i], tag + fn + ' jdqd'))
         del ws
     print('%s: k_update_system vs first principles, worst %.1e' % (name, worst))
+
+
+def test_referee_motion_is_the_se3_exponential():
+    """The referee's motion q (+) t v must be pinocchio's integrate: T_b Exp(t [v; w]) with the twist in the BODY frame.
+    Its closed form (first_principles.se3_exp) against scipy's matrix exponential of the 4x4 twist matrix."""
+    from scipy.linalg import expm
+    from tests.first_principles import se3_exp
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        v, w, t = rng.normal(size=3), rng.normal(size=3), rng.uniform(-1, 1)
+        X = np.zeros((4, 4))
+        X[:3, :3] = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        X[:3, 3] = v
+        E = expm(t * X)
+        R, p = se3_exp(v, w, t)
+        np.testing.assert_allclose(R, E[:3, :3], atol=1e-13)
+        np.testing.assert_allclose(p, E[:3, 3], atol=1e-13)
+    R, p = se3_exp(np.array([1., 2., 3.]), np.zeros(3), 0.5)  # pure translation
+    np.testing.assert_allclose(R, np.eye(3), atol=0)
+    np.testing.assert_allclose(p, [0.5, 1.0, 1.5], atol=1e-15)
+
+
+def test_referee_reproduces_the_reference_closed_form_two_link_fixture():
+    """The referee itself against the one closed form the reference holds (test/two_link_manipulator_test.py:19-48:
+    analytic Jacobian and its time derivative of the planar two-link arm, rows [angular; linear])."""
+    name = 'two_link_manipulator'
+    frames = [str(f) for f in FX[name + '/frames']]
+    e = frames.index('ee')
+    for k in range(STATES):
+        q, qd = fx(name, k, 'in_joint_pos'), fx(name, k, 'in_joint_vel')
+        J = np.zeros((6, 2))
+        J[3, 0] = -np.sin(q[0]) - np.sin(q[0] + q[1]); J[3, 1] = -np.sin(q[0] + q[1])
+        J[4, 0] = np.cos(q[0]) + np.cos(q[0] + q[1]); J[4, 1] = np.cos(q[0] + q[1])
+        J[2, :] = 1.
+        Jd = np.zeros((6, 2))
+        Jd[3, 0] = -np.cos(q[0]) * qd[0] - np.cos(q[0] + q[1]) * (qd[0] + qd[1]); Jd[3, 1] = -np.cos(q[0] + q[1]) * (qd[0] + qd[1])
+        Jd[4, 0] = -np.sin(q[0]) * qd[0] - np.sin(q[0] + q[1]) * (qd[0] + qd[1]); Jd[4, 1] = -np.sin(q[0] + q[1]) * (qd[0] + qd[1])
+        np.testing.assert_allclose(fx(name, k, 'frame_jac')[e], J, atol=1e-9)
+        np.testing.assert_allclose(fx(name, k, 'frame_vel')[e], J @ qd, atol=1e-9)
+        np.testing.assert_allclose(fx(name, k, 'frame_jdqd')[e], Jd @ qd, atol=1e-8)
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/robot_model'), reason="reference checkout absent")

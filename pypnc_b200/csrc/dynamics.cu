@@ -552,16 +552,20 @@ void launch_update_system(const DevModel* dm, const DevFrames* dfr, const int4* 
     struct Entry { const void* fn; int dev; size_t smem; int ctas; };
     static Entry table[64];
     static int used = 0;
+    static std::mutex mu;
     int dev = 0;
     cudaGetDevice(&dev);
     const void* fn = reinterpret_cast<const void*>(kernel);
     int ctas_per_sm = 0;
-    for (int i = 0; i < used; i++)
-      if (table[i].fn == fn && table[i].dev == dev && table[i].smem == smem) ctas_per_sm = table[i].ctas;
-    if (ctas_per_sm == 0) {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, DYN_WARPS * 32, smem) != cudaSuccess || ctas_per_sm < 1)
-        ctas_per_sm = 1;
-      if (used < 64) table[used++] = Entry{fn, dev, smem, ctas_per_sm};
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      for (int i = 0; i < used; i++)
+        if (table[i].fn == fn && table[i].dev == dev && table[i].smem == smem) ctas_per_sm = table[i].ctas;
+      if (ctas_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, DYN_WARPS * 32, smem) != cudaSuccess || ctas_per_sm < 1)
+          ctas_per_sm = 1;
+        if (used < 64) table[used++] = Entry{fn, dev, smem, ctas_per_sm};
+      }
     }
     int grid = num_sms * ctas_per_sm;
     if (grid > need) grid = need;

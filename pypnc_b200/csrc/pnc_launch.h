@@ -1,5 +1,7 @@
 // pnc_launch.h -- host-side launch interface between capi.cu and the kernel files.
 #pragma once
+#include <mutex>
+
 #include "pnc_dev.cuh"
 
 namespace pnc {
@@ -119,6 +121,8 @@ struct SmemOptIn {
     struct Entry { const void* fn; int dev; size_t bytes; };
     static Entry table[256];
     static int used = 0;
+    static std::mutex mu;  // host threads driving different handles (one per GPU) may launch at the same time
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
     const void* fn = reinterpret_cast<const void*>(kernel);

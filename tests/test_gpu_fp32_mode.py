@@ -23,7 +23,7 @@ FIELDS = ('M', 'grav', 'cori', 'com', 'vcom', 'jcom', 'jcomdot', 'jcom_jdqd', 'f
           'frame_jdqd', 'qdot')
 # (robot, states, min share of states within 1e-4 of the fp64 oracle, max median error)
 CASES = [('atlas', 4096, 0.998, 1e-5), ('laikago', 4096, 0.92, 1e-5), ('valkyrie', 2048, 0.97, 2e-5),
-         ('draco3', 2048, 0.99, 2e-5), ('draco3_lb', 2048, 0.99, 2e-5)]
+         ('draco3', 2048, 0.99, 2e-5), ('draco3_lb', 2048, 0.985, 2e-5)]
 
 
 @pytest.mark.parametrize("name,B,min_share,max_median", CASES)

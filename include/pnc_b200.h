@@ -34,7 +34,9 @@
  * contact = [torque(3); force(3)] in world axes; all batched arrays are row-major with
  * the batch index first.  Pointers named d_* are DEVICE pointers, h_* HOST pointers.
  * Every call is asynchronous on `stream` (a cudaStream_t passed as void*) unless it
- * says otherwise; calls on one handle are stream-ordered, not re-entrant.
+ * says otherwise; calls on one handle are stream-ordered, not re-entrant.  Different handles may be driven
+ * from different host threads (e.g. one thread per GPU); the process-wide modes (pnc_set_termination,
+ * pnc_set_precision) are read at launch time and are meant to be set before the threads start.
  *
  * Return value: 0 on success, a negative PNC_E_* code on API misuse / CUDA failure.
  * Per-state solver outcomes are reported in `status[B]` (PNC_QP_*), never by abort.
